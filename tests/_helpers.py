@@ -1,0 +1,101 @@
+"""Shared helpers for multi-process service tests (CPU only)."""
+import asyncio
+import multiprocessing
+import socket
+import time
+from typing import Optional, Sequence, Tuple
+
+import numpy as np
+
+
+def product_func(*inputs) -> Tuple[np.ndarray]:
+    return (np.prod(inputs),)
+
+
+def free_port() -> int:
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _serve(port: int, n_clients: int, func_name: str, ready) -> None:
+    from pytensor_federated_b200 import service
+    from pytensor_federated_b200.rpc import Server
+
+    func = {"product": product_func}[func_name]
+
+    async def main():
+        svc = service.ArraysToArraysService(func)
+        svc._n_clients = n_clients  # fake load, like the reference's tests do
+        server = Server([svc])
+        await server.start("127.0.0.1", port)
+        ready.set()
+        await server.wait_closed()
+
+    asyncio.new_event_loop().run_until_complete(main())
+
+
+class ServerProcess:
+    """A node in a child process; ``terminate()`` is the fault-injection knob."""
+
+    def __init__(self, port: Optional[int] = None, n_clients: int = 0, func: str = "product"):
+        self.port = port or free_port()
+        ctx = multiprocessing.get_context("spawn")
+        self._ready = ctx.Event()
+        self._proc = ctx.Process(
+            target=_serve, args=(self.port, n_clients, func, self._ready), daemon=True
+        )
+
+    def start(self, timeout: float = 60.0) -> "ServerProcess":
+        self._proc.start()
+        if not self._ready.wait(timeout):
+            self.terminate()
+            raise RuntimeError("server did not come up")
+        return self
+
+    def terminate(self) -> None:
+        if self._proc.is_alive():
+            self._proc.terminate()
+        self._proc.join(10)
+
+    def __enter__(self):
+        return self.start()
+
+    def __exit__(self, *exc):
+        self.terminate()
+
+
+def start_fleet(loads: Sequence[int]):
+    servers = [ServerProcess(n_clients=n) for n in loads]
+    for s in servers:
+        s._proc.start()
+    deadline = time.time() + 90
+    for s in servers:
+        if not s._ready.wait(max(0.1, deadline - time.time())):
+            for t in servers:
+                t.terminate()
+            raise RuntimeError("fleet did not come up")
+    return servers
+
+
+def run_product_queries(client, n: int = 50) -> bool:
+    rng = np.random.default_rng()
+    try:
+        for _ in range(n):
+            a, b = rng.integers(0, 50, size=2)
+            (prod,) = client.evaluate(a, b)
+            assert prod == a * b
+    except Exception:
+        import traceback
+
+        traceback.print_exc()
+        return False
+    return True
+
+
+class ProductTester:
+    def __init__(self, client) -> None:
+        self.client = client
+
+    def run(self, n: int) -> bool:
+        return run_product_queries(self.client, n)
