@@ -1,0 +1,270 @@
+// Device-side federation protocol shared by every model kernel (sm_100a).
+//
+// One evaluation ("epoch") of a federated log-likelihood is ONE kernel per GPU:
+//
+//   prologue   rank 0 ("root", the client's GPU) reads theta from host-mapped
+//              pinned memory and stores it into every node's theta mailbox over
+//              NVLink (multimem.st through the NVSwitch multicast object when one
+//              exists, otherwise one P2P store per peer), then releases an epoch
+//              flag per node.  Every CTA of every node acquires its local flag.
+//   compute    model specific (linreg / GLM / ODE ...), per-CTA partials.
+//   epilogue   last CTA of each node sums the CTA partials in a fixed order and
+//              stores the node's [LL, dLL/dtheta] into the root's slot array over
+//              NVLink + releases a slot flag.  The root's last CTA acquires all
+//              slot flags, sums the nodes in rank order (deterministic), and
+//              writes the result + a completion flag into host-mapped memory.
+//
+// This replaces the reference's per-evaluation path of
+//   npproto encode -> HTTP/2 send -> decode -> compute -> encode -> recv -> decode
+// (/root/reference/pytensor_federated/service.py:150-158, :45-72) and the
+// client-side graph sum over nodes, with zero host involvement on the nodes.
+//
+// Memory-model notes: data is written with weak stores, then
+// __threadfence_system(); the flag is written with st.release.sys and read with
+// ld.acquire.sys (the acquire invalidates the SM's L1, and mailbox data is
+// re-read with ld.cg on top of that).  Epoch tags make stale flags detectable; every
+// spin is bounded by %globaltimer so a dead peer yields an error code instead
+// of a hung GPU.
+#pragma once
+#include <cstdint>
+#include <cuda_runtime.h>
+
+#define B200FED_MAX_WORLD 8
+
+// status bits OR-ed into the completion flag's upper byte
+#define B200FED_STATUS_SHIFT 56
+#define B200FED_EPOCH_MASK 0x00FFFFFFFFFFFFFFull
+#define B200FED_ERR_THETA_TIMEOUT 1ull
+#define B200FED_ERR_PEER_TIMEOUT 2ull
+#define B200FED_STOP_EPOCH 0x00FFFFFFFFFFFFFFull
+
+struct FedComm {
+    int rank;                 // 0 = root (client GPU)
+    int world;                // number of nodes (GPUs)
+    int n_theta;              // floats in the theta mailbox
+    int n_vals;               // doubles per node partial: [LL, grads...]
+    unsigned long long epoch; // this launch's epoch (root: passed by host; peer: see epoch_counter)
+    unsigned long long timeout_ns;
+
+    // --- root only ---------------------------------------------------------
+    const float* theta_src;                        // host-mapped pinned (or device) theta
+    float* peer_theta[B200FED_MAX_WORLD];          // every node's mailbox (incl. own)
+    unsigned long long* peer_flag[B200FED_MAX_WORLD];
+    float* mc_theta;                               // multicast alias of the mailbox (or null)
+    unsigned long long* mc_flag;                   // multicast alias of the flag (or null)
+    double* host_result;                           // host-mapped [n_vals]
+    unsigned long long* host_flag;                 // host-mapped completion flag
+
+    // --- every node ----------------------------------------------------------
+    float* theta_local;                            // own mailbox
+    unsigned long long* flag_local;                // own epoch flag
+    double* root_slots;                            // root's slot array [world][n_vals]   (peer memory)
+    unsigned long long* root_slot_flags;           // root's slot flags [world]             (peer memory)
+    double* cta_partials;                          // local scratch [grid][n_vals]
+    unsigned int* ticket;                          // local "last CTA" counter
+    unsigned long long* epoch_counter;             // peers: device-resident epoch (graph replay friendly); may be null
+    unsigned long long* done_flag;                 // host-mapped: last finished epoch on this node (peers' serve loop)
+    unsigned long long* trace;                     // optional device-timer ring [4 x u64 per epoch % 256] or null
+};
+
+namespace fed {
+
+__device__ __forceinline__ unsigned long long ld_acquire_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.acquire.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.release.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ld_relaxed_sys(const unsigned long long* p) {
+    unsigned long long v;
+    asm volatile("ld.relaxed.sys.global.u64 %0, [%1];" : "=l"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ float ld_cg_f32(const float* p) {
+    float v;
+    asm volatile("ld.global.cg.f32 %0, [%1];" : "=f"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ double ld_cg_f64(const double* p) {
+    double v;
+    asm volatile("ld.global.cg.f64 %0, [%1];" : "=d"(v) : "l"(p) : "memory");
+    return v;
+}
+__device__ __forceinline__ unsigned long long globaltimer() {
+    unsigned long long t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+// NVSwitch multicast store: one store instruction lands in every node's copy.
+__device__ __forceinline__ void multimem_st_f32(float* mc, float v) {
+    asm volatile("multimem.st.relaxed.sys.global.f32 [%0], %1;" ::"l"(mc), "f"(v) : "memory");
+}
+__device__ __forceinline__ void multimem_st_release_u64(unsigned long long* mc, unsigned long long v) {
+    asm volatile("multimem.st.release.sys.global.u64 [%0], %1;" ::"l"(mc), "l"(v) : "memory");
+}
+
+// Spin until *flag (epoch part) >= epoch.  Returns false on timeout.
+__device__ __forceinline__ bool wait_epoch(const unsigned long long* flag, unsigned long long epoch,
+                                           unsigned long long timeout_ns, unsigned long long* seen) {
+    unsigned long long t0 = globaltimer();
+    unsigned int spins = 0;
+    while (true) {
+        unsigned long long v = ld_acquire_sys(flag);
+        if ((v & B200FED_EPOCH_MASK) >= epoch) {
+            *seen = v;
+            return true;
+        }
+        if ((++spins & 0x3F) == 0) {
+            if (timeout_ns && globaltimer() - t0 > timeout_ns) {
+                *seen = v;
+                return false;
+            }
+            __nanosleep(64);
+        }
+    }
+}
+
+struct Prologue {
+    unsigned long long epoch;   // resolved epoch of this launch
+    bool stop;                  // root asked the nodes to drain
+    bool timed_out;
+};
+
+// Broadcast (root) + acquire (everyone).  Leaves theta[0..n_theta) in `theta_smem`.
+// Must be called by all threads of the CTA.
+__device__ __forceinline__ Prologue prologue(const FedComm& c, float* theta_smem) {
+    __shared__ unsigned long long s_seen;
+    __shared__ int s_ok;
+    unsigned long long epoch = c.epoch;
+    if (c.epoch_counter) epoch = *reinterpret_cast<volatile unsigned long long*>(c.epoch_counter) + 1ull;
+
+    if (c.rank == 0 && blockIdx.x == 0) {
+        // theta_src may live in host memory: read it once, fan it out over NVLink.
+        for (int i = threadIdx.x; i < c.n_theta; i += blockDim.x) {
+            float v = c.theta_src[i];
+            if (c.mc_theta) {
+                multimem_st_f32(c.mc_theta + i, v);
+            } else {
+                for (int p = 0; p < c.world; ++p) c.peer_theta[p][i] = v;
+            }
+        }
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            if (c.trace) c.trace[(epoch & 255) * 4 + 0] = globaltimer();
+            if (c.mc_flag) {
+                multimem_st_release_u64(c.mc_flag, epoch);
+            } else {
+                for (int p = 0; p < c.world; ++p) st_release_sys(c.peer_flag[p], epoch);
+            }
+        }
+    }
+    if (threadIdx.x == 0) {
+        unsigned long long seen = 0;
+        s_ok = wait_epoch(c.flag_local, epoch, c.timeout_ns, &seen) ? 1 : 0;
+        s_seen = seen;
+    }
+    __syncthreads();
+    Prologue r;
+    r.epoch = epoch;
+    r.timed_out = (s_ok == 0);
+    r.stop = ((s_seen & B200FED_EPOCH_MASK) == B200FED_STOP_EPOCH);
+    if (!r.timed_out && !r.stop) {
+        for (int i = threadIdx.x; i < c.n_theta; i += blockDim.x) theta_smem[i] = ld_cg_f32(c.theta_local + i);
+    }
+    __syncthreads();
+    return r;
+}
+
+// Every CTA has stored its partial into c.cta_partials[blockIdx.x * n_vals ...].
+// `scratch` is shared memory for at least 1 int.  Must be called by all threads.
+__device__ __forceinline__ void epilogue(const FedComm& c, const Prologue& pro, unsigned long long status_in) {
+    __shared__ int s_last;
+    __shared__ unsigned long long s_status;
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        unsigned int t = atomicAdd(c.ticket, 1u);
+        s_last = (t == gridDim.x - 1) ? 1 : 0;
+        s_status = status_in;
+    }
+    __syncthreads();
+    if (!s_last) return;
+    __threadfence();
+    const int nv = c.n_vals;
+    const unsigned long long epoch = pro.epoch;
+
+    if (pro.stop || pro.timed_out) {
+        // nothing was computed: just report and drain
+        if (threadIdx.x == 0) {
+            *c.ticket = 0;
+            if (c.epoch_counter) *c.epoch_counter = epoch;
+            unsigned long long st = pro.timed_out ? B200FED_ERR_THETA_TIMEOUT : 0ull;
+            unsigned long long word = (pro.stop ? B200FED_STOP_EPOCH : epoch) | (st << B200FED_STATUS_SHIFT);
+            if (c.done_flag) { *reinterpret_cast<volatile unsigned long long*>(c.done_flag) = word; }
+            if (c.rank == 0 && c.host_flag) {
+                __threadfence_system();
+                st_release_sys(c.host_flag, word);
+            }
+        }
+        return;
+    }
+
+    // 1) node partial = fixed-order sum over CTAs -> root's slot for this rank (NVLink store for peers)
+    double* my_slot = c.root_slots + (size_t)c.rank * nv;
+    for (int v = threadIdx.x; v < nv; v += blockDim.x) {
+        double s = 0.0;
+        for (unsigned int b = 0; b < gridDim.x; ++b) s += ld_cg_f64(c.cta_partials + (size_t)b * nv + v);
+        my_slot[v] = s;
+    }
+    __threadfence_system();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        if (c.trace) c.trace[(epoch & 255) * 4 + 1] = globaltimer();
+        st_release_sys(c.root_slot_flags + c.rank, epoch);
+    }
+
+    // 2) root: gather the nodes, ordered sum, publish to the host
+    if (c.rank == 0) {
+        if (threadIdx.x < c.world) {
+            unsigned long long seen;
+            bool ok = wait_epoch(c.root_slot_flags + threadIdx.x, epoch, c.timeout_ns, &seen);
+            if (!ok) atomicOr(&s_status, B200FED_ERR_PEER_TIMEOUT);
+        }
+        __syncthreads();
+        for (int v = threadIdx.x; v < nv; v += blockDim.x) {
+            double s = 0.0;
+            for (int p = 0; p < c.world; ++p) s += ld_cg_f64(c.root_slots + (size_t)p * nv + v);
+            c.host_result[v] = s;
+        }
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            if (c.trace) c.trace[(epoch & 255) * 4 + 2] = globaltimer();
+            st_release_sys(c.host_flag, epoch | (s_status << B200FED_STATUS_SHIFT));
+        }
+    }
+    if (threadIdx.x == 0) {
+        *c.ticket = 0;
+        if (c.epoch_counter) *c.epoch_counter = epoch;
+        if (c.done_flag) *reinterpret_cast<volatile unsigned long long*>(c.done_flag) = epoch | (s_status << B200FED_STATUS_SHIFT);
+    }
+}
+
+// block-wide sum of doubles; result valid in thread 0.  `buf` needs >= 32 doubles.
+__device__ __forceinline__ double block_sum(double v, double* buf) {
+    for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    const int w = threadIdx.x >> 5, l = threadIdx.x & 31;
+    __syncthreads();
+    if (l == 0) buf[w] = v;
+    __syncthreads();
+    if (w == 0) {
+        v = (l < (int)((blockDim.x + 31) >> 5)) ? buf[l] : 0.0;
+        for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);
+    }
+    return v;
+}
+
+}  // namespace fed

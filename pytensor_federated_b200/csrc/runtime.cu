@@ -1,0 +1,594 @@
+// Host runtime of the federation engine (C ABI, loaded with ctypes — no torch/pybind
+// headers, so the whole library compiles in seconds and carries no ABI coupling).
+//
+// An Engine owns, for ONE GPU ("node"):
+//   * the comm block (theta mailbox, epoch flag, slot array, slot flags) — allocated here
+//     with cudaMalloc (exportable through CUDA IPC) or supplied from outside (torch
+//     symmetric memory, which can also supply an NVSwitch multicast alias);
+//   * host-mapped pinned memory for theta (root: written by the client thread, read by the
+//     kernel over PCIe), for the result and for the completion flag (written by the kernel,
+//     polled by the client thread — no cudaStreamSynchronize on the evaluation path);
+//   * the model descriptor and the launch configuration.
+//
+// Root:  b200_engine_eval()  = memcpy theta -> launch -> spin on host flag -> copy result.
+// Peers: b200_engine_serve() = keep `ahead` kernels enqueued; each one waits ON THE DEVICE
+//        for the root's epoch flag, so a peer's host never sits on the critical path.
+//
+// The reference's counterpart of this file is its asyncio/gRPC client+server pair
+// (/root/reference/pytensor_federated/service.py:75-158, :326-423).
+#include <atomic>
+#include <chrono>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <string>
+#include <thread>
+#include <vector>
+
+#include <cuda_runtime.h>
+
+#include "fed_comm.cuh"
+#include "models.h"
+
+extern "C" {
+int b200_launch_linreg(const FedComm*, const LinregShard*, int, int, int, cudaStream_t);
+int b200_launch_glm_simt(const FedComm*, const GlmSegment*, const GlmParams*, int, cudaStream_t);
+size_t b200_glm_simt_smem(int, int, int);
+int b200_launch_glm_tc(const FedComm*, const GlmSegment*, const GlmParams*, const void* tmaps, int grid,
+                       cudaStream_t);
+int b200_glm_tc_prepare(const GlmSegment* segs_host, int n_segments, const GlmParams* prm, void** tmaps_dev);
+int b200_launch_ode(const FedComm*, const OdeShard*, int, int, cudaStream_t);
+}
+
+namespace {
+
+enum ModelKind { MODEL_NONE = 0, MODEL_LINREG = 1, MODEL_GLM_SIMT = 2, MODEL_GLM_TC = 3, MODEL_ODE = 4 };
+
+thread_local std::string g_last_error;
+
+int fail(const char* what, cudaError_t err) {
+    g_last_error = std::string(what) + ": " + cudaGetErrorString(err);
+    return (int)err ? (int)err : -1;
+}
+#define CK(expr)                                  \
+    do {                                          \
+        cudaError_t _e = (expr);                  \
+        if (_e != cudaSuccess) return fail(#expr, _e); \
+    } while (0)
+
+struct CommLayout {
+    size_t off_flag, off_theta, off_slots, off_slot_flags, bytes;
+};
+CommLayout comm_layout(int world, int n_theta, int n_vals) {
+    CommLayout L;
+    auto up = [](size_t v) { return (v + 255) & ~size_t(255); };
+    L.off_flag = 0;
+    L.off_theta = 256;
+    L.off_slots = up(L.off_theta + (size_t)n_theta * 4);
+    L.off_slot_flags = up(L.off_slots + (size_t)world * n_vals * 8);
+    L.bytes = up(L.off_slot_flags + (size_t)world * 8);
+    return L;
+}
+
+struct Engine {
+    int device = 0, rank = 0, world = 1, n_theta = 0, n_vals = 0;
+    int grid = 1, sm_count = 148;
+    cudaStream_t stream = nullptr;
+    bool owns_comm = false;
+    unsigned char* comm_local = nullptr;
+    unsigned char* comm_peer[B200FED_MAX_WORLD] = {};
+    unsigned char* comm_mc = nullptr;
+    CommLayout layout{};
+    // host-mapped
+    unsigned char* host_block = nullptr;      // [theta | result | flag | done | trace]
+    unsigned char* host_block_dev = nullptr;  // device alias
+    size_t h_off_theta = 0, h_off_result = 0, h_off_flag = 0, h_off_done = 0;
+    // device-local
+    double* cta_partials = nullptr;
+    unsigned int* ticket = nullptr;
+    unsigned long long* epoch_counter = nullptr;
+    unsigned long long* trace = nullptr;
+    unsigned long long epoch = 0;  // last launched epoch (root)
+    unsigned long long timeout_ns = 20ull * 1000 * 1000 * 1000;
+    unsigned long long launches = 0;
+    float* theta_dev = nullptr;   // optional device-resident theta source (device-timed benchmarking)
+    bool theta_from_device = false;
+    // model
+    ModelKind kind = MODEL_NONE;
+    std::vector<LinregShard> linreg;
+    LinregShard* linreg_dev = nullptr;
+    int linreg_f64 = 1;
+    std::vector<GlmSegment> glm_segs;
+    GlmSegment* glm_segs_dev = nullptr;
+    GlmParams glm{};
+    void* glm_tmaps_dev = nullptr;
+    std::vector<OdeShard> ode;
+    OdeShard* ode_dev = nullptr;
+    std::atomic<int> stop_serving{0};
+
+    float* h_theta() { return reinterpret_cast<float*>(host_block + h_off_theta); }
+    double* h_result() { return reinterpret_cast<double*>(host_block + h_off_result); }
+    volatile unsigned long long* h_flag() { return reinterpret_cast<volatile unsigned long long*>(host_block + h_off_flag); }
+    volatile unsigned long long* h_done() { return reinterpret_cast<volatile unsigned long long*>(host_block + h_off_done); }
+};
+
+void fill_comm(Engine* e, FedComm* c, bool root_uses_explicit_epoch) {
+    memset(c, 0, sizeof(*c));
+    c->rank = e->rank;
+    c->world = e->world;
+    c->n_theta = e->n_theta;
+    c->n_vals = e->n_vals;
+    c->timeout_ns = e->timeout_ns;
+    const CommLayout& L = e->layout;
+    c->theta_local = reinterpret_cast<float*>(e->comm_local + L.off_theta);
+    c->flag_local = reinterpret_cast<unsigned long long*>(e->comm_local + L.off_flag);
+    unsigned char* root_block = e->comm_peer[0];
+    c->root_slots = reinterpret_cast<double*>(root_block + L.off_slots);
+    c->root_slot_flags = reinterpret_cast<unsigned long long*>(root_block + L.off_slot_flags);
+    c->cta_partials = e->cta_partials;
+    c->ticket = e->ticket;
+    c->trace = e->trace;
+    c->done_flag = reinterpret_cast<unsigned long long*>(e->host_block_dev + e->h_off_done);
+    if (e->rank == 0) {
+        c->theta_src = e->theta_from_device ? e->theta_dev
+                                            : reinterpret_cast<const float*>(e->host_block_dev + e->h_off_theta);
+        for (int p = 0; p < e->world; ++p) {
+            c->peer_theta[p] = reinterpret_cast<float*>(e->comm_peer[p] + L.off_theta);
+            c->peer_flag[p] = reinterpret_cast<unsigned long long*>(e->comm_peer[p] + L.off_flag);
+        }
+        if (e->comm_mc) {
+            c->mc_theta = reinterpret_cast<float*>(e->comm_mc + L.off_theta);
+            c->mc_flag = reinterpret_cast<unsigned long long*>(e->comm_mc + L.off_flag);
+        }
+        c->host_result = reinterpret_cast<double*>(e->host_block_dev + e->h_off_result);
+        c->host_flag = reinterpret_cast<unsigned long long*>(e->host_block_dev + e->h_off_flag);
+        c->epoch_counter = root_uses_explicit_epoch ? nullptr : e->epoch_counter;
+    } else {
+        c->epoch_counter = e->epoch_counter;  // peers count epochs on the device
+    }
+}
+
+int launch_model(Engine* e, const FedComm* c) {
+    int rc = -1;
+    switch (e->kind) {
+        case MODEL_LINREG:
+            rc = b200_launch_linreg(c, e->linreg_dev, (int)e->linreg.size(), e->linreg_f64, e->grid, e->stream);
+            break;
+        case MODEL_GLM_SIMT:
+            rc = b200_launch_glm_simt(c, e->glm_segs_dev, &e->glm, e->grid, e->stream);
+            break;
+        case MODEL_GLM_TC:
+            rc = b200_launch_glm_tc(c, e->glm_segs_dev, &e->glm, e->glm_tmaps_dev, e->grid, e->stream);
+            break;
+        case MODEL_ODE:
+            rc = b200_launch_ode(c, e->ode_dev, (int)e->ode.size(), e->grid, e->stream);
+            break;
+        default:
+            g_last_error = "no model attached to the engine";
+            return -2;
+    }
+    if (rc != 0) {
+        g_last_error = std::string("kernel launch failed: ") + (rc > 0 ? cudaGetErrorString((cudaError_t)rc) : "unsupported shape");
+        return rc;
+    }
+    e->launches++;
+    return 0;
+}
+
+__global__ void fed_stop_kernel(FedComm comm) {
+    // root asks every node to drain its pre-enqueued kernels
+    if (threadIdx.x < comm.world) fed::st_release_sys(comm.peer_flag[threadIdx.x], B200FED_STOP_EPOCH);
+}
+
+__global__ void fed_reset_kernel(unsigned long long* flag, unsigned long long* slot_flags, int world,
+                                 unsigned int* ticket, unsigned long long* epoch_counter) {
+    if (threadIdx.x == 0) {
+        *flag = 0;
+        *ticket = 0;
+        *epoch_counter = 0;
+    }
+    if (threadIdx.x < world) slot_flags[threadIdx.x] = 0;
+}
+
+}  // namespace
+
+extern "C" {
+
+const char* b200_last_error() { return g_last_error.c_str(); }
+
+int b200_device_count() {
+    int n = 0;
+    if (cudaGetDeviceCount(&n) != cudaSuccess) return 0;
+    return n;
+}
+
+// ---- raw memory helpers (IPC bootstrap without torch) ----------------------------------
+int b200_malloc(int device, size_t bytes, void** out) {
+    CK(cudaSetDevice(device));
+    CK(cudaMalloc(out, bytes));
+    CK(cudaMemset(*out, 0, bytes));
+    return 0;
+}
+int b200_free(int device, void* p) {
+    CK(cudaSetDevice(device));
+    CK(cudaFree(p));
+    return 0;
+}
+int b200_ipc_get_handle(void* dptr, unsigned char* out64) {
+    cudaIpcMemHandle_t h;
+    CK(cudaIpcGetMemHandle(&h, dptr));
+    memcpy(out64, &h, sizeof(h));
+    return 0;
+}
+int b200_ipc_open_handle(int device, const unsigned char* in64, void** out) {
+    cudaIpcMemHandle_t h;
+    memcpy(&h, in64, sizeof(h));
+    CK(cudaSetDevice(device));
+    CK(cudaIpcOpenMemHandle(out, h, cudaIpcMemLazyEnablePeerAccess));
+    return 0;
+}
+int b200_ipc_close_handle(void* p) {
+    CK(cudaIpcCloseMemHandle(p));
+    return 0;
+}
+int b200_enable_peer_access(int device, int peer) {
+    CK(cudaSetDevice(device));
+    int can = 0;
+    CK(cudaDeviceCanAccessPeer(&can, device, peer));
+    if (!can) {
+        g_last_error = "peer access not supported between these devices";
+        return -3;
+    }
+    cudaError_t e = cudaDeviceEnablePeerAccess(peer, 0);
+    if (e != cudaSuccess && e != cudaErrorPeerAccessAlreadyEnabled) return fail("cudaDeviceEnablePeerAccess", e);
+    cudaGetLastError();
+    return 0;
+}
+
+// ---- engine ------------------------------------------------------------------------------
+size_t b200_comm_block_bytes(int world, int n_theta, int n_vals) { return comm_layout(world, n_theta, n_vals).bytes; }
+
+void* b200_engine_create(int device, int rank, int world, int n_theta, int n_vals, int max_grid) {
+    if (world < 1 || world > B200FED_MAX_WORLD || rank < 0 || rank >= world) {
+        g_last_error = "invalid rank/world";
+        return nullptr;
+    }
+    if (cudaSetDevice(device) != cudaSuccess) {
+        g_last_error = "cudaSetDevice failed";
+        return nullptr;
+    }
+    Engine* e = new Engine();
+    e->device = device;
+    e->rank = rank;
+    e->world = world;
+    e->n_theta = n_theta;
+    e->n_vals = n_vals;
+    e->layout = comm_layout(world, n_theta, n_vals);
+    cudaDeviceGetAttribute(&e->sm_count, cudaDevAttrMultiProcessorCount, device);
+    e->grid = max_grid > 0 ? max_grid : e->sm_count;
+    bool ok = cudaStreamCreateWithFlags(&e->stream, cudaStreamNonBlocking) == cudaSuccess;
+    // host-mapped block
+    auto up = [](size_t v) { return (v + 255) & ~size_t(255); };
+    e->h_off_theta = 0;
+    e->h_off_result = up((size_t)n_theta * 4);
+    e->h_off_flag = up(e->h_off_result + (size_t)n_vals * 8);
+    e->h_off_done = e->h_off_flag + 256;
+    const size_t hbytes = e->h_off_done + 256;
+    ok = ok && cudaHostAlloc((void**)&e->host_block, hbytes, cudaHostAllocMapped | cudaHostAllocPortable) == cudaSuccess;
+    if (ok) memset(e->host_block, 0, hbytes);
+    ok = ok && cudaHostGetDevicePointer((void**)&e->host_block_dev, e->host_block, 0) == cudaSuccess;
+    const int max_blocks = e->sm_count * 8;
+    ok = ok && cudaMalloc((void**)&e->cta_partials, (size_t)max_blocks * n_vals * 8) == cudaSuccess;
+    ok = ok && cudaMalloc((void**)&e->ticket, 256) == cudaSuccess;
+    ok = ok && cudaMalloc((void**)&e->epoch_counter, 256) == cudaSuccess;
+    ok = ok && cudaMalloc((void**)&e->trace, 256 * 4 * 8) == cudaSuccess;
+    ok = ok && cudaMalloc((void**)&e->theta_dev, (size_t)(n_theta > 0 ? n_theta : 1) * 4) == cudaSuccess;
+    if (ok) {
+        cudaMemset(e->ticket, 0, 256);
+        cudaMemset(e->epoch_counter, 0, 256);
+        cudaMemset(e->trace, 0, 256 * 4 * 8);
+        cudaMemset(e->theta_dev, 0, (size_t)(n_theta > 0 ? n_theta : 1) * 4);
+        cudaDeviceSynchronize();
+    }
+    if (!ok) {
+        g_last_error = std::string("engine allocation failed: ") + cudaGetErrorString(cudaGetLastError());
+        delete e;
+        return nullptr;
+    }
+    return e;
+}
+
+int b200_engine_max_blocks(void* h) { return static_cast<Engine*>(h)->sm_count * 8; }
+int b200_engine_sm_count(void* h) { return static_cast<Engine*>(h)->sm_count; }
+
+// Allocate the comm block here (cudaMalloc => CUDA-IPC exportable).
+int b200_engine_alloc_comm(void* h, void** out_ptr) {
+    Engine* e = static_cast<Engine*>(h);
+    CK(cudaSetDevice(e->device));
+    CK(cudaMalloc((void**)&e->comm_local, e->layout.bytes));
+    CK(cudaMemset(e->comm_local, 0, e->layout.bytes));
+    CK(cudaDeviceSynchronize());
+    e->owns_comm = true;
+    e->comm_peer[e->rank] = e->comm_local;
+    *out_ptr = e->comm_local;
+    return 0;
+}
+
+// Bind comm blocks: `peers[world]` are this process's views of every node's block
+// (own entry included); `mc` is the multicast alias or null.
+int b200_engine_bind_comm(void* h, void* local, void** peers, void* mc) {
+    Engine* e = static_cast<Engine*>(h);
+    e->comm_local = static_cast<unsigned char*>(local);
+    for (int p = 0; p < e->world; ++p) e->comm_peer[p] = static_cast<unsigned char*>(peers[p]);
+    e->comm_peer[e->rank] = e->comm_local;
+    e->comm_mc = static_cast<unsigned char*>(mc);
+    return 0;
+}
+
+int b200_engine_reset(void* h) {
+    Engine* e = static_cast<Engine*>(h);
+    CK(cudaSetDevice(e->device));
+    const CommLayout& L = e->layout;
+    fed_reset_kernel<<<1, 32, 0, e->stream>>>(reinterpret_cast<unsigned long long*>(e->comm_local + L.off_flag),
+                                              reinterpret_cast<unsigned long long*>(e->comm_local + L.off_slot_flags),
+                                              e->world, e->ticket, e->epoch_counter);
+    CK(cudaStreamSynchronize(e->stream));
+    e->epoch = 0;
+    *e->h_flag() = 0;
+    *e->h_done() = 0;
+    e->stop_serving = 0;
+    return 0;
+}
+
+void b200_engine_set_timeout(void* h, double seconds) {
+    static_cast<Engine*>(h)->timeout_ns = (unsigned long long)(seconds * 1e9);
+}
+void b200_engine_set_grid(void* h, int grid) { static_cast<Engine*>(h)->grid = grid; }
+int b200_engine_grid(void* h) { return static_cast<Engine*>(h)->grid; }
+unsigned long long b200_engine_launches(void* h) { return static_cast<Engine*>(h)->launches; }
+unsigned long long b200_engine_epoch(void* h) { return static_cast<Engine*>(h)->epoch; }
+void* b200_engine_stream(void* h) { return static_cast<Engine*>(h)->stream; }
+void* b200_engine_host_theta(void* h) { return static_cast<Engine*>(h)->h_theta(); }
+void* b200_engine_host_result(void* h) { return static_cast<Engine*>(h)->h_result(); }
+
+int b200_engine_set_linreg(void* h, int n_shards, const void** x, const void** y, const long long* n,
+                           const double* sigma, const int* theta_offset, int is_f64) {
+    Engine* e = static_cast<Engine*>(h);
+    CK(cudaSetDevice(e->device));
+    e->linreg.resize(n_shards);
+    long long total = 0;
+    for (int s = 0; s < n_shards; ++s) {
+        e->linreg[s] = LinregShard{x[s], y[s], n[s], sigma[s], theta_offset[s], 0};
+        total += n[s];
+    }
+    if (e->linreg_dev) cudaFree(e->linreg_dev);
+    CK(cudaMalloc((void**)&e->linreg_dev, sizeof(LinregShard) * (n_shards > 0 ? n_shards : 1)));
+    CK(cudaMemcpy(e->linreg_dev, e->linreg.data(), sizeof(LinregShard) * n_shards, cudaMemcpyHostToDevice));
+    e->linreg_f64 = is_f64;
+    e->kind = MODEL_LINREG;
+    // tiny data => one CTA is the lowest-latency configuration; grow with the data
+    long long want = (total + 256 * 64 - 1) / (256 * 64);
+    if (want < 1) want = 1;
+    if (want > e->sm_count * 4) want = e->sm_count * 4;
+    e->grid = (int)want;
+    return 0;
+}
+
+int b200_engine_set_glm(void* h, int n_segments, const void** X, const float** y, const void** scales,
+                        const long long* n_rows, const int* groups, int n_features, int ld, int n_groups,
+                        int n_chains, int family, int use_tensor_cores) {
+    Engine* e = static_cast<Engine*>(h);
+    CK(cudaSetDevice(e->device));
+    const int tile_rows = use_tensor_cores ? 128 : 8;
+    e->glm_segs.resize(n_segments);
+    long long tiles = 0;
+    for (int s = 0; s < n_segments; ++s) {
+        GlmSegment g{};
+        g.X = X[s];
+        g.y = y[s];
+        g.scales = scales ? scales[s] : nullptr;
+        g.n_rows = n_rows[s];
+        g.first_tile = tiles;
+        g.group = groups[s];
+        e->glm_segs[s] = g;
+        tiles += (n_rows[s] + tile_rows - 1) / tile_rows;
+    }
+    e->glm = GlmParams{n_segments, n_features, ld, n_groups, n_chains, family, tiles};
+    if (e->glm_segs_dev) cudaFree(e->glm_segs_dev);
+    CK(cudaMalloc((void**)&e->glm_segs_dev, sizeof(GlmSegment) * (n_segments > 0 ? n_segments : 1)));
+    CK(cudaMemcpy(e->glm_segs_dev, e->glm_segs.data(), sizeof(GlmSegment) * n_segments, cudaMemcpyHostToDevice));
+    if (use_tensor_cores) {
+        int rc = b200_glm_tc_prepare(e->glm_segs.data(), n_segments, &e->glm, &e->glm_tmaps_dev);
+        if (rc != 0) {
+            g_last_error = "tensor-core GLM path rejected this shape (rc=" + std::to_string(rc) + ")";
+            return rc;
+        }
+        e->kind = MODEL_GLM_TC;
+        e->grid = e->sm_count;
+    } else {
+        e->kind = MODEL_GLM_SIMT;
+        e->grid = e->sm_count * 2;
+    }
+    if ((long long)e->grid > tiles && tiles > 0) e->grid = (int)tiles;
+    return 0;
+}
+
+int b200_engine_set_ode(void* h, int n_shards, const float** t, const float** y0, const float** y_obs, const int* n_series,
+                        const int* n_t, const float* sigma, const int* substeps) {
+    Engine* e = static_cast<Engine*>(h);
+    CK(cudaSetDevice(e->device));
+    e->ode.resize(n_shards);
+    long long series = 0;
+    for (int s = 0; s < n_shards; ++s) {
+        e->ode[s] = OdeShard{t[s], y0[s], y_obs[s], n_series[s], n_t[s], sigma[s], substeps[s]};
+        series += n_series[s];
+    }
+    if (e->ode_dev) cudaFree(e->ode_dev);
+    CK(cudaMalloc((void**)&e->ode_dev, sizeof(OdeShard) * (n_shards > 0 ? n_shards : 1)));
+    CK(cudaMemcpy(e->ode_dev, e->ode.data(), sizeof(OdeShard) * n_shards, cudaMemcpyHostToDevice));
+    e->kind = MODEL_ODE;
+    long long want = (series + 127) / 128;
+    if (want < 1) want = 1;
+    if (want > e->sm_count * 4) want = e->sm_count * 4;
+    e->grid = (int)want;
+    return 0;
+}
+
+// Enqueue one evaluation without waiting (device-timed loops).  Root only.  theta is taken
+// from the device-resident copy when `theta_on_device` (set by b200_engine_set_device_theta).
+int b200_engine_launch(void* h) {
+    Engine* e = static_cast<Engine*>(h);
+    if (e->rank != 0) {
+        g_last_error = "only the root launches explicit epochs";
+        return -4;
+    }
+    FedComm c;
+    fill_comm(e, &c, true);
+    c.epoch = ++e->epoch;
+    return launch_model(e, &c);
+}
+
+int b200_engine_set_device_theta(void* h, const float* theta_host, int n, int enable) {
+    Engine* e = static_cast<Engine*>(h);
+    CK(cudaSetDevice(e->device));
+    if (theta_host && n > 0) CK(cudaMemcpy(e->theta_dev, theta_host, (size_t)n * 4, cudaMemcpyHostToDevice));
+    e->theta_from_device = enable != 0;
+    return 0;
+}
+
+// Wait (host spin on the mapped completion flag) for epoch `epoch`; copies the result.
+// Returns 0, or 1 = theta timeout, 2 = peer timeout (bit-or), -5 = host-side timeout.
+int b200_engine_wait(void* h, unsigned long long epoch, double* out, double timeout_s) {
+    Engine* e = static_cast<Engine*>(h);
+    volatile unsigned long long* flag = e->h_flag();
+    const auto t0 = std::chrono::steady_clock::now();
+    unsigned long long v;
+    unsigned spins = 0;
+    while (true) {
+        v = *flag;
+        if ((v & B200FED_EPOCH_MASK) >= epoch) break;
+        if ((++spins & 0xFFF) == 0) {
+            const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+            if (dt > timeout_s) {
+                cudaError_t err = cudaStreamQuery(e->stream);
+                g_last_error = std::string("timed out waiting for the completion flag; stream state: ") +
+                               cudaGetErrorString(err);
+                return -5;
+            }
+        }
+    }
+    std::atomic_thread_fence(std::memory_order_acquire);
+    if (out) memcpy(out, e->h_result(), (size_t)e->n_vals * 8);
+    return (int)(v >> B200FED_STATUS_SHIFT);
+}
+
+// The client call: theta (raw 32-bit words) -> [n_vals] doubles.
+int b200_engine_eval(void* h, const void* theta, int n_words, double* out, double timeout_s) {
+    Engine* e = static_cast<Engine*>(h);
+    if (n_words != e->n_theta) {
+        g_last_error = "theta has the wrong number of 32-bit words";
+        return -6;
+    }
+    memcpy(e->h_theta(), theta, (size_t)n_words * 4);
+    std::atomic_thread_fence(std::memory_order_release);
+    int rc = b200_engine_launch(h);
+    if (rc != 0) return rc;
+    return b200_engine_wait(h, e->epoch, out, timeout_s);
+}
+
+// Peer loop: keep up to `ahead` kernels enqueued until the root broadcasts STOP, the idle
+// timeout fires inside a kernel, or b200_engine_stop_serving() is called from another thread.
+// Returns the number of evaluated epochs (>= 0) or a negative error.
+long long b200_engine_serve(void* h, int ahead, long long max_epochs) {
+    Engine* e = static_cast<Engine*>(h);
+    if (cudaSetDevice(e->device) != cudaSuccess) return -1;
+    if (ahead < 1) ahead = 1;
+    FedComm c;
+    fill_comm(e, &c, false);
+    // epochs are absolute (device-resident counter); this call serves [base+1, base+max_epochs]
+    const unsigned long long base = *e->h_done() & B200FED_EPOCH_MASK;
+    if (base == B200FED_STOP_EPOCH) return 0;
+    unsigned long long launched = base;
+    long long served = 0;
+    while (!e->stop_serving.load()) {
+        const unsigned long long word = *e->h_done();
+        const unsigned long long done = word & B200FED_EPOCH_MASK;
+        const unsigned long long status = word >> B200FED_STATUS_SHIFT;
+        if (done == B200FED_STOP_EPOCH) break;
+        if (status & B200FED_ERR_THETA_TIMEOUT) {
+            g_last_error = "idle timeout: no theta arrived from the root";
+            cudaStreamSynchronize(e->stream);
+            return -7;
+        }
+        served = (long long)(done - base);
+        if (max_epochs > 0 && (long long)(launched - base) >= max_epochs) {
+            if (done >= launched) break;
+            std::this_thread::yield();
+            continue;
+        }
+        if (launched - done < (unsigned long long)ahead) {
+            int rc = launch_model(e, &c);
+            if (rc != 0) return -8;
+            launched++;
+        } else {
+            std::this_thread::yield();
+        }
+    }
+    cudaError_t err = cudaStreamSynchronize(e->stream);
+    if (err != cudaSuccess) {
+        g_last_error = std::string("serve loop: ") + cudaGetErrorString(err);
+        return -9;
+    }
+    const unsigned long long word = *e->h_done();
+    if ((word & B200FED_EPOCH_MASK) != B200FED_STOP_EPOCH) served = (long long)((word & B200FED_EPOCH_MASK) - base);
+    return served;
+}
+
+void b200_engine_stop_serving(void* h) { static_cast<Engine*>(h)->stop_serving = 1; }
+
+// Root: tell every node to drain (STOP epoch is sticky and larger than any real epoch).
+int b200_engine_stop_peers(void* h) {
+    Engine* e = static_cast<Engine*>(h);
+    if (e->rank != 0) return 0;
+    CK(cudaSetDevice(e->device));
+    FedComm c;
+    fill_comm(e, &c, true);
+    fed_stop_kernel<<<1, 32, 0, e->stream>>>(c);
+    CK(cudaStreamSynchronize(e->stream));
+    return 0;
+}
+
+int b200_engine_sync(void* h) {
+    Engine* e = static_cast<Engine*>(h);
+    CK(cudaStreamSynchronize(e->stream));
+    return 0;
+}
+
+// Device-timer trace of epoch `epoch`: [theta released, node partial released, result released] (ns)
+int b200_engine_trace(void* h, unsigned long long epoch, unsigned long long* out4) {
+    Engine* e = static_cast<Engine*>(h);
+    CK(cudaMemcpy(out4, e->trace + (epoch & 255) * 4, 32, cudaMemcpyDeviceToHost));
+    return 0;
+}
+
+void b200_engine_destroy(void* h) {
+    Engine* e = static_cast<Engine*>(h);
+    if (!e) return;
+    cudaSetDevice(e->device);
+    cudaStreamSynchronize(e->stream);
+    if (e->owns_comm && e->comm_local) cudaFree(e->comm_local);
+    if (e->host_block) cudaFreeHost(e->host_block);
+    cudaFree(e->cta_partials);
+    cudaFree(e->ticket);
+    cudaFree(e->epoch_counter);
+    cudaFree(e->trace);
+    cudaFree(e->theta_dev);
+    if (e->linreg_dev) cudaFree(e->linreg_dev);
+    if (e->glm_segs_dev) cudaFree(e->glm_segs_dev);
+    if (e->glm_tmaps_dev) cudaFree(e->glm_tmaps_dev);
+    if (e->ode_dev) cudaFree(e->ode_dev);
+    cudaStreamDestroy(e->stream);
+    delete e;
+}
+
+}  // extern "C"

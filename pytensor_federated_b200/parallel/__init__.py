@@ -1,0 +1,4 @@
+"""Multi-GPU execution: the fused NVLink engine and the collective (NCCL/gloo) baseline."""
+from .engine import FederatedEngine, FederationError, FederationTimeout
+
+__all__ = ["FederatedEngine", "FederationError", "FederationTimeout"]

@@ -1,0 +1,139 @@
+"""Engine plumbing on CPU: collective backend, single process and 2-rank gloo."""
+import os
+import socket
+
+import numpy as np
+import pytest
+import torch
+import torch.multiprocessing as mp
+
+from pytensor_federated_b200.models import GlmShards, LinregShards, OdeShards, make_demo_data, synth_lv_shard
+from pytensor_federated_b200.parallel import FederatedEngine, FederationError
+
+pytestmark = pytest.mark.timeout(300)
+
+
+def _scipy_linreg(x, y, sigma, a, b):
+    import scipy.stats
+
+    return scipy.stats.norm.logpdf(y, loc=a + b * x, scale=sigma).sum()
+
+
+def test_linreg_reference_matches_scipy_and_finite_differences():
+    x, y, sigma = make_demo_data()
+    model = LinregShards([x], [y], [sigma])
+    eng = FederatedEngine(model, backend="collective")
+    logp, da, db = eng.evaluate(np.array(0.4), np.array(1.2))
+    assert logp.shape == () and da.shape == () and db.shape == ()
+    np.testing.assert_allclose(logp, _scipy_linreg(x, y, sigma, 0.4, 1.2), rtol=1e-12)
+    eps = 1e-6
+    fd_a = (_scipy_linreg(x, y, sigma, 0.4 + eps, 1.2) - _scipy_linreg(x, y, sigma, 0.4 - eps, 1.2)) / (2 * eps)
+    fd_b = (_scipy_linreg(x, y, sigma, 0.4, 1.2 + eps) - _scipy_linreg(x, y, sigma, 0.4, 1.2 - eps)) / (2 * eps)
+    np.testing.assert_allclose([da, db], [fd_a, fd_b], rtol=1e-6)
+    eng.shutdown()
+    with pytest.raises(FederationError):
+        eng.evaluate(np.array(0.0), np.array(0.0))
+
+
+def test_linreg_per_shard_parameters():
+    rng = np.random.default_rng(1)
+    xs = [rng.normal(size=20) for _ in range(3)]
+    ys = [rng.normal(size=20) for _ in range(3)]
+    model = LinregShards(xs, ys, [0.5, 1.0, 2.0])
+    eng = FederatedEngine(model, backend="collective")
+    a = np.array([0.1, 0.2, 0.3])
+    logp, da, db = eng.evaluate(a, np.array(0.7))
+    assert da.shape == (3,) and db.shape == ()
+    expected = sum(_scipy_linreg(x, y, s, ai, 0.7) for x, y, s, ai in zip(xs, ys, [0.5, 1.0, 2.0], a))
+    np.testing.assert_allclose(logp, expected, rtol=1e-12)
+
+
+def test_glm_reference_gradient_matches_autograd():
+    torch.manual_seed(0)
+    X = torch.randn(300, 16).to(torch.bfloat16)
+    y = (torch.rand(300) < 0.5).float()
+    for family in ("logistic", "poisson", "gaussian"):
+        model = GlmShards([X[:100], X[100:]], [y[:100], y[100:]], groups=[0, 1], n_groups=2, family=family)
+        ic = np.array([0.2, -0.1])
+        beta = np.linspace(-0.2, 0.2, 16)
+        logp, d_ic, d_beta = FederatedEngine(model, backend="collective").evaluate(ic, beta)
+        t_ic = torch.tensor(ic, requires_grad=True)
+        t_b = torch.tensor(beta, requires_grad=True)
+        eta = X.double() @ t_b + torch.cat([t_ic[0].expand(100), t_ic[1].expand(200)])
+        if family == "logistic":
+            ll = (y.double() * eta - torch.nn.functional.softplus(eta)).sum()
+        elif family == "poisson":
+            ll = (y.double() * eta - torch.exp(eta)).sum()
+        else:
+            ll = (-0.5 * (y.double() - eta) ** 2 - 0.918938533204672742).sum()
+        ll.backward()
+        np.testing.assert_allclose(logp, ll.item(), rtol=2e-5)
+        np.testing.assert_allclose(d_ic, t_ic.grad.numpy(), rtol=2e-4, atol=1e-4)
+        np.testing.assert_allclose(d_beta, t_b.grad.numpy(), rtol=2e-4, atol=1e-4)
+
+
+def test_ode_reference_gradient_matches_finite_differences():
+    t, y0, obs, sigma = synth_lv_shard(5, 6, seed=3, device="cpu")
+    model = OdeShards([t], [y0], [obs], [sigma], substeps=4)
+    th = np.array([0.9, 0.45, 0.75, 0.25])
+    # the oracle itself is float64 end to end (theta only becomes float32 in the mailbox)
+    logp, grad = model.reference([th])
+    eps = 1e-6
+    for k in range(4):
+        d = np.zeros(4)
+        d[k] = eps
+        fd = (model.reference([th + d])[0] - model.reference([th - d])[0]) / (2 * eps)
+        np.testing.assert_allclose(grad[k], fd, rtol=1e-5, atol=1e-6)
+    logp_e, grad_e = FederatedEngine(model, backend="collective").evaluate(th)
+    np.testing.assert_allclose(logp_e, logp, rtol=1e-5)
+    np.testing.assert_allclose(grad_e, grad, rtol=1e-3, atol=1e-2)
+
+
+def _free_port():
+    with socket.socket() as s:
+        s.bind(("127.0.0.1", 0))
+        return s.getsockname()[1]
+
+
+def _gloo_worker(rank, world, port, out_queue):
+    import torch.distributed as dist
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(10 + rank)  # every rank has its own private shard
+    x, y = rng.normal(size=50), rng.normal(size=50)
+    model = LinregShards([x], [y], [0.8], local_ids=[rank], n_shards_total=world)
+    eng = FederatedEngine(model, backend="collective")
+    if rank == 0:
+        logp, da, db = eng.evaluate(np.array(0.3), np.array(-0.2))
+        logp2, *_ = eng.evaluate(np.array(0.0), np.array(0.0))
+        eng.shutdown()
+        out_queue.put((float(logp), float(da), float(db), float(logp2)))
+    else:
+        served = eng.serve()
+        eng.shutdown()
+        out_queue.put(("served", served))
+    dist.destroy_process_group()
+
+
+def test_two_rank_gloo_federation_sums_private_shards():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_gloo_worker, args=(r, 2, port, q)) for r in range(2)]
+    for p in procs:
+        p.start()
+    results = [q.get(timeout=240) for _ in procs]
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+    served = [r for r in results if r[0] == "served"][0]
+    root = [r for r in results if r[0] != "served"][0]
+    assert served == ("served", 2)
+    expected = 0.0
+    for rank in range(2):
+        rng = np.random.default_rng(10 + rank)
+        x, y = rng.normal(size=50), rng.normal(size=50)
+        expected += _scipy_linreg(x, y, 0.8, 0.3, -0.2)
+    np.testing.assert_allclose(root[0], expected, rtol=1e-12)

@@ -1,0 +1,124 @@
+"""Numerics of the fused sm_100a kernels vs plain PyTorch references (needs a B200)."""
+import numpy as np
+import pytest
+import torch
+
+from pytensor_federated_b200.models import (
+    GlmShards,
+    LinregShards,
+    OdeShards,
+    make_demo_data,
+    synth_logistic_shard,
+    synth_lv_shard,
+)
+from pytensor_federated_b200.parallel import FederatedEngine
+
+pytestmark = [pytest.mark.gpu, pytest.mark.timeout(600)]
+
+
+@pytest.fixture(scope="module")
+def dev():
+    if not torch.cuda.is_available():
+        pytest.skip("no CUDA device")
+    from pytensor_federated_b200.ops import native
+
+    native.load()  # a GPU box without the native library is a failure, not a skip
+    return torch.device("cuda:0")
+
+
+def test_linreg_demo_model_matches_float64_oracle(dev):
+    import scipy.stats
+
+    x, y, sigma = make_demo_data()
+    model = LinregShards([x], [y], [sigma], device=dev)
+    with FederatedEngine(model) as eng:
+        assert eng.backend == "fused"
+        for a, b in [(0.4, 1.2), (1.5, 0.5), (-3.0, 2.0)]:
+            logp, da, db = eng.evaluate(np.array(a), np.array(b))
+            expected = scipy.stats.norm.logpdf(y, loc=a + b * x, scale=sigma).sum()
+            np.testing.assert_allclose(logp, expected, rtol=1e-12)
+            r = y - (a + b * x)
+            np.testing.assert_allclose(da, r.sum() / sigma**2, rtol=1e-11, atol=1e-11)
+            np.testing.assert_allclose(db, (r * x).sum() / sigma**2, rtol=1e-11, atol=1e-11)
+        assert eng.kernel_launches == 3
+
+
+def test_linreg_many_shards_large_and_float32(dev):
+    rng = np.random.default_rng(0)
+    sizes = [10, 1000, 70001, 333]
+    xs = [rng.normal(size=n) for n in sizes]
+    ys = [1.0 + 0.5 * x + rng.normal(scale=0.3, size=x.size) for x in xs]
+    sig = [0.3, 0.5, 0.7, 1.1]
+    a = np.array([0.9, 1.0, 1.1, 1.2])
+    for dtype, rtol in ((torch.float64, 1e-11), (torch.float32, 1e-5)):
+        model = LinregShards(xs, ys, sig, device=dev, dtype=dtype)
+        with FederatedEngine(model) as eng:
+            got = eng.evaluate(a, np.array(0.45))
+            want = model.reference([a, np.array(0.45)])
+            for g, w in zip(got, want):
+                np.testing.assert_allclose(g, w, rtol=rtol, atol=1e-6)
+            per = LinregShards.per_shard(eng.evaluate_raw([a, np.array(0.45)]))
+            assert per.shape == (4, 3)
+
+
+@pytest.mark.parametrize("family", ["logistic", "poisson", "gaussian"])
+@pytest.mark.parametrize("P", [256, 64, 512])
+def test_glm_simt_matches_reference(dev, family, P):
+    torch.manual_seed(1)
+    rows = [1000, 77, 4099, 8]
+    Xs, ys = [], []
+    for i, n in enumerate(rows):
+        X, y, _ = synth_logistic_shard(n, P, seed=i, device=dev, beta_scale=0.05)
+        Xs.append(X)
+        ys.append(y)
+    model = GlmShards(Xs, ys, groups=[0, 1, 0, 2], n_groups=3, family=family, kernel="simt")
+    ic = np.array([0.3, -0.2, 0.1])
+    beta = (np.random.default_rng(2).normal(size=P) * 0.03).astype(np.float32)
+    with FederatedEngine(model) as eng:
+        logp, d_ic, d_beta = eng.evaluate(ic, beta)
+    w_logp, w_ic, w_beta = model.unpack_result(model.reference_partial([ic, beta], dtype=torch.float64))
+    np.testing.assert_allclose(logp, w_logp, rtol=2e-5)
+    np.testing.assert_allclose(d_ic, w_ic, rtol=1e-4, atol=2e-3)
+    np.testing.assert_allclose(d_beta, w_beta, rtol=1e-4, atol=2e-3 * np.sqrt(sum(rows)))
+
+
+def test_glm_simt_is_deterministic(dev):
+    X, y, _ = synth_logistic_shard(50_000, 256, seed=5, device=dev)
+    model = GlmShards([X], [y], kernel="simt")
+    beta = np.full(256, 0.01, dtype=np.float32)
+    with FederatedEngine(model) as eng:
+        a = [v.copy() for v in eng.evaluate(np.array([0.0]), beta)]
+        for _ in range(3):
+            b = eng.evaluate(np.array([0.0]), beta)
+            for u, v in zip(a, b):
+                assert np.array_equal(u, v)  # fixed-order reductions: bit-identical
+
+
+def test_ode_matches_float64_oracle(dev):
+    shards = [synth_lv_shard(300, 12, seed=s, device=dev) for s in range(2)]
+    model = OdeShards([s[0] for s in shards], [s[1] for s in shards], [s[2] for s in shards], [s[3] for s in shards])
+    th = np.array([0.95, 0.42, 0.78, 0.21])
+    with FederatedEngine(model) as eng:
+        logp, grad = eng.evaluate(th)
+    w_logp, w_grad = model.reference([th.astype(np.float32).astype(np.float64)])
+    np.testing.assert_allclose(logp, w_logp, rtol=2e-4)
+    np.testing.assert_allclose(grad, w_grad, rtol=5e-3, atol=1.0)
+
+
+def test_service_client_reaches_gpu_node_through_local_registry(dev):
+    """ArraysToArraysServiceClient("gpu", 0) -> fused engine, no sockets, no codec."""
+    from pytensor_federated_b200 import LogpGradServiceClient, service
+
+    x, y, sigma = make_demo_data()
+    model = LinregShards([x], [y], [sigma], device=dev)
+    with FederatedEngine(model) as eng:
+        service.register_local_node("gpu", 0, eng.evaluate)
+        try:
+            client = LogpGradServiceClient("gpu", 0)
+            logp, grads = client.evaluate(np.array(0.4), np.array(1.2))
+            want = model.reference([np.array(0.4), np.array(1.2)])
+            np.testing.assert_allclose(logp, want[0], rtol=1e-12)
+            np.testing.assert_allclose(grads, want[1:], rtol=1e-11)
+            del client
+        finally:
+            service.unregister_local_node("gpu", 0)
