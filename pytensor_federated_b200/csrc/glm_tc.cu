@@ -1,5 +1,598 @@
-// placeholder until the tcgen05 kernel lands (next commit)
+// Federated GLM log-likelihood + gradient on the 5th-gen tensor cores (tcgen05 + TMEM + TMA).
+//
+// Per 128-row tile of the bf16 design matrix X (read from HBM exactly ONCE per evaluation):
+//
+//   TMA        X[128 x P] -> smem, 128B-swizzled 64-feature panels (cp.async.bulk.tensor)
+//   MMA #1     eta[128 x N1] = X_tile (A, K-major) . Theta^T (B, K-major)      -> TMEM
+//              Theta holds, per MCMC chain, a 3-way bf16 split (hi, mid, lo) of the fp32
+//              coefficients, so eta keeps ~fp32 accuracy although the operands are bf16.
+//   epilogue   tcgen05.ld eta; link + log-likelihood; residual r = dll/deta;
+//              r is split into (hi, lo) bf16 and stored to smem as the B operand of MMA #2
+//   MMA #2     G[P x N2] += X_tile^T (A, **MN-major view of the very same smem tile**) . R
+//              accumulated in TMEM across tiles, flushed to fp64 registers every kFlush tiles
+//
+// so the gradient GEMM costs no second pass over X.  Chains are batched along N (the MMA is
+// otherwise idle: the kernel is HBM-bound), which is what makes tensor cores pay here.
+// Roles: warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane), warps 2-5 = epilogue.
+// The federation prologue/epilogue (theta broadcast, NVLink reduce) is fed_comm.cuh.
+//
+// Workload: BASELINE.json "federated logistic GLM, 10M rows x 256 features per shard, bf16".
+// Nothing comparable exists in the reference (its model is /root/reference/demo_node.py:31-43).
+#include <cuda.h>
+#include <cuda_bf16.h>
+#include <cuda_runtime.h>
+
 #include "fed_comm.cuh"
 #include "models.h"
-extern "C" int b200_launch_glm_tc(const FedComm*, const GlmSegment*, const GlmParams*, const void*, int, cudaStream_t) { return -1; }
-extern "C" int b200_glm_tc_prepare(const GlmSegment*, int, const GlmParams*, void**) { return -1; }
+
+namespace tc {
+
+constexpr int kTileM = 128;          // rows per tile (UMMA M for MMA #1, UMMA K-extent for MMA #2)
+constexpr int kPanel = 64;           // features per 128-byte swizzle span
+constexpr int kPanelBytes = kTileM * 128;  // 16 KB
+constexpr int kThreads = 192;
+constexpr int kFlush = 32;           // tiles between TMEM -> fp64 flushes of the gradient
+constexpr int kMaxSegs = 64;
+
+// ------------------------------------------------------------------ PTX wrappers
+__device__ __forceinline__ uint32_t smem_u32(const void* p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+__device__ __forceinline__ void mbar_init(uint64_t* bar, uint32_t count) {
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(smem_u32(bar)), "r"(count));
+}
+__device__ __forceinline__ void mbar_arrive(uint64_t* bar) {
+    asm volatile("mbarrier.arrive.shared::cta.b64 _, [%0];" ::"r"(smem_u32(bar)) : "memory");
+}
+__device__ __forceinline__ void mbar_expect_tx(uint64_t* bar, uint32_t bytes) {
+    asm volatile("mbarrier.arrive.expect_tx.shared::cta.b64 _, [%0], %1;" ::"r"(smem_u32(bar)), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
+    uint32_t ok;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(ok)
+        : "r"(smem_u32(bar)), "r"(parity)
+        : "memory");
+    return ok != 0;
+}
+// Bounded wait: a pipeline bug must surface as a launch failure, never as a hung GPU.
+__device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
+    if (mbar_try_wait(bar, parity)) return;
+    const unsigned long long t0 = fed::globaltimer();
+    while (!mbar_try_wait(bar, parity)) {
+        if (fed::globaltimer() - t0 > 4000000000ull) __trap();
+    }
+}
+__device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
+__device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
+__device__ __forceinline__ void tc_fence_after() { asm volatile("tcgen05.fence::after_thread_sync;" ::: "memory"); }
+
+__device__ __forceinline__ void tma_load_2d(void* smem_dst, const CUtensorMap* map, int c0, int c1, uint64_t* bar) {
+    asm volatile(
+        "cp.async.bulk.tensor.2d.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1, {%2, %3}], [%4];" ::"r"(
+            smem_u32(smem_dst)),
+        "l"(map), "r"(c0), "r"(c1), "r"(smem_u32(bar))
+        : "memory");
+}
+__device__ __forceinline__ void tma_prefetch_desc(const CUtensorMap* map) {
+    asm volatile("prefetch.tensormap [%0];" ::"l"(map) : "memory");
+}
+
+__device__ __forceinline__ void tmem_alloc(uint32_t* smem_out, uint32_t cols) {
+    asm volatile("tcgen05.alloc.cta_group::1.sync.aligned.shared::cta.b32 [%0], %1;" ::"r"(smem_u32(smem_out)), "r"(cols)
+                 : "memory");
+    asm volatile("tcgen05.relinquish_alloc_permit.cta_group::1.sync.aligned;" ::: "memory");
+}
+__device__ __forceinline__ void tmem_dealloc(uint32_t addr, uint32_t cols) {
+    asm volatile("tcgen05.dealloc.cta_group::1.sync.aligned.b32 %0, %1;" ::"r"(addr), "r"(cols) : "memory");
+}
+__device__ __forceinline__ void umma_commit(uint64_t* bar) {
+    asm volatile("tcgen05.commit.cta_group::1.mbarrier::arrive::one.shared::cluster.b64 [%0];" ::"r"(smem_u32(bar))
+                 : "memory");
+}
+__device__ __forceinline__ void umma_bf16(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc, uint32_t accumulate) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::f16 [%0], %1, %2, %3, p;\n\t"
+        "}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate)
+        : "memory");
+}
+__device__ __forceinline__ void tmem_ld_x4(uint32_t taddr, float (&v)[4]) {
+    uint32_t a, b, c, d;
+    asm volatile("tcgen05.ld.sync.aligned.32x32b.x4.b32 {%0, %1, %2, %3}, [%4];"
+                 : "=r"(a), "=r"(b), "=r"(c), "=r"(d)
+                 : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+    v[0] = __uint_as_float(a); v[1] = __uint_as_float(b); v[2] = __uint_as_float(c); v[3] = __uint_as_float(d);
+}
+__device__ __forceinline__ void tmem_ld_x16(uint32_t taddr, float (&v)[16]) {
+    uint32_t r[16];
+    asm volatile(
+        "tcgen05.ld.sync.aligned.32x32b.x16.b32 {%0, %1, %2, %3, %4, %5, %6, %7, %8, %9, %10, %11, %12, %13, %14, %15}, [%16];"
+        : "=r"(r[0]), "=r"(r[1]), "=r"(r[2]), "=r"(r[3]), "=r"(r[4]), "=r"(r[5]), "=r"(r[6]), "=r"(r[7]), "=r"(r[8]),
+          "=r"(r[9]), "=r"(r[10]), "=r"(r[11]), "=r"(r[12]), "=r"(r[13]), "=r"(r[14]), "=r"(r[15])
+        : "r"(taddr));
+    asm volatile("tcgen05.wait::ld.sync.aligned;" ::: "memory");
+#pragma unroll
+    for (int i = 0; i < 16; ++i) v[i] = __uint_as_float(r[i]);
+}
+
+// ------------------------------------------------------------------ descriptors
+// Shared-memory matrix descriptor (sm_100): start>>4 [0,14) | LBO>>4 [16,30) | SBO>>4 [32,46) |
+// version=1 [46,48) | layout type [61,64) (0 = none/interleave, 2 = 128B swizzle).
+__device__ __forceinline__ uint64_t make_desc(uint32_t saddr, uint32_t lbo_bytes, uint32_t sbo_bytes, uint32_t layout) {
+    uint64_t d = 0;
+    d |= (uint64_t)((saddr >> 4) & 0x3FFF);
+    d |= (uint64_t)((lbo_bytes >> 4) & 0x3FFF) << 16;
+    d |= (uint64_t)((sbo_bytes >> 4) & 0x3FFF) << 32;
+    d |= (uint64_t)1 << 46;
+    d |= (uint64_t)(layout & 7) << 61;
+    return d;
+}
+// Instruction descriptor for kind::f16 with bf16 operands and fp32 accumulation.
+__host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn_major, int b_mn_major) {
+    return (1u << 4)      // D format: f32
+           | (1u << 7)    // A format: bf16
+           | (1u << 10)   // B format: bf16
+           | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) | ((uint32_t)(N >> 3) << 17) |
+           ((uint32_t)(M >> 4) << 24);
+}
+
+__device__ __forceinline__ void link_loglik(int family, float y, float eta, float& ll, float& r) {
+    if (family == 0) {
+        const float e = __expf(-fabsf(eta));
+        const float sp = fmaxf(eta, 0.f) + __logf(1.f + e);
+        const float inv = __fdividef(1.f, 1.f + e);
+        const float p = eta >= 0.f ? inv : e * inv;
+        ll = y * eta - sp;
+        r = y - p;
+    } else if (family == 1) {
+        const float mu = __expf(eta);
+        ll = y * eta - mu;
+        r = y - mu;
+    } else {
+        const float d = y - eta;
+        ll = -0.5f * d * d - 0.918938533204672742f;
+        r = d;
+    }
+}
+
+struct SmemLayout {
+    uint32_t stages, stage_bytes, off_theta_b, theta_b_bytes, off_r, r_bytes, off_theta_f, off_segs, off_gi, off_red,
+        off_bars, off_tmem, total;
+};
+__host__ __device__ inline SmemLayout smem_layout(int P, int n1, int n2, int n_theta, int n_groups, int chains) {
+    SmemLayout L;
+    const uint32_t panels = P / kPanel;
+    L.stage_bytes = panels * kPanelBytes;
+    L.theta_b_bytes = panels * n1 * 128;
+    L.r_bytes = kTileM * n2 * 2;
+    const uint32_t fixed = L.theta_b_bytes + 2 * L.r_bytes + ((n_theta * 4 + 15) & ~15) + kMaxSegs * (uint32_t)sizeof(GlmSegment) +
+                           ((chains * n_groups * 8 + 15) & ~15) + 32 * 8 + 256 + 1024 /*alignment slack*/;
+    uint32_t stages = (227u * 1024u - fixed) / L.stage_bytes;
+    if (stages > 4) stages = 4;
+    L.stages = stages;
+    uint32_t o = stages * L.stage_bytes;
+    L.off_theta_b = o; o += L.theta_b_bytes;
+    L.off_r = o; o += 2 * L.r_bytes;
+    L.off_theta_f = o; o += (n_theta * 4 + 15) & ~15;
+    L.off_segs = o; o += kMaxSegs * (uint32_t)sizeof(GlmSegment);
+    L.off_gi = o; o += (chains * n_groups * 8 + 15) & ~15;
+    L.off_red = o; o += 32 * 8;
+    L.off_bars = o; o += 192;
+    L.off_tmem = o; o += 64;
+    L.total = o + 1024;
+    return L;
+}
+
+// KC = chains per launch.  N1 = pad16(3 KC) eta columns, N2 = pad16(2 KC) residual columns.
+template <int KC>
+struct Cfg {
+    static constexpr int N1 = ((3 * KC + 15) / 16) * 16;
+    static constexpr int N2 = ((2 * KC + 15) / 16) * 16;
+};
+
+template <int KC>
+__global__ void __launch_bounds__(kThreads, 1)
+fed_glm_tc_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParams prm, const CUtensorMap* __restrict__ tmaps) {
+    constexpr int N1 = Cfg<KC>::N1;
+    constexpr int N2 = Cfg<KC>::N2;
+    extern __shared__ unsigned char smem_dyn[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
+
+    const int P = prm.n_features;
+    const int G = prm.n_groups;
+    const int NH = P / 128;           // 128-feature halves (UMMA M of MMA #2)
+    const int panels = P / kPanel;
+    const SmemLayout L = smem_layout(P, N1, N2, comm.n_theta, G, KC);
+    const int S = (int)L.stages;
+    const int nch = prm.n_chains < KC ? prm.n_chains : KC;  // chains actually present in theta
+
+    unsigned char* theta_b = smem + L.off_theta_b;
+    unsigned char* r_buf = smem + L.off_r;
+    float* theta_f = reinterpret_cast<float*>(smem + L.off_theta_f);
+    GlmSegment* segs = reinterpret_cast<GlmSegment*>(smem + L.off_segs);
+    double* gi_acc = reinterpret_cast<double*>(smem + L.off_gi);
+    double* red = reinterpret_cast<double*>(smem + L.off_red);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.off_bars);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L.off_tmem);
+    uint64_t* bar_full = bars;            // [4]
+    uint64_t* bar_empty = bars + 4;       // [4]
+    uint64_t* bar_eta_full = bars + 8;    // [2]
+    uint64_t* bar_eta_empty = bars + 10;  // [2]
+    uint64_t* bar_r_full = bars + 12;     // [2]
+    uint64_t* bar_r_empty = bars + 14;    // [2]
+    uint64_t* bar_g_full = bars + 16;     // [2]
+    uint64_t* bar_g_empty = bars + 18;    // [2]
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    fed::Prologue pro = fed::prologue(comm, theta_f);
+    const bool active = !pro.stop && !pro.timed_out;
+
+    const long long T = prm.total_tiles;
+    const long long n_it = (T > (long long)blockIdx.x) ? (T - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    constexpr uint32_t kTmemCols = (2 * N1 + 2 * 4 * N2) <= 128 ? 128 : ((2 * N1 + 2 * 4 * N2) <= 256 ? 256 : 512);
+
+    double ll_total[KC];
+#pragma unroll
+    for (int k = 0; k < KC; ++k) ll_total[k] = 0.0;
+    double g_acc[4][KC];  // [half][chain] for feature (half*128 + row); epilogue threads only
+#pragma unroll
+    for (int h = 0; h < 4; ++h)
+#pragma unroll
+        for (int k = 0; k < KC; ++k) g_acc[h][k] = 0.0;
+
+    if (active) {
+        // ---------------- one-time setup ------------------------------------------------------
+        for (int i = threadIdx.x; i < prm.n_segments; i += blockDim.x) segs[i] = segs_g[i];
+        for (int i = threadIdx.x; i < KC * G; i += blockDim.x) gi_acc[i] = 0.0;
+        // Theta^T as the K-major, 128B-swizzled B operand of MMA #1: row n = 3*chain + term
+        for (int idx = threadIdx.x; idx < panels * N1 * 8; idx += blockDim.x) {
+            const int j = idx & 7;              // 16-byte chunk (8 features) within the 128-byte row
+            const int n = (idx >> 3) % N1;
+            const int pnl = idx / (8 * N1);
+            const int chain = n / 3, term = n % 3;
+            uint32_t packed[4] = {0, 0, 0, 0};
+            if (chain < nch) {
+#pragma unroll
+                for (int e = 0; e < 8; ++e) {
+                    const float v = theta_f[chain * (G + P) + G + pnl * kPanel + j * 8 + e];
+                    const __nv_bfloat16 hi = __float2bfloat16_rn(v);
+                    const float rem1 = v - __bfloat162float(hi);
+                    const __nv_bfloat16 mid = __float2bfloat16_rn(rem1);
+                    const __nv_bfloat16 lo = __float2bfloat16_rn(rem1 - __bfloat162float(mid));
+                    const __nv_bfloat16 pick = term == 0 ? hi : (term == 1 ? mid : lo);
+                    const uint32_t bits = (uint32_t)__bfloat16_as_ushort(pick);
+                    packed[e >> 1] |= bits << ((e & 1) * 16);
+                }
+            }
+            uint4* dst = reinterpret_cast<uint4*>(theta_b + pnl * (N1 * 128) + n * 128 + ((j ^ (n & 7)) * 16));
+            *dst = make_uint4(packed[0], packed[1], packed[2], packed[3]);
+        }
+        for (int i = threadIdx.x; i < (int)(2 * L.r_bytes / 16); i += blockDim.x)
+            reinterpret_cast<uint4*>(r_buf)[i] = make_uint4(0, 0, 0, 0);
+        fence_proxy_async();
+        if (threadIdx.x == 0) {
+            for (int i = 0; i < 4; ++i) { mbar_init(&bar_full[i], 1); mbar_init(&bar_empty[i], 1); }
+            for (int i = 0; i < 2; ++i) {
+                mbar_init(&bar_eta_full[i], 1);
+                mbar_init(&bar_eta_empty[i], 128);
+                mbar_init(&bar_r_full[i], 128);
+                mbar_init(&bar_r_empty[i], 1);
+                mbar_init(&bar_g_full[i], 1);
+                mbar_init(&bar_g_empty[i], 128);
+            }
+            fence_barrier_init();
+        }
+        if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
+        const uint32_t tmem_base = *tmem_slot;
+        const uint32_t tmem_eta = tmem_base;                 // 2 buffers x N1 columns
+        const uint32_t tmem_g = tmem_base + 2 * N1;          // 2 buffers x NH x N2 columns
+
+        if (warp == 0) {
+            // ================= TMA producer ====================================================
+            if (lane == 0) {
+                for (int i = 0; i < prm.n_segments; ++i) tma_prefetch_desc(&tmaps[i]);
+                int s_idx = 0;
+                for (long long it = 0; it < n_it; ++it) {
+                    const long long tile = blockIdx.x + it * gridDim.x;
+                    while (s_idx + 1 < prm.n_segments && segs[s_idx + 1].first_tile <= tile) ++s_idx;
+                    const int st = (int)(it % S);
+                    const uint32_t ph = (uint32_t)((it / S) & 1);
+                    mbar_wait(&bar_empty[st], ph ^ 1);
+                    const int row0 = (int)((tile - segs[s_idx].first_tile) * kTileM);
+                    mbar_expect_tx(&bar_full[st], L.stage_bytes);
+                    unsigned char* dst = smem + (size_t)st * L.stage_bytes;
+                    for (int pnl = 0; pnl < panels; ++pnl)
+                        tma_load_2d(dst + pnl * kPanelBytes, &tmaps[s_idx], pnl * kPanel, row0, &bar_full[st]);
+                }
+            }
+        } else if (warp == 1) {
+            // ================= MMA issuer ======================================================
+            if (lane == 0) {
+                constexpr uint32_t idesc1 = make_idesc(128, N1, 0, 0);
+                constexpr uint32_t idesc2 = make_idesc(128, N2, 1, 1);
+                const uint32_t theta_b_addr = smem_u32(theta_b);
+                const uint32_t r_addr = smem_u32(r_buf);
+                const uint32_t r_lbo = (N2 / 8) * 128;  // stride between 8-row K groups of R
+                auto mma2 = [&](long long j) {
+                    const int st = (int)(j % S);
+                    const int b = (int)(j & 1);
+                    const uint32_t bph = (uint32_t)((j >> 1) & 1);
+                    const long long period = j / kFlush;
+                    const int gb = (int)(period & 1);
+                    const bool first = (j % kFlush) == 0;
+                    const bool last = (j % kFlush) == kFlush - 1 || j == n_it - 1;
+                    mbar_wait(&bar_r_full[b], bph);
+                    if (first) mbar_wait(&bar_g_empty[gb], (uint32_t)(((period >> 1) & 1) ^ 1));
+                    tc_fence_after();
+                    const uint32_t x_addr = smem_u32(smem + (size_t)st * L.stage_bytes);
+                    for (int h = 0; h < NH; ++h) {
+#pragma unroll
+                        for (int ks = 0; ks < kTileM / 16; ++ks) {
+                            // A = X^T: MN-major (features contiguous), 128B swizzle.
+                            // LBO = stride between 64-feature panels, SBO = stride between 8-row groups.
+                            const uint64_t adesc =
+                                make_desc(x_addr + (2 * h) * kPanelBytes + ks * 2 * 1024, kPanelBytes, 1024, 2);
+                            // B = R: MN-major (chain columns contiguous), no swizzle.
+                            // LBO = stride between 8-row K groups, SBO = stride between 8-column groups.
+                            const uint64_t bdesc = make_desc(r_addr + b * L.r_bytes + ks * 2 * r_lbo, r_lbo, 128, 0);
+                            umma_bf16(tmem_g + (gb * NH + h) * N2, adesc, bdesc, idesc2, (first && ks == 0) ? 0u : 1u);
+                        }
+                    }
+                    umma_commit(&bar_empty[st]);
+                    umma_commit(&bar_r_empty[b]);
+                    if (last) umma_commit(&bar_g_full[gb]);
+                };
+                for (long long it = 0; it < n_it; ++it) {
+                    const int st = (int)(it % S);
+                    const uint32_t ph = (uint32_t)((it / S) & 1);
+                    const int b = (int)(it & 1);
+                    const uint32_t bph = (uint32_t)((it >> 1) & 1);
+                    mbar_wait(&bar_full[st], ph);
+                    mbar_wait(&bar_eta_empty[b], bph ^ 1);
+                    tc_fence_after();
+                    const uint32_t x_addr = smem_u32(smem + (size_t)st * L.stage_bytes);
+                    for (int pnl = 0; pnl < panels; ++pnl) {
+#pragma unroll
+                        for (int ks = 0; ks < kPanel / 16; ++ks) {
+                            const uint64_t adesc = make_desc(x_addr + pnl * kPanelBytes + ks * 32, 16, 1024, 2);
+                            const uint64_t bdesc = make_desc(theta_b_addr + pnl * (N1 * 128) + ks * 32, 16, 1024, 2);
+                            umma_bf16(tmem_eta + b * N1, adesc, bdesc, idesc1, (pnl | ks) ? 1u : 0u);
+                        }
+                    }
+                    umma_commit(&bar_eta_full[b]);
+                    if (it > 0) mma2(it - 1);
+                }
+                if (n_it > 0) mma2(n_it - 1);
+            }
+        } else {
+            // ================= epilogue warps (2..5) ===========================================
+            const int q = warp & 3;                 // TMEM lane quarter this warp may access
+            const int row = q * 32 + lane;          // row of the tile == TMEM lane
+            const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+            int s_idx = 0;
+            float ll_acc[KC];
+            float gi_cur[KC];
+#pragma unroll
+            for (int k = 0; k < KC; ++k) ll_acc[k] = gi_cur[k] = 0.f;
+            int cur_group = n_it > 0 ? -1 : 0;
+            const uint32_t r_lbo = (N2 / 8) * 128;
+            for (long long it = 0; it < n_it; ++it) {
+                const long long tile = blockIdx.x + it * gridDim.x;
+                while (s_idx + 1 < prm.n_segments && segs[s_idx + 1].first_tile <= tile) ++s_idx;
+                const GlmSegment& seg = segs[s_idx];
+                if (seg.group != cur_group) {
+                    if (cur_group >= 0) {
+#pragma unroll
+                        for (int k = 0; k < KC; ++k) {
+                            atomicAdd(&gi_acc[k * G + cur_group], (double)gi_cur[k]);
+                            gi_cur[k] = 0.f;
+                        }
+                    }
+                    cur_group = seg.group;
+                }
+                const long long grow = (tile - seg.first_tile) * kTileM + row;
+                const bool valid = grow < seg.n_rows;
+                const float y = valid ? __ldg(seg.y + grow) : 0.f;
+                const int b = (int)(it & 1);
+                const uint32_t bph = (uint32_t)((it >> 1) & 1);
+
+                mbar_wait(&bar_eta_full[b], bph);
+                tc_fence_after();
+                float eta[KC];
+                if constexpr (KC == 1) {
+                    float v[4];
+                    tmem_ld_x4(tmem_eta + lane_addr + b * N1, v);
+                    eta[0] = (v[0] + v[1]) + v[2];
+                } else {
+#pragma unroll
+                    for (int c0 = 0; c0 < N1; c0 += 16) {
+                        float v[16];
+                        tmem_ld_x16(tmem_eta + lane_addr + b * N1 + c0, v);
+#pragma unroll
+                        for (int c = 0; c < 16; ++c) {
+                            const int n = c0 + c;
+                            if (n < 3 * KC) {
+                                if (n % 3 == 0) eta[n / 3] = v[c];
+                                else eta[n / 3] += v[c];
+                            }
+                        }
+                    }
+                }
+                tc_fence_before();
+                mbar_arrive(&bar_eta_empty[b]);
+
+                // link, likelihood, residual -> (hi, lo) bf16 columns of R
+                uint32_t rpk[KC];
+#pragma unroll
+                for (int k = 0; k < KC; ++k) {
+                    float ll = 0.f, r = 0.f;
+                    if (valid && k < nch) link_loglik(prm.family, y, eta[k] + theta_f[k * (G + P) + seg.group], ll, r);
+                    ll_acc[k] += ll;
+                    gi_cur[k] += r;
+                    const __nv_bfloat16 hi = __float2bfloat16_rn(r);
+                    const __nv_bfloat16 lo = __float2bfloat16_rn(r - __bfloat162float(hi));
+                    rpk[k] = (uint32_t)__bfloat16_as_ushort(hi) | ((uint32_t)__bfloat16_as_ushort(lo) << 16);
+                }
+                mbar_wait(&bar_r_empty[b], bph ^ 1);
+                {
+                    unsigned char* rrow = r_buf + b * L.r_bytes + (row >> 3) * r_lbo + (row & 7) * 16;
+#pragma unroll
+                    for (int c8 = 0; c8 < N2 / 8; ++c8) {
+                        uint32_t w[4];
+#pragma unroll
+                        for (int i = 0; i < 4; ++i) {
+                            const int k = c8 * 4 + i;  // columns (2k, 2k+1) = chain k's (hi, lo)
+                            w[i] = k < KC ? rpk[k < KC ? k : 0] : 0u;
+                        }
+                        *reinterpret_cast<uint4*>(rrow + c8 * 128) = make_uint4(w[0], w[1], w[2], w[3]);
+                    }
+                }
+                fence_proxy_async();
+                mbar_arrive(&bar_r_full[b]);
+
+                // gradient flush: TMEM accumulator -> fp64 registers once per period
+                const bool last = (it % kFlush) == kFlush - 1 || it == n_it - 1;
+                if (last) {
+                    const long long period = it / kFlush;
+                    const int gb = (int)(period & 1);
+                    mbar_wait(&bar_g_full[gb], (uint32_t)((period >> 1) & 1));
+                    tc_fence_after();
+                    for (int h = 0; h < NH; ++h) {
+                        if constexpr (KC == 1) {
+                            float v[4];
+                            tmem_ld_x4(tmem_g + lane_addr + (gb * NH + h) * N2, v);
+                            g_acc[h][0] += (double)v[0] + (double)v[1];
+                        } else {
+#pragma unroll
+                            for (int c0 = 0; c0 < N2; c0 += 16) {
+                                float v[16];
+                                tmem_ld_x16(tmem_g + lane_addr + (gb * NH + h) * N2 + c0, v);
+#pragma unroll
+                                for (int c = 0; c < 16; c += 2) {
+                                    const int k = (c0 + c) / 2;
+                                    if (k < KC) g_acc[h][k] += (double)v[c] + (double)v[c + 1];
+                                }
+                            }
+                        }
+                    }
+                    tc_fence_before();
+                    mbar_arrive(&bar_g_empty[gb]);
+#pragma unroll
+                    for (int k = 0; k < KC; ++k) {
+                        ll_total[k] += (double)ll_acc[k];
+                        ll_acc[k] = 0.f;
+                    }
+                }
+            }
+            if (cur_group >= 0) {
+#pragma unroll
+                for (int k = 0; k < KC; ++k) atomicAdd(&gi_acc[k * G + cur_group], (double)gi_cur[k]);
+            }
+        }
+
+        // ---------------- CTA partial -> global scratch ------------------------------------------
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
+        if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
+        double* out = comm.cta_partials + (size_t)blockIdx.x * comm.n_vals;
+        // layout per chain: [LL, gi[G], g[P]]
+#pragma unroll
+        for (int k = 0; k < KC; ++k) {
+            const double ll_block = fed::block_sum(ll_total[k], red);
+            if (threadIdx.x == 0 && k < nch) out[k * (1 + G + P)] = ll_block;
+        }
+        for (int i = threadIdx.x; i < nch * G; i += blockDim.x) out[(i / G) * (1 + G + P) + 1 + (i % G)] = gi_acc[i];
+        if (warp >= 2) {
+            const int row = (warp & 3) * 32 + lane;
+            for (int h = 0; h < NH; ++h)
+#pragma unroll
+                for (int k = 0; k < KC; ++k)
+                    if (k < nch) out[k * (1 + G + P) + 1 + G + h * 128 + row] = g_acc[h][k];
+        }
+    }
+    fed::epilogue(comm, pro, 0ull);
+}
+
+}  // namespace tc
+
+// ------------------------------------------------------------------ host side
+namespace {
+typedef CUresult (*EncodeTiledFn)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                  const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                  CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn get_encode() {
+    static EncodeTiledFn fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn>(p);
+    }
+    return fn;
+}
+int chains_bucket(int k) { return k <= 1 ? 1 : (k <= 4 ? 4 : (k <= 8 ? 8 : 0)); }
+}  // namespace
+
+// Builds one TMA descriptor per segment ([n_rows, P] bf16, box = 64 features x 128 rows, 128B swizzle).
+extern "C" int b200_glm_tc_prepare(const GlmSegment* segs_host, int n_segments, const GlmParams* prm, void** tmaps_dev) {
+    if (prm->n_features % 128 != 0 || prm->n_features > 384 || prm->n_features < 128) return -11;
+    if (n_segments > tc::kMaxSegs) return -12;
+    if (chains_bucket(prm->n_chains) == 0) return -13;
+    if ((prm->ld * 2) % 16 != 0) return -14;
+    EncodeTiledFn encode = get_encode();
+    if (!encode) return -15;
+    CUtensorMap* host = new CUtensorMap[n_segments];
+    for (int s = 0; s < n_segments; ++s) {
+        if (((uintptr_t)segs_host[s].X & 15) != 0) { delete[] host; return -16; }
+        cuuint64_t dims[2] = {(cuuint64_t)prm->n_features, (cuuint64_t)segs_host[s].n_rows};
+        cuuint64_t strides[1] = {(cuuint64_t)prm->ld * 2};
+        cuuint32_t box[2] = {(cuuint32_t)tc::kPanel, (cuuint32_t)tc::kTileM};
+        cuuint32_t estr[2] = {1, 1};
+        CUresult r = encode(&host[s], CU_TENSOR_MAP_DATA_TYPE_BFLOAT16, 2, const_cast<void*>(segs_host[s].X), dims, strides,
+                            box, estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B,
+                            CU_TENSOR_MAP_L2_PROMOTION_L2_256B, CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { delete[] host; return -17; }
+    }
+    if (*tmaps_dev) cudaFree(*tmaps_dev);
+    cudaError_t e = cudaMalloc(tmaps_dev, sizeof(CUtensorMap) * n_segments);
+    if (e == cudaSuccess) e = cudaMemcpy(*tmaps_dev, host, sizeof(CUtensorMap) * n_segments, cudaMemcpyHostToDevice);
+    delete[] host;
+    return e == cudaSuccess ? 0 : (int)e;
+}
+
+extern "C" int b200_launch_glm_tc(const FedComm* comm, const GlmSegment* segs_dev, const GlmParams* prm, const void* tmaps,
+                                  int grid, cudaStream_t stream) {
+    const int kc = chains_bucket(prm->n_chains);
+    if (kc == 0) return -1;
+    const CUtensorMap* maps = reinterpret_cast<const CUtensorMap*>(tmaps);
+#define LAUNCH_TC(KC)                                                                                              \
+    do {                                                                                                           \
+        const tc::SmemLayout L = tc::smem_layout(prm->n_features, tc::Cfg<KC>::N1, tc::Cfg<KC>::N2, comm->n_theta,  \
+                                                 prm->n_groups, KC);                                               \
+        if (L.stages < 2) return -2;                                                                               \
+        cudaFuncSetAttribute(tc::fed_glm_tc_kernel<KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total); \
+        tc::fed_glm_tc_kernel<KC><<<grid, tc::kThreads, L.total, stream>>>(*comm, segs_dev, *prm, maps);            \
+    } while (0)
+    if (kc == 1) LAUNCH_TC(1);
+    else if (kc == 4) LAUNCH_TC(4);
+    else LAUNCH_TC(8);
+#undef LAUNCH_TC
+    return (int)cudaGetLastError();
+}

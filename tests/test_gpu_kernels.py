@@ -82,6 +82,66 @@ def test_glm_simt_matches_reference(dev, family, P):
     np.testing.assert_allclose(d_beta, w_beta, rtol=1e-4, atol=2e-3 * np.sqrt(sum(rows)))
 
 
+def _glm_case(dev, rows, P, groups, n_groups, seed=0):
+    Xs, ys = [], []
+    for i, n in enumerate(rows):
+        X, y, _ = synth_logistic_shard(n, P, seed=seed + i, device=dev, beta_scale=0.05)
+        Xs.append(X)
+        ys.append(y)
+    return Xs, ys
+
+
+@pytest.mark.parametrize("P", [256, 128, 384])
+@pytest.mark.parametrize("family", ["logistic", "gaussian"])
+def test_glm_tensor_core_matches_reference(dev, family, P):
+    rows = [128 * 37, 77, 4099, 128, 1]
+    Xs, ys = _glm_case(dev, rows, P, None, 3)
+    model = GlmShards(Xs, ys, groups=[0, 1, 0, 2, 1], n_groups=3, family=family, kernel="tc")
+    ic = np.array([0.3, -0.2, 0.1])
+    beta = (np.random.default_rng(2).normal(size=P) * 0.03).astype(np.float32)
+    with FederatedEngine(model) as eng:
+        logp, d_ic, d_beta = eng.evaluate(ic, beta)
+        again = eng.evaluate(ic, beta)
+    w_logp, w_ic, w_beta = model.unpack_result(model.reference_partial([ic, beta], dtype=torch.float64))
+    np.testing.assert_allclose(logp, w_logp, rtol=2e-5)
+    np.testing.assert_allclose(d_ic, w_ic, rtol=1e-4, atol=2e-3)
+    np.testing.assert_allclose(d_beta, w_beta, rtol=1e-4, atol=2e-3 * np.sqrt(sum(rows)))
+    for u, v in zip((logp, d_ic, d_beta), again):
+        assert np.array_equal(u, v)
+
+
+@pytest.mark.parametrize("K", [2, 4, 8])
+def test_glm_tensor_core_batches_chains(dev, K):
+    rows = [128 * 50 + 5, 3000]
+    Xs, ys = _glm_case(dev, rows, 256, None, 2, seed=9)
+    model = GlmShards(Xs, ys, groups=[0, 1], n_groups=2, n_chains=K, kernel="tc")
+    rng = np.random.default_rng(4)
+    ic = rng.normal(size=(K, 2)).astype(np.float32) * 0.2
+    beta = rng.normal(size=(K, 256)).astype(np.float32) * 0.03
+    with FederatedEngine(model) as eng:
+        logp, d_ic, d_beta = eng.evaluate(ic, beta)
+    assert logp.shape == (K,) and d_ic.shape == (K, 2) and d_beta.shape == (K, 256)
+    w = model.unpack_result(model.reference_partial([ic, beta], dtype=torch.float64))
+    np.testing.assert_allclose(logp, w[0], rtol=2e-5)
+    np.testing.assert_allclose(d_ic, w[1], rtol=1e-4, atol=2e-3)
+    np.testing.assert_allclose(d_beta, w[2], rtol=1e-4, atol=0.2)
+
+
+def test_glm_tensor_core_many_tiles_flushes_accumulator(dev):
+    """> kFlush tiles per CTA so the TMEM->fp64 flush and the G double buffer are exercised."""
+    X, y, _ = synth_logistic_shard(148 * 128 * 70 + 13, 256, seed=21, device=dev)
+    model_tc = GlmShards([X], [y], kernel="tc")
+    model_simt = GlmShards([X], [y], kernel="simt")
+    beta = (np.random.default_rng(3).normal(size=256) * 0.02).astype(np.float32)
+    with FederatedEngine(model_tc) as eng:
+        a = eng.evaluate(np.array([0.1]), beta)
+    with FederatedEngine(model_simt) as eng:
+        b = eng.evaluate(np.array([0.1]), beta)
+    np.testing.assert_allclose(a[0], b[0], rtol=1e-6)
+    np.testing.assert_allclose(a[1], b[1], rtol=1e-4, atol=0.05)
+    np.testing.assert_allclose(a[2], b[2], rtol=1e-4, atol=0.05)
+
+
 def test_glm_simt_is_deterministic(dev):
     X, y, _ = synth_logistic_shard(50_000, 256, seed=5, device=dev)
     model = GlmShards([X], [y], kernel="simt")
