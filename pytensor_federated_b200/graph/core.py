@@ -1,0 +1,814 @@
+"""A small symbolic graph IR with the slice of PyTensor's API that the federated Ops need.
+
+Why this exists: the reference's L4 layer (``/root/reference/pytensor_federated/op_async.py``,
+``wrapper_ops.py``) is written against PyTensor (``Op``, ``Apply``, ``FunctionGraph``,
+``optdb``, ``pytensor.grad``, ``DisconnectedType`` — list in SURVEY.md §2.5).  PyTensor is not
+available in the B200 image, so the same Op sources run on this IR when PyTensor is missing
+(see :mod:`pytensor_federated_b200._graph_backend`), which makes ``make_node`` / ``perform`` /
+``grad`` / graph fusion executable and testable here, and gives the in-repo samplers
+(:mod:`pytensor_federated_b200.sampling`) a differentiable model language.
+
+It is deliberately tiny: dense NumPy evaluation, reverse-mode autodiff over a handful of
+elementwise/reduction ops, a merge pass, and an optimiser database with tags and positions.
+Names and call signatures follow PyTensor so user code ports in either direction.
+"""
+from __future__ import annotations
+
+import itertools
+from typing import Any, Callable, Dict, Iterable, List, Optional, Sequence, Tuple, Union
+
+import numpy as np
+
+# ----------------------------------------------------------------------------- types
+
+
+class Type:
+    def __call__(self, name: Optional[str] = None) -> "Variable":
+        return Variable(self, None, None, name)
+
+    def filter(self, value):
+        return value
+
+
+class TensorType(Type):
+    def __init__(self, dtype: str = "float64", shape: Tuple[Optional[int], ...] = ()) -> None:
+        self.dtype = str(np.dtype(dtype))
+        self.shape = tuple(shape)
+
+    @property
+    def ndim(self) -> int:
+        return len(self.shape)
+
+    def filter(self, value):
+        arr = np.asarray(value, dtype=self.dtype)
+        if arr.ndim != self.ndim:
+            raise TypeError(f"Expected {self.ndim} dimensions, got array of shape {arr.shape}")
+        return arr
+
+    def __eq__(self, other) -> bool:
+        return isinstance(other, TensorType) and other.dtype == self.dtype and other.ndim == self.ndim
+
+    def __hash__(self) -> int:
+        return hash((self.dtype, self.ndim))
+
+    def __repr__(self) -> str:
+        return f"TensorType({self.dtype}, shape={self.shape})"
+
+
+class DisconnectedType(Type):
+    """Type of the gradient w.r.t. an output that the cost does not depend on."""
+
+    def __repr__(self) -> str:
+        return "DisconnectedType"
+
+
+class NullType(Type):
+    pass
+
+
+# ----------------------------------------------------------------------------- graph nodes
+
+_var_counter = itertools.count()
+
+
+class Variable:
+    def __init__(self, type: Type, owner: Optional["Apply"], index: Optional[int], name: Optional[str] = None):
+        self.type = type
+        self.owner = owner
+        self.index = index
+        self.name = name
+        self._id = next(_var_counter)
+
+    # sugar ------------------------------------------------------------------------------
+    @property
+    def ndim(self) -> int:
+        return self.type.ndim
+
+    @property
+    def dtype(self) -> str:
+        return self.type.dtype
+
+    def __add__(self, other): return add(self, other)
+    def __radd__(self, other): return add(other, self)
+    def __sub__(self, other): return sub(self, other)
+    def __rsub__(self, other): return sub(other, self)
+    def __mul__(self, other): return mul(self, other)
+    def __rmul__(self, other): return mul(other, self)
+    def __truediv__(self, other): return true_div(self, other)
+    def __rtruediv__(self, other): return true_div(other, self)
+    def __neg__(self): return neg(self)
+    def __pow__(self, p): return power(self, p)
+    def __getitem__(self, idx): return Subtensor(idx)(self)
+    def sum(self, axis=None): return Sum(axis)(self)
+
+    def eval(self, inputs_to_values: Optional[Dict["Variable", Any]] = None):
+        inputs_to_values = inputs_to_values or {}
+        ins = list(inputs_to_values.keys())
+        fn = function(ins, self, mode="FAST_COMPILE")
+        return fn(*[inputs_to_values[i] for i in ins])
+
+    def __repr__(self) -> str:
+        if self.name:
+            return self.name
+        if self.owner is not None:
+            return f"{type(self.owner.op).__name__}.{self.index}"
+        return f"<{self.type}>"
+
+    __hash__ = object.__hash__
+
+
+class Constant(Variable):
+    def __init__(self, type: Type, data, name: Optional[str] = None) -> None:
+        super().__init__(type, None, None, name)
+        self.data = data
+
+    def signature(self):
+        arr = np.asarray(self.data)
+        return (str(arr.dtype), arr.shape, arr.tobytes())
+
+    def __repr__(self) -> str:
+        return self.name or f"Constant({self.data})"
+
+
+class Apply:
+    def __init__(self, op: "Op", inputs: Sequence[Variable], outputs: Sequence[Variable]) -> None:
+        self.op = op
+        self.inputs = list(inputs)
+        self.outputs = list(outputs)
+        for i, out in enumerate(self.outputs):
+            out.owner = self
+            out.index = i
+
+    @property
+    def nin(self) -> int:
+        return len(self.inputs)
+
+    @property
+    def nout(self) -> int:
+        return len(self.outputs)
+
+    def __repr__(self) -> str:
+        return f"{type(self.op).__name__}({', '.join(map(repr, self.inputs))})"
+
+
+OutputStorageType = List[List[Optional[Any]]]
+
+
+class Op:
+    """``make_node`` builds the Apply, ``perform`` computes, ``grad`` differentiates."""
+
+    __props__: Tuple[str, ...] = ()
+    default_output: Optional[int] = None
+
+    def make_node(self, *inputs) -> Apply:
+        raise NotImplementedError
+
+    def perform(self, node: Apply, inputs: Sequence[Any], output_storage: OutputStorageType) -> None:
+        raise NotImplementedError
+
+    def grad(self, inputs: Sequence[Variable], output_grads: Sequence[Variable]) -> List[Variable]:
+        raise NotImplementedError(f"{type(self).__name__} has no grad()")
+
+    def __call__(self, *inputs, **kwargs):
+        node = self.make_node(*inputs)
+        if self.default_output is not None:
+            return node.outputs[self.default_output]
+        if len(node.outputs) == 1:
+            return node.outputs[0]
+        return list(node.outputs)
+
+    def _props(self):
+        return tuple(getattr(self, p) for p in self.__props__)
+
+    def __eq__(self, other) -> bool:
+        if self.__props__:
+            return type(self) is type(other) and self._props() == other._props()
+        return self is other
+
+    def __hash__(self) -> int:
+        if self.__props__:
+            try:
+                return hash((type(self), self._props()))
+            except TypeError:
+                return hash(type(self))
+        return id(self)
+
+
+# ----------------------------------------------------------------------------- helpers
+
+
+def as_tensor(x, name: Optional[str] = None, dtype: Optional[str] = None) -> Variable:
+    if isinstance(x, Variable):
+        return x
+    arr = np.asarray(x, dtype=dtype)
+    if arr.dtype.kind in "iub" and dtype is None:
+        arr = arr.astype("float64") if arr.dtype.kind == "b" else arr
+    return Constant(TensorType(arr.dtype, (None,) * arr.ndim), arr, name)
+
+
+as_tensor_variable = as_tensor
+
+
+def scalar(name: Optional[str] = None, dtype: str = "float64") -> Variable:
+    return TensorType(dtype, ())(name)
+
+
+def vector(name: Optional[str] = None, dtype: str = "float64") -> Variable:
+    return TensorType(dtype, (None,))(name)
+
+
+def matrix(name: Optional[str] = None, dtype: str = "float64") -> Variable:
+    return TensorType(dtype, (None, None))(name)
+
+
+dscalar, dvector, dmatrix = scalar, vector, matrix
+
+
+def _out_type(*inputs: Variable) -> TensorType:
+    nd = max(i.type.ndim for i in inputs)
+    dt = np.result_type(*[i.type.dtype for i in inputs])
+    return TensorType(dt, (None,) * nd)
+
+
+class Elemwise(Op):
+    """Broadcasting NumPy ufunc with a hand-written derivative."""
+
+    __props__ = ("name",)
+
+    def __init__(self, name: str, fn: Callable, grad_fn: Callable, float_out: bool = False) -> None:
+        self.name = name
+        self._fn = fn
+        self._grad_fn = grad_fn
+        self._float_out = float_out
+
+    def make_node(self, *inputs) -> Apply:
+        ins = [as_tensor(i) for i in inputs]
+        t = _out_type(*ins)
+        if self._float_out and np.dtype(t.dtype).kind in "iub":
+            t = TensorType("float64", t.shape)
+        return Apply(self, ins, [t()])
+
+    def perform(self, node, inputs, output_storage) -> None:
+        output_storage[0][0] = np.asarray(self._fn(*inputs), dtype=node.outputs[0].type.dtype)
+
+    def grad(self, inputs, output_grads):
+        (g,) = output_grads
+        out = self(*inputs)
+        return [reduce_to(gi, x) for gi, x in zip(self._grad_fn(inputs, out, g), inputs)]
+
+
+class ReduceTo(Op):
+    """Sums ``g`` down to the runtime shape of ``like`` (undoes broadcasting in backprop)."""
+
+    __props__ = ()
+
+    def make_node(self, g, like) -> Apply:
+        g, like = as_tensor(g), as_tensor(like)
+        return Apply(self, [g, like], [TensorType(g.type.dtype, like.type.shape)()])
+
+    def perform(self, node, inputs, output_storage) -> None:
+        g, like = inputs
+        g = np.asarray(g)
+        shape = np.shape(like)
+        while g.ndim > len(shape):
+            g = g.sum(axis=0)
+        for ax, n in enumerate(shape):
+            if n == 1 and g.shape[ax] != 1:
+                g = g.sum(axis=ax, keepdims=True)
+        output_storage[0][0] = np.asarray(g, dtype=node.outputs[0].type.dtype).reshape(shape)
+
+    def grad(self, inputs, output_grads):
+        g, like = inputs
+        (gz,) = output_grads
+        return [gz + zeros_like(g), DisconnectedType()()]
+
+
+def reduce_to(g: Variable, like: Variable) -> Variable:
+    if isinstance(g.type, DisconnectedType):
+        return g
+    if g.type.ndim == like.type.ndim == 0:
+        return g
+    return ReduceTo()(g, like)
+
+
+class Sum(Op):
+    __props__ = ("axis",)
+
+    def __init__(self, axis=None) -> None:
+        self.axis = axis
+
+    def make_node(self, x) -> Apply:
+        x = as_tensor(x)
+        nd = 0 if self.axis is None else x.type.ndim - 1
+        return Apply(self, [x], [TensorType(x.type.dtype, (None,) * nd)()])
+
+    def perform(self, node, inputs, output_storage) -> None:
+        output_storage[0][0] = np.asarray(np.sum(inputs[0], axis=self.axis))
+
+    def grad(self, inputs, output_grads):
+        (x,) = inputs
+        (g,) = output_grads
+        if self.axis is None:
+            return [g + zeros_like(x)]
+        return [ExpandDims(self.axis)(g) + zeros_like(x)]
+
+
+class ExpandDims(Op):
+    __props__ = ("axis",)
+
+    def __init__(self, axis: int) -> None:
+        self.axis = axis
+
+    def make_node(self, x) -> Apply:
+        x = as_tensor(x)
+        return Apply(self, [x], [TensorType(x.type.dtype, (None,) * (x.type.ndim + 1))()])
+
+    def perform(self, node, inputs, output_storage) -> None:
+        output_storage[0][0] = np.expand_dims(inputs[0], self.axis)
+
+    def grad(self, inputs, output_grads):
+        return [Sum(self.axis)(output_grads[0])]
+
+
+class Subtensor(Op):
+    """``x[idx]`` with a static integer or slice index."""
+
+    __props__ = ("idx_key",)
+
+    def __init__(self, idx) -> None:
+        self.idx = idx
+        self.idx_key = repr(idx)
+
+    def make_node(self, x) -> Apply:
+        x = as_tensor(x)
+        probe = np.empty((2,) * x.type.ndim)[self.idx]
+        return Apply(self, [x], [TensorType(x.type.dtype, (None,) * probe.ndim)()])
+
+    def perform(self, node, inputs, output_storage) -> None:
+        output_storage[0][0] = np.asarray(inputs[0][self.idx])
+
+    def grad(self, inputs, output_grads):
+        return [IncSubtensorZeros(self.idx)(inputs[0], output_grads[0])]
+
+
+class IncSubtensorZeros(Op):
+    __props__ = ("idx_key",)
+
+    def __init__(self, idx) -> None:
+        self.idx = idx
+        self.idx_key = repr(idx)
+
+    def make_node(self, like, g) -> Apply:
+        like, g = as_tensor(like), as_tensor(g)
+        return Apply(self, [like, g], [like.type()])
+
+    def perform(self, node, inputs, output_storage) -> None:
+        like, g = inputs
+        out = np.zeros(np.shape(like), dtype=node.outputs[0].type.dtype)
+        out[self.idx] = g
+        output_storage[0][0] = out
+
+    def grad(self, inputs, output_grads):
+        return [DisconnectedType()(), Subtensor(self.idx)(output_grads[0])]
+
+
+class ZerosLike(Op):
+    __props__ = ()
+
+    def make_node(self, x) -> Apply:
+        x = as_tensor(x)
+        dt = x.type.dtype if np.dtype(x.type.dtype).kind == "f" else "float64"
+        return Apply(self, [x], [TensorType(dt, x.type.shape)()])
+
+    def perform(self, node, inputs, output_storage) -> None:
+        output_storage[0][0] = np.zeros(np.shape(inputs[0]), dtype=node.outputs[0].type.dtype)
+
+    def grad(self, inputs, output_grads):
+        return [DisconnectedType()()]
+
+
+def zeros_like(x) -> Variable:
+    return ZerosLike()(x)
+
+
+class Stack(Op):
+    """Stacks scalars into a vector (``at.stack``)."""
+
+    __props__ = ()
+
+    def make_node(self, *xs) -> Apply:
+        xs = [as_tensor(x) for x in xs]
+        return Apply(self, xs, [TensorType("float64", (None,))()])
+
+    def perform(self, node, inputs, output_storage) -> None:
+        output_storage[0][0] = np.asarray([float(np.asarray(x)) for x in inputs])
+
+    def grad(self, inputs, output_grads):
+        (g,) = output_grads
+        return [g[i] for i in range(len(inputs))]
+
+
+def stack(xs) -> Variable:
+    return Stack()(*xs)
+
+
+_add = Elemwise("add", np.add, lambda ins, out, g: [g, g])
+_sub = Elemwise("sub", np.subtract, lambda ins, out, g: [g, neg(g)])
+_mul = Elemwise("mul", np.multiply, lambda ins, out, g: [g * ins[1], g * ins[0]])
+_div = Elemwise("true_div", np.true_divide, lambda ins, out, g: [g / ins[1], neg(g * ins[0] / (ins[1] * ins[1]))], True)
+_neg = Elemwise("neg", np.negative, lambda ins, out, g: [neg(g)])
+_exp = Elemwise("exp", np.exp, lambda ins, out, g: [g * out], True)
+_log = Elemwise("log", np.log, lambda ins, out, g: [g / ins[0]], True)
+_sqr = Elemwise("sqr", np.square, lambda ins, out, g: [g * 2.0 * ins[0]])
+_sqrt = Elemwise("sqrt", np.sqrt, lambda ins, out, g: [g / (2.0 * out)], True)
+_sigmoid = Elemwise("sigmoid", lambda x: 1.0 / (1.0 + np.exp(-x)), lambda ins, out, g: [g * out * (1.0 - out)], True)
+_softplus = Elemwise("softplus", lambda x: np.logaddexp(0.0, x), lambda ins, out, g: [g * sigmoid(ins[0])], True)
+
+
+def add(a, b): return _add(a, b)
+def sub(a, b): return _sub(a, b)
+def mul(a, b): return _mul(a, b)
+def true_div(a, b): return _div(a, b)
+def neg(a): return _neg(a)
+def exp(a): return _exp(a)
+def log(a): return _log(a)
+def sqr(a): return _sqr(a)
+def sqrt(a): return _sqrt(a)
+def sigmoid(a): return _sigmoid(a)
+def softplus(a): return _softplus(a)
+
+
+def power(a, p):
+    if isinstance(p, (int, float)) and p == 2:
+        return sqr(a)
+    return exp(as_tensor(float(p)) * log(a)) if isinstance(p, (int, float)) else exp(p * log(a))
+
+
+def sum(x, axis=None):  # noqa: A001 - mirrors pytensor.tensor.sum
+    return as_tensor(x).sum(axis)
+
+
+# ----------------------------------------------------------------------------- traversal
+
+
+def ancestors_applies(outputs: Iterable[Variable]) -> List[Apply]:
+    """Apply nodes needed for ``outputs`` in a deterministic topological order."""
+    order: List[Apply] = []
+    seen = set()
+    stack_: List[Tuple[Apply, int]] = []
+    for out in outputs:
+        if out.owner is not None and id(out.owner) not in seen:
+            stack_.append((out.owner, 0))
+            while stack_:
+                node, i = stack_.pop()
+                if id(node) in seen:
+                    continue
+                if i < len(node.inputs):
+                    stack_.append((node, i + 1))
+                    parent = node.inputs[i].owner
+                    if parent is not None and id(parent) not in seen:
+                        stack_.append((parent, 0))
+                else:
+                    seen.add(id(node))
+                    order.append(node)
+    return order
+
+
+def apply_depends_on(apply: Apply, depends_on: Union[Apply, Sequence[Apply]]) -> bool:
+    """True when ``apply`` (transitively) consumes an output of ``depends_on``."""
+    targets = {id(depends_on)} if isinstance(depends_on, Apply) else {id(d) for d in depends_on}
+    seen = set()
+    todo = [apply]
+    while todo:
+        node = todo.pop()
+        for inp in node.inputs:
+            parent = inp.owner
+            if parent is None or id(parent) in seen:
+                continue
+            if id(parent) in targets:
+                return True
+            seen.add(id(parent))
+            todo.append(parent)
+    return False
+
+
+# ----------------------------------------------------------------------------- autodiff
+
+
+def grad(cost: Variable, wrt: Union[Variable, Sequence[Variable]], disconnected_inputs: str = "zero"):
+    """Reverse-mode gradient of a scalar ``cost``.
+
+    Outputs the cost does not depend on receive a ``DisconnectedType`` gradient variable, which
+    is how ``LogpGradOp.grad`` recognises that nobody differentiates through its gradient
+    outputs (reference: ``wrapper_ops.py:122-125``).
+    """
+    single = isinstance(wrt, Variable)
+    wrts = [wrt] if single else list(wrt)
+    if cost.type.ndim != 0:
+        raise TypeError("grad() needs a scalar cost")
+    grads: Dict[int, Variable] = {id(cost): as_tensor(1.0)}
+    keep = {id(cost): cost}
+    for node in reversed(ancestors_applies([cost])):
+        if not any(id(o) in grads for o in node.outputs):
+            continue
+        ogs = [grads.get(id(o)) if id(o) in grads else DisconnectedType()() for o in node.outputs]
+        igs = node.op.grad(node.inputs, ogs)
+        if len(igs) != len(node.inputs):
+            raise ValueError(f"{type(node.op).__name__}.grad returned {len(igs)} gradients for {len(node.inputs)} inputs")
+        for inp, g in zip(node.inputs, igs):
+            if g is None or isinstance(g.type, (DisconnectedType, NullType)):
+                continue
+            if id(inp) in grads:
+                grads[id(inp)] = grads[id(inp)] + g
+            else:
+                grads[id(inp)] = g
+                keep[id(inp)] = inp
+    result = []
+    for w in wrts:
+        if id(w) in grads:
+            result.append(grads[id(w)])
+        elif disconnected_inputs == "raise":
+            raise ValueError(f"{w} is not part of the cost's graph")
+        else:
+            result.append(zeros_like(w))
+    return result[0] if single else result
+
+
+# ----------------------------------------------------------------------------- FunctionGraph
+
+
+class Feature:
+    def on_attach(self, fgraph: "FunctionGraph") -> None:
+        pass
+
+
+class ReplaceValidate(Feature):
+    """Adds ``replace_all_validate``: apply replacements, roll back if the graph breaks."""
+
+    def on_attach(self, fgraph: "FunctionGraph") -> None:
+        if hasattr(fgraph, "replace_all_validate"):
+            return
+
+        def replace_all_validate(pairs, reason=None):
+            snapshot = fgraph._snapshot()
+            try:
+                fgraph.replace_all(pairs, reason=reason)
+                fgraph.toposort()  # raises on cycles / dangling inputs
+            except Exception:
+                fgraph._restore(snapshot)
+                raise
+
+        fgraph.replace_all_validate = replace_all_validate
+
+
+class FunctionGraph:
+    def __init__(self, inputs: Sequence[Variable], outputs: Sequence[Variable], clone: bool = True) -> None:
+        if clone:
+            inputs, outputs = clone_graph(inputs, outputs)
+        self.inputs = list(inputs)
+        self.outputs = list(outputs)
+        self._features: List[Feature] = []
+
+    def attach_feature(self, feature: Feature) -> None:
+        if any(type(f) is type(feature) for f in self._features):
+            return
+        self._features.append(feature)
+        feature.on_attach(self)
+
+    @property
+    def apply_nodes(self) -> List[Apply]:
+        return ancestors_applies(self.outputs)
+
+    def toposort(self) -> List[Apply]:
+        order = ancestors_applies(self.outputs)
+        known = {id(v) for v in self.inputs}
+        for node in order:
+            for inp in node.inputs:
+                if inp.owner is None and not isinstance(inp, Constant) and id(inp) not in known:
+                    raise ValueError(f"Graph input {inp} is not an input of the FunctionGraph")
+        return order
+
+    def replace_all(self, pairs, reason=None) -> None:
+        mapping = {id(old): new for old, new in pairs}
+        if not mapping:
+            return
+        for node in ancestors_applies(self.outputs):
+            for i, inp in enumerate(node.inputs):
+                if id(inp) in mapping:
+                    node.inputs[i] = mapping[id(inp)]
+        for i, out in enumerate(self.outputs):
+            if id(out) in mapping:
+                self.outputs[i] = mapping[id(out)]
+        # replacements may themselves consume replaced variables (none of ours do); re-run once
+        for node in ancestors_applies(self.outputs):
+            for i, inp in enumerate(node.inputs):
+                if id(inp) in mapping and mapping[id(inp)] is not inp:
+                    node.inputs[i] = mapping[id(inp)]
+
+    def replace(self, old: Variable, new: Variable, reason=None) -> None:
+        self.replace_all([(old, new)], reason=reason)
+
+    def _snapshot(self):
+        return list(self.outputs), [(n, list(n.inputs)) for n in ancestors_applies(self.outputs)]
+
+    def _restore(self, snap) -> None:
+        outputs, nodes = snap
+        self.outputs = outputs
+        for node, inputs in nodes:
+            node.inputs = inputs
+
+
+def clone_graph(inputs: Sequence[Variable], outputs: Sequence[Variable]):
+    """Copies the Apply nodes between ``inputs`` and ``outputs`` (Ops are shared)."""
+    memo: Dict[int, Variable] = {}
+    new_inputs = []
+    for v in inputs:
+        nv = Variable(v.type, None, None, v.name)
+        memo[id(v)] = nv
+        new_inputs.append(nv)
+    for node in ancestors_applies(outputs):
+        ins = []
+        for inp in node.inputs:
+            if id(inp) not in memo:
+                memo[id(inp)] = inp  # constants and free variables are shared
+            ins.append(memo[id(inp)])
+        outs = [Variable(o.type, None, None, o.name) for o in node.outputs]
+        Apply(node.op, ins, outs)
+        for o, no in zip(node.outputs, outs):
+            memo[id(o)] = no
+    return new_inputs, [memo.get(id(o), o) for o in outputs]
+
+
+# ----------------------------------------------------------------------------- rewriting
+
+
+class GraphRewriter:
+    def add_requirements(self, fgraph: FunctionGraph) -> None:
+        pass
+
+    def apply(self, fgraph: FunctionGraph) -> None:
+        raise NotImplementedError
+
+    def rewrite(self, fgraph: FunctionGraph) -> None:
+        self.add_requirements(fgraph)
+        self.apply(fgraph)
+
+
+class MergeOptimizer(GraphRewriter):
+    """Deduplicates equal constants and Apply nodes with equal op and identical inputs.
+
+    This is what makes ``LogpGradOp.grad`` cost no second remote call: its re-application of
+    the same Op instance to the same inputs is merged into the forward node.
+    """
+
+    def apply(self, fgraph: FunctionGraph) -> None:
+        changed = True
+        while changed:
+            changed = False
+            const_seen: Dict[Any, Variable] = {}
+            node_seen: Dict[Any, Apply] = {}
+            pairs = []
+            for node in fgraph.toposort():
+                for i, inp in enumerate(node.inputs):
+                    if isinstance(inp, Constant):
+                        sig = inp.signature()
+                        if sig in const_seen and const_seen[sig] is not inp:
+                            node.inputs[i] = const_seen[sig]
+                        else:
+                            const_seen.setdefault(sig, inp)
+                try:
+                    key = (node.op, tuple(id(i) for i in node.inputs))
+                    hash(key)
+                except TypeError:
+                    continue
+                other = node_seen.get(key)
+                if other is None:
+                    node_seen[key] = node
+                elif other is not node:
+                    pairs.extend(zip(node.outputs, other.outputs))
+            if pairs:
+                fgraph.replace_all(pairs, reason="merge")
+                changed = True
+
+
+class OptimizerDB:
+    """Named rewriters with tags and positions (``pytensor.compile.optdb`` subset)."""
+
+    def __init__(self) -> None:
+        self._entries: Dict[str, Tuple[GraphRewriter, Tuple[str, ...], float]] = {}
+
+    def register(self, name: str, rewriter: GraphRewriter, *tags: str, position: float = 50.0) -> None:
+        if name in self._entries:
+            raise ValueError(f"The name {name!r} is already registered.")
+        self._entries[name] = (rewriter, tuple(tags), float(position))
+
+    def __contains__(self, name: str) -> bool:
+        return name in self._entries
+
+    def __getitem__(self, name: str) -> GraphRewriter:
+        return self._entries[name][0]
+
+    def remove(self, name: str) -> None:
+        self._entries.pop(name, None)
+
+    def query(self, *tags: str, exclude: Sequence[str] = ()) -> List[GraphRewriter]:
+        picked = [
+            (pos, name, rw)
+            for name, (rw, t, pos) in self._entries.items()
+            if name not in exclude and any(tag in t for tag in tags)
+        ]
+        return [rw for _, _, rw in sorted(picked, key=lambda e: (e[0], e[1]))]
+
+
+optdb = OptimizerDB()
+optdb.register("merge1", MergeOptimizer(), "fast_run", "fast_compile", position=0)
+optdb.register("merge2", MergeOptimizer(), "fast_run", position=49)
+
+MODES = {"FAST_RUN": "fast_run", "FAST_COMPILE": "fast_compile"}
+default_mode = "FAST_RUN"
+
+
+class Mode:
+    def __init__(self, name: str = "FAST_RUN", excluding: Sequence[str] = ()) -> None:
+        self.name = name
+        self._excluding = tuple(excluding)
+
+    def excluding(self, *names: str) -> "Mode":
+        return Mode(self.name, self._excluding + names)
+
+
+def get_mode(mode) -> Mode:
+    if isinstance(mode, Mode):
+        return mode
+    return Mode(mode or default_mode)
+
+
+# ----------------------------------------------------------------------------- compilation
+
+
+class Function:
+    def __init__(self, fgraph: FunctionGraph, single_output: bool) -> None:
+        self.fgraph = fgraph
+        self.maker = self  # pytensor spelling: fn.maker.fgraph
+        self._single = single_output
+        self._order = fgraph.toposort()
+
+    def __call__(self, *args):
+        if len(args) != len(self.fgraph.inputs):
+            raise TypeError(f"Expected {len(self.fgraph.inputs)} inputs, got {len(args)}")
+        values: Dict[int, Any] = {}
+        for var, arg in zip(self.fgraph.inputs, args):
+            values[id(var)] = var.type.filter(arg)
+
+        def value_of(v: Variable):
+            if isinstance(v, Constant):
+                return v.data
+            return values[id(v)]
+
+        for node in self._order:
+            storage: OutputStorageType = [[None] for _ in node.outputs]
+            node.op.perform(node, [value_of(i) for i in node.inputs], storage)
+            for out, cell in zip(node.outputs, storage):
+                values[id(out)] = cell[0]
+        results = [value_of(o) for o in self.fgraph.outputs]
+        return results[0] if self._single else results
+
+
+def function(inputs: Sequence[Variable], outputs, mode=None, **_ignored) -> Function:
+    """Compiles ``outputs = f(inputs)``; ``mode`` is ``"FAST_RUN"`` (default), ``"FAST_COMPILE"``
+    or a :class:`Mode`.  FAST_RUN applies every rewriter tagged ``fast_run`` in position order
+    (the federated ``fuse_asyncs`` pass registers itself there at position 90)."""
+    single = isinstance(outputs, Variable)
+    outs = [outputs] if single else list(outputs)
+    fgraph = FunctionGraph(list(inputs), outs, clone=True)
+    m = get_mode(mode)
+    for rewriter in optdb.query(MODES.get(m.name, "fast_run"), exclude=m._excluding):
+        rewriter.rewrite(fgraph)
+    return Function(fgraph, single)
+
+
+class FromFunctionOp(Op):
+    """Wraps a Python function ``fn(*arrays) -> array(s)`` as an Op with declared types."""
+
+    def __init__(self, fn: Callable, itypes: Sequence[Type], otypes: Sequence[Type], infer_shape=None) -> None:
+        self.__fn = fn
+        self.itypes = list(itypes)
+        self.otypes = list(otypes)
+        self.__infer_shape = infer_shape
+
+    def make_node(self, *inputs) -> Apply:
+        if len(inputs) != len(self.itypes):
+            raise ValueError(f"Expected {len(self.itypes)} inputs, got {len(inputs)}")
+        ins = [as_tensor(i) for i in inputs]
+        for i, (var, t) in enumerate(zip(ins, self.itypes)):
+            if isinstance(t, TensorType) and var.type.ndim != t.ndim:
+                raise TypeError(f"Input {i} has {var.type.ndim} dimensions, expected {t.ndim}")
+        return Apply(self, ins, [t() for t in self.otypes])
+
+    def perform(self, node, inputs, output_storage) -> None:
+        outs = self.__fn(*inputs)
+        if not isinstance(outs, (list, tuple)):
+            outs = (outs,)
+        assert len(outs) == len(output_storage)
+        for cell, value in zip(output_storage, outs):
+            cell[0] = value

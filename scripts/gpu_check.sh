@@ -27,11 +27,17 @@ fi
 
 if [[ $STAGE == all || $STAGE == ncu ]]; then
   for K in ${KERNELS:-simt}; do
-    timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -c 60 --csv \
+    timeout 600 ncu --metrics gpu__time_duration.sum --clock-control none -k regex:fed_ -c 60 --csv \
         --log-file $OUT/launches_$K.csv python bench.py --rows 2000000 --steps 3 --warmup 3 --kernel $K > $OUT/ncu_launches_$K.log 2>&1
     timeout 900 ncu --set full --clock-control none --import-source on -k regex:fed_glm -s 3 -c 1 \
         -o $OUT/prof_glm_$K -f python bench.py --rows 2000000 --steps 2 --warmup 3 --kernel $K > $OUT/ncu_full_$K.log 2>&1
     tail -3 $OUT/ncu_full_$K.log
+  done
+fi
+if [[ $STAGE == chains ]]; then
+  for C in ${CHAINS:-4 8}; do
+    timeout 900 python bench.py --steps 20 --warmup 3 --kernel tc --chains $C --out $OUT/bench_full_tc_chains.jsonl > $OUT/bench_full_tc_c$C.log 2>&1
+    tail -1 $OUT/bench_full_tc_c$C.log
   done
 fi
 echo "gpu_check done"
