@@ -13,7 +13,8 @@
 //
 // so the gradient GEMM costs no second pass over X.  Chains are batched along N (the MMA is
 // otherwise idle: the kernel is HBM-bound), which is what makes tensor cores pay here.
-// Roles: warp 0 = TMA producer, warp 1 = MMA issuer (one elected lane), warps 2-5 = epilogue.
+// Roles: warp 0 = TMA producer, warp 1 = MMA #1 issuer, warps 2-5 = epilogue, warp 6 = MMA #2
+// issuer (separate issuers so the gradient MMA of tile t never queues behind the TMA of tile t+1).
 // The federation prologue/epilogue (theta broadcast, NVLink reduce) is fed_comm.cuh.
 //
 // Workload: BASELINE.json "federated logistic GLM, 10M rows x 256 features per shard, bf16".
@@ -30,7 +31,7 @@ namespace tc {
 constexpr int kTileM = 128;          // rows per tile (UMMA M for MMA #1, UMMA K-extent for MMA #2)
 constexpr int kPanel = 64;           // features per 128-byte swizzle span
 constexpr int kPanelBytes = kTileM * 128;  // 16 KB
-constexpr int kThreads = 192;
+constexpr int kThreads = 224;          // warps: 0 TMA, 1 MMA#1 issuer, 2-5 epilogue, 6 MMA#2 issuer
 constexpr int kFlush = 32;           // tiles between TMEM -> fp64 flushes of the gradient
 constexpr int kMaxSegs = 64;
 
@@ -321,14 +322,37 @@ fed_glm_tc_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParams
                 }
             }
         } else if (warp == 1) {
-            // ================= MMA issuer ======================================================
+            // ================= MMA #1 issuer: eta = X . Theta^T ================================
             if (lane == 0) {
                 constexpr uint32_t idesc1 = make_idesc(128, N1, 0, 0);
-                constexpr uint32_t idesc2 = make_idesc(128, N2, 1, 1);
                 const uint32_t theta_b_addr = smem_u32(theta_b);
+                for (long long it = 0; it < n_it; ++it) {
+                    const int st = (int)(it % S);
+                    const uint32_t ph = (uint32_t)((it / S) & 1);
+                    const int b = (int)(it & 1);
+                    const uint32_t bph = (uint32_t)((it >> 1) & 1);
+                    mbar_wait(&bar_eta_empty[b], bph ^ 1);
+                    mbar_wait(&bar_full[st], ph);
+                    tc_fence_after();
+                    const uint32_t x_addr = smem_u32(smem + (size_t)st * L.stage_bytes);
+                    for (int pnl = 0; pnl < panels; ++pnl) {
+#pragma unroll
+                        for (int ks = 0; ks < kPanel / 16; ++ks) {
+                            const uint64_t adesc = make_desc(x_addr + pnl * kPanelBytes + ks * 32, 16, 1024, 2);
+                            const uint64_t bdesc = make_desc(theta_b_addr + pnl * (N1 * 128) + ks * 32, 16, 1024, 2);
+                            umma_bf16(tmem_eta + b * N1, adesc, bdesc, idesc1, (pnl | ks) ? 1u : 0u);
+                        }
+                    }
+                    umma_commit(&bar_eta_full[b]);
+                }
+            }
+        } else if (warp == 6) {
+            // ================= MMA #2 issuer: G += X^T . R ======================================
+            if (lane == 0) {
+                constexpr uint32_t idesc2 = make_idesc(128, N2, 1, 1);
                 const uint32_t r_addr = smem_u32(r_buf);
                 const uint32_t r_lbo = (N2 / 8) * 128;  // stride between 8-row K groups of R
-                auto mma2 = [&](long long j) {
+                for (long long j = 0; j < n_it; ++j) {
                     const int st = (int)(j % S);
                     const int b = (int)(j & 1);
                     const uint32_t bph = (uint32_t)((j >> 1) & 1);
@@ -336,8 +360,8 @@ fed_glm_tc_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParams
                     const int gb = (int)(period & 1);
                     const bool first = (j % kFlush) == 0;
                     const bool last = (j % kFlush) == kFlush - 1 || j == n_it - 1;
-                    mbar_wait(&bar_r_full[b], bph);
                     if (first) mbar_wait(&bar_g_empty[gb], (uint32_t)(((period >> 1) & 1) ^ 1));
+                    mbar_wait(&bar_r_full[b], bph);
                     tc_fence_after();
                     const uint32_t x_addr = smem_u32(smem + (size_t)st * L.stage_bytes);
                     for (int h = 0; h < NH; ++h) {
@@ -353,31 +377,10 @@ fed_glm_tc_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParams
                             umma_bf16(tmem_g + (gb * NH + h) * N2, adesc, bdesc, idesc2, (first && ks == 0) ? 0u : 1u);
                         }
                     }
-                    umma_commit(&bar_empty[st]);
-                    umma_commit(&bar_r_empty[b]);
+                    umma_commit(&bar_empty[st]);    // X stage may be refilled
+                    umma_commit(&bar_r_empty[b]);   // R buffer may be rewritten
                     if (last) umma_commit(&bar_g_full[gb]);
-                };
-                for (long long it = 0; it < n_it; ++it) {
-                    const int st = (int)(it % S);
-                    const uint32_t ph = (uint32_t)((it / S) & 1);
-                    const int b = (int)(it & 1);
-                    const uint32_t bph = (uint32_t)((it >> 1) & 1);
-                    mbar_wait(&bar_full[st], ph);
-                    mbar_wait(&bar_eta_empty[b], bph ^ 1);
-                    tc_fence_after();
-                    const uint32_t x_addr = smem_u32(smem + (size_t)st * L.stage_bytes);
-                    for (int pnl = 0; pnl < panels; ++pnl) {
-#pragma unroll
-                        for (int ks = 0; ks < kPanel / 16; ++ks) {
-                            const uint64_t adesc = make_desc(x_addr + pnl * kPanelBytes + ks * 32, 16, 1024, 2);
-                            const uint64_t bdesc = make_desc(theta_b_addr + pnl * (N1 * 128) + ks * 32, 16, 1024, 2);
-                            umma_bf16(tmem_eta + b * N1, adesc, bdesc, idesc1, (pnl | ks) ? 1u : 0u);
-                        }
-                    }
-                    umma_commit(&bar_eta_full[b]);
-                    if (it > 0) mma2(it - 1);
                 }
-                if (n_it > 0) mma2(n_it - 1);
             }
         } else {
             // ================= epilogue warps (2..5) ===========================================
@@ -518,7 +521,7 @@ fed_glm_tc_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParams
             if (threadIdx.x == 0 && k < nch) out[k * (1 + G + P)] = ll_block;
         }
         for (int i = threadIdx.x; i < nch * G; i += blockDim.x) out[(i / G) * (1 + G + P) + 1 + (i % G)] = gi_acc[i];
-        if (warp >= 2) {
+        if (warp >= 2 && warp <= 5) {
             const int row = (warp & 3) * 32 + lane;
             for (int h = 0; h < NH; ++h)
 #pragma unroll

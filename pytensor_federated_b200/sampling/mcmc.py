@@ -1,0 +1,264 @@
+"""MAP, HMC and NUTS over a flat parameter vector."""
+from __future__ import annotations
+
+import dataclasses
+import math
+from typing import Callable, Dict, Optional, Tuple
+
+import numpy as np
+
+LogpDlogp = Callable[[np.ndarray], Tuple[float, np.ndarray]]
+
+
+@dataclasses.dataclass
+class SamplerResult:
+    samples: np.ndarray            # [draws, dim]
+    logp: np.ndarray               # [draws]
+    accept_rate: float
+    step_size: float
+    n_logp_evals: int
+    tree_depth: Optional[np.ndarray] = None
+    divergences: int = 0
+
+    def summary(self, names=None) -> Dict[str, Dict[str, float]]:
+        names = names or [f"theta[{i}]" for i in range(self.samples.shape[1])]
+        out = {}
+        for i, n in enumerate(names):
+            col = self.samples[:, i]
+            out[n] = {"mean": float(col.mean()), "sd": float(col.std(ddof=1)) if len(col) > 1 else 0.0,
+                      "median": float(np.median(col)), "ess": float(effective_sample_size(col))}
+        return out
+
+
+def effective_sample_size(x: np.ndarray) -> float:
+    """Geyer initial-positive-sequence ESS of one chain."""
+    x = np.asarray(x, dtype=np.float64)
+    n = len(x)
+    if n < 4 or np.var(x) == 0:
+        return float(n)
+    xc = x - x.mean()
+    f = np.fft.rfft(xc, 2 * n)
+    acf = np.fft.irfft(f * np.conj(f))[:n].real
+    acf /= acf[0]
+    s = 0.0
+    for k in range(1, n - 1, 2):
+        pair = acf[k] + acf[k + 1]
+        if pair < 0:
+            break
+        s += pair
+    return float(n / max(1.0, 1.0 + 2.0 * s))
+
+
+def find_map(logp_dlogp: LogpDlogp, x0: np.ndarray, *, maxiter: int = 500, tol: float = 1e-10):
+    """Maximum a posteriori by L-BFGS-B on ``-logp`` (the reference calls ``pm.find_MAP()``)."""
+    import scipy.optimize
+
+    n_evals = 0
+
+    def objective(x):
+        nonlocal n_evals
+        n_evals += 1
+        lp, g = logp_dlogp(np.asarray(x, dtype=np.float64))
+        return -float(lp), -np.asarray(g, dtype=np.float64)
+
+    res = scipy.optimize.minimize(objective, np.asarray(x0, dtype=np.float64), jac=True, method="L-BFGS-B",
+                                  options={"maxiter": maxiter, "ftol": tol, "gtol": 1e-8})
+    return res.x, {"logp": -float(res.fun), "n_evals": n_evals, "converged": bool(res.success), "message": str(res.message)}
+
+
+class _DualAveraging:
+    """Nesterov dual averaging of log(step size) (Hoffman & Gelman 2014, §3.2)."""
+
+    def __init__(self, eps0: float, target: float = 0.8, gamma: float = 0.05, t0: float = 10.0, kappa: float = 0.75):
+        self.mu = math.log(10.0 * eps0)
+        self.target, self.gamma, self.t0, self.kappa = target, gamma, t0, kappa
+        self.h_bar = 0.0
+        self.log_eps_bar = 0.0
+        self.t = 0
+
+    def update(self, accept: float) -> float:
+        self.t += 1
+        w = 1.0 / (self.t + self.t0)
+        self.h_bar = (1 - w) * self.h_bar + w * (self.target - accept)
+        log_eps = self.mu - math.sqrt(self.t) / self.gamma * self.h_bar
+        eta = self.t ** (-self.kappa)
+        self.log_eps_bar = eta * log_eps + (1 - eta) * self.log_eps_bar
+        return math.exp(log_eps)
+
+    def final(self) -> float:
+        return math.exp(self.log_eps_bar)
+
+
+def _find_reasonable_step(logp_dlogp, x, lp, g, rng, inv_mass) -> Tuple[float, int]:
+    eps, n = 1.0, 0
+    p = rng.normal(size=x.shape) / np.sqrt(inv_mass)
+
+    def trial(e):
+        ph = p + 0.5 * e * g
+        xn = x + e * inv_mass * ph
+        lpn, gn = logp_dlogp(xn)
+        pn = ph + 0.5 * e * gn
+        return lpn - 0.5 * np.sum(inv_mass * pn * pn) - (lp - 0.5 * np.sum(inv_mass * p * p))
+
+    d = trial(eps)
+    n += 1
+    direction = 1.0 if (np.isfinite(d) and d > math.log(0.5)) else -1.0
+    for _ in range(50):
+        eps *= 2.0**direction
+        d = trial(eps)
+        n += 1
+        ok = np.isfinite(d) and d > math.log(0.5)
+        if (direction > 0 and not ok) or (direction < 0 and ok):
+            break
+    return eps, n
+
+
+def hmc_sample(logp_dlogp: LogpDlogp, x0: np.ndarray, *, draws: int = 500, tune: int = 500, n_leapfrog: int = 16,
+               step_size: Optional[float] = None, target_accept: float = 0.8, seed: int = 0,
+               adapt_mass: bool = True) -> SamplerResult:
+    """Static-trajectory HMC with dual-averaging step size and diagonal mass adaptation."""
+    rng = np.random.default_rng(seed)
+    x = np.asarray(x0, dtype=np.float64).copy()
+    lp, g = logp_dlogp(x)
+    n_evals = 1
+    inv_mass = np.ones_like(x)
+    if step_size is None:
+        step_size, k = _find_reasonable_step(logp_dlogp, x, lp, g, rng, inv_mass)
+        n_evals += k
+    da = _DualAveraging(step_size, target_accept)
+    eps = step_size
+    samples = np.empty((draws, x.size))
+    lps = np.empty(draws)
+    acc_sum, warm = 0.0, []
+    for it in range(tune + draws):
+        p = rng.normal(size=x.shape) / np.sqrt(inv_mass)
+        h0 = lp - 0.5 * np.sum(inv_mass * p * p)
+        xn, pn, lpn, gn = x, p, lp, g
+        ok = True
+        jitter = eps * rng.uniform(0.8, 1.2)
+        for _ in range(n_leapfrog):
+            pn = pn + 0.5 * jitter * gn
+            xn = xn + jitter * inv_mass * pn
+            lpn, gn = logp_dlogp(xn)
+            n_evals += 1
+            if not np.isfinite(lpn):
+                ok = False
+                break
+            pn = pn + 0.5 * jitter * gn
+        h1 = lpn - 0.5 * np.sum(inv_mass * pn * pn) if ok else -np.inf
+        a = min(1.0, math.exp(min(0.0, h1 - h0))) if np.isfinite(h1) else 0.0
+        if rng.uniform() < a:
+            x, lp, g = xn, lpn, gn
+        if it < tune:
+            eps = da.update(a)
+            warm.append(x.copy())
+            if adapt_mass and it == int(0.6 * tune) and len(warm) > 20:
+                var = np.var(np.asarray(warm[len(warm) // 3:]), axis=0)
+                inv_mass = np.where(var > 1e-12, var, 1.0)
+                da = _DualAveraging(eps, target_accept)
+            if it == tune - 1:
+                eps = da.final()
+        else:
+            samples[it - tune] = x
+            lps[it - tune] = lp
+            acc_sum += a
+    return SamplerResult(samples, lps, acc_sum / max(1, draws), eps, n_evals)
+
+
+def nuts_sample(logp_dlogp: LogpDlogp, x0: np.ndarray, *, draws: int = 200, tune: int = 500, max_depth: int = 8,
+                target_accept: float = 0.8, seed: int = 0, adapt_mass: bool = True) -> SamplerResult:
+    """No-U-Turn sampler (multinomial variant, iterative tree doubling, diagonal mass matrix)."""
+    rng = np.random.default_rng(seed)
+    x = np.asarray(x0, dtype=np.float64).copy()
+    lp, g = logp_dlogp(x)
+    counter = {"n": 1, "div": 0}
+    inv_mass = np.ones_like(x)
+    eps, k = _find_reasonable_step(logp_dlogp, x, lp, g, rng, inv_mass)
+    counter["n"] += k
+    da = _DualAveraging(eps, target_accept)
+
+    def leapfrog(xq, pq, gq, e):
+        ph = pq + 0.5 * e * gq
+        xn = xq + e * inv_mass * ph
+        lpn, gn = logp_dlogp(xn)
+        counter["n"] += 1
+        return xn, ph + 0.5 * e * gn, lpn, gn
+
+    def uturn(xm, xp, pm, pp):
+        d = xp - xm
+        return np.dot(d, inv_mass * pm) < 0 or np.dot(d, inv_mass * pp) < 0
+
+    def build_tree(xq, pq, gq, direction, depth, e, h0):
+        """Returns the subtree: edges, proposal, log-weight, stop flag, accept stats."""
+        if depth == 0:
+            xn, pn, lpn, gn = leapfrog(xq, pq, gq, direction * e)
+            h = lpn - 0.5 * np.sum(inv_mass * pn * pn) if np.isfinite(lpn) else -np.inf
+            diverged = not np.isfinite(h) or (h0 - h) > 1000.0
+            if diverged:
+                counter["div"] += 1
+            acc = min(1.0, math.exp(min(0.0, h - h0))) if np.isfinite(h) else 0.0
+            return (xn, pn, gn, xn, pn, gn, xn, lpn, gn, h - h0 if np.isfinite(h) else -np.inf, diverged, acc, 1)
+        (xm, pm, gm, xp, pp, gp, xprop, lpprop, gprop, logw, stop, acc, n) = build_tree(xq, pq, gq, direction, depth - 1, e, h0)
+        if not stop:
+            if direction < 0:
+                (xm, pm, gm, _, _, _, x2, lp2, g2, logw2, stop2, acc2, n2) = build_tree(xm, pm, gm, direction, depth - 1, e, h0)
+            else:
+                (_, _, _, xp, pp, gp, x2, lp2, g2, logw2, stop2, acc2, n2) = build_tree(xp, pp, gp, direction, depth - 1, e, h0)
+            tot = np.logaddexp(logw, logw2)
+            if np.isfinite(logw2) and math.log(rng.uniform() + 1e-300) < logw2 - tot:
+                xprop, lpprop, gprop = x2, lp2, g2
+            logw = tot
+            acc += acc2
+            n += n2
+            stop = stop2 or uturn(xm, xp, pm, pp)
+        return (xm, pm, gm, xp, pp, gp, xprop, lpprop, gprop, logw, stop, acc, n)
+
+    samples = np.empty((draws, x.size))
+    lps = np.empty(draws)
+    depths = np.empty(draws, dtype=np.int64)
+    acc_total = 0.0
+    warm = []
+    for it in range(tune + draws):
+        p = rng.normal(size=x.shape) / np.sqrt(inv_mass)
+        h0 = lp - 0.5 * np.sum(inv_mass * p * p)
+        xm = xp = x
+        pm = pp = p
+        gm = gp = g
+        logw = 0.0
+        depth = 0
+        acc_sum, n_sum = 0.0, 0
+        x_new, lp_new, g_new = x, lp, g
+        while depth < max_depth:
+            direction = 1 if rng.uniform() < 0.5 else -1
+            if direction < 0:
+                (xm, pm, gm, _, _, _, x2, lp2, g2, logw2, stop2, a2, n2) = build_tree(xm, pm, gm, -1, depth, eps, h0)
+            else:
+                (_, _, _, xp, pp, gp, x2, lp2, g2, logw2, stop2, a2, n2) = build_tree(xp, pp, gp, 1, depth, eps, h0)
+            acc_sum += a2
+            n_sum += n2
+            if stop2:
+                break
+            if np.isfinite(logw2) and math.log(rng.uniform() + 1e-300) < logw2 - logw:
+                x_new, lp_new, g_new = x2, lp2, g2
+            logw = np.logaddexp(logw, logw2)
+            depth += 1
+            if uturn(xm, xp, pm, pp):
+                break
+        x, lp, g = x_new, lp_new, g_new
+        a = acc_sum / max(1, n_sum)
+        if it < tune:
+            eps = da.update(a)
+            warm.append(x.copy())
+            if adapt_mass and it == int(0.6 * tune) and len(warm) > 20:
+                var = np.var(np.asarray(warm[len(warm) // 3:]), axis=0)
+                inv_mass = np.where(var > 1e-12, var, 1.0)
+                da = _DualAveraging(eps, target_accept)
+            if it == tune - 1:
+                eps = da.final()
+                counter["div"] = 0  # report post-warm-up divergences only
+        else:
+            samples[it - tune] = x
+            lps[it - tune] = lp
+            depths[it - tune] = depth
+            acc_total += a
+    return SamplerResult(samples, lps, acc_total / max(1, draws), eps, counter["n"], depths, counter["div"])

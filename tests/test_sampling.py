@@ -1,0 +1,78 @@
+"""Inference drivers on analytic targets and on a federated linear model (CPU)."""
+import numpy as np
+import pytest
+
+from pytensor_federated_b200 import LogpGradOp
+from pytensor_federated_b200.models import LinregShards, make_demo_data
+from pytensor_federated_b200.parallel import FederatedEngine
+from pytensor_federated_b200.sampling import Model, find_map, hmc_sample, nuts_sample
+from pytensor_federated_b200.sampling.mcmc import effective_sample_size
+
+pytestmark = pytest.mark.timeout(300)
+
+
+def _gauss(mu, sd):
+    mu, sd = np.asarray(mu, float), np.asarray(sd, float)
+
+    def f(x):
+        z = (x - mu) / sd
+        return float(-0.5 * np.sum(z * z)), -z / sd
+
+    return f
+
+
+def test_find_map_quadratic():
+    x, info = find_map(_gauss([1.0, -2.0, 0.5], [1.0, 0.1, 3.0]), np.zeros(3))
+    np.testing.assert_allclose(x, [1.0, -2.0, 0.5], atol=1e-5)
+    assert info["converged"]
+
+
+@pytest.mark.parametrize("sampler", [hmc_sample, nuts_sample])
+def test_samplers_recover_gaussian_moments(sampler):
+    mu, sd = np.array([1.0, -2.0, 0.5]), np.array([1.0, 0.2, 3.0])
+    res = sampler(_gauss(mu, sd), np.zeros(3), draws=1500, tune=600, seed=3)
+    assert res.accept_rate > 0.55
+    assert np.all(np.abs(res.samples.mean(0) - mu) < 4 * sd / np.sqrt(200))
+    np.testing.assert_allclose(res.samples.std(0), sd, rtol=0.2)
+    assert effective_sample_size(res.samples[:, 0]) > 100
+    assert set(res.summary(["a", "b", "c"])) == {"a", "b", "c"}
+
+
+def test_model_builder_gradient_matches_finite_differences():
+    m = Model()
+    mu = m.Normal("mu", 0.0, 2.0)
+    a = m.Normal("a", mu, 0.5, size=3)
+    m.Potential("pot", (a * a).sum() * -0.1)
+    theta = np.array([0.3, 0.1, -0.2, 0.4])
+    lp, g = m.logp_dlogp(theta)
+    eps = 1e-6
+    for i in range(4):
+        d = np.zeros(4)
+        d[i] = eps
+        fd = (m.logp_dlogp(theta + d)[0] - m.logp_dlogp(theta - d)[0]) / (2 * eps)
+        np.testing.assert_allclose(g[i], fd, rtol=1e-5, atol=1e-7)
+    assert m.names() == ["mu", "a[0]", "a[1]", "a[2]"]
+
+
+def test_federated_linear_model_map_and_nuts():
+    """The reference demo end to end, minus PyMC: MAP + NUTS through a LogpGradOp."""
+    x, y, sigma = make_demo_data()
+    eng = FederatedEngine(LinregShards([x], [y], [sigma]), backend="collective")
+    op = LogpGradOp(eng.logp_grad)
+    m = Model()
+    intercept = m.Normal("intercept", 0.0, 10.0)
+    slope = m.Normal("slope", 0.0, 10.0)
+    logp, *_ = op(intercept, slope)
+    m.Potential("likelihood", logp)
+    import scipy.stats
+
+    mle = scipy.stats.linregress(x, y)
+    theta_map, info = find_map(m.logp_dlogp, np.zeros(2))
+    np.testing.assert_allclose(theta_map, [mle.intercept, mle.slope], atol=2e-3)
+    res = nuts_sample(m.logp_dlogp, theta_map, draws=300, tune=300, seed=1)
+    np.testing.assert_allclose(np.median(res.samples[:, 1]), mle.slope, atol=0.1)
+    assert res.divergences == 0
+    # one engine evaluation per logp+gradient evaluation (merge pass), not two
+    before = eng.n_evals
+    m.logp_dlogp(theta_map)
+    assert eng.n_evals == before + 1
