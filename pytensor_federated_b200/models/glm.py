@@ -105,7 +105,17 @@ class GlmShards(ShardModel):
             return True
         if self.kernel == "simt":
             return False
-        return self.n_chains > 1 or self.n_features > 512
+        # auto: the tcgen05 kernel wherever its shape constraints hold (it is faster even for one
+        # chain: TMA streaming + the X tile reused from smem for both GEMMs)
+        import torch
+
+        tc_ok = (
+            self.n_features % 128 == 0 and 128 <= self.n_features <= 384 and self.n_chains <= 8
+            and self.Xs[0].dtype == torch.bfloat16 and len(self.Xs) <= 64
+        )
+        if not tc_ok and self.n_chains > 1:
+            raise ValueError("multi-chain evaluation needs the tensor-core kernel (P % 128 == 0, P <= 384, K <= 8)")
+        return tc_ok
 
     def attach(self, lib, handle) -> None:
         from ..ops import native
