@@ -26,6 +26,9 @@ __global__ void __launch_bounds__(256) fed_linreg_kernel(FedComm comm, const Lin
     if (!pro.stop && !pro.timed_out) {
         const double* theta = reinterpret_cast<const double*>(theta_words);
         double* out = comm.cta_partials + (size_t)blockIdx.x * comm.n_vals;
+        // entries of shards that live on other nodes must read as zero in the cross-node sum
+        for (int i = threadIdx.x; i < comm.n_vals; i += blockDim.x) out[i] = 0.0;
+        __syncthreads();
         for (int s = 0; s < n_shards; ++s) {
             const LinregShard sh = shards[s];
             const double a = theta[sh.theta_offset];
@@ -58,9 +61,10 @@ __global__ void __launch_bounds__(256) fed_linreg_kernel(FedComm comm, const Lin
                     }
                 }
                 const double log_norm = -log(sh.sigma) - 0.91893853320467274178;  // -log(sigma*sqrt(2*pi))
-                out[s * 3 + 0] = -0.5 * s_rr * inv_var + (double)n_here * log_norm;
-                out[s * 3 + 1] = s_r * inv_var;
-                out[s * 3 + 2] = s_rx * inv_var;
+                const int gs = sh.theta_offset / 2;  // global shard index
+                out[gs * 3 + 0] = -0.5 * s_rr * inv_var + (double)n_here * log_norm;
+                out[gs * 3 + 1] = s_r * inv_var;
+                out[gs * 3 + 2] = s_rx * inv_var;
             }
         }
     }

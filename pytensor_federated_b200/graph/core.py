@@ -99,6 +99,7 @@ class Variable:
     def __neg__(self): return neg(self)
     def __pow__(self, p): return power(self, p)
     def __getitem__(self, idx): return Subtensor(idx)(self)
+    def __iter__(self): raise TypeError("symbolic variables are not iterable")
     def sum(self, axis=None): return Sum(axis)(self)
 
     def eval(self, inputs_to_values: Optional[Dict["Variable", Any]] = None):
@@ -341,8 +342,11 @@ class Subtensor(Op):
 
     def make_node(self, x) -> Apply:
         x = as_tensor(x)
-        probe = np.empty((2,) * x.type.ndim)[self.idx]
-        return Apply(self, [x], [TensorType(x.type.dtype, (None,) * probe.ndim)()])
+        idx = self.idx if isinstance(self.idx, tuple) else (self.idx,)
+        # NB: ``sum`` is shadowed by the symbolic sum of this module
+        dropped = len([i for i in idx if isinstance(i, (int, np.integer))])
+        added = len([i for i in idx if i is None])
+        return Apply(self, [x], [TensorType(x.type.dtype, (None,) * (x.type.ndim - dropped + added))()])
 
     def perform(self, node, inputs, output_storage) -> None:
         output_storage[0][0] = np.asarray(inputs[0][self.idx])
