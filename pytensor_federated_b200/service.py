@@ -347,6 +347,9 @@ class ClientPrivates:
         self.stream = stream
         self.local = local
         self.loop = asyncio._get_running_loop()
+        # One request/response pair at a time per stream: several coroutines of a fused graph
+        # node may share one client object (the reference relies on FIFO luck here).
+        self.lock = asyncio.Lock() if self.loop is not None else None
 
     @staticmethod
     async def connect(host: str, port: int) -> "ClientPrivates":
@@ -436,7 +439,8 @@ async def _connect_evaluate_async(
     """
     priv = await _get_connection(cid, hosts_and_ports)
     if use_stream:
-        output = await _streamed_evaluate(input, priv.stream)
+        async with priv.lock:
+            output = await _streamed_evaluate(input, priv.stream)
     else:
         import grpc
 
@@ -451,7 +455,20 @@ async def _connect_evaluate_async(
     return output
 
 
+_connect_locks: Dict[Tuple[str, int], asyncio.Lock] = {}
+
+
 async def _get_connection(cid: str, hosts_and_ports: Sequence[HostPort]) -> ClientPrivates:
+    # concurrent first calls of one client (fused graph node) must not race to connect
+    key = (cid, id(asyncio.get_running_loop()))
+    lock = _connect_locks.get(key)
+    if lock is None:
+        lock = _connect_locks[key] = asyncio.Lock()
+    async with lock:
+        return await _get_connection_locked(cid, hosts_and_ports)
+
+
+async def _get_connection_locked(cid: str, hosts_and_ports: Sequence[HostPort]) -> ClientPrivates:
     priv = _privates.get(cid)
     if priv is not None and priv.local is None and priv.loop is not asyncio._get_running_loop():
         # grpc.aio objects are bound to the loop they were created on.
