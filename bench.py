@@ -36,7 +36,7 @@ def parse_args():
     p.add_argument("--rows", type=int, default=10_000_000, help="rows per shard")
     p.add_argument("--features", type=int, default=256)
     p.add_argument("--shards", type=int, default=8)
-    p.add_argument("--kernel", default=os.environ.get("B200FED_GLM_KERNEL", "auto"), choices=["auto", "simt", "tc"])
+    p.add_argument("--kernel", default=os.environ.get("B200FED_GLM_KERNEL", "auto"), choices=["auto", "simt", "tc", "fp8"])
     p.add_argument("--chains", type=int, default=1)
     p.add_argument("--out", default=None, help="also append the JSON line to this file")
     return p.parse_args()
@@ -110,7 +110,7 @@ def run_b200(args):
     import torch
     import torch.distributed as dist
 
-    from pytensor_federated_b200.models import GlmShards, synth_logistic_shard
+    from pytensor_federated_b200.models import Fp8GlmShards, GlmShards, synth_logistic_shard, synth_logistic_shard_fp8
     from pytensor_federated_b200.parallel import FederatedEngine
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -127,21 +127,30 @@ def run_b200(args):
 
     # ---- data: this rank's share of the 8 shards -------------------------------------------
     my_shards = [s for s in range(args.shards) if s % world == rank]
-    Xs, ys = [], []
+    Xs, ys, scs = [], [], []
     for s in my_shards:
-        X, y, _ = synth_logistic_shard(args.rows, args.features, seed=1000 + s, device=dev)
+        if args.kernel == "fp8":
+            X, sc, y = synth_logistic_shard_fp8(args.rows, args.features, seed=1000 + s, device=dev)
+            scs.append(sc)
+        else:
+            X, y, _ = synth_logistic_shard(args.rows, args.features, seed=1000 + s, device=dev)
         Xs.append(X)
         ys.append(y)
     torch.cuda.synchronize()
     backend = "fused" if args.impl == "b200" else "collective"
-    model = GlmShards(Xs, ys, n_groups=1, family="logistic", n_chains=args.chains, kernel=args.kernel)
+    n_groups = 1
+    if args.kernel == "fp8":  # hierarchical config: one partial-pooling group (intercept) per shard
+        n_groups = args.shards
+        model = Fp8GlmShards(Xs, scs, ys, groups=my_shards, n_groups=n_groups)
+    else:
+        model = GlmShards(Xs, ys, n_groups=1, family="logistic", n_chains=args.chains, kernel=args.kernel)
     eng = FederatedEngine(model, backend=backend, timeout=120.0)
 
     rng = np.random.default_rng(7)
     P, K = args.features, args.chains
 
     def draw_theta():
-        ic = rng.normal(size=(K, 1) if K > 1 else (1,)).astype(np.float32) * 0.1
+        ic = rng.normal(size=(K, n_groups) if K > 1 else (n_groups,)).astype(np.float32) * 0.1
         beta = rng.normal(size=(K, P) if K > 1 else (P,)).astype(np.float32) * 0.02
         return ic, beta
 
@@ -248,11 +257,12 @@ def run_b200(args):
         "higher_is_better": True,
         "scaling": "strong",
         "vs_baseline": None,
-        "dtype": "bf16",
+        "dtype": "fp8-e4m3 block-scaled (32x32 UE8M0)" if args.kernel == "fp8" else "bf16",
         "data": "synthetic",
         "impl": args.impl,
         "config": {
-            "model": "federated logistic GLM (logp + gradient)",
+            "model": "hierarchical logistic GLM, one group intercept per shard (logp + gradient)" if args.kernel == "fp8"
+            else "federated logistic GLM (logp + gradient)",
             "shards": args.shards,
             "rows_per_shard": args.rows,
             "features": args.features,

@@ -1,0 +1,477 @@
+// Federated logistic GLM on a BLOCK-SCALED FP8 design matrix (tcgen05.mma kind::mxf8f6f4.block_scale).
+//
+// Storage: X as e4m3 bytes + one UE8M0 scale per 32 x 32 block (32 rows x 32 features):
+//     x[r, f] = e4m3(Xq[r, f]) * 2^(S[r/32, f/32] - 127)
+// i.e. 1.03 bytes per element instead of 2 for bf16 -> the HBM-bound evaluation gets ~2x faster.
+//
+// Both GEMMs consume the quantised tile directly; the dequantisation is done by the tensor core:
+//   MMA #1  eta[128 x 16] += Xq_tile[:, 32-feature block] . Theta^T   scale-factor-A column per
+//           feature block, whose 4 bytes are the scales of the tile's 4 row groups (the TMEM
+//           scale layout keeps the scales of rows m, m+32, m+64, m+96 in one 32-bit word and is
+//           replicated over lanes; with 32-row blocks every lane holds the same word).
+//   MMA #2  G[128 feat x 16] += Xq_tile^T[:, 32-row group] . R   scale-factor-A column per
+//           (feature half, row group), bytes = the 4 feature blocks of that half.
+//   Scale-factor-B is the constant 2^0.
+// Theta and the residuals are themselves e4m3: theta is a 5-term, r a 4-term radix-16 expansion
+// (term k carries weight 16^-k), the terms sit in separate N columns and are recombined in the
+// epilogue in fp32, so the low precision of the operands does not leak into the result.
+//
+// Pipeline/roles as in glm_tc.cu; scale words are written to TMEM two tiles ahead by the
+// epilogue warps (tcgen05.st), 4-deep ring.  Workload: BASELINE.json "hierarchical GLM, 8
+// partial-pooling groups (one per GPU), fp8 block-scaled design matrix" (groups = intercepts).
+#include <cuda.h>
+#include <cuda_fp8.h>
+#include <cuda_runtime.h>
+
+#include "fed_comm.cuh"
+#include "models.h"
+#include "tc_common.cuh"
+
+namespace fp8 {
+using namespace tc;
+
+constexpr int kTile = 128;            // rows per tile
+constexpr int kPanelF = 128;          // features per 128-byte swizzle span (1 byte / element)
+constexpr int kPanelB = kTile * 128;  // 16 KB
+constexpr int kThreadsF = 224;        // warps: 0 TMA, 1 MMA#1, 2-5 epilogue, 6 MMA#2
+constexpr int kFlushF = 32;
+constexpr int kN = 16;                // MMA N for both GEMMs
+constexpr int kThetaTerms = 5;
+constexpr int kResidTerms = 4;
+constexpr int kSfRing = 4;
+constexpr int kMaxSegsF = 64;
+
+__device__ __forceinline__ void umma_fp8_block_scaled(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
+                                                      uint32_t accumulate, uint32_t tmem_sfa, uint32_t tmem_sfb) {
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "setp.ne.b32 p, %4, 0;\n\t"
+        "tcgen05.mma.cta_group::1.kind::mxf8f6f4.block_scale [%0], %1, %2, %3, [%5], [%6], p;\n\t"
+        "}" ::"r"(tmem_d),
+        "l"(adesc), "l"(bdesc), "r"(idesc), "r"(accumulate), "r"(tmem_sfa), "r"(tmem_sfb)
+        : "memory");
+}
+// Block-scaled instruction descriptor: e4m3 x e4m3 -> f32, UE8M0 scales, K = 32.
+__host__ __device__ constexpr uint32_t make_idesc_bs(int M, int N, int a_mn_major, int b_mn_major) {
+    return ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) | ((uint32_t)(N >> 3) << 17) | (1u << 23) |
+           ((uint32_t)(M >> 4) << 24);
+}
+__device__ __forceinline__ void tmem_st_x8(uint32_t taddr, const uint32_t (&w)[8]) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x8.b32 [%0], {%1, %2, %3, %4, %5, %6, %7, %8};" ::"r"(taddr), "r"(w[0]),
+                 "r"(w[1]), "r"(w[2]), "r"(w[3]), "r"(w[4]), "r"(w[5]), "r"(w[6]), "r"(w[7])
+                 : "memory");
+}
+__device__ __forceinline__ void tmem_st_x1(uint32_t taddr, uint32_t w) {
+    asm volatile("tcgen05.st.sync.aligned.32x32b.x1.b32 [%0], {%1};" ::"r"(taddr), "r"(w) : "memory");
+}
+__device__ __forceinline__ void tmem_wait_st() { asm volatile("tcgen05.wait::st.sync.aligned;" ::: "memory"); }
+
+__device__ __forceinline__ uint8_t to_e4m3(float v) {
+    return (uint8_t)__nv_cvt_float_to_fp8(v, __NV_SATFINITE, __NV_E4M3);
+}
+__device__ __forceinline__ float from_e4m3(uint8_t b) {
+    const __half_raw h = __nv_cvt_fp8_to_halfraw(b, __NV_E4M3);
+    return __half2float(*reinterpret_cast<const __half*>(&h));
+}
+// radix-16 expansion: v ~= sum_k terms[k] * 16^-k, each term an e4m3 of magnitude <= 448
+template <int T>
+__device__ __forceinline__ void expand16(float v, uint8_t (&terms)[T]) {
+    float rem = v;
+#pragma unroll
+    for (int k = 0; k < T; ++k) {
+        terms[k] = to_e4m3(rem);
+        rem = (rem - from_e4m3(terms[k])) * 16.f;
+    }
+}
+
+struct SmemLayoutF {
+    uint32_t stages, stage_bytes, off_theta_b, theta_b_bytes, off_r, r_bytes, off_theta_f, off_segs, off_gi, off_red,
+        off_bars, off_tmem, total;
+};
+__host__ __device__ inline SmemLayoutF smem_layout(int P, int n_theta, int n_groups) {
+    SmemLayoutF L;
+    const uint32_t panels = P / kPanelF;
+    L.stage_bytes = panels * kPanelB;
+    L.theta_b_bytes = panels * kN * 128;
+    L.r_bytes = kTile * kN;  // 1 byte per element
+    const uint32_t fixed = L.theta_b_bytes + 2 * L.r_bytes + ((n_theta * 4 + 15) & ~15) + kMaxSegsF * (uint32_t)sizeof(GlmSegment) +
+                           ((n_groups * 8 + 15) & ~15) + 32 * 8 + 512 + 1024;
+    uint32_t stages = (227u * 1024u - fixed) / L.stage_bytes;
+    if (stages > 6) stages = 6;
+    L.stages = stages;
+    uint32_t o = stages * L.stage_bytes;
+    L.off_theta_b = o; o += L.theta_b_bytes;
+    L.off_r = o; o += 2 * L.r_bytes;
+    L.off_theta_f = o; o += (n_theta * 4 + 15) & ~15;
+    L.off_segs = o; o += kMaxSegsF * (uint32_t)sizeof(GlmSegment);
+    L.off_gi = o; o += (n_groups * 8 + 15) & ~15;
+    L.off_red = o; o += 32 * 8;
+    L.off_bars = o; o += 320;
+    L.off_tmem = o; o += 64;
+    L.total = o + 1024;
+    return L;
+}
+
+__global__ void __launch_bounds__(kThreadsF, 1)
+fed_glm_fp8_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParams prm, const CUtensorMap* __restrict__ tmaps) {
+    extern __shared__ unsigned char smem_dyn[];
+    unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
+
+    const int P = prm.n_features;
+    const int G = prm.n_groups;
+    const int NH = P / 128;       // 128-feature panels == UMMA M blocks of MMA #2
+    const int NFB = P / 32;       // 32-feature scale blocks == K steps of MMA #1
+    const SmemLayoutF L = smem_layout(P, comm.n_theta, G);
+    const int S = (int)L.stages;
+
+    unsigned char* theta_b = smem + L.off_theta_b;
+    unsigned char* r_buf = smem + L.off_r;
+    float* theta_f = reinterpret_cast<float*>(smem + L.off_theta_f);
+    GlmSegment* segs = reinterpret_cast<GlmSegment*>(smem + L.off_segs);
+    double* gi_acc = reinterpret_cast<double*>(smem + L.off_gi);
+    double* red = reinterpret_cast<double*>(smem + L.off_red);
+    uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.off_bars);
+    uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L.off_tmem);
+    float* theta_norm = reinterpret_cast<float*>(smem + L.off_tmem + 16);  // c: theta = c * sum_k t_k 16^-k
+    uint64_t* bar_full = bars;            // [6]
+    uint64_t* bar_empty = bars + 6;       // [6]
+    uint64_t* bar_eta_full = bars + 12;   // [2]
+    uint64_t* bar_eta_empty = bars + 14;  // [2]
+    uint64_t* bar_r_full = bars + 16;     // [2]
+    uint64_t* bar_r_empty = bars + 18;    // [2]
+    uint64_t* bar_g_full = bars + 20;     // [2]
+    uint64_t* bar_g_empty = bars + 22;    // [2]
+    uint64_t* bar_sf_full = bars + 24;    // [4]
+
+    const int warp = threadIdx.x >> 5;
+    const int lane = threadIdx.x & 31;
+
+    fed::Prologue pro = fed::prologue(comm, theta_f);
+    const bool active = !pro.stop && !pro.timed_out;
+    const long long T = prm.total_tiles;
+    const long long n_it = (T > (long long)blockIdx.x) ? (T - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    constexpr uint32_t kTmemCols = 256;
+    constexpr float kResidNorm = 1.f / 256.f;  // r = kResidNorm * sum_k t_k 16^-k, |r| <= 1
+
+    double ll_total = 0.0;
+    double g_acc[4] = {0.0, 0.0, 0.0, 0.0};
+
+    if (active) {
+        for (int i = threadIdx.x; i < prm.n_segments; i += blockDim.x) segs[i] = segs_g[i];
+        for (int i = threadIdx.x; i < G; i += blockDim.x) gi_acc[i] = 0.0;
+        // ---- theta normalisation: power of two c with max|beta| / c in [128, 256)
+        if (warp == 0) {
+            float m = 0.f;
+            for (int f = lane; f < P; f += 32) m = fmaxf(m, fabsf(theta_f[G + f]));
+            for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+            if (lane == 0) {
+                int e = 0;
+                if (m > 0.f) {
+                    frexpf(m, &e);      // m = frac * 2^e, frac in [0.5, 1)
+                    e -= 8;             // m / 2^(e-8) in [128, 256)
+                }
+                *theta_norm = ldexpf(1.f, e);
+            }
+        }
+        __syncthreads();
+        const float c_theta = *theta_norm;
+        const float inv_c = 1.f / c_theta;
+        // ---- Theta^T as the K-major, 128B-swizzled e4m3 B operand: row n = term n (n < 5)
+        for (int idx = threadIdx.x; idx < NH * kN * 8; idx += blockDim.x) {
+            const int j = idx & 7;                 // 16-byte chunk = 16 features
+            const int n = (idx >> 3) % kN;
+            const int pnl = idx / (8 * kN);
+            uint32_t packed[4] = {0, 0, 0, 0};
+            if (n < kThetaTerms) {
+#pragma unroll
+                for (int e = 0; e < 16; ++e) {
+                    uint8_t terms[kThetaTerms];
+                    expand16<kThetaTerms>(theta_f[G + pnl * kPanelF + j * 16 + e] * inv_c, terms);
+                    packed[e >> 2] |= (uint32_t)terms[n] << ((e & 3) * 8);
+                }
+            }
+            *reinterpret_cast<uint4*>(theta_b + pnl * (kN * 128) + n * 128 + ((j ^ (n & 7)) * 16)) =
+                make_uint4(packed[0], packed[1], packed[2], packed[3]);
+        }
+        for (int i = threadIdx.x; i < (int)(2 * L.r_bytes / 16); i += blockDim.x)
+            reinterpret_cast<uint4*>(r_buf)[i] = make_uint4(0, 0, 0, 0);
+        fence_proxy_async();
+        if (threadIdx.x == 0) {
+            for (int i = 0; i < 6; ++i) { mbar_init(&bar_full[i], 1); mbar_init(&bar_empty[i], 1); }
+            for (int i = 0; i < 2; ++i) {
+                mbar_init(&bar_eta_full[i], 1);
+                mbar_init(&bar_eta_empty[i], 128);
+                mbar_init(&bar_r_full[i], 128);
+                mbar_init(&bar_r_empty[i], 1);
+                mbar_init(&bar_g_full[i], 1);
+                mbar_init(&bar_g_empty[i], 128);
+            }
+            for (int i = 0; i < kSfRing; ++i) mbar_init(&bar_sf_full[i], 128);
+            fence_barrier_init();
+        }
+        if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
+        const uint32_t tmem_base = *tmem_slot;
+        const uint32_t tmem_eta = tmem_base;                    // 2 x 16
+        const uint32_t tmem_g = tmem_base + 32;                 // 2 buffers x NH x 16  (<= 128)
+        const uint32_t tmem_sfa1 = tmem_base + 160;             // ring x 8 columns
+        const uint32_t tmem_sfa2 = tmem_base + 160 + kSfRing * 8;   // ring x 8 columns
+        const uint32_t tmem_sfb = tmem_base + 160 + kSfRing * 16;   // 4 columns of 2^0
+
+        if (warp == 0) {
+            if (lane == 0) {
+                for (int i = 0; i < prm.n_segments; ++i) tma_prefetch_desc(&tmaps[i]);
+                int s_idx = 0;
+                for (long long it = 0; it < n_it; ++it) {
+                    const long long tile = blockIdx.x + it * gridDim.x;
+                    while (s_idx + 1 < prm.n_segments && segs[s_idx + 1].first_tile <= tile) ++s_idx;
+                    const int st = (int)(it % S);
+                    const uint32_t ph = (uint32_t)((it / S) & 1);
+                    mbar_wait(&bar_empty[st], ph ^ 1);
+                    const int row0 = (int)((tile - segs[s_idx].first_tile) * kTile);
+                    mbar_expect_tx(&bar_full[st], L.stage_bytes);
+                    unsigned char* dst = smem + (size_t)st * L.stage_bytes;
+                    for (int pnl = 0; pnl < NH; ++pnl)
+                        tma_load_2d(dst + pnl * kPanelB, &tmaps[s_idx], pnl * kPanelF, row0, &bar_full[st]);
+                }
+            }
+        } else if (warp == 1) {
+            if (lane == 0) {
+                constexpr uint32_t idesc1 = make_idesc_bs(128, kN, 0, 0);
+                const uint32_t theta_b_addr = smem_u32(theta_b);
+                for (long long it = 0; it < n_it; ++it) {
+                    const int st = (int)(it % S);
+                    const uint32_t ph = (uint32_t)((it / S) & 1);
+                    const int b = (int)(it & 1);
+                    const uint32_t bph = (uint32_t)((it >> 1) & 1);
+                    const int sfb = (int)(it % kSfRing);
+                    mbar_wait(&bar_sf_full[sfb], (uint32_t)((it / kSfRing) & 1));
+                    mbar_wait(&bar_eta_empty[b], bph ^ 1);
+                    mbar_wait(&bar_full[st], ph);
+                    tc_fence_after();
+                    const uint32_t x_addr = smem_u32(smem + (size_t)st * L.stage_bytes);
+                    for (int fb = 0; fb < NFB; ++fb) {
+                        const int pnl = fb >> 2, ks = fb & 3;   // 4 K-steps of 32 features per 128-feature panel
+                        const uint64_t adesc = make_desc(x_addr + pnl * kPanelB + ks * 32, 16, 1024, 2);
+                        const uint64_t bdesc = make_desc(theta_b_addr + pnl * (kN * 128) + ks * 32, 16, 1024, 2);
+                        umma_fp8_block_scaled(tmem_eta + b * kN, adesc, bdesc, idesc1, fb ? 1u : 0u,
+                                              tmem_sfa1 + sfb * 8 + fb, tmem_sfb);
+                    }
+                    umma_commit(&bar_eta_full[b]);
+                }
+            }
+        } else if (warp == 6) {
+            if (lane == 0) {
+                constexpr uint32_t idesc2 = make_idesc_bs(128, kN, 1, 1);
+                const uint32_t r_addr = smem_u32(r_buf);
+                for (long long j = 0; j < n_it; ++j) {
+                    const int st = (int)(j % S);
+                    const int b = (int)(j & 1);
+                    const uint32_t bph = (uint32_t)((j >> 1) & 1);
+                    const long long period = j / kFlushF;
+                    const int gb = (int)(period & 1);
+                    const bool first = (j % kFlushF) == 0;
+                    const bool last = (j % kFlushF) == kFlushF - 1 || j == n_it - 1;
+                    const int sfb = (int)(j % kSfRing);
+                    if (first) mbar_wait(&bar_g_empty[gb], (uint32_t)(((period >> 1) & 1) ^ 1));
+                    mbar_wait(&bar_r_full[b], bph);
+                    tc_fence_after();
+                    const uint32_t x_addr = smem_u32(smem + (size_t)st * L.stage_bytes);
+                    for (int h = 0; h < NH; ++h) {
+#pragma unroll
+                        for (int q = 0; q < 4; ++q) {   // K step = one 32-row group
+                            const uint64_t adesc = make_desc(x_addr + h * kPanelB + q * 4 * 1024, kPanelB, 1024, 2);
+                            const uint64_t bdesc = make_desc(r_addr + b * L.r_bytes + q * 4 * 128, 128, 128, 0);
+                            umma_fp8_block_scaled(tmem_g + (gb * NH + h) * kN, adesc, bdesc, idesc2,
+                                                  (first && q == 0) ? 0u : 1u, tmem_sfa2 + sfb * 8 + h * 4 + q, tmem_sfb);
+                        }
+                    }
+                    umma_commit(&bar_empty[st]);
+                    umma_commit(&bar_r_empty[b]);
+                    if (last) umma_commit(&bar_g_full[gb]);
+                }
+            }
+        } else {
+            // ================= epilogue warps (2..5) ===========================================
+            const int q4 = warp & 3;
+            const int row = q4 * 32 + lane;
+            const uint32_t lane_addr = (uint32_t)(q4 * 32) << 16;
+            // scale-factor-B: 2^0 everywhere
+#pragma unroll
+            for (int cidx = 0; cidx < 4; ++cidx) tmem_st_x1(tmem_sfb + lane_addr + cidx, 0x7F7F7F7Fu);
+
+            // writes the scale words of tile `t_it` into ring slot t_it % kSfRing
+            auto write_scales = [&](long long t_it, int& sidx) {
+                const long long tile = blockIdx.x + t_it * gridDim.x;
+                while (sidx + 1 < prm.n_segments && segs[sidx + 1].first_tile <= tile) ++sidx;
+                const GlmSegment& sg = segs[sidx];
+                // scales: [row_block(32 rows)][feature_block(32)] bytes, padded to whole tiles
+                const uint8_t* sp = reinterpret_cast<const uint8_t*>(sg.scales) + (tile - sg.first_tile) * 4 * NFB;
+                uint32_t rows4[4][4];  // [q][word]: NFB <= 16 bytes per row group
+#pragma unroll
+                for (int q = 0; q < 4; ++q)
+#pragma unroll
+                    for (int w = 0; w < 4; ++w)
+                        rows4[q][w] = (w * 4 < NFB) ? __ldg(reinterpret_cast<const uint32_t*>(sp + q * NFB + w * 4)) : 0x7F7F7F7Fu;
+                uint32_t sfa1[8], sfa2[8];
+#pragma unroll
+                for (int fb = 0; fb < 8; ++fb) {
+                    // byte q of column fb = scale of (row group q, feature block fb)
+                    const int w = fb >> 2, sh = (fb & 3) * 8;
+                    sfa1[fb] = ((rows4[0][w] >> sh) & 0xFF) | (((rows4[1][w] >> sh) & 0xFF) << 8) |
+                               (((rows4[2][w] >> sh) & 0xFF) << 16) | (((rows4[3][w] >> sh) & 0xFF) << 24);
+                }
+#pragma unroll
+                for (int h = 0; h < 2; ++h)
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) sfa2[h * 4 + q] = rows4[q][h];  // bytes = feature blocks 4h..4h+3
+                const int slot = (int)(t_it % kSfRing);
+                tmem_st_x8(tmem_sfa1 + lane_addr + slot * 8, sfa1);
+                tmem_st_x8(tmem_sfa2 + lane_addr + slot * 8, sfa2);
+                tmem_wait_st();
+                tc_fence_before();
+                mbar_arrive(&bar_sf_full[slot]);
+            };
+            int sf_sidx = 0;
+            if (n_it > 0) write_scales(0, sf_sidx);
+            if (n_it > 1) write_scales(1, sf_sidx);
+
+            int s_idx = 0;
+            float ll_acc = 0.f, gi_cur = 0.f;
+            int cur_group = n_it > 0 ? -1 : 0;
+            for (long long it = 0; it < n_it; ++it) {
+                const long long tile = blockIdx.x + it * gridDim.x;
+                while (s_idx + 1 < prm.n_segments && segs[s_idx + 1].first_tile <= tile) ++s_idx;
+                const GlmSegment& seg = segs[s_idx];
+                if (seg.group != cur_group) {
+                    if (cur_group >= 0) {
+                        atomicAdd(&gi_acc[cur_group], (double)gi_cur);
+                        gi_cur = 0.f;
+                    }
+                    cur_group = seg.group;
+                }
+                const long long grow = (tile - seg.first_tile) * kTile + row;
+                const bool valid = grow < seg.n_rows;
+                const float y = valid ? __ldg(seg.y + grow) : 0.f;
+                const int b = (int)(it & 1);
+                const uint32_t bph = (uint32_t)((it >> 1) & 1);
+
+                mbar_wait(&bar_eta_full[b], bph);
+                tc_fence_after();
+                float v[16];
+                tmem_ld_x16(tmem_eta + lane_addr + b * kN, v);
+                tc_fence_before();
+                mbar_arrive(&bar_eta_empty[b]);
+                const float eta = c_theta * (v[0] + v[1] * (1.f / 16) + v[2] * (1.f / 256) + v[3] * (1.f / 4096) +
+                                             v[4] * (1.f / 65536)) + theta_f[seg.group];
+                float ll = 0.f, r = 0.f;
+                if (valid) link_loglik(0, y, eta, ll, r);
+                ll_acc += ll;
+                gi_cur += r;
+                uint8_t rt[kResidTerms];
+                expand16<kResidTerms>(r * 256.f, rt);
+                mbar_wait(&bar_r_empty[b], bph ^ 1);
+                *reinterpret_cast<uint4*>(r_buf + b * L.r_bytes + (row >> 3) * 128 + (row & 7) * 16) =
+                    make_uint4((uint32_t)rt[0] | ((uint32_t)rt[1] << 8) | ((uint32_t)rt[2] << 16) | ((uint32_t)rt[3] << 24), 0, 0, 0);
+                fence_proxy_async();
+                mbar_arrive(&bar_r_full[b]);
+
+                // scales for tile it+2: its ring slot was last used by tile it-2, whose MMAs are complete
+                // (we just passed r_empty of tile it-2 and eta_full of tile it)
+                if (it + 2 < n_it) write_scales(it + 2, sf_sidx);
+
+                const bool last = (it % kFlushF) == kFlushF - 1 || it == n_it - 1;
+                if (last) {
+                    const long long period = it / kFlushF;
+                    const int gb = (int)(period & 1);
+                    mbar_wait(&bar_g_full[gb], (uint32_t)((period >> 1) & 1));
+                    tc_fence_after();
+                    for (int h = 0; h < NH; ++h) {
+                        float gv[4];
+                        tmem_ld_x4(tmem_g + lane_addr + (gb * NH + h) * kN, gv);
+                        g_acc[h] += (double)kResidNorm * ((double)gv[0] + (double)gv[1] * (1.0 / 16) + (double)gv[2] * (1.0 / 256) +
+                                                           (double)gv[3] * (1.0 / 4096));
+                    }
+                    tc_fence_before();
+                    mbar_arrive(&bar_g_empty[gb]);
+                    ll_total += (double)ll_acc;
+                    ll_acc = 0.f;
+                }
+            }
+            ll_total += (double)ll_acc;
+            if (cur_group >= 0) atomicAdd(&gi_acc[cur_group], (double)gi_cur);
+        }
+
+        tc_fence_before();
+        __syncthreads();
+        tc_fence_after();
+        if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
+        double* out = comm.cta_partials + (size_t)blockIdx.x * comm.n_vals;
+        const double ll_block = fed::block_sum(ll_total, red);
+        if (threadIdx.x == 0) out[0] = ll_block;
+        for (int i = threadIdx.x; i < G; i += blockDim.x) out[1 + i] = gi_acc[i];
+        if (warp >= 2 && warp <= 5) {
+            const int row = (warp & 3) * 32 + lane;
+            for (int h = 0; h < NH; ++h) out[1 + G + h * 128 + row] = g_acc[h];
+        }
+    }
+    fed::epilogue(comm, pro, 0ull);
+}
+
+}  // namespace fp8
+
+namespace {
+typedef CUresult (*EncodeTiledFn8)(CUtensorMap*, CUtensorMapDataType, cuuint32_t, void*, const cuuint64_t*, const cuuint64_t*,
+                                   const cuuint32_t*, const cuuint32_t*, CUtensorMapInterleave, CUtensorMapSwizzle,
+                                   CUtensorMapL2promotion, CUtensorMapFloatOOBfill);
+EncodeTiledFn8 get_encode8() {
+    static EncodeTiledFn8 fn = nullptr;
+    if (!fn) {
+        void* p = nullptr;
+        cudaDriverEntryPointQueryResult q;
+        if (cudaGetDriverEntryPoint("cuTensorMapEncodeTiled", &p, cudaEnableDefault, &q) == cudaSuccess &&
+            q == cudaDriverEntryPointSuccess)
+            fn = reinterpret_cast<EncodeTiledFn8>(p);
+    }
+    return fn;
+}
+}  // namespace
+
+extern "C" int b200_glm_fp8_prepare(const GlmSegment* segs_host, int n_segments, const GlmParams* prm, void** tmaps_dev) {
+    if (prm->n_features != 128 && prm->n_features != 256) return -21;   // NFB <= 8 scale columns per tile
+    if (n_segments > fp8::kMaxSegsF) return -22;
+    if (prm->n_chains != 1 || prm->family != 0) return -23;
+    if (prm->ld % 16 != 0) return -24;
+    EncodeTiledFn8 encode = get_encode8();
+    if (!encode) return -25;
+    CUtensorMap* host = new CUtensorMap[n_segments];
+    for (int s = 0; s < n_segments; ++s) {
+        if (((uintptr_t)segs_host[s].X & 15) != 0 || segs_host[s].scales == nullptr) { delete[] host; return -26; }
+        cuuint64_t dims[2] = {(cuuint64_t)prm->n_features, (cuuint64_t)segs_host[s].n_rows};
+        cuuint64_t strides[1] = {(cuuint64_t)prm->ld};
+        cuuint32_t box[2] = {(cuuint32_t)fp8::kPanelF, (cuuint32_t)fp8::kTile};
+        cuuint32_t estr[2] = {1, 1};
+        CUresult r = encode(&host[s], CU_TENSOR_MAP_DATA_TYPE_UINT8, 2, const_cast<void*>(segs_host[s].X), dims, strides, box,
+                            estr, CU_TENSOR_MAP_INTERLEAVE_NONE, CU_TENSOR_MAP_SWIZZLE_128B, CU_TENSOR_MAP_L2_PROMOTION_L2_256B,
+                            CU_TENSOR_MAP_FLOAT_OOB_FILL_NONE);
+        if (r != CUDA_SUCCESS) { delete[] host; return -27; }
+    }
+    if (*tmaps_dev) cudaFree(*tmaps_dev);
+    cudaError_t e = cudaMalloc(tmaps_dev, sizeof(CUtensorMap) * n_segments);
+    if (e == cudaSuccess) e = cudaMemcpy(*tmaps_dev, host, sizeof(CUtensorMap) * n_segments, cudaMemcpyHostToDevice);
+    delete[] host;
+    return e == cudaSuccess ? 0 : (int)e;
+}
+
+extern "C" int b200_launch_glm_fp8(const FedComm* comm, const GlmSegment* segs_dev, const GlmParams* prm, const void* tmaps,
+                                   int grid, cudaStream_t stream) {
+    const fp8::SmemLayoutF L = fp8::smem_layout(prm->n_features, comm->n_theta, prm->n_groups);
+    if (L.stages < 2) return -2;
+    cudaFuncSetAttribute(fp8::fed_glm_fp8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total);
+    fp8::fed_glm_fp8_kernel<<<grid, fp8::kThreadsF, L.total, stream>>>(*comm, segs_dev, *prm,
+                                                                       reinterpret_cast<const CUtensorMap*>(tmaps));
+    return (int)cudaGetLastError();
+}

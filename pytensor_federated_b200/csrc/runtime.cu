@@ -38,11 +38,13 @@ int b200_launch_glm_tc(const FedComm*, const GlmSegment*, const GlmParams*, cons
                        cudaStream_t);
 int b200_glm_tc_prepare(const GlmSegment* segs_host, int n_segments, const GlmParams* prm, void** tmaps_dev);
 int b200_launch_ode(const FedComm*, const OdeShard*, int, int, cudaStream_t);
+int b200_launch_glm_fp8(const FedComm*, const GlmSegment*, const GlmParams*, const void* tmaps, int grid, cudaStream_t);
+int b200_glm_fp8_prepare(const GlmSegment* segs_host, int n_segments, const GlmParams* prm, void** tmaps_dev);
 }
 
 namespace {
 
-enum ModelKind { MODEL_NONE = 0, MODEL_LINREG = 1, MODEL_GLM_SIMT = 2, MODEL_GLM_TC = 3, MODEL_ODE = 4 };
+enum ModelKind { MODEL_NONE = 0, MODEL_LINREG = 1, MODEL_GLM_SIMT = 2, MODEL_GLM_TC = 3, MODEL_ODE = 4, MODEL_GLM_FP8 = 5 };
 
 thread_local std::string g_last_error;
 
@@ -162,6 +164,9 @@ int launch_model(Engine* e, const FedComm* c) {
             break;
         case MODEL_ODE:
             rc = b200_launch_ode(c, e->ode_dev, (int)e->ode.size(), e->grid, e->stream);
+            break;
+        case MODEL_GLM_FP8:
+            rc = b200_launch_glm_fp8(c, e->glm_segs_dev, &e->glm, e->glm_tmaps_dev, e->grid, e->stream);
             break;
         default:
             g_last_error = "no model attached to the engine";
@@ -397,7 +402,15 @@ int b200_engine_set_glm(void* h, int n_segments, const void** X, const float** y
     if (e->glm_segs_dev) cudaFree(e->glm_segs_dev);
     CK(cudaMalloc((void**)&e->glm_segs_dev, sizeof(GlmSegment) * (n_segments > 0 ? n_segments : 1)));
     CK(cudaMemcpy(e->glm_segs_dev, e->glm_segs.data(), sizeof(GlmSegment) * n_segments, cudaMemcpyHostToDevice));
-    if (use_tensor_cores) {
+    if (use_tensor_cores == 2) {  // block-scaled fp8
+        int rc = b200_glm_fp8_prepare(e->glm_segs.data(), n_segments, &e->glm, &e->glm_tmaps_dev);
+        if (rc != 0) {
+            g_last_error = "fp8 GLM path rejected this shape (rc=" + std::to_string(rc) + ")";
+            return rc;
+        }
+        e->kind = MODEL_GLM_FP8;
+        e->grid = e->sm_count;
+    } else if (use_tensor_cores) {
         int rc = b200_glm_tc_prepare(e->glm_segs.data(), n_segments, &e->glm, &e->glm_tmaps_dev);
         if (rc != 0) {
             g_last_error = "tensor-core GLM path rejected this shape (rc=" + std::to_string(rc) + ")";

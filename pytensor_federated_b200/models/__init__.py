@@ -1,6 +1,6 @@
 """Model families with fused sm_100a kernels (and eager PyTorch oracles)."""
 from .base import ShardModel
-from .glm import GlmShards, synth_logistic_shard
+from .glm import Fp8GlmShards, GlmShards, dequantize_block_fp8, quantize_block_fp8, synth_logistic_shard, synth_logistic_shard_fp8
 from .linreg import LinregShards, make_demo_data
 from .ode import OdeShards, synth_lv_shard
 
@@ -9,7 +9,11 @@ __all__ = [
     "LinregShards",
     "make_demo_data",
     "GlmShards",
+    "Fp8GlmShards",
+    "quantize_block_fp8",
+    "dequantize_block_fp8",
     "synth_logistic_shard",
+    "synth_logistic_shard_fp8",
     "OdeShards",
     "synth_lv_shard",
 ]

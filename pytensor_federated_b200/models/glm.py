@@ -83,13 +83,17 @@ class GlmShards(ShardModel):
         th = out.view(np.float32).reshape(self.n_chains, self.n_params)
         ic = np.asarray(intercept, dtype=np.float32)
         bt = np.asarray(beta, dtype=np.float32)
-        self._batched = bt.ndim == 2
-        self._icpt_shape = ic.shape
+        self._note_shapes(inputs)
         th[:, : self.n_groups] = ic.reshape(self.n_chains, -1) if self._batched else ic.reshape(1, -1)
         th[:, self.n_groups :] = bt.reshape(self.n_chains, self.n_features)
 
     _batched = False
     _icpt_shape = ()
+
+    def _note_shapes(self, inputs) -> None:
+        intercept, beta = inputs
+        self._batched = np.ndim(beta) == 2
+        self._icpt_shape = np.shape(intercept)
 
     def unpack_result(self, vals: np.ndarray) -> List[np.ndarray]:
         v = np.asarray(vals, dtype=np.float64).reshape(self.n_chains, 1 + self.n_params)
@@ -100,7 +104,9 @@ class GlmShards(ShardModel):
         return [np.asarray(v[0, 0]), v[0, 1 : 1 + G].reshape(self._icpt_shape).copy(), v[0, 1 + G :].copy()]
 
     # -- native ----------------------------------------------------------------------------
-    def use_tensor_cores(self) -> bool:
+    def use_tensor_cores(self):
+        if self.kernel == "fp8":
+            return 2
         if self.kernel == "tc":
             return True
         if self.kernel == "simt":
@@ -140,6 +146,7 @@ class GlmShards(ShardModel):
 
         dtype = dtype or torch.float32
         intercept, beta = inputs
+        self._note_shapes(inputs)
         ic = torch.as_tensor(np.asarray(intercept, dtype=np.float64)).reshape(self.n_chains, -1)
         bt = torch.as_tensor(np.asarray(beta, dtype=np.float64)).reshape(self.n_chains, self.n_features)
         out = torch.zeros(self.n_chains, 1 + self.n_params, dtype=torch.float64)
@@ -174,6 +181,70 @@ class GlmShards(ShardModel):
         return int(4 * self.n_rows * self.n_features * self.n_chains)
 
 
+def quantize_block_fp8(X, block: int = 32):
+    """Block-scaled FP8 quantisation of a design matrix (MX-style, 32 x 32 blocks).
+
+    Returns ``(Xq, scales)``: ``Xq`` e4m3 bytes ``[n, P]`` (``torch.float8_e4m3fn``) and UE8M0 scale
+    bytes ``[4 * ceil(n / 128), P / 32]`` (rows padded to whole 128-row tiles with 2^0), with
+    ``X[r, f] ~= float(Xq[r, f]) * 2 ** (scales[r // 32, f // 32] - 127)``.
+    """
+    import torch
+
+    n, P = X.shape
+    if P % block:
+        raise ValueError("P must be a multiple of 32")
+    n_rb = (n + block - 1) // block
+    n_rb_pad = ((n + 127) // 128) * 4
+    Xf = X.float()
+    pad = n_rb * block - n
+    if pad:
+        Xf = torch.cat([Xf, torch.zeros(pad, P, device=X.device)], 0)
+    blocks = Xf.view(n_rb, block, P // block, block)
+    amax = blocks.abs().amax(dim=(1, 3))                                  # [n_rb, P/32]
+    # power-of-two scale such that amax / scale <= 448 (e4m3 max)
+    exp = torch.ceil(torch.log2(torch.clamp(amax, min=2.0**-100) / 448.0)).clamp(-127, 127)
+    exp = torch.where(amax > 0, exp, torch.zeros_like(exp))
+    scale = torch.exp2(exp)
+    q = (blocks / scale[:, None, :, None]).reshape(n_rb * block, P)[:n].to(torch.float8_e4m3fn)
+    scales = torch.full((n_rb_pad, P // block), 127, dtype=torch.uint8, device=X.device)
+    scales[:n_rb] = (exp + 127).to(torch.uint8)
+    return q.contiguous(), scales.contiguous()
+
+
+def dequantize_block_fp8(Xq, scales, block: int = 32):
+    import torch
+
+    n, P = Xq.shape
+    s = torch.exp2(scales.float() - 127.0)                                 # [n_rb_pad, P/32]
+    s_full = s.repeat_interleave(block, 0)[:n].repeat_interleave(block, 1)
+    return Xq.float() * s_full
+
+
+class Fp8GlmShards(GlmShards):
+    """GLM shards whose design matrices are block-scaled FP8 (``quantize_block_fp8``).
+
+    The hierarchical-GLM configuration of BASELINE.json: one partial-pooling group (intercept) per
+    shard/GPU, e4m3 design matrix with 32 x 32 UE8M0 block scales, evaluated by ``csrc/glm_fp8.cu``
+    (``tcgen05.mma.kind::mxf8f6f4.block_scale``).  Logistic family, one chain per launch.
+    """
+
+    def __init__(self, Xqs, scales, ys, *, groups=None, n_groups: int = 1) -> None:
+        super().__init__(Xqs, ys, groups=groups, n_groups=n_groups, family="logistic", n_chains=1, kernel="fp8",
+                         scales=scales)
+
+    @classmethod
+    def from_dense(cls, Xs, ys, **kw):
+        pairs = [quantize_block_fp8(X) for X in Xs]
+        return cls([p[0] for p in pairs], [p[1] for p in pairs], ys, **kw)
+
+    def _dequant(self, X):
+        idx = next(i for i, Xi in enumerate(self.Xs) if Xi is X)
+        return dequantize_block_fp8(X, self.scales[idx])
+
+    def bytes_per_eval(self) -> int:
+        return int(sum(X.shape[0] * (self.n_features + 4) + s.numel() for X, s in zip(self.Xs, self.scales)))
+
+
 def synth_logistic_shard(n_rows: int, n_features: int, *, seed: int, device, chunk_rows: int = 1 << 20,
                          beta_scale: float = 0.05):
     """Synthetic logistic-regression shard generated on the device in chunks
@@ -192,3 +263,28 @@ def synth_logistic_shard(n_rows: int, n_features: int, *, seed: int, device, chu
         p = torch.sigmoid(xb.float() @ beta_true + 0.3)
         y[r0:r1] = (torch.rand(r1 - r0, generator=gen, device=device) < p).float()
     return X, y, beta_true
+
+
+def synth_logistic_shard_fp8(n_rows: int, n_features: int, *, seed: int, device, chunk_rows: int = 1 << 20):
+    """Like :func:`synth_logistic_shard` but quantised chunk-wise to block-scaled FP8 (never holds
+    the fp32 matrix): returns ``(Xq e4m3 [n, P], scales uint8 [4*ceil(n/128), P/32], y)``."""
+    import torch
+
+    assert chunk_rows % 128 == 0
+    gen = torch.Generator(device=device)
+    gen.manual_seed(seed)
+    beta_true = (torch.randn(n_features, generator=gen, device=device) * 0.05).float()
+    col_scale = torch.exp(torch.randn(n_features, generator=gen, device=device) * 0.5)  # heterogeneous feature scales
+    Xq = torch.empty(n_rows, n_features, dtype=torch.float8_e4m3fn, device=device)
+    scales = torch.full((((n_rows + 127) // 128) * 4, n_features // 32), 127, dtype=torch.uint8, device=device)
+    y = torch.empty(n_rows, dtype=torch.float32, device=device)
+    for r0 in range(0, n_rows, chunk_rows):
+        r1 = min(n_rows, r0 + chunk_rows)
+        xb = torch.randn(r1 - r0, n_features, generator=gen, device=device) * col_scale
+        q, s = quantize_block_fp8(xb)
+        Xq[r0:r1] = q
+        scales[r0 // 32 : r0 // 32 + s.shape[0]] = s
+        xd = dequantize_block_fp8(q, s)
+        p = torch.sigmoid(xd @ (beta_true / col_scale) + 0.3)
+        y[r0:r1] = (torch.rand(r1 - r0, generator=gen, device=device) < p).float()
+    return Xq, scales, y

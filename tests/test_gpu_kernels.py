@@ -4,6 +4,7 @@ import pytest
 import torch
 
 from pytensor_federated_b200.models import (
+    Fp8GlmShards,
     GlmShards,
     LinregShards,
     OdeShards,
@@ -140,6 +141,33 @@ def test_glm_tensor_core_many_tiles_flushes_accumulator(dev):
     np.testing.assert_allclose(a[0], b[0], rtol=1e-6)
     np.testing.assert_allclose(a[1], b[1], rtol=1e-4, atol=0.05)
     np.testing.assert_allclose(a[2], b[2], rtol=1e-4, atol=0.05)
+
+
+@pytest.mark.parametrize("P", [256, 128])
+def test_glm_fp8_block_scaled_matches_dequantised_reference(dev, P):
+    """kind::mxf8f6f4.block_scale kernel vs fp64 maths on the dequantised matrix."""
+    torch.manual_seed(3)
+    rows = [128 * 40 + 7, 999, 128]
+    Xs, ys = [], []
+    for i, n in enumerate(rows):
+        # heterogeneous row/feature magnitudes so that the block scales really differ
+        X = torch.randn(n, P, device=dev) * torch.exp(torch.randn(P, device=dev)) * torch.exp(
+            0.5 * torch.randn(n, 1, device=dev))
+        Xs.append(X)
+        ys.append((torch.rand(n, device=dev) < 0.4).float())
+    model = Fp8GlmShards.from_dense(Xs, ys, groups=[0, 1, 2], n_groups=3)
+    assert len({int(v) for s in model.scales for v in s.flatten().tolist()}) > 3
+    ic = np.array([0.2, -0.3, 0.05])
+    beta = (np.random.default_rng(5).normal(size=P) * 0.02).astype(np.float32)
+    with FederatedEngine(model) as eng:
+        logp, d_ic, d_beta = eng.evaluate(ic, beta)
+        again = eng.evaluate(ic, beta)
+    w_logp, w_ic, w_beta = model.unpack_result(model.reference_partial([ic, beta], dtype=torch.float64))
+    np.testing.assert_allclose(logp, w_logp, rtol=2e-5)
+    np.testing.assert_allclose(d_ic, w_ic, rtol=1e-4, atol=5e-3)
+    np.testing.assert_allclose(d_beta, w_beta, rtol=2e-4, atol=2e-4 * np.abs(w_beta).max())
+    for u, v in zip((logp, d_ic, d_beta), again):
+        assert np.array_equal(u, v)
 
 
 def test_glm_simt_is_deterministic(dev):
