@@ -152,13 +152,12 @@ __device__ __forceinline__ Prologue prologue(const FedComm& c, float* theta_smem
         }
         __threadfence_system();
         __syncthreads();
-        if (threadIdx.x == 0) {
-            if (c.trace) c.trace[(epoch & 255) * 4 + 0] = globaltimer();
-            if (c.mc_flag) {
-                multimem_st_release_u64(c.mc_flag, epoch);
-            } else {
-                for (int p = 0; p < c.world; ++p) st_release_sys(c.peer_flag[p], epoch);
-            }
+        if (threadIdx.x == 0 && c.trace) c.trace[(epoch & 255) * 4 + 0] = globaltimer();
+        if (c.mc_flag) {
+            if (threadIdx.x == 0) multimem_st_release_u64(c.mc_flag, epoch);
+        } else if (threadIdx.x < c.world) {
+            // one releasing thread per node: the system-scope fences run in parallel, not in series
+            st_release_sys(c.peer_flag[threadIdx.x], epoch);
         }
     }
     if (threadIdx.x == 0) {

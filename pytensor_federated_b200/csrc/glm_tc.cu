@@ -32,7 +32,7 @@ namespace tc {
 constexpr int kTileM = 128;          // rows per tile (UMMA M for MMA #1, UMMA K-extent for MMA #2)
 constexpr int kPanel = 64;           // features per 128-byte swizzle span
 constexpr int kPanelBytes = kTileM * 128;  // 16 KB
-constexpr int kThreads = 224;          // warps: 0 TMA, 1 MMA#1 issuer, 2-5 epilogue, 6 MMA#2 issuer
+// warps: 0 TMA, 1 MMA#1 issuer, 2-5 epilogue group 0, 6 MMA#2 issuer, 7-10 epilogue group 1 (KC >= 4)
 constexpr int kFlush = 32;           // tiles between TMEM -> fp64 flushes of the gradient
 constexpr int kMaxSegs = 64;
 
@@ -69,13 +69,18 @@ template <int KC>
 struct Cfg {
     static constexpr int N1 = ((3 * KC + 15) / 16) * 16;
     static constexpr int N2 = ((2 * KC + 15) / 16) * 16;
+    static constexpr int EG = KC >= 4 ? 2 : 1;          // epilogue warp groups
+    static constexpr int KH = KC / EG;                  // chains per group
+    static constexpr int kThreads = 224 + (EG - 1) * 128;
 };
 
 template <int KC>
-__global__ void __launch_bounds__(kThreads, 1)
+__global__ void __launch_bounds__(Cfg<KC>::kThreads, 1)
 fed_glm_tc_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParams prm, const CUtensorMap* __restrict__ tmaps) {
     constexpr int N1 = Cfg<KC>::N1;
     constexpr int N2 = Cfg<KC>::N2;
+    constexpr int EG = Cfg<KC>::EG;
+    constexpr int KH = Cfg<KC>::KH;
     extern __shared__ unsigned char smem_dyn[];
     unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
 
@@ -114,14 +119,14 @@ fed_glm_tc_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParams
     const long long n_it = (T > (long long)blockIdx.x) ? (T - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
     constexpr uint32_t kTmemCols = (2 * N1 + 2 * 4 * N2) <= 128 ? 128 : ((2 * N1 + 2 * 4 * N2) <= 256 ? 256 : 512);
 
-    double ll_total[KC];
+    double ll_total[KH];
 #pragma unroll
-    for (int k = 0; k < KC; ++k) ll_total[k] = 0.0;
-    double g_acc[4][KC];  // [half][chain] for feature (half*128 + row); epilogue threads only
+    for (int k = 0; k < KH; ++k) ll_total[k] = 0.0;
+    double g_acc[4][KH];  // [half][own chain] for feature (half*128 + row); epilogue threads only
 #pragma unroll
     for (int h = 0; h < 4; ++h)
 #pragma unroll
-        for (int k = 0; k < KC; ++k) g_acc[h][k] = 0.0;
+        for (int k = 0; k < KH; ++k) g_acc[h][k] = 0.0;
 
     if (active) {
         // ---------------- one-time setup ------------------------------------------------------
@@ -157,11 +162,11 @@ fed_glm_tc_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParams
             for (int i = 0; i < 4; ++i) { mbar_init(&bar_full[i], 1); mbar_init(&bar_empty[i], 1); }
             for (int i = 0; i < 2; ++i) {
                 mbar_init(&bar_eta_full[i], 1);
-                mbar_init(&bar_eta_empty[i], 128);
-                mbar_init(&bar_r_full[i], 128);
+                mbar_init(&bar_eta_empty[i], 128 * EG);
+                mbar_init(&bar_r_full[i], 128 * EG);
                 mbar_init(&bar_r_empty[i], 1);
                 mbar_init(&bar_g_full[i], 1);
-                mbar_init(&bar_g_empty[i], 128);
+                mbar_init(&bar_g_empty[i], 128 * EG);
             }
             fence_barrier_init();
         }
@@ -253,17 +258,23 @@ fed_glm_tc_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParams
                 }
             }
         } else {
-            // ================= epilogue warps (2..5) ===========================================
+            // ================= epilogue warps: group 0 = warps 2-5, group 1 = warps 7-10 ==========
+            // Chains are split between the groups (each owns KH of the KC chains: its eta columns,
+            // its residual columns, its gradient columns), so no cross-group combine is needed.
+            const int eg = warp >= 7 ? 1 : 0;
             const int q = warp & 3;                 // TMEM lane quarter this warp may access
             const int row = q * 32 + lane;          // row of the tile == TMEM lane
             const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
+            const int k0 = eg * KH;                 // first chain of this group
             int s_idx = 0;
-            float ll_acc[KC];
-            float gi_cur[KC];
+            float ll_acc[KH];
+            float gi_cur[KH];
 #pragma unroll
-            for (int k = 0; k < KC; ++k) ll_acc[k] = gi_cur[k] = 0.f;
+            for (int k = 0; k < KH; ++k) ll_acc[k] = gi_cur[k] = 0.f;
             int cur_group = n_it > 0 ? -1 : 0;
             const uint32_t r_lbo = (N2 / 8) * 128;
+            constexpr int kEtaLoads = (3 * KH + 3) / 4;
+            constexpr int kGLoads = (2 * KH + 3) / 4;
             for (long long it = 0; it < n_it; ++it) {
                 const long long tile = blockIdx.x + it * gridDim.x;
                 while (s_idx + 1 < prm.n_segments && segs[s_idx + 1].first_tile <= tile) ++s_idx;
@@ -271,8 +282,8 @@ fed_glm_tc_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParams
                 if (seg.group != cur_group) {
                     if (cur_group >= 0) {
 #pragma unroll
-                        for (int k = 0; k < KC; ++k) {
-                            atomicAdd(&gi_acc[k * G + cur_group], (double)gi_cur[k]);
+                        for (int k = 0; k < KH; ++k) {
+                            atomicAdd(&gi_acc[(k0 + k) * G + cur_group], (double)gi_cur[k]);
                             gi_cur[k] = 0.f;
                         }
                     }
@@ -286,35 +297,24 @@ fed_glm_tc_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParams
 
                 mbar_wait(&bar_eta_full[b], bph);
                 tc_fence_after();
-                float eta[KC];
-                if constexpr (KC == 1) {
+                float ev[kEtaLoads * 4];
+#pragma unroll
+                for (int i = 0; i < kEtaLoads; ++i) {
                     float v[4];
-                    tmem_ld_x4(tmem_eta + lane_addr + b * N1, v);
-                    eta[0] = (v[0] + v[1]) + v[2];
-                } else {
-#pragma unroll
-                    for (int c0 = 0; c0 < N1; c0 += 16) {
-                        float v[16];
-                        tmem_ld_x16(tmem_eta + lane_addr + b * N1 + c0, v);
-#pragma unroll
-                        for (int c = 0; c < 16; ++c) {
-                            const int n = c0 + c;
-                            if (n < 3 * KC) {
-                                if (n % 3 == 0) eta[n / 3] = v[c];
-                                else eta[n / 3] += v[c];
-                            }
-                        }
-                    }
+                    tmem_ld_x4(tmem_eta + lane_addr + b * N1 + 3 * k0 + 4 * i, v);
+                    ev[4 * i + 0] = v[0]; ev[4 * i + 1] = v[1]; ev[4 * i + 2] = v[2]; ev[4 * i + 3] = v[3];
                 }
                 tc_fence_before();
                 mbar_arrive(&bar_eta_empty[b]);
 
                 // link, likelihood, residual -> (hi, lo) bf16 columns of R
-                uint32_t rpk[KC];
+                uint32_t rpk[KH];
 #pragma unroll
-                for (int k = 0; k < KC; ++k) {
+                for (int k = 0; k < KH; ++k) {
+                    const float eta = (ev[3 * k] + ev[3 * k + 1]) + ev[3 * k + 2];
                     float ll = 0.f, r = 0.f;
-                    if (valid && k < nch) link_loglik(prm.family, y, eta[k] + theta_f[k * (G + P) + seg.group], ll, r);
+                    if (valid && (k0 + k) < nch)
+                        link_loglik(prm.family, y, eta + theta_f[(k0 + k) * (G + P) + seg.group], ll, r);
                     ll_acc[k] += ll;
                     gi_cur[k] += r;
                     const __nv_bfloat16 hi = __float2bfloat16_rn(r);
@@ -323,16 +323,17 @@ fed_glm_tc_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParams
                 }
                 mbar_wait(&bar_r_empty[b], bph ^ 1);
                 {
+                    // chain k owns columns (2k, 2k+1): 4 bytes at (k / 4) * 128 + (k % 4) * 4 of the row
                     unsigned char* rrow = r_buf + b * L.r_bytes + (row >> 3) * r_lbo + (row & 7) * 16;
-#pragma unroll
-                    for (int c8 = 0; c8 < N2 / 8; ++c8) {
-                        uint32_t w[4];
-#pragma unroll
-                        for (int i = 0; i < 4; ++i) {
-                            const int k = c8 * 4 + i;  // columns (2k, 2k+1) = chain k's (hi, lo)
-                            w[i] = k < KC ? rpk[k < KC ? k : 0] : 0u;
-                        }
-                        *reinterpret_cast<uint4*>(rrow + c8 * 128) = make_uint4(w[0], w[1], w[2], w[3]);
+                    if constexpr (KH == 8) {
+                        *reinterpret_cast<uint4*>(rrow + (k0 / 4) * 128) = make_uint4(rpk[0], rpk[1], rpk[2], rpk[3]);
+                        *reinterpret_cast<uint4*>(rrow + (k0 / 4 + 1) * 128) = make_uint4(rpk[4], rpk[5], rpk[6], rpk[7]);
+                    } else if constexpr (KH == 4) {
+                        *reinterpret_cast<uint4*>(rrow + (k0 / 4) * 128) = make_uint4(rpk[0], rpk[1], rpk[2], rpk[3]);
+                    } else if constexpr (KH == 2) {
+                        *reinterpret_cast<uint2*>(rrow + (k0 / 4) * 128 + (k0 % 4) * 4) = make_uint2(rpk[0], rpk[1]);
+                    } else {
+                        *reinterpret_cast<uint32_t*>(rrow + (k0 / 4) * 128 + (k0 % 4) * 4) = rpk[0];
                     }
                 }
                 fence_proxy_async();
@@ -346,27 +347,18 @@ fed_glm_tc_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParams
                     mbar_wait(&bar_g_full[gb], (uint32_t)((period >> 1) & 1));
                     tc_fence_after();
                     for (int h = 0; h < NH; ++h) {
-                        if constexpr (KC == 1) {
+#pragma unroll
+                        for (int i = 0; i < kGLoads; ++i) {
                             float v[4];
-                            tmem_ld_x4(tmem_g + lane_addr + (gb * NH + h) * N2, v);
-                            g_acc[h][0] += (double)v[0] + (double)v[1];
-                        } else {
-#pragma unroll
-                            for (int c0 = 0; c0 < N2; c0 += 16) {
-                                float v[16];
-                                tmem_ld_x16(tmem_g + lane_addr + (gb * NH + h) * N2 + c0, v);
-#pragma unroll
-                                for (int c = 0; c < 16; c += 2) {
-                                    const int k = (c0 + c) / 2;
-                                    if (k < KC) g_acc[h][k] += (double)v[c] + (double)v[c + 1];
-                                }
-                            }
+                            tmem_ld_x4(tmem_g + lane_addr + (gb * NH + h) * N2 + 2 * k0 + 4 * i, v);
+                            if (2 * i < KH) g_acc[h][2 * i] += (double)v[0] + (double)v[1];
+                            if (2 * i + 1 < KH) g_acc[h][2 * i + 1] += (double)v[2] + (double)v[3];
                         }
                     }
                     tc_fence_before();
                     mbar_arrive(&bar_g_empty[gb]);
 #pragma unroll
-                    for (int k = 0; k < KC; ++k) {
+                    for (int k = 0; k < KH; ++k) {
                         ll_total[k] += (double)ll_acc[k];
                         ll_acc[k] = 0.f;
                     }
@@ -374,7 +366,7 @@ fed_glm_tc_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParams
             }
             if (cur_group >= 0) {
 #pragma unroll
-                for (int k = 0; k < KC; ++k) atomicAdd(&gi_acc[k * G + cur_group], (double)gi_cur[k]);
+                for (int k = 0; k < KH; ++k) atomicAdd(&gi_acc[(k0 + k) * G + cur_group], (double)gi_cur[k]);
             }
         }
 
@@ -385,18 +377,24 @@ fed_glm_tc_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParams
         if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
         double* out = comm.cta_partials + (size_t)blockIdx.x * comm.n_vals;
         // layout per chain: [LL, gi[G], g[P]]
+        const bool is_epi = (warp >= 2 && warp <= 5) || warp >= 7;
+        const int my_k0 = (warp >= 7 ? 1 : 0) * KH;
 #pragma unroll
         for (int k = 0; k < KC; ++k) {
-            const double ll_block = fed::block_sum(ll_total[k], red);
+            double mine = 0.0;
+#pragma unroll
+            for (int kk = 0; kk < KH; ++kk)
+                if (is_epi && my_k0 + kk == k) mine = ll_total[kk];
+            const double ll_block = fed::block_sum(mine, red);
             if (threadIdx.x == 0 && k < nch) out[k * (1 + G + P)] = ll_block;
         }
         for (int i = threadIdx.x; i < nch * G; i += blockDim.x) out[(i / G) * (1 + G + P) + 1 + (i % G)] = gi_acc[i];
-        if (warp >= 2 && warp <= 5) {
+        if (is_epi) {
             const int row = (warp & 3) * 32 + lane;
             for (int h = 0; h < NH; ++h)
 #pragma unroll
-                for (int k = 0; k < KC; ++k)
-                    if (k < nch) out[k * (1 + G + P) + 1 + G + h * 128 + row] = g_acc[h][k];
+                for (int kk = 0; kk < KH; ++kk)
+                    if (my_k0 + kk < nch) out[(my_k0 + kk) * (1 + G + P) + 1 + G + h * 128 + row] = g_acc[h][kk];
         }
     }
     fed::epilogue(comm, pro, 0ull);
@@ -420,7 +418,7 @@ EncodeTiledFn get_encode() {
     }
     return fn;
 }
-int chains_bucket(int k) { return k <= 1 ? 1 : (k <= 4 ? 4 : (k <= 8 ? 8 : 0)); }
+int chains_bucket(int k) { return k <= 1 ? 1 : (k <= 4 ? 4 : (k <= 8 ? 8 : (k <= 16 ? 16 : 0))); }
 }  // namespace
 
 // Builds one TMA descriptor per segment ([n_rows, P] bf16, box = 64 features x 128 rows, 128B swizzle).
@@ -461,11 +459,12 @@ extern "C" int b200_launch_glm_tc(const FedComm* comm, const GlmSegment* segs_de
                                                  prm->n_groups, KC);                                               \
         if (L.stages < 2) return -2;                                                                               \
         cudaFuncSetAttribute(tc::fed_glm_tc_kernel<KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total); \
-        tc::fed_glm_tc_kernel<KC><<<grid, tc::kThreads, L.total, stream>>>(*comm, segs_dev, *prm, maps);            \
+        tc::fed_glm_tc_kernel<KC><<<grid, tc::Cfg<KC>::kThreads, L.total, stream>>>(*comm, segs_dev, *prm, maps);            \
     } while (0)
     if (kc == 1) LAUNCH_TC(1);
     else if (kc == 4) LAUNCH_TC(4);
-    else LAUNCH_TC(8);
+    else if (kc == 8) LAUNCH_TC(8);
+    else LAUNCH_TC(16);
 #undef LAUNCH_TC
     return (int)cudaGetLastError();
 }

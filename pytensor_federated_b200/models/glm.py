@@ -116,11 +116,11 @@ class GlmShards(ShardModel):
         import torch
 
         tc_ok = (
-            self.n_features % 128 == 0 and 128 <= self.n_features <= 384 and self.n_chains <= 8
+            self.n_features % 128 == 0 and 128 <= self.n_features <= 384 and self.n_chains <= 16
             and self.Xs[0].dtype == torch.bfloat16 and len(self.Xs) <= 64
         )
         if not tc_ok and self.n_chains > 1:
-            raise ValueError("multi-chain evaluation needs the tensor-core kernel (P % 128 == 0, P <= 384, K <= 8)")
+            raise ValueError("multi-chain evaluation needs the tensor-core kernel (P % 128 == 0, P <= 384, K <= 16)")
         return tc_ok
 
     def attach(self, lib, handle) -> None:

@@ -35,7 +35,7 @@ if [[ $STAGE == all || $STAGE == ncu ]]; then
   done
 fi
 if [[ $STAGE == chains ]]; then
-  for C in ${CHAINS:-4 8}; do
+  for C in ${CHAINS:-4 8 16}; do
     timeout 900 python bench.py --steps 20 --warmup 3 --kernel tc --chains $C --out $OUT/bench_full_tc_chains.jsonl > $OUT/bench_full_tc_c$C.log 2>&1
     tail -1 $OUT/bench_full_tc_c$C.log
   done

@@ -111,7 +111,7 @@ def test_glm_tensor_core_matches_reference(dev, family, P):
         assert np.array_equal(u, v)
 
 
-@pytest.mark.parametrize("K", [2, 4, 8])
+@pytest.mark.parametrize("K", [2, 3, 4, 8, 13, 16])
 def test_glm_tensor_core_batches_chains(dev, K):
     rows = [128 * 50 + 5, 3000]
     Xs, ys = _glm_case(dev, rows, 256, None, 2, seed=9)
