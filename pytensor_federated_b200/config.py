@@ -1,0 +1,74 @@
+"""Runtime configuration: one dataclass, environment overrides.
+
+The reference has no configuration system (constructor kwargs and hard-coded constants only,
+SURVEY.md §5 "Config / flag system"); its kwargs are kept verbatim on the public classes and the
+knobs that were constants there are gathered here.
+
+Environment variables (all optional):
+
+``B200FED_COMM``            ``auto`` | ``symm`` | ``ipc`` — how peers' comm blocks are mapped
+``B200FED_NO_MULTICAST``    set to disable NVSwitch multicast stores (P2P stores instead)
+``B200FED_GLM_KERNEL``      ``auto`` | ``tc`` | ``simt`` | ``fp8``
+``B200FED_TIMEOUT``         seconds a node may stay silent before ``FederationTimeout``
+``B200FED_SERVE_AHEAD``     kernels a peer keeps pre-enqueued
+``B200FED_CONNECT_SLEEP``   ``"lo,hi"`` seconds of the balanced-connect de-synchronisation pause
+``B200FED_PROBE_TIMEOUT``   seconds to wait for a ``GetLoad`` answer
+``B200FED_GRAPH_BACKEND``   ``auto`` | ``builtin`` — graph IR of the Op layer
+"""
+from __future__ import annotations
+
+import dataclasses
+import os
+from typing import Tuple
+
+
+def _env_float(name: str, default: float) -> float:
+    try:
+        return float(os.environ[name])
+    except (KeyError, ValueError):
+        return default
+
+
+def _env_int(name: str, default: int) -> int:
+    try:
+        return int(os.environ[name])
+    except (KeyError, ValueError):
+        return default
+
+
+def _env_pair(name: str, default: Tuple[float, float]) -> Tuple[float, float]:
+    try:
+        lo, hi = (float(x) for x in os.environ[name].split(","))
+        return lo, hi
+    except (KeyError, ValueError):
+        return default
+
+
+@dataclasses.dataclass
+class FederationConfig:
+    comm: str = "auto"
+    multicast: bool = True
+    glm_kernel: str = "auto"
+    timeout: float = 20.0
+    serve_ahead: int = 8
+    connect_sleep: Tuple[float, float] = (0.2, 2.0)
+    probe_timeout: float = 5.0
+    retries: int = 2
+    graph_backend: str = "auto"
+
+    @classmethod
+    def from_env(cls) -> "FederationConfig":
+        return cls(
+            comm=os.environ.get("B200FED_COMM", "auto"),
+            multicast=not os.environ.get("B200FED_NO_MULTICAST"),
+            glm_kernel=os.environ.get("B200FED_GLM_KERNEL", "auto"),
+            timeout=_env_float("B200FED_TIMEOUT", 20.0),
+            serve_ahead=_env_int("B200FED_SERVE_AHEAD", 8),
+            connect_sleep=_env_pair("B200FED_CONNECT_SLEEP", (0.2, 2.0)),
+            probe_timeout=_env_float("B200FED_PROBE_TIMEOUT", 5.0),
+            graph_backend=os.environ.get("B200FED_GRAPH_BACKEND", "auto"),
+        )
+
+
+def get_config() -> FederationConfig:
+    return FederationConfig.from_env()

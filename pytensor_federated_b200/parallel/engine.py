@@ -63,11 +63,17 @@ class FederatedEngine:
         backend: str = "auto",
         group=None,
         device=None,
-        timeout: float = 20.0,
+        timeout: Optional[float] = None,
         comm: Optional[str] = None,
         grid: Optional[int] = None,
     ) -> None:
         import torch
+
+        from ..config import get_config
+
+        cfg = get_config()
+        timeout = cfg.timeout if timeout is None else timeout
+        self._serve_ahead = cfg.serve_ahead
 
         self.model = model
         dist = _dist()
@@ -93,7 +99,7 @@ class FederatedEngine:
         self.comm_mode = "none"
         self.n_evals = 0
         if backend == "fused":
-            self._init_fused(comm or os.environ.get("B200FED_COMM", "auto"), grid)
+            self._init_fused(comm or cfg.comm, grid)
 
     # ------------------------------------------------------------------ fused backend
     def _init_fused(self, comm: str, grid: Optional[int]) -> None:
@@ -329,7 +335,7 @@ class FederatedEngine:
         return default_inputs_from_words(self.model, words)
 
     # ------------------------------------------------------------------ peers
-    def serve(self, max_epochs: int = 0, ahead: int = 8) -> int:
+    def serve(self, max_epochs: int = 0, ahead: Optional[int] = None) -> int:
         """Peer ranks: answer the root's evaluations until it shuts the federation down.
 
         Returns the number of evaluations served.
@@ -339,6 +345,7 @@ class FederatedEngine:
         if self.backend == "fused":
             from ..ops import native
 
+            ahead = self._serve_ahead if ahead is None else ahead
             n = int(self._lib.b200_engine_serve(self._handle, int(ahead), int(max_epochs)))
             if n < 0:
                 if n == -7:

@@ -1,0 +1,15 @@
+from pytensor_federated_b200.config import FederationConfig, get_config
+
+
+def test_defaults_and_env_overrides(monkeypatch):
+    for k in ("B200FED_COMM", "B200FED_TIMEOUT", "B200FED_CONNECT_SLEEP", "B200FED_NO_MULTICAST"):
+        monkeypatch.delenv(k, raising=False)
+    cfg = get_config()
+    assert cfg == FederationConfig()
+    monkeypatch.setenv("B200FED_COMM", "ipc")
+    monkeypatch.setenv("B200FED_TIMEOUT", "3.5")
+    monkeypatch.setenv("B200FED_CONNECT_SLEEP", "0,0")
+    monkeypatch.setenv("B200FED_NO_MULTICAST", "1")
+    monkeypatch.setenv("B200FED_SERVE_AHEAD", "not-a-number")
+    cfg = get_config()
+    assert (cfg.comm, cfg.timeout, cfg.connect_sleep, cfg.multicast, cfg.serve_ahead) == ("ipc", 3.5, (0.0, 0.0), False, 8)
