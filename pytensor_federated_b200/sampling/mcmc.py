@@ -19,6 +19,33 @@ class SamplerResult:
     n_logp_evals: int
     tree_depth: Optional[np.ndarray] = None
     divergences: int = 0
+    inv_mass: Optional[np.ndarray] = None       # adapted diagonal inverse mass matrix
+    rng_state: Optional[dict] = None            # numpy Generator state after the last draw
+
+    # -- checkpoint / resume (the reference keeps no sampler state; PyMC does it for its users) --
+    def save(self, path: str) -> None:
+        """Writes everything needed to continue the chain to ``path`` (``.npz``)."""
+        import json
+
+        np.savez(
+            path, samples=self.samples, logp=self.logp, accept_rate=self.accept_rate, step_size=self.step_size,
+            n_logp_evals=self.n_logp_evals, divergences=self.divergences,
+            tree_depth=self.tree_depth if self.tree_depth is not None else np.zeros(0, dtype=np.int64),
+            inv_mass=self.inv_mass if self.inv_mass is not None else np.zeros(0),
+            rng_state=np.frombuffer(json.dumps(self.rng_state, default=int).encode(), dtype=np.uint8),
+        )
+
+    @classmethod
+    def load(cls, path: str) -> "SamplerResult":
+        import json
+
+        z = np.load(path if str(path).endswith(".npz") else str(path) + ".npz")
+        rng_state = json.loads(bytes(z["rng_state"]).decode()) if z["rng_state"].size else None
+        return cls(
+            samples=z["samples"], logp=z["logp"], accept_rate=float(z["accept_rate"]), step_size=float(z["step_size"]),
+            n_logp_evals=int(z["n_logp_evals"]), tree_depth=z["tree_depth"] if z["tree_depth"].size else None,
+            divergences=int(z["divergences"]), inv_mass=z["inv_mass"] if z["inv_mass"].size else None, rng_state=rng_state,
+        )
 
     def summary(self, names=None) -> Dict[str, Dict[str, float]]:
         names = names or [f"theta[{i}]" for i in range(self.samples.shape[1])]
@@ -165,16 +192,31 @@ def hmc_sample(logp_dlogp: LogpDlogp, x0: np.ndarray, *, draws: int = 500, tune:
     return SamplerResult(samples, lps, acc_sum / max(1, draws), eps, n_evals)
 
 
-def nuts_sample(logp_dlogp: LogpDlogp, x0: np.ndarray, *, draws: int = 200, tune: int = 500, max_depth: int = 8,
-                target_accept: float = 0.8, seed: int = 0, adapt_mass: bool = True) -> SamplerResult:
-    """No-U-Turn sampler (multinomial variant, iterative tree doubling, diagonal mass matrix)."""
+def nuts_sample(logp_dlogp: LogpDlogp, x0: Optional[np.ndarray] = None, *, draws: int = 200, tune: int = 500,
+                max_depth: int = 8, target_accept: float = 0.8, seed: int = 0, adapt_mass: bool = True,
+                resume: Optional[SamplerResult] = None) -> SamplerResult:
+    """No-U-Turn sampler (multinomial variant, iterative tree doubling, diagonal mass matrix).
+
+    ``resume=<SamplerResult>`` continues a finished/checkpointed chain: starts at its last draw with
+    its adapted step size, mass matrix and random-number state, and skips warm-up.
+    """
     rng = np.random.default_rng(seed)
+    if resume is not None:
+        x0 = resume.samples[-1]
+        tune = 0
+        if resume.rng_state is not None:
+            rng.bit_generator.state = resume.rng_state
     x = np.asarray(x0, dtype=np.float64).copy()
     lp, g = logp_dlogp(x)
     counter = {"n": 1, "div": 0}
     inv_mass = np.ones_like(x)
-    eps, k = _find_reasonable_step(logp_dlogp, x, lp, g, rng, inv_mass)
-    counter["n"] += k
+    if resume is not None:
+        eps = resume.step_size
+        if resume.inv_mass is not None:
+            inv_mass = np.asarray(resume.inv_mass, dtype=np.float64)
+    else:
+        eps, k = _find_reasonable_step(logp_dlogp, x, lp, g, rng, inv_mass)
+        counter["n"] += k
     da = _DualAveraging(eps, target_accept)
 
     def leapfrog(xq, pq, gq, e):
@@ -261,4 +303,5 @@ def nuts_sample(logp_dlogp: LogpDlogp, x0: np.ndarray, *, draws: int = 200, tune
             lps[it - tune] = lp
             depths[it - tune] = depth
             acc_total += a
-    return SamplerResult(samples, lps, acc_total / max(1, draws), eps, counter["n"], depths, counter["div"])
+    return SamplerResult(samples, lps, acc_total / max(1, draws), eps, counter["n"], depths, counter["div"],
+                         inv_mass=inv_mass.copy(), rng_state=rng.bit_generator.state)

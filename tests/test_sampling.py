@@ -76,3 +76,18 @@ def test_federated_linear_model_map_and_nuts():
     before = eng.n_evals
     m.logp_dlogp(theta_map)
     assert eng.n_evals == before + 1
+
+
+def test_checkpoint_and_resume_continue_the_same_chain(tmp_path):
+    from pytensor_federated_b200.sampling import SamplerResult
+
+    target = _gauss([0.5, -1.0], [1.0, 0.3])
+    full = nuts_sample(target, np.zeros(2), draws=120, tune=200, seed=5)
+    first = nuts_sample(target, np.zeros(2), draws=60, tune=200, seed=5)
+    first.save(tmp_path / "chain")
+    restored = SamplerResult.load(tmp_path / "chain")
+    assert restored.step_size == first.step_size
+    np.testing.assert_array_equal(restored.inv_mass, first.inv_mass)
+    second = nuts_sample(target, resume=restored, draws=60)
+    # identical random stream + identical adaptation => the resumed half reproduces the uninterrupted run
+    np.testing.assert_allclose(np.concatenate([first.samples, second.samples]), full.samples, rtol=0, atol=1e-12)
