@@ -210,3 +210,14 @@ def test_service_client_reaches_gpu_node_through_local_registry(dev):
             del client
         finally:
             service.unregister_local_node("gpu", 0)
+
+
+def test_device_timer_trace_orders_the_phases(dev):
+    """Tracing subsystem: %globaltimer stamps of theta release -> node partial -> result release."""
+    x, y, sigma = make_demo_data()
+    with FederatedEngine(LinregShards([x], [y], [sigma], device=dev)) as eng:
+        for i in range(5):
+            eng.evaluate(np.array(0.1 * i), np.array(0.5))
+        t_theta, t_partial, t_result = eng.trace(5)
+        assert 0 < t_theta <= t_partial <= t_result
+        assert (t_result - t_theta) < 5_000_000  # the whole fused evaluation is far below 5 ms
