@@ -174,6 +174,38 @@ class GlmShards(ShardModel):
     def _dequant(self, X):
         return X
 
+    def eager_partial(self, inputs) -> np.ndarray:
+        """Stock-PyTorch evaluation as a practitioner would write it: two bf16 GEMMs (X @ beta, then
+        r @ X) plus elementwise ops — the compute step of the NCCL baseline ("baseline B").  Reads the
+        design matrix twice; no custom kernels."""
+        import torch
+
+        if self.Xs[0].dtype != torch.bfloat16:
+            return self.reference_partial(inputs)
+        intercept, beta = inputs
+        self._note_shapes(inputs)
+        ic = torch.as_tensor(np.asarray(intercept, dtype=np.float32)).reshape(self.n_chains, -1).to(self.device)
+        bt = torch.as_tensor(np.asarray(beta, dtype=np.float32)).reshape(self.n_chains, self.n_features).to(self.device)
+        out = torch.zeros(self.n_chains, 1 + self.n_params, dtype=torch.float64, device=self.device)
+        for X, y, g in zip(self.Xs, self.ys, self.groups):
+            eta = (X @ bt.T.to(torch.bfloat16)).float() + ic[:, g]          # [n, K]
+            yy = y.unsqueeze(1)
+            if self.family == "logistic":
+                ll = yy * eta - torch.nn.functional.softplus(eta)
+                r = yy - torch.sigmoid(eta)
+            elif self.family == "poisson":
+                mu = torch.exp(eta)
+                ll = yy * eta - mu
+                r = yy - mu
+            else:
+                d = yy - eta
+                ll = -0.5 * d * d - 0.918938533204672742
+                r = d
+            out[:, 0] += ll.sum(0).double()
+            out[:, 1 + g] += r.sum(0).double()
+            out[:, 1 + self.n_groups :] += (r.T.to(torch.bfloat16) @ X).double()
+        return out.reshape(-1).cpu().numpy()
+
     def bytes_per_eval(self) -> int:
         return int(sum(X.shape[0] * (self.n_features * X.element_size() + 4) for X in self.Xs))
 

@@ -321,7 +321,9 @@ class FederatedEngine:
             return None
         words = header[1:].cpu().numpy().astype(np.uint32)
         inputs = self._unpack_words(words)
-        partial = torch.from_numpy(np.asarray(m.reference_partial(inputs), dtype=np.float64)).to(self.device)
+        compute = getattr(m, "eager_partial", None) if self.device.type == "cuda" else None
+        compute = compute or m.reference_partial
+        partial = torch.from_numpy(np.asarray(compute(inputs), dtype=np.float64)).to(self.device)
         if self.world > 1:
             dist.reduce(partial, dst=dist.get_global_rank(self.group, 0) if self.group else 0, group=self.group)
         return partial.cpu().numpy()
