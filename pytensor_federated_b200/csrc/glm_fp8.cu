@@ -4,13 +4,18 @@
 //     x[r, f] = e4m3(Xq[r, f]) * 2^(S[r/32, f/32] - 127)
 // i.e. 1.03 bytes per element instead of 2 for bf16 -> the HBM-bound evaluation gets ~2x faster.
 //
-// Both GEMMs consume the quantised tile directly; the dequantisation is done by the tensor core:
-//   MMA #1  eta[128 x 16] += Xq_tile[:, 32-feature block] . Theta^T   scale-factor-A column per
-//           feature block, whose 4 bytes are the scales of the tile's 4 row groups (the TMEM
-//           scale layout keeps the scales of rows m, m+32, m+64, m+96 in one 32-bit word and is
-//           replicated over lanes; with 32-row blocks every lane holds the same word).
-//   MMA #2  G[128 feat x 16] += Xq_tile^T[:, 32-row group] . R   scale-factor-A column per
-//           (feature half, row group), bytes = the 4 feature blocks of that half.
+// Both GEMMs consume the quantised tile directly; the dequantisation is done by the tensor core.
+// TMEM scale-factor layout (cta_group::1, M = 128, 32-element blocks): the scale of operand row m
+// for K-block j sits in lane m % 32 (replicated in all four 32-lane subpartitions), 32-bit column
+// base + 4*(j/4) + m/32, byte j % 4 — the byte is selected by the instruction descriptor's sf_id.
+// With 32-row x 32-feature blocks every lane holds the same word, so the epilogue warps can
+// write the scale words with plain tcgen05.st:
+//   MMA #1  eta[128 x 16] += Xq_tile[:, feature block fb] . Theta^T     rows m -> row group m/32:
+//           column 4*(fb/4) + q holds the scales of (row group q, feature blocks 4*(fb/4)..+3),
+//           sf_id = fb % 4.
+//   MMA #2  G[128 feat x 16] += Xq_tile^T[:, row group q] . R           rows m -> feature block
+//           4h + m/32: column 4h + qq holds the scales of (row groups 0..3, feature block 4h+qq),
+//           sf_id = q.
 //   Scale-factor-B is the constant 2^0.
 // Theta and the residuals are themselves e4m3: theta is a 5-term, r a 4-term radix-16 expansion
 // (term k carries weight 16^-k), the terms sit in separate N columns and are recombined in the
@@ -257,8 +262,8 @@ fed_glm_fp8_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParam
                         const int pnl = fb >> 2, ks = fb & 3;   // 4 K-steps of 32 features per 128-feature panel
                         const uint64_t adesc = make_desc(x_addr + pnl * kPanelB + ks * 32, 16, 1024, 2);
                         const uint64_t bdesc = make_desc(theta_b_addr + pnl * (kN * 128) + ks * 32, 16, 1024, 2);
-                        umma_fp8_block_scaled(tmem_eta + b * kN, adesc, bdesc, idesc1, fb ? 1u : 0u,
-                                              tmem_sfa1 + sfb * 8 + fb, tmem_sfb);
+                        umma_fp8_block_scaled(tmem_eta + b * kN, adesc, bdesc, idesc1 | ((uint32_t)(fb & 3) << 29), fb ? 1u : 0u,
+                                              tmem_sfa1 + sfb * 8 + (fb >> 2) * 4, tmem_sfb);
                     }
                     umma_commit(&bar_eta_full[b]);
                 }
@@ -285,8 +290,8 @@ fed_glm_fp8_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParam
                         for (int q = 0; q < 4; ++q) {   // K step = one 32-row group
                             const uint64_t adesc = make_desc(x_addr + h * kPanelB + q * 4 * 1024, kPanelB, 1024, 2);
                             const uint64_t bdesc = make_desc(r_addr + b * L.r_bytes + q * 4 * 128, 128, 128, 0);
-                            umma_fp8_block_scaled(tmem_g + (gb * NH + h) * kN, adesc, bdesc, idesc2,
-                                                  (first && q == 0) ? 0u : 1u, tmem_sfa2 + sfb * 8 + h * 4 + q, tmem_sfb);
+                            umma_fp8_block_scaled(tmem_g + (gb * NH + h) * kN, adesc, bdesc, idesc2 | ((uint32_t)q << 29),
+                                                  (first && q == 0) ? 0u : 1u, tmem_sfa2 + sfb * 8 + h * 4, tmem_sfb);
                         }
                     }
                     umma_commit(&bar_empty[st]);
@@ -317,17 +322,20 @@ fed_glm_fp8_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParam
                     for (int w = 0; w < 4; ++w)
                         rows4[q][w] = (w * 4 < NFB) ? __ldg(reinterpret_cast<const uint32_t*>(sp + q * NFB + w * 4)) : 0x7F7F7F7Fu;
                 uint32_t sfa1[8], sfa2[8];
+                // MMA #1: column 4g + q = scale bytes of (row group q, feature blocks 4g .. 4g+3)
 #pragma unroll
-                for (int fb = 0; fb < 8; ++fb) {
-                    // byte q of column fb = scale of (row group q, feature block fb)
-                    const int w = fb >> 2, sh = (fb & 3) * 8;
-                    sfa1[fb] = ((rows4[0][w] >> sh) & 0xFF) | (((rows4[1][w] >> sh) & 0xFF) << 8) |
-                               (((rows4[2][w] >> sh) & 0xFF) << 16) | (((rows4[3][w] >> sh) & 0xFF) << 24);
-                }
+                for (int g = 0; g < 2; ++g)
+#pragma unroll
+                    for (int q = 0; q < 4; ++q) sfa1[g * 4 + q] = rows4[q][g];
+                // MMA #2: column 4h + qq = scale bytes of (row groups 0..3, feature block 4h + qq)
 #pragma unroll
                 for (int h = 0; h < 2; ++h)
 #pragma unroll
-                    for (int q = 0; q < 4; ++q) sfa2[h * 4 + q] = rows4[q][h];  // bytes = feature blocks 4h..4h+3
+                    for (int qq = 0; qq < 4; ++qq) {
+                        const int sh = qq * 8;
+                        sfa2[h * 4 + qq] = ((rows4[0][h] >> sh) & 0xFF) | (((rows4[1][h] >> sh) & 0xFF) << 8) |
+                                           (((rows4[2][h] >> sh) & 0xFF) << 16) | (((rows4[3][h] >> sh) & 0xFF) << 24);
+                    }
                 const int slot = (int)(t_it % kSfRing);
                 tmem_st_x8(tmem_sfa1 + lane_addr + slot * 8, sfa1);
                 tmem_st_x8(tmem_sfa2 + lane_addr + slot * 8, sfa2);
