@@ -140,6 +140,18 @@ __device__ __forceinline__ Prologue prologue(const FedComm& c, float* theta_smem
     unsigned long long epoch = c.epoch;
     if (c.epoch_counter) epoch = *reinterpret_cast<volatile unsigned long long*>(c.epoch_counter) + 1ull;
 
+    if (c.world == 1 && gridDim.x == 1) {
+        // Single node, single CTA (tiny models): no mailbox round trip, no flags — theta goes
+        // straight from (host-mapped) memory into shared memory.  Latency path.
+        for (int i = threadIdx.x; i < c.n_theta; i += blockDim.x) theta_smem[i] = c.theta_src[i];
+        if (threadIdx.x == 0 && c.trace) c.trace[(epoch & 255) * 4 + 0] = globaltimer();
+        __syncthreads();
+        Prologue r0;
+        r0.epoch = epoch;
+        r0.stop = false;
+        r0.timed_out = false;
+        return r0;
+    }
     if (c.rank == 0 && blockIdx.x == 0) {
         // theta_src may live in host memory: read it once, fan it out over NVLink.
         for (int i = threadIdx.x; i < c.n_theta; i += blockDim.x) {
@@ -182,6 +194,23 @@ __device__ __forceinline__ Prologue prologue(const FedComm& c, float* theta_smem
 __device__ __forceinline__ void epilogue(const FedComm& c, const Prologue& pro, unsigned long long status_in) {
     __shared__ int s_last;
     __shared__ unsigned long long s_status;
+    if (c.world == 1 && gridDim.x == 1) {
+        // latency path: the only CTA's partial IS the result
+        __syncthreads();
+        for (int v = threadIdx.x; v < c.n_vals; v += blockDim.x) c.host_result[v] = c.cta_partials[v];
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            if (c.trace) {
+                c.trace[(pro.epoch & 255) * 4 + 1] = globaltimer();
+                c.trace[(pro.epoch & 255) * 4 + 2] = globaltimer();
+            }
+            st_release_sys(c.host_flag, pro.epoch | (status_in << B200FED_STATUS_SHIFT));
+            if (c.epoch_counter) *c.epoch_counter = pro.epoch;
+            if (c.done_flag) *reinterpret_cast<volatile unsigned long long*>(c.done_flag) = pro.epoch;
+        }
+        return;
+    }
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) {

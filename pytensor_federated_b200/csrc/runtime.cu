@@ -376,6 +376,9 @@ int b200_engine_set_linreg(void* h, int n_shards, const void** x, const void** y
     if (want < 1) want = 1;
     if (want > e->sm_count * 4) want = e->sm_count * 4;
     e->grid = (int)want;
+    long long max_n = 0;
+    for (int s = 0; s < n_shards; ++s) max_n = n[s] > max_n ? n[s] : max_n;
+    if (want == 1 && max_n <= 4096) e->grid = -1;  // small mode: one CTA, one warp per shard
     return 0;
 }
 
