@@ -229,6 +229,7 @@ def run_b200(args):
         dist.all_reduce(peer_launches, op=dist.ReduceOp.SUM)
     comm_mode = eng.comm_mode
     bytes_per_eval = model.bytes_per_eval()
+    flops_per_eval = model.flops_per_eval()
     n_theta_words, n_vals = model.n_theta_words, model.n_vals
     eng.shutdown()
     if world > 1:
@@ -276,6 +277,15 @@ def run_b200(args):
             "l2_policy": "inputs (>= 5 GB per GPU) are larger than the 126 MB L2; no flush needed",
             "hbm_bytes_per_eval_per_gpu": bytes_per_eval,
             "hbm_roofline_frac_of_measured": (bytes_per_eval / (ms_per_step * 1e-3)) / (hbm * 1e9),
+            # three-term roofline of the fused broadcast->compute->reduce kernel (seconds per eval per GPU):
+            # HBM stream of the shard, tensor-core time of the two skinny GEMMs (N padded to 16 columns each),
+            # NVLink bytes (theta in, partial out) at the measured 770 GB/s peer bandwidth
+            "roofline_s": {
+                "hbm": bytes_per_eval / (hbm * 1e9),
+                "tensor": flops_per_eval * (32.0 / max(1, 4 * K)) / (peaks.get("bf16_tflops", 1590.0) * 1e12),
+                "nvlink": (n_theta_words * 4 + n_vals * 8) / 770e9,
+                "bound": "hbm",
+            },
         },
         "clocks": result["clocks"],
         "e2e": {

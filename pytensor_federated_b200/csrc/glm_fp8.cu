@@ -38,7 +38,7 @@ using namespace tc;
 constexpr int kTile = 128;            // rows per tile
 constexpr int kPanelF = 128;          // features per 128-byte swizzle span (1 byte / element)
 constexpr int kPanelB = kTile * 128;  // 16 KB
-constexpr int kThreadsF = 224;        // warps: 0 TMA, 1 MMA#1, 2-5 epilogue, 6 MMA#2
+constexpr int kThreadsF = 352;        // warps: 0 TMA, 1 MMA#1, 2-5 epilogue A (even tiles), 6 MMA#2, 7-10 epilogue B (odd tiles)
 constexpr int kFlushF = 32;
 constexpr int kN = 16;                // MMA N for both GEMMs
 constexpr int kThetaTerms = 5;
@@ -300,7 +300,11 @@ fed_glm_fp8_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParam
                 }
             }
         } else {
-            // ================= epilogue warps (2..5) ===========================================
+            // ================= epilogue warps: group A = 2..5 (even tiles), group B = 7..10 (odd) =
+            // The per-tile epilogue is a long serial chain (barrier wake-up, TMEM load, link maths,
+            // smem store + proxy fence, TMEM scale stores); two groups ping-pong so that two tiles'
+            // chains overlap.  Group g owns eta/R buffer g, so every barrier still sees 128 arrivals.
+            const int eg = warp >= 7 ? 1 : 0;
             const int q4 = warp & 3;
             const int row = q4 * 32 + lane;
             const uint32_t lane_addr = (uint32_t)(q4 * 32) << 16;
@@ -344,13 +348,12 @@ fed_glm_fp8_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParam
                 mbar_arrive(&bar_sf_full[slot]);
             };
             int sf_sidx = 0;
-            if (n_it > 0) write_scales(0, sf_sidx);
-            if (n_it > 1) write_scales(1, sf_sidx);
+            if (eg < n_it) write_scales(eg, sf_sidx);
 
             int s_idx = 0;
             float ll_acc = 0.f, gi_cur = 0.f;
-            int cur_group = n_it > 0 ? -1 : 0;
-            for (long long it = 0; it < n_it; ++it) {
+            int cur_group = -1;
+            for (long long it = eg; it < n_it; it += 2) {
                 const long long tile = blockIdx.x + it * gridDim.x;
                 while (s_idx + 1 < prm.n_segments && segs[s_idx + 1].first_tile <= tile) ++s_idx;
                 const GlmSegment& seg = segs[s_idx];
@@ -387,10 +390,11 @@ fed_glm_fp8_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParam
                 fence_proxy_async();
                 mbar_arrive(&bar_r_full[b]);
 
-                // scales for tile it+2: its ring slot was last used by tile it-2, whose MMAs are complete
-                // (we just passed r_empty of tile it-2 and eta_full of tile it)
+                // scales for this group's next tile (it+2): its ring slot was last used by tile it-2,
+                // whose MMAs are complete (we just passed r_empty of tile it-2 and eta_full of tile it)
                 if (it + 2 < n_it) write_scales(it + 2, sf_sidx);
 
+                // the gradient accumulator of a period is flushed by whichever group owns its last tile
                 const bool last = (it % kFlushF) == kFlushF - 1 || it == n_it - 1;
                 if (last) {
                     const long long period = it / kFlushF;
@@ -424,6 +428,11 @@ fed_glm_fp8_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParam
         if (warp >= 2 && warp <= 5) {
             const int row = (warp & 3) * 32 + lane;
             for (int h = 0; h < NH; ++h) out[1 + G + h * 128 + row] = g_acc[h];
+        }
+        __syncthreads();
+        if (warp >= 7) {  // group B flushed the periods whose last tile was odd
+            const int row = (warp & 3) * 32 + lane;
+            for (int h = 0; h < NH; ++h) out[1 + G + h * 128 + row] += g_acc[h];
         }
     }
     fed::epilogue(comm, pro, 0ull);
