@@ -69,8 +69,12 @@ template <int KC>
 struct Cfg {
     static constexpr int N1 = ((3 * KC + 15) / 16) * 16;
     static constexpr int N2 = ((2 * KC + 15) / 16) * 16;
-    static constexpr int EG = KC >= 4 ? 2 : 1;          // epilogue warp groups
-    static constexpr int KH = KC / EG;                  // chains per group
+    // Two epilogue warp groups.  KC >= 4: the groups split the chains (each tile is handled by both).
+    // KC == 1: the groups ping-pong on alternate tiles (PP), overlapping two tiles' serial chains.
+    static constexpr bool PP = KC == 1;
+    static constexpr int EG = (KC >= 4 || PP) ? 2 : 1;
+    static constexpr int KH = PP ? KC : KC / EG;        // chains per group
+    static constexpr int kArrive = PP ? 128 : 128 * EG; // arrivals per eta/R/G barrier phase
     static constexpr int kThreads = 224 + (EG - 1) * 128;
 };
 
@@ -81,6 +85,9 @@ fed_glm_tc_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParams
     constexpr int N2 = Cfg<KC>::N2;
     constexpr int EG = Cfg<KC>::EG;
     constexpr int KH = Cfg<KC>::KH;
+    constexpr bool PP = Cfg<KC>::PP;
+    constexpr int kArrive = Cfg<KC>::kArrive;
+    (void)EG;
     extern __shared__ unsigned char smem_dyn[];
     unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
 
@@ -162,11 +169,11 @@ fed_glm_tc_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParams
             for (int i = 0; i < 4; ++i) { mbar_init(&bar_full[i], 1); mbar_init(&bar_empty[i], 1); }
             for (int i = 0; i < 2; ++i) {
                 mbar_init(&bar_eta_full[i], 1);
-                mbar_init(&bar_eta_empty[i], 128 * EG);
-                mbar_init(&bar_r_full[i], 128 * EG);
+                mbar_init(&bar_eta_empty[i], kArrive);
+                mbar_init(&bar_r_full[i], kArrive);
                 mbar_init(&bar_r_empty[i], 1);
                 mbar_init(&bar_g_full[i], 1);
-                mbar_init(&bar_g_empty[i], 128 * EG);
+                mbar_init(&bar_g_empty[i], kArrive);
             }
             fence_barrier_init();
         }
@@ -265,17 +272,17 @@ fed_glm_tc_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParams
             const int q = warp & 3;                 // TMEM lane quarter this warp may access
             const int row = q * 32 + lane;          // row of the tile == TMEM lane
             const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-            const int k0 = eg * KH;                 // first chain of this group
+            const int k0 = PP ? 0 : eg * KH;        // first chain of this group
             int s_idx = 0;
             float ll_acc[KH];
             float gi_cur[KH];
 #pragma unroll
             for (int k = 0; k < KH; ++k) ll_acc[k] = gi_cur[k] = 0.f;
-            int cur_group = n_it > 0 ? -1 : 0;
+            int cur_group = -1;
             const uint32_t r_lbo = (N2 / 8) * 128;
             constexpr int kEtaLoads = (3 * KH + 3) / 4;
             constexpr int kGLoads = (2 * KH + 3) / 4;
-            for (long long it = 0; it < n_it; ++it) {
+            for (long long it = PP ? eg : 0; it < n_it; it += PP ? 2 : 1) {
                 const long long tile = blockIdx.x + it * gridDim.x;
                 while (s_idx + 1 < prm.n_segments && segs[s_idx + 1].first_tile <= tile) ++s_idx;
                 const GlmSegment& seg = segs[s_idx];
@@ -364,6 +371,8 @@ fed_glm_tc_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParams
                     }
                 }
             }
+#pragma unroll
+            for (int k = 0; k < KH; ++k) ll_total[k] += (double)ll_acc[k];  // rows since this group's last flush
             if (cur_group >= 0) {
 #pragma unroll
                 for (int k = 0; k < KH; ++k) atomicAdd(&gi_acc[(k0 + k) * G + cur_group], (double)gi_cur[k]);
@@ -378,7 +387,7 @@ fed_glm_tc_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParams
         double* out = comm.cta_partials + (size_t)blockIdx.x * comm.n_vals;
         // layout per chain: [LL, gi[G], g[P]]
         const bool is_epi = (warp >= 2 && warp <= 5) || warp >= 7;
-        const int my_k0 = (warp >= 7 ? 1 : 0) * KH;
+        const int my_k0 = PP ? 0 : (warp >= 7 ? 1 : 0) * KH;
 #pragma unroll
         for (int k = 0; k < KC; ++k) {
             double mine = 0.0;
@@ -389,12 +398,19 @@ fed_glm_tc_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParams
             if (threadIdx.x == 0 && k < nch) out[k * (1 + G + P)] = ll_block;
         }
         for (int i = threadIdx.x; i < nch * G; i += blockDim.x) out[(i / G) * (1 + G + P) + 1 + (i % G)] = gi_acc[i];
-        if (is_epi) {
+        if (is_epi && (!PP || warp <= 5)) {
             const int row = (warp & 3) * 32 + lane;
             for (int h = 0; h < NH; ++h)
 #pragma unroll
                 for (int kk = 0; kk < KH; ++kk)
                     if (my_k0 + kk < nch) out[(my_k0 + kk) * (1 + G + P) + 1 + G + h * 128 + row] = g_acc[h][kk];
+        }
+        if constexpr (PP) {  // the second group flushed the periods whose last tile was odd
+            __syncthreads();
+            if (warp >= 7) {
+                const int row = (warp & 3) * 32 + lane;
+                for (int h = 0; h < NH; ++h) out[1 + G + h * 128 + row] += g_acc[h][0];
+            }
         }
     }
     fed::epilogue(comm, pro, 0ull);
