@@ -32,7 +32,7 @@ namespace tc {
 constexpr int kTileM = 128;          // rows per tile (UMMA M for MMA #1, UMMA K-extent for MMA #2)
 constexpr int kPanel = 64;           // features per 128-byte swizzle span
 constexpr int kPanelBytes = kTileM * 128;  // 16 KB
-// warps: 0 TMA, 1 MMA#1 issuer, 2-5 epilogue group 0, 6 MMA#2 issuer, 7-10 epilogue group 1 (KC >= 4)
+// warps: 0 TMA, 1 MMA#1 issuer, 2-5 epilogue group 0, 6 MMA#2 issuer, 7.. further epilogue groups
 constexpr int kFlush = 32;           // tiles between TMEM -> fp64 flushes of the gradient
 constexpr int kMaxSegs = 64;
 
@@ -69,12 +69,15 @@ template <int KC>
 struct Cfg {
     static constexpr int N1 = ((3 * KC + 15) / 16) * 16;
     static constexpr int N2 = ((2 * KC + 15) / 16) * 16;
-    // Two epilogue warp groups.  KC >= 4: the groups split the chains (each tile is handled by both).
-    // KC == 1: the groups ping-pong on alternate tiles (PP), overlapping two tiles' serial chains.
-    static constexpr bool PP = KC == 1;
-    static constexpr int EG = (KC >= 4 || PP) ? 2 : 1;
-    static constexpr int KH = PP ? KC : KC / EG;        // chains per group
-    static constexpr int kArrive = PP ? 128 : 128 * EG; // arrivals per eta/R/G barrier phase
+    // Epilogue warp groups (128 threads each).  The per-tile epilogue is a serial chain, so it is
+    // parallelised two ways: EGC groups split the chains of a tile (KC >= 4), and EGT = 2 groups
+    // ping-pong on alternate tiles so that two tiles' chains overlap.  Group g: chains of
+    // cg = g % EGC, tiles of parity tp = g / EGC.
+    static constexpr int EGC = KC >= 4 ? 2 : 1;
+    static constexpr int EGT = 2;
+    static constexpr int EG = EGC * EGT;
+    static constexpr int KH = KC / EGC;                 // chains per group
+    static constexpr int kArrive = 128 * EGC;           // arrivals per eta/R/G barrier phase
     static constexpr int kThreads = 224 + (EG - 1) * 128;
 };
 
@@ -85,7 +88,8 @@ fed_glm_tc_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParams
     constexpr int N2 = Cfg<KC>::N2;
     constexpr int EG = Cfg<KC>::EG;
     constexpr int KH = Cfg<KC>::KH;
-    constexpr bool PP = Cfg<KC>::PP;
+    constexpr int EGC = Cfg<KC>::EGC;
+    constexpr int EGT = Cfg<KC>::EGT;
     constexpr int kArrive = Cfg<KC>::kArrive;
     (void)EG;
     extern __shared__ unsigned char smem_dyn[];
@@ -265,14 +269,14 @@ fed_glm_tc_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParams
                 }
             }
         } else {
-            // ================= epilogue warps: group 0 = warps 2-5, group 1 = warps 7-10 ==========
-            // Chains are split between the groups (each owns KH of the KC chains: its eta columns,
-            // its residual columns, its gradient columns), so no cross-group combine is needed.
-            const int eg = warp >= 7 ? 1 : 0;
+            // ================= epilogue warps: group 0 = warps 2-5, group g >= 1 = warps 7+4(g-1) .. =====
+            const int eg = warp <= 5 ? 0 : (warp - 7) / 4 + 1;
+            const int cg = eg % EGC;                // which chains
+            const int tp = eg / EGC;                // which tile parity
             const int q = warp & 3;                 // TMEM lane quarter this warp may access
             const int row = q * 32 + lane;          // row of the tile == TMEM lane
             const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
-            const int k0 = PP ? 0 : eg * KH;        // first chain of this group
+            const int k0 = cg * KH;                 // first chain of this group
             int s_idx = 0;
             float ll_acc[KH];
             float gi_cur[KH];
@@ -282,7 +286,7 @@ fed_glm_tc_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParams
             const uint32_t r_lbo = (N2 / 8) * 128;
             constexpr int kEtaLoads = (3 * KH + 3) / 4;
             constexpr int kGLoads = (2 * KH + 3) / 4;
-            for (long long it = PP ? eg : 0; it < n_it; it += PP ? 2 : 1) {
+            for (long long it = tp; it < n_it; it += EGT) {
                 const long long tile = blockIdx.x + it * gridDim.x;
                 while (s_idx + 1 < prm.n_segments && segs[s_idx + 1].first_tile <= tile) ++s_idx;
                 const GlmSegment& seg = segs[s_idx];
@@ -387,7 +391,9 @@ fed_glm_tc_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParams
         double* out = comm.cta_partials + (size_t)blockIdx.x * comm.n_vals;
         // layout per chain: [LL, gi[G], g[P]]
         const bool is_epi = (warp >= 2 && warp <= 5) || warp >= 7;
-        const int my_k0 = PP ? 0 : (warp >= 7 ? 1 : 0) * KH;
+        const int my_g = warp <= 5 ? 0 : (warp - 7) / 4 + 1;
+        const int my_k0 = (my_g % EGC) * KH;
+        const int my_tp = my_g / EGC;
 #pragma unroll
         for (int k = 0; k < KC; ++k) {
             double mine = 0.0;
@@ -398,19 +404,19 @@ fed_glm_tc_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParams
             if (threadIdx.x == 0 && k < nch) out[k * (1 + G + P)] = ll_block;
         }
         for (int i = threadIdx.x; i < nch * G; i += blockDim.x) out[(i / G) * (1 + G + P) + 1 + (i % G)] = gi_acc[i];
-        if (is_epi && (!PP || warp <= 5)) {
-            const int row = (warp & 3) * 32 + lane;
-            for (int h = 0; h < NH; ++h)
-#pragma unroll
-                for (int kk = 0; kk < KH; ++kk)
-                    if (my_k0 + kk < nch) out[(my_k0 + kk) * (1 + G + P) + 1 + G + h * 128 + row] = g_acc[h][kk];
-        }
-        if constexpr (PP) {  // the second group flushed the periods whose last tile was odd
-            __syncthreads();
-            if (warp >= 7) {
+        // gradient: the two tile-parity groups of a chain each flushed part of the periods
+        for (int pass = 0; pass < EGT; ++pass) {
+            if (is_epi && my_tp == pass) {
                 const int row = (warp & 3) * 32 + lane;
-                for (int h = 0; h < NH; ++h) out[1 + G + h * 128 + row] += g_acc[h][0];
+                for (int h = 0; h < NH; ++h)
+#pragma unroll
+                    for (int kk = 0; kk < KH; ++kk)
+                        if (my_k0 + kk < nch) {
+                            double* dst = &out[(my_k0 + kk) * (1 + G + P) + 1 + G + h * 128 + row];
+                            *dst = pass == 0 ? g_acc[h][kk] : *dst + g_acc[h][kk];
+                        }
             }
+            __syncthreads();
         }
     }
     fed::epilogue(comm, pro, 0ull);
