@@ -208,10 +208,10 @@ def run_b200(args):
         clocks = sampler.stop()
         result = dict(dev_ms=dev_ms, e2e_s=e2e_s, launches=launches, checksum=checksum, clocks=clocks)
     else:
+        # peers: each phase serves exactly as many epochs as the root evaluates; their kernels wait
+        # on the device for the root's epoch flag, the host only keeps the queue filled
         eng.serve(max_epochs=W)
         barrier()
-        t_ev0, t_ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-        t_ev0.record()
         eng.serve(max_epochs=S)
         barrier()
         eng.serve(max_epochs=S)
