@@ -98,6 +98,7 @@ class FederatedEngine:
         self._keepalive = []
         self.comm_mode = "none"
         self.n_evals = 0
+        self._stop_seen = False
         if backend == "fused":
             self._init_fused(comm or cfg.comm, grid)
 
@@ -361,6 +362,7 @@ class FederatedEngine:
         while max_epochs <= 0 or served < max_epochs:
             header = torch.zeros(1 + max(1, m.n_theta_words), dtype=torch.float64)
             if self._collective_round(header) is None:
+                self._stop_seen = True  # the root's shutdown broadcast has been consumed
                 break
             served += 1
         return served
@@ -380,6 +382,13 @@ class FederatedEngine:
                     header = torch.zeros(1 + max(1, self.model.n_theta_words), dtype=torch.float64)
                     header[0] = _STOP
                     self._collective_round(header)
+            elif (not self.is_root) and self.world > 1 and self.backend == "collective" and not self._stop_seen:
+                # Collectives must match on every rank: a peer that is not inside serve() (it served a
+                # bounded number of epochs) still has to take part in the root's STOP broadcast.
+                import torch
+
+                header = torch.zeros(1 + max(1, self.model.n_theta_words), dtype=torch.float64)
+                self._collective_round(header)
         finally:
             if self._handle is not None:
                 if self.world > 1 and self._dist_ready:

@@ -117,6 +117,47 @@ def _gloo_worker(rank, world, port, out_queue):
     dist.destroy_process_group()
 
 
+def _gloo_phased_worker(rank, world, port, out_queue):
+    """bench.py's structure: peers serve bounded phases, then everybody shuts down."""
+    import torch.distributed as dist
+
+    os.environ["MASTER_ADDR"] = "127.0.0.1"
+    os.environ["MASTER_PORT"] = str(port)
+    dist.init_process_group("gloo", rank=rank, world_size=world)
+    rng = np.random.default_rng(10 + rank)
+    x, y = rng.normal(size=50), rng.normal(size=50)
+    eng = FederatedEngine(LinregShards([x], [y], [0.8], local_ids=[rank], n_shards_total=world), backend="collective")
+    if rank == 0:
+        for _ in range(3):
+            eng.evaluate(np.array(0.3), np.array(-0.2))
+        dist.barrier()
+        for _ in range(2):
+            eng.evaluate(np.array(0.1), np.array(0.2))
+        dist.barrier()
+    else:
+        assert eng.serve(max_epochs=3) == 3
+        dist.barrier()
+        assert eng.serve(max_epochs=2) == 2
+        dist.barrier()
+    eng.shutdown()  # must not dead-lock although the peers are not inside serve()
+    out_queue.put(("done", rank))
+    dist.destroy_process_group()
+
+
+def test_bounded_serve_phases_then_shutdown_do_not_deadlock():
+    ctx = mp.get_context("spawn")
+    q = ctx.Queue()
+    port = _free_port()
+    procs = [ctx.Process(target=_gloo_phased_worker, args=(r, 3, port, q)) for r in range(3)]
+    for p in procs:
+        p.start()
+    done = sorted(q.get(timeout=120)[1] for _ in procs)
+    assert done == [0, 1, 2]
+    for p in procs:
+        p.join(60)
+        assert p.exitcode == 0
+
+
 def test_two_rank_gloo_federation_sums_private_shards():
     ctx = mp.get_context("spawn")
     q = ctx.Queue()
