@@ -43,23 +43,44 @@ def parse_args():
 
 
 class ClockSampler:
-    """nvidia-smi clocks + throttle reasons sampled DURING the timed region."""
+    """SM clock + throttle reasons sampled DURING the timed region.
+
+    NVML is polled from a thread every 5 ms (timed regions can be as short as tens of milliseconds
+    at N = 8); falls back to an ``nvidia-smi -lms`` subprocess when pynvml is unavailable.
+    """
 
     QUERY = (
         "index,clocks.sm,clocks.max.sm,power.draw,clocks_event_reasons.active,"
         "clocks_event_reasons.hw_slowdown,clocks_event_reasons.hw_thermal_slowdown,"
         "clocks_event_reasons.sw_thermal_slowdown,clocks_event_reasons.sw_power_cap"
     )
+    REASON_BITS = {0x4: "sw_power_cap", 0x8: "hw_slowdown", 0x20: "sw_thermal_slowdown", 0x40: "hw_thermal_slowdown"}
 
     def __init__(self, gpu_index: int = 0):
         self.gpu_index = gpu_index
         self.lines = []
         self.proc = None
+        self.samples = []       # (sm_mhz, max_mhz, power_w, reason_mask)
+        self._stop = threading.Event()
+        self._nvml = None
 
     def start(self):
         try:
+            import pynvml
+
+            pynvml.nvmlInit()
+            visible = os.environ.get("CUDA_VISIBLE_DEVICES")
+            phys = int(visible.split(",")[self.gpu_index]) if visible and visible.split(",")[0].isdigit() else self.gpu_index
+            self._handle = pynvml.nvmlDeviceGetHandleByIndex(phys)
+            self._nvml = pynvml
+            self.thread = threading.Thread(target=self._poll, daemon=True)
+            self.thread.start()
+            return self
+        except Exception:
+            self._nvml = None
+        try:
             self.proc = subprocess.Popen(
-                ["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "100",
+                ["nvidia-smi", f"--query-gpu={self.QUERY}", "--format=csv,noheader,nounits", "-lms", "20",
                  "-i", str(self.gpu_index)],
                 stdout=subprocess.PIPE, stderr=subprocess.DEVNULL, text=True,
             )
@@ -69,11 +90,42 @@ class ClockSampler:
             self.proc = None
         return self
 
+    def _poll(self):
+        nv = self._nvml
+        get_reasons = getattr(nv, "nvmlDeviceGetCurrentClocksEventReasons", None) or nv.nvmlDeviceGetCurrentClocksThrottleReasons
+        while not self._stop.is_set():
+            try:
+                sm = nv.nvmlDeviceGetClockInfo(self._handle, nv.NVML_CLOCK_SM)
+                mx = nv.nvmlDeviceGetMaxClockInfo(self._handle, nv.NVML_CLOCK_SM)
+                pw = nv.nvmlDeviceGetPowerUsage(self._handle) / 1000.0
+                self.samples.append((float(sm), float(mx), pw, int(get_reasons(self._handle))))
+            except Exception:
+                pass
+            time.sleep(0.005)
+
     def _pump(self):
         for line in self.proc.stdout:
             self.lines.append(line.strip())
 
     def stop(self):
+        if self._nvml is not None:
+            self._stop.set()
+            self.thread.join(1.0)
+            if not self.samples:
+                return {"sm_mhz": None, "sm_max_mhz": None, "samples": 0, "reasons": ["no NVML samples"]}
+            reasons = set()
+            for _, _, _, mask in self.samples:
+                for bit, name in self.REASON_BITS.items():
+                    if mask & bit:
+                        reasons.add(name)
+            return {
+                "sm_mhz": statistics.median(s[0] for s in self.samples),
+                "sm_max_mhz": max(s[1] for s in self.samples),
+                "power_w_max": max(s[2] for s in self.samples),
+                "samples": len(self.samples),
+                "reasons": sorted(reasons),
+                "source": "nvml",
+            }
         if self.proc is None:
             return {"sm_mhz": None, "sm_max_mhz": None, "reasons": ["nvidia-smi unavailable"]}
         self.proc.terminate()
@@ -102,6 +154,7 @@ class ClockSampler:
             "power_w_max": max(power) if power else None,
             "samples": len(sm),
             "reasons": sorted(reasons),
+            "source": "nvidia-smi",
         }
 
 
