@@ -37,7 +37,7 @@ constexpr int kFlush = 32;           // tiles between TMEM -> fp64 flushes of th
 constexpr int kMaxSegs = 64;
 
 struct SmemLayout {
-    uint32_t stages, stage_bytes, off_theta_b, theta_b_bytes, off_r, r_bytes, off_theta_f, off_segs, off_gi, off_red,
+    uint32_t stages, stage_bytes, off_theta_b, theta_b_bytes, off_r, r_bytes, off_theta_f, off_icpt, off_segs, off_gi, off_red,
         off_bars, off_tmem, total;
 };
 __host__ __device__ inline SmemLayout smem_layout(int P, int n1, int n2, int n_theta, int n_groups, int chains) {
@@ -46,15 +46,19 @@ __host__ __device__ inline SmemLayout smem_layout(int P, int n1, int n2, int n_t
     L.stage_bytes = panels * kPanelBytes;
     L.theta_b_bytes = panels * n1 * 128;
     L.r_bytes = kTileM * n2 * 2;
-    const uint32_t fixed = L.theta_b_bytes + 2 * L.r_bytes + ((n_theta * 4 + 15) & ~15) + kMaxSegs * (uint32_t)sizeof(GlmSegment) +
-                           ((chains * n_groups * 8 + 15) & ~15) + 32 * 8 + 256 + 1024 /*alignment slack*/;
+    // theta (fp32) is staged inside the (not yet used) TMA stage ring and is dead once the bf16 B operand
+    // and the intercept table are built, so it costs no shared memory of its own.
+    const uint32_t fixed = L.theta_b_bytes + 2 * L.r_bytes + ((chains * n_groups * 4 + 15) & ~15) +
+                           kMaxSegs * (uint32_t)sizeof(GlmSegment) + ((chains * n_groups * 8 + 15) & ~15) + 32 * 8 + 256 +
+                           1024 /*alignment slack*/;
     uint32_t stages = (227u * 1024u - fixed) / L.stage_bytes;
     if (stages > 4) stages = 4;
     L.stages = stages;
     uint32_t o = stages * L.stage_bytes;
     L.off_theta_b = o; o += L.theta_b_bytes;
     L.off_r = o; o += 2 * L.r_bytes;
-    L.off_theta_f = o; o += (n_theta * 4 + 15) & ~15;
+    L.off_theta_f = 0;  // aliases stage 0.. (needs n_theta * 4 <= stages * stage_bytes)
+    L.off_icpt = o; o += (chains * n_groups * 4 + 15) & ~15;
     L.off_segs = o; o += kMaxSegs * (uint32_t)sizeof(GlmSegment);
     L.off_gi = o; o += (chains * n_groups * 8 + 15) & ~15;
     L.off_red = o; o += 32 * 8;
@@ -105,7 +109,8 @@ fed_glm_tc_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParams
 
     unsigned char* theta_b = smem + L.off_theta_b;
     unsigned char* r_buf = smem + L.off_r;
-    float* theta_f = reinterpret_cast<float*>(smem + L.off_theta_f);
+    float* theta_f = reinterpret_cast<float*>(smem + L.off_theta_f);  // valid until the setup barrier only
+    float* icpt = reinterpret_cast<float*>(smem + L.off_icpt);        // [KC][G] intercepts
     GlmSegment* segs = reinterpret_cast<GlmSegment*>(smem + L.off_segs);
     double* gi_acc = reinterpret_cast<double*>(smem + L.off_gi);
     double* red = reinterpret_cast<double*>(smem + L.off_red);
@@ -142,7 +147,10 @@ fed_glm_tc_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParams
     if (active) {
         // ---------------- one-time setup ------------------------------------------------------
         for (int i = threadIdx.x; i < prm.n_segments; i += blockDim.x) segs[i] = segs_g[i];
-        for (int i = threadIdx.x; i < KC * G; i += blockDim.x) gi_acc[i] = 0.0;
+        for (int i = threadIdx.x; i < KC * G; i += blockDim.x) {
+            gi_acc[i] = 0.0;
+            icpt[i] = (i / G) < nch ? theta_f[(i / G) * (G + P) + (i % G)] : 0.f;
+        }
         // Theta^T as the K-major, 128B-swizzled B operand of MMA #1: row n = 3*chain + term
         for (int idx = threadIdx.x; idx < panels * N1 * 8; idx += blockDim.x) {
             const int j = idx & 7;              // 16-byte chunk (8 features) within the 128-byte row
@@ -325,7 +333,7 @@ fed_glm_tc_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParams
                     const float eta = (ev[3 * k] + ev[3 * k + 1]) + ev[3 * k + 2];
                     float ll = 0.f, r = 0.f;
                     if (valid && (k0 + k) < nch)
-                        link_loglik(prm.family, y, eta + theta_f[(k0 + k) * (G + P) + seg.group], ll, r);
+                        link_loglik(prm.family, y, eta + icpt[(k0 + k) * G + seg.group], ll, r);
                     ll_acc[k] += ll;
                     gi_cur[k] += r;
                     const __nv_bfloat16 hi = __float2bfloat16_rn(r);
