@@ -111,12 +111,13 @@ class GetLoadParams:
 class GetLoadResult:
     """Result message of a GetLoad query."""
 
-    __slots__ = ("n_clients", "percent_cpu", "percent_ram")
+    __slots__ = ("n_clients", "percent_cpu", "percent_ram", "gpu")
 
     def __init__(self, n_clients: int = 0, percent_cpu: float = 0.0, percent_ram: float = 0.0):
         self.n_clients = n_clients
         self.percent_cpu = percent_cpu
         self.percent_ram = percent_ram
+        self.gpu = None  # optional (SM %, HBM %) — local only, never on the wire
 
     def __bytes__(self) -> bytes:
         return (

@@ -90,13 +90,33 @@ def _run_compute_func(func_input: InputArrays, func: ComputeFunc) -> OutputArray
     )
 
 
+def gpu_load(gpu_index: int) -> Optional[Tuple[float, float]]:
+    """``(SM utilisation %, HBM used %)`` of a GPU via NVML, or ``None`` when NVML is unavailable.
+
+    Kept out of the wire message (the proto has exactly three fields); exposed as
+    ``GetLoadResult.percent_gpu`` / ``.percent_hbm`` attributes on the serving side and in the
+    in-process registry so that custom balancing policies can use them.
+    """
+    try:
+        import pynvml
+
+        pynvml.nvmlInit()
+        h = pynvml.nvmlDeviceGetHandleByIndex(int(gpu_index))
+        util = pynvml.nvmlDeviceGetUtilizationRates(h)
+        mem = pynvml.nvmlDeviceGetMemoryInfo(h)
+        return float(util.gpu), 100.0 * float(mem.used) / float(mem.total)
+    except Exception:  # noqa: BLE001 - no driver / no NVML on CPU boxes
+        return None
+
+
 class ArraysToArraysService(ArraysToArraysServiceBase):
     """Serves a ``ComputeFunc`` over the ``ArraysToArraysService`` gRPC schema."""
 
-    def __init__(self, compute_func: ComputeFunc, *, offload: bool = False) -> None:
+    def __init__(self, compute_func: ComputeFunc, *, offload: bool = False, gpu_index: Optional[int] = None) -> None:
         self._compute_func = compute_func
         self._n_clients = 0
         self._offload = offload
+        self._gpu_index = gpu_index
         # psutil's load average needs one priming call to start monitoring.
         self.determine_load()
         super().__init__()
@@ -104,11 +124,14 @@ class ArraysToArraysService(ArraysToArraysServiceBase):
     def determine_load(self) -> GetLoadResult:
         """Current load: open evaluation streams, CPU % (1-min loadavg), RAM %."""
         load_1, _, _ = psutil.getloadavg()
-        return GetLoadResult(
+        result = GetLoadResult(
             n_clients=self._n_clients,
             percent_cpu=load_1 / psutil.cpu_count() * 100,
             percent_ram=psutil.virtual_memory().percent,
         )
+        if self._gpu_index is not None:
+            result.gpu = gpu_load(self._gpu_index)  # local attribute, not serialised
+        return result
 
     async def _run(self, input_arrays: InputArrays) -> OutputArrays:
         if self._offload:

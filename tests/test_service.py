@@ -58,6 +58,17 @@ def test_determine_load(mock_cpu_count, mock_getloadavg):
     assert 0 < load.percent_ram < 100
 
 
+def test_gpu_load_is_optional_and_never_serialised():
+    svc = service.ArraysToArraysService(product_func, gpu_index=0)
+    load = svc.determine_load()
+    assert load.gpu is None or (0 <= load.gpu[0] <= 100 and 0 <= load.gpu[1] <= 100)
+    with mock.patch.object(service, "gpu_load", return_value=(37.0, 12.5)):
+        load = svc.determine_load()
+    assert load.gpu == (37.0, 12.5)
+    decoded = GetLoadResult.FromString(bytes(load))
+    assert decoded.gpu is None and decoded.n_clients == load.n_clients
+
+
 def test_stream_counts_clients_even_on_errors():
     svc = service.ArraysToArraysService(product_func)
 
