@@ -243,8 +243,18 @@ __device__ __forceinline__ void epilogue(const FedComm& c, const Prologue& pro, 
     // 1) node partial = fixed-order sum over CTAs -> root's slot for this rank (NVLink store for peers)
     double* my_slot = c.root_slots + (size_t)c.rank * nv;
     for (int v = threadIdx.x; v < nv; v += blockDim.x) {
+        // fixed summation order (b = 0, 1, 2, ...) => bit-reproducible; loads are issued 8 at a time
+        // so that the L2 latencies overlap instead of adding up (148 CTAs x ~0.3 us otherwise)
         double s = 0.0;
-        for (unsigned int b = 0; b < gridDim.x; ++b) s += ld_cg_f64(c.cta_partials + (size_t)b * nv + v);
+        unsigned int b = 0;
+        for (; b + 8 <= gridDim.x; b += 8) {
+            double t[8];
+#pragma unroll
+            for (int j = 0; j < 8; ++j) t[j] = ld_cg_f64(c.cta_partials + (size_t)(b + j) * nv + v);
+#pragma unroll
+            for (int j = 0; j < 8; ++j) s += t[j];
+        }
+        for (; b < gridDim.x; ++b) s += ld_cg_f64(c.cta_partials + (size_t)b * nv + v);
         my_slot[v] = s;
     }
     __threadfence_system();

@@ -312,19 +312,22 @@ fed_glm_fp8_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParam
 #pragma unroll
             for (int cidx = 0; cidx < 4; ++cidx) tmem_st_x1(tmem_sfb + lane_addr + cidx, 0x7F7F7F7Fu);
 
-            // writes the scale words of tile `t_it` into ring slot t_it % kSfRing
-            auto write_scales = [&](long long t_it, int& sidx) {
+            // Scale words of a tile: loaded from global memory early (load_scales, results are not
+            // consumed until store_scales) so that the L2/HBM latency never sits on the per-tile chain.
+            auto load_scales = [&](long long t_it, int& sidx, uint32_t (&rows4)[4][4]) {
                 const long long tile = blockIdx.x + t_it * gridDim.x;
                 while (sidx + 1 < prm.n_segments && segs[sidx + 1].first_tile <= tile) ++sidx;
                 const GlmSegment& sg = segs[sidx];
                 // scales: [row_block(32 rows)][feature_block(32)] bytes, padded to whole tiles
                 const uint8_t* sp = reinterpret_cast<const uint8_t*>(sg.scales) + (tile - sg.first_tile) * 4 * NFB;
-                uint32_t rows4[4][4];  // [q][word]: NFB <= 16 bytes per row group
 #pragma unroll
                 for (int q = 0; q < 4; ++q)
 #pragma unroll
                     for (int w = 0; w < 4; ++w)
                         rows4[q][w] = (w * 4 < NFB) ? __ldg(reinterpret_cast<const uint32_t*>(sp + q * NFB + w * 4)) : 0x7F7F7F7Fu;
+            };
+            // writes the scale words of tile `t_it` into ring slot t_it % kSfRing
+            auto store_scales = [&](long long t_it, const uint32_t (&rows4)[4][4]) {
                 uint32_t sfa1[8], sfa2[8];
                 // MMA #1: column 4g + q = scale bytes of (row group q, feature blocks 4g .. 4g+3)
 #pragma unroll
@@ -346,6 +349,11 @@ fed_glm_fp8_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParam
                 tmem_wait_st();
                 tc_fence_before();
                 mbar_arrive(&bar_sf_full[slot]);
+            };
+            auto write_scales = [&](long long t_it, int& sidx) {
+                uint32_t rows4[4][4];
+                load_scales(t_it, sidx, rows4);
+                store_scales(t_it, rows4);
             };
             int sf_sidx = 0;
             if (eg < n_it) write_scales(eg, sf_sidx);
@@ -369,6 +377,8 @@ fed_glm_fp8_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParam
                 const float y = valid ? __ldg(seg.y + grow) : 0.f;
                 const int b = (int)(it & 1);
                 const uint32_t bph = (uint32_t)((it >> 1) & 1);
+                uint32_t next_scales[4][4];
+                if (it + 2 < n_it) load_scales(it + 2, sf_sidx, next_scales);  // consumed at the end of this iteration
 
                 mbar_wait(&bar_eta_full[b], bph);
                 tc_fence_after();
@@ -392,7 +402,7 @@ fed_glm_fp8_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParam
 
                 // scales for this group's next tile (it+2): its ring slot was last used by tile it-2,
                 // whose MMAs are complete (we just passed r_empty of tile it-2 and eta_full of tile it)
-                if (it + 2 < n_it) write_scales(it + 2, sf_sidx);
+                if (it + 2 < n_it) store_scales(it + 2, next_scales);
 
                 // the gradient accumulator of a period is flushed by whichever group owns its last tile
                 const bool last = (it % kFlushF) == kFlushF - 1 || it == n_it - 1;
