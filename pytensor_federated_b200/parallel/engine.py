@@ -126,11 +126,7 @@ class FederatedEngine:
         native.check(lib.b200_engine_reset(self._handle), "engine reset")
         if self.world > 1:
             _dist().barrier(group=self.group)
-        # views of the pinned host blocks (zero-copy packing / unpacking)
-        th_ptr = lib.b200_engine_host_theta(self._handle)
-        self._theta_words = np.ctypeslib.as_array(
-            C.cast(th_ptr, C.POINTER(C.c_uint32)), shape=(max(1, m.n_theta_words),)
-        )
+        # staging buffers handed to the native eval call (which copies into / out of pinned memory)
         self._stage = np.zeros(max(1, m.n_theta_words), dtype=np.uint32)
         self._out = np.zeros(m.n_vals, dtype=np.float64)
         self._stage_p = self._stage.ctypes.data_as(C.c_void_p)

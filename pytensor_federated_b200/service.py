@@ -541,6 +541,8 @@ class ArraysToArraysServiceClient:
     def __del__(self):
         try:
             _id = thread_pid_id(self)
+            for key in [k for k in _connect_locks if k[0] == _id]:
+                _connect_locks.pop(key, None)
             priv = _privates.pop(_id, None)
             if priv is None:
                 return
