@@ -32,17 +32,78 @@ CHANNEL_OPTIONS = (
 )
 
 
-class _ArraysMessage:
-    """Shared implementation of ``InputArrays`` and ``OutputArrays``."""
+def encode_arrays_message(arrays, uuid: str = "") -> bytes:
+    """One Input/OutputArrays message from NumPy arrays — native codec when built, else Python."""
+    import numpy as np
 
-    __slots__ = ("items", "uuid")
+    from .npproto import native_codec
+    from .npproto.utils import ndarray_from_numpy
+
+    arrs = [np.asarray(a) for a in arrays]
+    if native_codec.available() and not any(a.dtype.hasobject for a in arrs):
+        return native_codec.encode_arrays(arrs, uuid)
+    parts = [_pb.enc_len_field(1, bytes(ndarray_from_numpy(a))) for a in arrs]
+    if uuid:
+        parts.append(_pb.enc_len_field(2, uuid.encode("utf-8")))
+    return b"".join(parts)
+
+
+class _ArraysMessage:
+    """Shared implementation of ``InputArrays`` and ``OutputArrays``.
+
+    Public surface as in the reference (``items``, ``uuid``, ``bytes(msg)``, ``parse``).  Internally a
+    message can also carry its wire bytes and/or the decoded NumPy arrays, so that the hot path
+    (``from_arrays`` -> wire -> ``parse`` -> ``arrays``) goes through the native codec
+    (``csrc/codec.cu``) without ever materialising per-item Python message objects.
+    """
+
+    __slots__ = ("_items", "uuid", "_payload", "_arrays")
 
     def __init__(self, items: Optional[Sequence[Ndarray]] = None, uuid: str = "") -> None:
-        self.items: List[Ndarray] = list(items) if items is not None else []
+        self._items: Optional[List[Ndarray]] = list(items) if items is not None else []
         self.uuid = uuid
+        self._payload: Optional[bytes] = None
+        self._arrays = None
+
+    @classmethod
+    def from_arrays(cls, arrays, uuid: str = ""):
+        """Builds the message straight from NumPy arrays (encodes once, natively when possible)."""
+        msg = cls.__new__(cls)
+        msg._items = None
+        msg.uuid = uuid
+        msg._payload = encode_arrays_message(arrays, uuid)
+        msg._arrays = None
+        return msg
+
+    @property
+    def items(self) -> List[Ndarray]:
+        if self._items is None:
+            self._items = []
+            for field, wt, value in _pb.iter_fields(self._payload):
+                if field == 1 and wt == _pb.WIRE_LEN:
+                    self._items.append(Ndarray().parse(value))
+            self._payload = None  # the item list may be mutated from now on
+        return self._items
+
+    @items.setter
+    def items(self, value) -> None:
+        self._items = list(value)
+        self._payload = None
+        self._arrays = None
+
+    @property
+    def arrays(self):
+        """The items as NumPy arrays (zero-copy, read-only views over the wire bytes)."""
+        if self._arrays is None:
+            from .npproto.utils import ndarray_to_numpy
+
+            self._arrays = [ndarray_to_numpy(i) for i in self.items]
+        return self._arrays
 
     def __bytes__(self) -> bytes:
-        parts = [_pb.enc_len_field(1, bytes(item)) for item in self.items]
+        if self._payload is not None:
+            return self._payload
+        parts = [_pb.enc_len_field(1, bytes(item)) for item in self._items]
         if self.uuid:
             parts.append(_pb.enc_len_field(2, self.uuid.encode("utf-8")))
         return b"".join(parts)
@@ -50,13 +111,24 @@ class _ArraysMessage:
     SerializeToString = __bytes__
 
     def parse(self, data):
-        self.items = []
+        from .npproto import native_codec
+
+        self._payload = bytes(data)
+        self._items = None
+        self._arrays = None
         self.uuid = ""
-        for field, wt, value in _pb.iter_fields(data):
-            if field == 1 and wt == _pb.WIRE_LEN:
-                self.items.append(Ndarray().parse(value))
-            elif field == 2 and wt == _pb.WIRE_LEN:
+        if native_codec.available():
+            try:
+                self._arrays, self.uuid = native_codec.decode_arrays(self._payload)
+                return self
+            except TypeError:  # object arrays: Python path below
+                self._arrays = None
+        for field, wt, value in _pb.iter_fields(self._payload):
+            if field == 2 and wt == _pb.WIRE_LEN:
                 self.uuid = bytes(value).decode("utf-8")
+            elif field == 1 and wt == _pb.WIRE_LEN:
+                pass  # items are parsed lazily
+            # other fields: skipped (validated by iter_fields)
         return self
 
     @classmethod

@@ -82,12 +82,8 @@ def _run_compute_func(func_input: InputArrays, func: ComputeFunc) -> OutputArray
 
     Reference: ``service.py:45-72``.
     """
-    inputs = [ndarray_to_numpy(i) for i in func_input.items]
-    outputs = func(*inputs)
-    return OutputArrays(
-        items=[ndarray_from_numpy(np.asarray(o)) for o in outputs],
-        uuid=func_input.uuid,
-    )
+    outputs = func(*func_input.arrays)
+    return OutputArrays.from_arrays([np.asarray(o) for o in outputs], uuid=func_input.uuid)
 
 
 def gpu_load(gpu_index: int) -> Optional[Tuple[float, float]]:
@@ -603,10 +599,7 @@ class ArraysToArraysServiceClient:
                         raise StreamTerminatedError("Local node was unregistered.")
                     return _evaluate_local(priv.local, inputs)
                 if input is None:
-                    input = InputArrays(
-                        items=[ndarray_from_numpy(np.asarray(i)) for i in inputs],
-                        uuid=str(uuid.uuid4()),
-                    )
+                    input = InputArrays.from_arrays([np.asarray(i) for i in inputs], uuid=str(uuid.uuid4()))
                 output = await _connect_evaluate_async(input, cid, hap, use_stream)
                 break
             except StreamTerminatedError as ex:
@@ -620,7 +613,7 @@ class ArraysToArraysServiceClient:
             raise StreamTerminatedError(
                 f"Evaluation failed after {retries + 1} attempt(s): {last_error}"
             )
-        return [ndarray_to_numpy(o) for o in output.items]
+        return list(output.arrays)
 
 
 def _evaluate_local(node: LocalNode, inputs) -> List[np.ndarray]:
