@@ -40,11 +40,12 @@ int b200_glm_tc_prepare(const GlmSegment* segs_host, int n_segments, const GlmPa
 int b200_launch_ode(const FedComm*, const OdeShard*, int, int, cudaStream_t);
 int b200_launch_glm_fp8(const FedComm*, const GlmSegment*, const GlmParams*, const void* tmaps, int grid, cudaStream_t);
 int b200_glm_fp8_prepare(const GlmSegment* segs_host, int n_segments, const GlmParams* prm, void** tmaps_dev);
+int b200_launch_glm_generic(const FedComm*, const GlmSegment*, const GlmParams*, int elem_bytes, int grid, cudaStream_t);
 }
 
 namespace {
 
-enum ModelKind { MODEL_NONE = 0, MODEL_LINREG = 1, MODEL_GLM_SIMT = 2, MODEL_GLM_TC = 3, MODEL_ODE = 4, MODEL_GLM_FP8 = 5 };
+enum ModelKind { MODEL_NONE = 0, MODEL_LINREG = 1, MODEL_GLM_SIMT = 2, MODEL_GLM_TC = 3, MODEL_ODE = 4, MODEL_GLM_FP8 = 5, MODEL_GLM_GENERIC = 6 };
 
 thread_local std::string g_last_error;
 
@@ -104,6 +105,7 @@ struct Engine {
     GlmSegment* glm_segs_dev = nullptr;
     GlmParams glm{};
     void* glm_tmaps_dev = nullptr;
+    int glm_elem_bytes = 2;
     std::vector<OdeShard> ode;
     OdeShard* ode_dev = nullptr;
     std::atomic<int> stop_serving{0};
@@ -167,6 +169,9 @@ int launch_model(Engine* e, const FedComm* c) {
             break;
         case MODEL_GLM_FP8:
             rc = b200_launch_glm_fp8(c, e->glm_segs_dev, &e->glm, e->glm_tmaps_dev, e->grid, e->stream);
+            break;
+        case MODEL_GLM_GENERIC:
+            rc = b200_launch_glm_generic(c, e->glm_segs_dev, &e->glm, e->glm_elem_bytes, e->grid, e->stream);
             break;
         default:
             g_last_error = "no model attached to the engine";
@@ -387,7 +392,7 @@ int b200_engine_set_glm(void* h, int n_segments, const void** X, const float** y
                         int n_chains, int family, int use_tensor_cores) {
     Engine* e = static_cast<Engine*>(h);
     CK(cudaSetDevice(e->device));
-    const int tile_rows = use_tensor_cores ? 128 : 8;
+    const int tile_rows = (use_tensor_cores == 1 || use_tensor_cores == 2) ? 128 : 8;
     e->glm_segs.resize(n_segments);
     long long tiles = 0;
     for (int s = 0; s < n_segments; ++s) {
@@ -405,7 +410,11 @@ int b200_engine_set_glm(void* h, int n_segments, const void** X, const float** y
     if (e->glm_segs_dev) cudaFree(e->glm_segs_dev);
     CK(cudaMalloc((void**)&e->glm_segs_dev, sizeof(GlmSegment) * (n_segments > 0 ? n_segments : 1)));
     CK(cudaMemcpy(e->glm_segs_dev, e->glm_segs.data(), sizeof(GlmSegment) * n_segments, cudaMemcpyHostToDevice));
-    if (use_tensor_cores == 2) {  // block-scaled fp8
+    if (use_tensor_cores == 3 || use_tensor_cores == 4) {  // general-shape fallback
+        e->glm_elem_bytes = use_tensor_cores == 3 ? 2 : 4;
+        e->kind = MODEL_GLM_GENERIC;
+        e->grid = e->sm_count * 2;
+    } else if (use_tensor_cores == 2) {  // block-scaled fp8
         int rc = b200_glm_fp8_prepare(e->glm_segs.data(), n_segments, &e->glm, &e->glm_tmaps_dev);
         if (rc != 0) {
             g_last_error = "fp8 GLM path rejected this shape (rc=" + std::to_string(rc) + ")";

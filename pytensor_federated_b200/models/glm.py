@@ -105,23 +105,39 @@ class GlmShards(ShardModel):
 
     # -- native ----------------------------------------------------------------------------
     def use_tensor_cores(self):
+        """Kernel selector passed to the runtime: 0 = SIMT, 1 = tcgen05 (bf16), 2 = block-scaled fp8,
+        3 / 4 = general-shape fallback (bf16 / fp32 design matrix)."""
+        import torch
+
+        X0 = self.Xs[0]
         if self.kernel == "fp8":
             return 2
         if self.kernel == "tc":
-            return True
+            return 1
         if self.kernel == "simt":
-            return False
-        # auto: the tcgen05 kernel wherever its shape constraints hold (it is faster even for one
-        # chain: TMA streaming + the X tile reused from smem for both GEMMs)
-        import torch
-
-        tc_ok = (
-            self.n_features % 128 == 0 and 128 <= self.n_features <= 384 and self.n_chains <= 16
-            and self.Xs[0].dtype == torch.bfloat16 and len(self.Xs) <= 64
-        )
-        if not tc_ok and self.n_chains > 1:
-            raise ValueError("multi-chain evaluation needs the tensor-core kernel (P % 128 == 0, P <= 384, K <= 16)")
-        return tc_ok
+            return 0
+        generic = 3 if X0.dtype == torch.bfloat16 else (4 if X0.dtype == torch.float32 else None)
+        if self.kernel == "generic":
+            if generic is None:
+                raise ValueError("the general-shape kernel needs a bf16 or fp32 design matrix")
+            return generic
+        # auto: the tcgen05 kernel wherever its shape constraints hold (it is faster even for one chain:
+        # TMA streaming + the X tile reused from smem for both GEMMs), then SIMT, then the general kernel
+        bf16 = X0.dtype == torch.bfloat16
+        tc_ok = (bf16 and self.n_features % 128 == 0 and 128 <= self.n_features <= 384 and self.n_chains <= 16
+                 and len(self.Xs) <= 64 and all(X.data_ptr() % 16 == 0 for X in self.Xs) and self.ld % 8 == 0)
+        if tc_ok:
+            return 1
+        if self.n_chains > 1:
+            raise ValueError("multi-chain evaluation needs the tensor-core kernel (bf16, P % 128 == 0, P <= 384, K <= 16)")
+        simt_ok = (bf16 and self.n_features % 8 == 0 and self.n_features <= 512 and self.ld % 8 == 0
+                   and all(X.data_ptr() % 16 == 0 for X in self.Xs))
+        if simt_ok:
+            return 0
+        if generic is not None and self.n_features <= 1024:
+            return generic
+        raise ValueError(f"no fused GLM kernel for dtype {X0.dtype} with {self.n_features} features; "
+                         "serve this model through ArraysToArraysService instead")
 
     def attach(self, lib, handle) -> None:
         from ..ops import native

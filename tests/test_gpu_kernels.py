@@ -170,6 +170,28 @@ def test_glm_fp8_block_scaled_matches_dequantised_reference(dev, P):
         assert np.array_equal(u, v)
 
 
+@pytest.mark.parametrize("P,dtype", [(37, torch.float32), (200, torch.bfloat16), (700, torch.float32), (1000, torch.bfloat16)])
+def test_glm_general_shape_fallback(dev, P, dtype):
+    """Shapes none of the fast kernels accept (odd P, fp32 X, non-contiguous rows) still run fused."""
+    torch.manual_seed(7)
+    rows = [301, 64, 5]
+    Xs, ys = [], []
+    for n in rows:
+        big = torch.randn(n, P + 3, device=dev).to(dtype)
+        Xs.append(big[:, 1 : 1 + P])            # row stride P + 3, misaligned start
+        ys.append((torch.rand(n, device=dev) < 0.5).float())
+    model = GlmShards(Xs, ys, groups=[0, 1, 0], n_groups=2, family="logistic")
+    assert model.use_tensor_cores() in (3, 4)
+    ic = np.array([0.1, -0.2])
+    beta = (np.random.default_rng(1).normal(size=P) * 0.05).astype(np.float32)
+    with FederatedEngine(model) as eng:
+        logp, d_ic, d_beta = eng.evaluate(ic, beta)
+    w = model.unpack_result(model.reference_partial([ic, beta], dtype=torch.float64))
+    np.testing.assert_allclose(logp, w[0], rtol=2e-5)
+    np.testing.assert_allclose(d_ic, w[1], rtol=1e-4, atol=2e-3)
+    np.testing.assert_allclose(d_beta, w[2], rtol=1e-4, atol=2e-3)
+
+
 def test_glm_simt_is_deterministic(dev):
     X, y, _ = synth_logistic_shard(50_000, 256, seed=5, device=dev)
     model = GlmShards([X], [y], kernel="simt")
