@@ -17,6 +17,14 @@ constexpr int kWarpsG = 8;
 __device__ __forceinline__ float load_elem(const __nv_bfloat16* p) { return __bfloat162float(*p); }
 __device__ __forceinline__ float load_elem(const float* p) { return __ldg(p); }
 
+#ifdef B200FED_CUSTOM_LINK
+// User-supplied likelihood (see models/custom.py): the macro body assigns `ll` (log-likelihood of one
+// observation) and `r` (d ll / d eta) from `y` and `eta`.  Compiled into its own shared object.
+__device__ __forceinline__ void link_loglik_g(int family, float y, float eta, float& ll, float& r) {
+    (void)family;
+    B200FED_CUSTOM_LINK
+}
+#else
 __device__ __forceinline__ void link_loglik_g(int family, float y, float eta, float& ll, float& r) {
     if (family == 0) {
         const float e = __expf(-fabsf(eta));
@@ -35,6 +43,10 @@ __device__ __forceinline__ void link_loglik_g(int family, float y, float eta, fl
         r = d;
     }
 }
+#endif
+#ifndef B200FED_GENERIC_ENTRY
+#define B200FED_GENERIC_ENTRY b200_launch_glm_generic
+#endif
 
 template <typename T, int J>  // J = ceil(P / 32) rounded up to 8 / 16 / 32
 __global__ void __launch_bounds__(kWarpsG * 32, 2)
@@ -139,7 +151,7 @@ int launch_generic(const FedComm* comm, const GlmSegment* segs, const GlmParams*
 }  // namespace
 
 // elem_bytes: 2 = bf16, 4 = fp32
-extern "C" int b200_launch_glm_generic(const FedComm* comm, const GlmSegment* segs_dev, const GlmParams* prm, int elem_bytes,
+extern "C" int B200FED_GENERIC_ENTRY(const FedComm* comm, const GlmSegment* segs_dev, const GlmParams* prm, int elem_bytes,
                                        int grid, cudaStream_t stream) {
     if (prm->n_chains != 1 || prm->n_features < 1 || prm->n_features > 1024) return -1;
     const int j = (prm->n_features + 31) / 32;

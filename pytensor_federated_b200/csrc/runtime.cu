@@ -106,6 +106,8 @@ struct Engine {
     GlmParams glm{};
     void* glm_tmaps_dev = nullptr;
     int glm_elem_bytes = 2;
+    // launcher of a user-compiled likelihood (models/custom.py); null = built-in families
+    int (*custom_launcher)(const FedComm*, const GlmSegment*, const GlmParams*, int, int, cudaStream_t) = nullptr;
     std::vector<OdeShard> ode;
     OdeShard* ode_dev = nullptr;
     std::atomic<int> stop_serving{0};
@@ -171,7 +173,8 @@ int launch_model(Engine* e, const FedComm* c) {
             rc = b200_launch_glm_fp8(c, e->glm_segs_dev, &e->glm, e->glm_tmaps_dev, e->grid, e->stream);
             break;
         case MODEL_GLM_GENERIC:
-            rc = b200_launch_glm_generic(c, e->glm_segs_dev, &e->glm, e->glm_elem_bytes, e->grid, e->stream);
+            rc = (e->custom_launcher ? e->custom_launcher : b200_launch_glm_generic)(c, e->glm_segs_dev, &e->glm,
+                                                                                      e->glm_elem_bytes, e->grid, e->stream);
             break;
         default:
             g_last_error = "no model attached to the engine";
@@ -436,6 +439,12 @@ int b200_engine_set_glm(void* h, int n_segments, const void** X, const float** y
     }
     if ((long long)e->grid > tiles && tiles > 0) e->grid = (int)tiles;
     return 0;
+}
+
+// Installs the launcher of a separately compiled likelihood (same signature as b200_launch_glm_generic).
+void b200_engine_set_custom_launcher(void* h, void* fn) {
+    static_cast<Engine*>(h)->custom_launcher =
+        reinterpret_cast<int (*)(const FedComm*, const GlmSegment*, const GlmParams*, int, int, cudaStream_t)>(fn);
 }
 
 int b200_engine_set_ode(void* h, int n_shards, const float** t, const float** y0, const float** y_obs, const int* n_series,

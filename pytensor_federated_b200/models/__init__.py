@@ -1,11 +1,13 @@
 """Model families with fused sm_100a kernels (and eager PyTorch oracles)."""
 from .base import ShardModel
+from .custom import CustomFamily
 from .glm import Fp8GlmShards, GlmShards, dequantize_block_fp8, quantize_block_fp8, synth_logistic_shard, synth_logistic_shard_fp8
 from .linreg import LinregShards, make_demo_data
 from .ode import OdeShards, synth_lv_shard
 
 __all__ = [
     "ShardModel",
+    "CustomFamily",
     "LinregShards",
     "make_demo_data",
     "GlmShards",

@@ -19,6 +19,10 @@ from .base import ShardModel
 FAMILIES = {"logistic": 0, "poisson": 1, "gaussian": 2}
 
 
+def _family_code(family) -> int:
+    return family.code_id if hasattr(family, "code_id") else FAMILIES[family]
+
+
 class GlmShards(ShardModel):
     """The GLM segments that live on ONE GPU.
 
@@ -110,6 +114,10 @@ class GlmShards(ShardModel):
         import torch
 
         X0 = self.Xs[0]
+        if hasattr(self.family, "code_id"):  # user-compiled likelihood: general-shape kernel
+            if X0.dtype not in (torch.bfloat16, torch.float32) or self.n_chains != 1 or self.n_features > 1024:
+                raise ValueError("custom likelihoods need a bf16/fp32 design matrix, one chain and P <= 1024")
+            return 3 if X0.dtype == torch.bfloat16 else 4
         if self.kernel == "fp8":
             return 2
         if self.kernel == "tc":
@@ -151,10 +159,12 @@ class GlmShards(ShardModel):
         native.check(
             lib.b200_engine_set_glm(
                 handle, n, Xp, yp, sp, rows, grp, self.n_features, self.ld, self.n_groups,
-                self.n_chains, FAMILIES[self.family], int(self.use_tensor_cores()),
+                self.n_chains, _family_code(self.family), int(self.use_tensor_cores()),
             ),
             "set_glm",
         )
+        if hasattr(self.family, "code_id"):
+            lib.b200_engine_set_custom_launcher(handle, C.c_void_p(self.family.launcher_address()))
 
     # -- eager oracle (also the compute step of the NCCL baseline) ---------------------------
     def reference_partial(self, inputs, *, dtype=None) -> np.ndarray:
@@ -171,7 +181,11 @@ class GlmShards(ShardModel):
             B = bt.to(self.device, dtype)                          # [K, P]
             eta = Xf @ B.T + ic[:, g].to(self.device, dtype)        # [n, K]
             yy = y.to(dtype).unsqueeze(1)
-            if self.family == "logistic":
+            if hasattr(self.family, "code_id"):
+                if self.family.torch_fn is None:
+                    raise ValueError("this CustomFamily has no torch_fn oracle")
+                ll, r = self.family.torch_fn(yy, eta)
+            elif self.family == "logistic":
                 ll = yy * eta - torch.nn.functional.softplus(eta)
                 r = yy - torch.sigmoid(eta)
             elif self.family == "poisson":

@@ -4,6 +4,7 @@ import pytest
 import torch
 
 from pytensor_federated_b200.models import (
+    CustomFamily,
     Fp8GlmShards,
     GlmShards,
     LinregShards,
@@ -190,6 +191,26 @@ def test_glm_general_shape_fallback(dev, P, dtype):
     np.testing.assert_allclose(logp, w[0], rtol=2e-5)
     np.testing.assert_allclose(d_ic, w[1], rtol=1e-4, atol=2e-3)
     np.testing.assert_allclose(d_beta, w[2], rtol=1e-4, atol=2e-3)
+
+
+def test_custom_likelihood_runs_inside_the_fused_kernel(dev):
+    """A user-supplied likelihood (Student-t regression), compiled with nvcc at runtime."""
+    family = CustomFamily(
+        "const float d = y - eta; ll = -2.5f * log1pf(d * d * 0.25f); r = 5.f * d / (4.f + d * d);",
+        torch_fn=lambda y, eta: (-2.5 * torch.log1p((y - eta) ** 2 / 4), 5 * (y - eta) / (4 + (y - eta) ** 2)),
+    )
+    torch.manual_seed(11)
+    X = torch.randn(5000, 96, device=dev).to(torch.bfloat16)
+    y = (X.float() @ torch.randn(96, device=dev) * 0.1 + torch.distributions.StudentT(4.0).sample((5000,)).to(dev)).float()
+    model = GlmShards([X[:3000], X[3000:]], [y[:3000], y[3000:]], groups=[0, 1], n_groups=2, family=family)
+    beta = (np.random.default_rng(3).normal(size=96) * 0.05).astype(np.float32)
+    ic = np.array([0.05, -0.1])
+    with FederatedEngine(model) as eng:
+        logp, d_ic, d_beta = eng.evaluate(ic, beta)
+    w = model.unpack_result(model.reference_partial([ic, beta], dtype=torch.float64))
+    np.testing.assert_allclose(logp, w[0], rtol=2e-5)
+    np.testing.assert_allclose(d_ic, w[1], rtol=1e-4, atol=5e-3)
+    np.testing.assert_allclose(d_beta, w[2], rtol=1e-4, atol=5e-3)
 
 
 def test_glm_simt_is_deterministic(dev):
