@@ -7,7 +7,8 @@ dual-averaging step-size adaptation — on top of any ``logp_dlogp(theta) -> (fl
 callable, plus a minimal model builder over the graph IR.  With PyMC installed the Ops plug into
 ``pm.Potential`` exactly as the reference's do.
 """
+from .batched import BatchedResult, glm_batch_fn, hmc_sample_batched
 from .mcmc import SamplerResult, find_map, hmc_sample, nuts_sample
 from .model import Model
 
-__all__ = ["Model", "SamplerResult", "find_map", "hmc_sample", "nuts_sample"]
+__all__ = ["Model", "SamplerResult", "find_map", "hmc_sample", "nuts_sample", "BatchedResult", "hmc_sample_batched", "glm_batch_fn"]

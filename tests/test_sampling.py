@@ -91,3 +91,43 @@ def test_checkpoint_and_resume_continue_the_same_chain(tmp_path):
     second = nuts_sample(target, resume=restored, draws=60)
     # identical random stream + identical adaptation => the resumed half reproduces the uninterrupted run
     np.testing.assert_allclose(np.concatenate([first.samples, second.samples]), full.samples, rtol=0, atol=1e-12)
+
+
+def test_batched_hmc_runs_chains_in_lock_step():
+    from pytensor_federated_b200.sampling import hmc_sample_batched
+
+    mu, sd = np.array([1.0, -2.0, 0.5]), np.array([1.0, 0.2, 3.0])
+    calls = []
+
+    def batch(theta):
+        calls.append(theta.shape)
+        z = (theta - mu) / sd
+        return -0.5 * np.sum(z * z, axis=1), -z / sd
+
+    K = 6
+    res = hmc_sample_batched(batch, np.zeros((K, 3)), draws=600, tune=400, n_leapfrog=12, seed=2)
+    assert res.samples.shape == (600, K, 3) and set(calls) == {(K, 3)}
+    assert res.n_batched_evals == 1 + (600 + 400) * 12          # ONE batched call per leapfrog step, not K
+    pooled = res.samples.reshape(-1, 3)
+    assert np.all(np.abs(pooled.mean(0) - mu) < 4 * sd / np.sqrt(300))
+    np.testing.assert_allclose(pooled.std(0), sd, rtol=0.15)
+    assert np.all(res.rhat() < 1.1) and np.all(res.accept_rate > 0.5)
+
+
+def test_batched_hmc_on_a_multichain_glm_engine():
+    """K chains of a logistic GLM through the collective (CPU) engine: one evaluate per leapfrog."""
+    import torch
+
+    from pytensor_federated_b200.models import GlmShards
+    from pytensor_federated_b200.sampling import glm_batch_fn, hmc_sample_batched
+
+    torch.manual_seed(0)
+    X = torch.randn(400, 4).to(torch.bfloat16)
+    beta_true = np.array([0.8, -0.5, 0.0, 0.3])
+    y = (torch.rand(400) < torch.sigmoid(X.float() @ torch.tensor(beta_true, dtype=torch.float32) + 0.2)).float()
+    K = 4
+    eng = FederatedEngine(GlmShards([X], [y], n_chains=K, kernel="simt"), backend="collective")
+    res = hmc_sample_batched(glm_batch_fn(eng, 1), np.zeros((K, 5)), draws=150, tune=150, n_leapfrog=8, step_size=0.05, seed=1)
+    assert eng.n_evals == res.n_batched_evals
+    post = res.samples.reshape(-1, 5).mean(0)
+    np.testing.assert_allclose(post[1:], beta_true, atol=0.35)
