@@ -101,6 +101,23 @@ def main():
         emit(config=f"hierarchical logistic GLM, 8 groups x {args.fp8_rows} x 256, fp8 block-scaled, 1 GPU", backend="fused",
              evals_per_s=rate, latency_us=lat, hbm_bytes_per_eval=model.bytes_per_eval(),
              hbm_tb_per_s=model.bytes_per_eval() * rate / 1e12)
+    # 5) sampling throughput: lock-step HMC, K chains per fused launch (tcgen05 kernel) vs K = 1
+    from pytensor_federated_b200.models import GlmShards, synth_logistic_shard
+    from pytensor_federated_b200.sampling import glm_batch_fn, hmc_sample_batched
+
+    Xs, ys = [], []
+    for s in range(8):
+        X, yy, _ = synth_logistic_shard(1_000_000, 256, seed=2000 + s, device=dev)
+        Xs.append(X); ys.append(yy)
+    for K in (1, 16):
+        with FederatedEngine(GlmShards(Xs, ys, n_chains=K, kernel="tc"), timeout=60) as eng:
+            t0 = time.perf_counter()
+            res = hmc_sample_batched(glm_batch_fn(eng, 1), np.zeros((K, 257)), draws=20, tune=20, n_leapfrog=8,
+                                     step_size=2e-4, seed=1)
+            dt = time.perf_counter() - t0
+            emit(config="lock-step HMC on logistic GLM 8 x 1M x 256 (bf16), 1 GPU", chains=K, backend="fused",
+                 fused_launches=res.n_batched_evals, leapfrog_steps_per_s=K * res.n_batched_evals / dt,
+                 launches_per_s=res.n_batched_evals / dt, accept_rate=float(res.accept_rate.mean()))
     if args.out:
         with open(args.out, "a") as fh:
             for l in lines:
