@@ -101,7 +101,7 @@ __host__ __device__ inline SmemLayoutF smem_layout(int P, int n_theta, int n_gro
     L.theta_b_bytes = panels * kN * 128;
     L.r_bytes = kTile * kN;  // 1 byte per element
     const uint32_t fixed = L.theta_b_bytes + 2 * L.r_bytes + ((n_theta * 4 + 15) & ~15) + kMaxSegsF * (uint32_t)sizeof(GlmSegment) +
-                           ((n_groups * 8 + 15) & ~15) + 32 * 8 + 512 + 1024;
+                           ((3 * n_groups * 8 + 15) & ~15) + 32 * 8 + 512 + 1024;
     uint32_t stages = (227u * 1024u - fixed) / L.stage_bytes;
     if (stages > 6) stages = 6;
     L.stages = stages;
@@ -110,7 +110,7 @@ __host__ __device__ inline SmemLayoutF smem_layout(int P, int n_theta, int n_gro
     L.off_r = o; o += 2 * L.r_bytes;
     L.off_theta_f = o; o += (n_theta * 4 + 15) & ~15;
     L.off_segs = o; o += kMaxSegsF * (uint32_t)sizeof(GlmSegment);
-    L.off_gi = o; o += (n_groups * 8 + 15) & ~15;
+    L.off_gi = o; o += (3 * n_groups * 8 + 15) & ~15;
     L.off_red = o; o += 32 * 8;
     L.off_bars = o; o += 320;
     L.off_tmem = o; o += 64;
@@ -118,6 +118,7 @@ __host__ __device__ inline SmemLayoutF smem_layout(int P, int n_theta, int n_gro
     return L;
 }
 
+template <int KF>  // chains per launch: 1 or 3 (3 x 5 theta terms and 3 x 4 residual terms fit the 16 MMA columns)
 __global__ void __launch_bounds__(kThreadsF, 1)
 fed_glm_fp8_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParams prm, const CUtensorMap* __restrict__ tmaps) {
     extern __shared__ unsigned char smem_dyn[];
@@ -159,16 +160,25 @@ fed_glm_fp8_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParam
     constexpr uint32_t kTmemCols = 256;
     constexpr float kResidNorm = 1.f / 256.f;  // r = kResidNorm * sum_k t_k 16^-k, |r| <= 1
 
-    double ll_total = 0.0;
-    double g_acc[4] = {0.0, 0.0, 0.0, 0.0};
+    const int nch = prm.n_chains < KF ? prm.n_chains : KF;
+    const int PG = G + P;  // parameters per chain
+    double ll_total[KF];
+    double g_acc[4][KF];
+#pragma unroll
+    for (int k = 0; k < KF; ++k) {
+        ll_total[k] = 0.0;
+#pragma unroll
+        for (int h = 0; h < 4; ++h) g_acc[h][k] = 0.0;
+    }
 
     if (active) {
         for (int i = threadIdx.x; i < prm.n_segments; i += blockDim.x) segs[i] = segs_g[i];
-        for (int i = threadIdx.x; i < G; i += blockDim.x) gi_acc[i] = 0.0;
-        // ---- theta normalisation: power of two c with max|beta| / c in [128, 256)
-        if (warp == 0) {
+        for (int i = threadIdx.x; i < KF * G; i += blockDim.x) gi_acc[i] = 0.0;
+        // ---- theta normalisation per chain: power of two c with max|beta| / c in [128, 256)
+        if (warp < KF) {
             float m = 0.f;
-            for (int f = lane; f < P; f += 32) m = fmaxf(m, fabsf(theta_f[G + f]));
+            if (warp < nch)
+                for (int f = lane; f < P; f += 32) m = fmaxf(m, fabsf(theta_f[warp * PG + G + f]));
             for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
             if (lane == 0) {
                 int e = 0;
@@ -176,24 +186,27 @@ fed_glm_fp8_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParam
                     frexpf(m, &e);      // m = frac * 2^e, frac in [0.5, 1)
                     e -= 8;             // m / 2^(e-8) in [128, 256)
                 }
-                *theta_norm = ldexpf(1.f, e);
+                theta_norm[warp] = ldexpf(1.f, e);
             }
         }
         __syncthreads();
-        const float c_theta = *theta_norm;
-        const float inv_c = 1.f / c_theta;
-        // ---- Theta^T as the K-major, 128B-swizzled e4m3 B operand: row n = term n (n < 5)
+        float c_theta[KF];
+#pragma unroll
+        for (int k = 0; k < KF; ++k) c_theta[k] = theta_norm[k];
+        // ---- Theta^T as the K-major, 128B-swizzled e4m3 B operand: row n = 5 * chain + term
         for (int idx = threadIdx.x; idx < NH * kN * 8; idx += blockDim.x) {
             const int j = idx & 7;                 // 16-byte chunk = 16 features
             const int n = (idx >> 3) % kN;
             const int pnl = idx / (8 * kN);
+            const int chain = n / kThetaTerms, term = n % kThetaTerms;
             uint32_t packed[4] = {0, 0, 0, 0};
-            if (n < kThetaTerms) {
+            if (chain < nch) {
+                const float inv_c = 1.f / theta_norm[chain];
 #pragma unroll
                 for (int e = 0; e < 16; ++e) {
                     uint8_t terms[kThetaTerms];
-                    expand16<kThetaTerms>(theta_f[G + pnl * kPanelF + j * 16 + e] * inv_c, terms);
-                    packed[e >> 2] |= (uint32_t)terms[n] << ((e & 3) * 8);
+                    expand16<kThetaTerms>(theta_f[chain * PG + G + pnl * kPanelF + j * 16 + e] * inv_c, terms);
+                    packed[e >> 2] |= (uint32_t)terms[term] << ((e & 3) * 8);
                 }
             }
             *reinterpret_cast<uint4*>(theta_b + pnl * (kN * 128) + n * 128 + ((j ^ (n & 7)) * 16)) =
@@ -359,7 +372,9 @@ fed_glm_fp8_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParam
             if (eg < n_it) write_scales(eg, sf_sidx);
 
             int s_idx = 0;
-            float ll_acc = 0.f, gi_cur = 0.f;
+            float ll_acc[KF], gi_cur[KF];
+#pragma unroll
+            for (int k = 0; k < KF; ++k) ll_acc[k] = gi_cur[k] = 0.f;
             int cur_group = -1;
             for (long long it = eg; it < n_it; it += 2) {
                 const long long tile = blockIdx.x + it * gridDim.x;
@@ -367,8 +382,11 @@ fed_glm_fp8_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParam
                 const GlmSegment& seg = segs[s_idx];
                 if (seg.group != cur_group) {
                     if (cur_group >= 0) {
-                        atomicAdd(&gi_acc[cur_group], (double)gi_cur);
-                        gi_cur = 0.f;
+#pragma unroll
+                        for (int k = 0; k < KF; ++k) {
+                            atomicAdd(&gi_acc[k * G + cur_group], (double)gi_cur[k]);
+                            gi_cur[k] = 0.f;
+                        }
                     }
                     cur_group = seg.group;
                 }
@@ -386,17 +404,23 @@ fed_glm_fp8_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParam
                 tmem_ld_x16(tmem_eta + lane_addr + b * kN, v);
                 tc_fence_before();
                 mbar_arrive(&bar_eta_empty[b]);
-                const float eta = c_theta * (v[0] + v[1] * (1.f / 16) + v[2] * (1.f / 256) + v[3] * (1.f / 4096) +
-                                             v[4] * (1.f / 65536)) + theta_f[seg.group];
-                float ll = 0.f, r = 0.f;
-                if (valid) link_loglik(0, y, eta, ll, r);
-                ll_acc += ll;
-                gi_cur += r;
-                uint8_t rt[kResidTerms];
-                expand16<kResidTerms>(r * 256.f, rt);
+                uint32_t rwords[4] = {0, 0, 0, 0};  // 16 residual bytes of this row: 4 terms per chain
+#pragma unroll
+                for (int k = 0; k < KF; ++k) {
+                    const float* vk = v + kThetaTerms * k;
+                    const float eta = c_theta[k] * (vk[0] + vk[1] * (1.f / 16) + vk[2] * (1.f / 256) + vk[3] * (1.f / 4096) +
+                                                    vk[4] * (1.f / 65536)) + theta_f[k * PG + seg.group];
+                    float ll = 0.f, r = 0.f;
+                    if (valid && k < nch) link_loglik(0, y, eta, ll, r);
+                    ll_acc[k] += ll;
+                    gi_cur[k] += r;
+                    uint8_t rt[kResidTerms];
+                    expand16<kResidTerms>(r * 256.f, rt);
+                    rwords[k] = (uint32_t)rt[0] | ((uint32_t)rt[1] << 8) | ((uint32_t)rt[2] << 16) | ((uint32_t)rt[3] << 24);
+                }
                 mbar_wait(&bar_r_empty[b], bph ^ 1);
                 *reinterpret_cast<uint4*>(r_buf + b * L.r_bytes + (row >> 3) * 128 + (row & 7) * 16) =
-                    make_uint4((uint32_t)rt[0] | ((uint32_t)rt[1] << 8) | ((uint32_t)rt[2] << 16) | ((uint32_t)rt[3] << 24), 0, 0, 0);
+                    make_uint4(rwords[0], rwords[1], rwords[2], rwords[3]);
                 fence_proxy_async();
                 mbar_arrive(&bar_r_full[b]);
 
@@ -412,19 +436,27 @@ fed_glm_fp8_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParam
                     mbar_wait(&bar_g_full[gb], (uint32_t)((period >> 1) & 1));
                     tc_fence_after();
                     for (int h = 0; h < NH; ++h) {
-                        float gv[4];
-                        tmem_ld_x4(tmem_g + lane_addr + (gb * NH + h) * kN, gv);
-                        g_acc[h] += (double)kResidNorm * ((double)gv[0] + (double)gv[1] * (1.0 / 16) + (double)gv[2] * (1.0 / 256) +
-                                                           (double)gv[3] * (1.0 / 4096));
+                        float gv[16];
+                        tmem_ld_x16(tmem_g + lane_addr + (gb * NH + h) * kN, gv);
+#pragma unroll
+                        for (int k = 0; k < KF; ++k)
+                            g_acc[h][k] += (double)kResidNorm * ((double)gv[4 * k] + (double)gv[4 * k + 1] * (1.0 / 16) +
+                                                                  (double)gv[4 * k + 2] * (1.0 / 256) + (double)gv[4 * k + 3] * (1.0 / 4096));
                     }
                     tc_fence_before();
                     mbar_arrive(&bar_g_empty[gb]);
-                    ll_total += (double)ll_acc;
-                    ll_acc = 0.f;
+#pragma unroll
+                    for (int k = 0; k < KF; ++k) {
+                        ll_total[k] += (double)ll_acc[k];
+                        ll_acc[k] = 0.f;
+                    }
                 }
             }
-            ll_total += (double)ll_acc;
-            if (cur_group >= 0) atomicAdd(&gi_acc[cur_group], (double)gi_cur);
+#pragma unroll
+            for (int k = 0; k < KF; ++k) {
+                ll_total[k] += (double)ll_acc[k];
+                if (cur_group >= 0) atomicAdd(&gi_acc[k * G + cur_group], (double)gi_cur[k]);
+            }
         }
 
         tc_fence_before();
@@ -432,17 +464,24 @@ fed_glm_fp8_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParam
         tc_fence_after();
         if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
         double* out = comm.cta_partials + (size_t)blockIdx.x * comm.n_vals;
-        const double ll_block = fed::block_sum(ll_total, red);
-        if (threadIdx.x == 0) out[0] = ll_block;
-        for (int i = threadIdx.x; i < G; i += blockDim.x) out[1 + i] = gi_acc[i];
-        if (warp >= 2 && warp <= 5) {
-            const int row = (warp & 3) * 32 + lane;
-            for (int h = 0; h < NH; ++h) out[1 + G + h * 128 + row] = g_acc[h];
+#pragma unroll
+        for (int k = 0; k < KF; ++k) {
+            const double ll_block = fed::block_sum(ll_total[k], red);
+            if (threadIdx.x == 0 && k < nch) out[k * (1 + PG)] = ll_block;
         }
-        __syncthreads();
-        if (warp >= 7) {  // group B flushed the periods whose last tile was odd
-            const int row = (warp & 3) * 32 + lane;
-            for (int h = 0; h < NH; ++h) out[1 + G + h * 128 + row] += g_acc[h];
+        for (int i = threadIdx.x; i < nch * G; i += blockDim.x) out[(i / G) * (1 + PG) + 1 + (i % G)] = gi_acc[i];
+        for (int pass = 0; pass < 2; ++pass) {  // group A first, then group B adds its periods
+            if ((pass == 0 && warp >= 2 && warp <= 5) || (pass == 1 && warp >= 7)) {
+                const int row = (warp & 3) * 32 + lane;
+                for (int h = 0; h < NH; ++h)
+#pragma unroll
+                    for (int k = 0; k < KF; ++k)
+                        if (k < nch) {
+                            double* dst = &out[k * (1 + PG) + 1 + G + h * 128 + row];
+                            *dst = pass == 0 ? g_acc[h][k] : *dst + g_acc[h][k];
+                        }
+            }
+            __syncthreads();
         }
     }
     fed::epilogue(comm, pro, 0ull);
@@ -470,7 +509,7 @@ EncodeTiledFn8 get_encode8() {
 extern "C" int b200_glm_fp8_prepare(const GlmSegment* segs_host, int n_segments, const GlmParams* prm, void** tmaps_dev) {
     if (prm->n_features != 128 && prm->n_features != 256) return -21;   // NFB <= 8 scale columns per tile
     if (n_segments > fp8::kMaxSegsF) return -22;
-    if (prm->n_chains != 1 || prm->family != 0) return -23;
+    if (prm->n_chains < 1 || prm->n_chains > 3 || prm->family != 0) return -23;
     if (prm->ld % 16 != 0) return -24;
     EncodeTiledFn8 encode = get_encode8();
     if (!encode) return -25;
@@ -497,8 +536,13 @@ extern "C" int b200_launch_glm_fp8(const FedComm* comm, const GlmSegment* segs_d
                                    int grid, cudaStream_t stream) {
     const fp8::SmemLayoutF L = fp8::smem_layout(prm->n_features, comm->n_theta, prm->n_groups);
     if (L.stages < 2) return -2;
-    cudaFuncSetAttribute(fp8::fed_glm_fp8_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total);
-    fp8::fed_glm_fp8_kernel<<<grid, fp8::kThreadsF, L.total, stream>>>(*comm, segs_dev, *prm,
-                                                                       reinterpret_cast<const CUtensorMap*>(tmaps));
+    const CUtensorMap* maps = reinterpret_cast<const CUtensorMap*>(tmaps);
+    if (prm->n_chains == 1) {
+        cudaFuncSetAttribute(fp8::fed_glm_fp8_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total);
+        fp8::fed_glm_fp8_kernel<1><<<grid, fp8::kThreadsF, L.total, stream>>>(*comm, segs_dev, *prm, maps);
+    } else {
+        cudaFuncSetAttribute(fp8::fed_glm_fp8_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total);
+        fp8::fed_glm_fp8_kernel<3><<<grid, fp8::kThreadsF, L.total, stream>>>(*comm, segs_dev, *prm, maps);
+    }
     return (int)cudaGetLastError();
 }

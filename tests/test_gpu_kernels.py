@@ -171,6 +171,25 @@ def test_glm_fp8_block_scaled_matches_dequantised_reference(dev, P):
         assert np.array_equal(u, v)
 
 
+@pytest.mark.parametrize("K", [2, 3])
+def test_glm_fp8_batches_chains(dev, K):
+    torch.manual_seed(5)
+    rows = [128 * 33 + 9, 700]
+    Xs = [torch.randn(n, 256, device=dev) * torch.exp(0.7 * torch.randn(256, device=dev)) for n in rows]
+    ys = [(torch.rand(n, device=dev) < 0.45).float() for n in rows]
+    model = Fp8GlmShards.from_dense(Xs, ys, groups=[0, 1], n_groups=2, n_chains=K)
+    rng = np.random.default_rng(8)
+    ic = (rng.normal(size=(K, 2)) * 0.2).astype(np.float32)
+    beta = (rng.normal(size=(K, 256)) * np.array([0.02, 0.2, 0.002])[:K, None]).astype(np.float32)  # different scales per chain
+    with FederatedEngine(model) as eng:
+        logp, d_ic, d_beta = eng.evaluate(ic, beta)
+    assert logp.shape == (K,) and d_beta.shape == (K, 256)
+    w = model.unpack_result(model.reference_partial([ic, beta], dtype=torch.float64))
+    np.testing.assert_allclose(logp, w[0], rtol=2e-5)
+    np.testing.assert_allclose(d_ic, w[1], rtol=1e-4, atol=5e-3)
+    np.testing.assert_allclose(d_beta, w[2], rtol=2e-4, atol=2e-4 * np.abs(w[2]).max())
+
+
 @pytest.mark.parametrize("P,dtype", [(37, torch.float32), (200, torch.bfloat16), (700, torch.float32), (1000, torch.bfloat16)])
 def test_glm_general_shape_fallback(dev, P, dtype):
     """Shapes none of the fast kernels accept (odd P, fp32 X, non-contiguous rows) still run fused."""
