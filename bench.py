@@ -194,7 +194,7 @@ def run_b200(args):
     n_groups = 1
     if args.kernel == "fp8":  # hierarchical config: one partial-pooling group (intercept) per shard
         n_groups = args.shards
-        model = Fp8GlmShards(Xs, scs, ys, groups=my_shards, n_groups=n_groups)
+        model = Fp8GlmShards(Xs, scs, ys, groups=my_shards, n_groups=n_groups, n_chains=args.chains)
     else:
         model = GlmShards(Xs, ys, n_groups=1, family="logistic", n_chains=args.chains, kernel=args.kernel)
     eng = FederatedEngine(model, backend=backend, timeout=120.0)
