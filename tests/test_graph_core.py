@@ -1,0 +1,80 @@
+"""The built-in graph IR: autodiff of every primitive vs finite differences, merge, FunctionGraph."""
+import numpy as np
+import pytest
+
+from pytensor_federated_b200.graph import core as G
+
+
+def _fd(f, x, eps=1e-6):
+    x = np.asarray(x, dtype=np.float64)
+    g = np.zeros_like(x)
+    it = np.nditer(x, flags=["multi_index"])
+    for _ in it:
+        d = np.zeros_like(x)
+        d[it.multi_index] = eps
+        g[it.multi_index] = (f(x + d) - f(x - d)) / (2 * eps)
+    return g
+
+
+CASES = {
+    "add-mul-broadcast": lambda v, s: ((v * s + v) * 2.0).sum(),
+    "sub-div": lambda v, s: ((v - s) / (v * v + 1.0)).sum(),
+    "exp-log": lambda v, s: (G.exp(v * 0.3) + G.log(v * v + 1.5) * s).sum(),
+    "sqr-sqrt-pow": lambda v, s: (G.sqrt(v * v + 2.0) + (v ** 2) * s + (v * v + 1.0) ** 1.5).sum(),
+    "sigmoid-softplus": lambda v, s: (G.sigmoid(v) * s + G.softplus(v - s)).sum(),
+    "neg-index-stack": lambda v, s: (-v[0] * v[2] + G.stack([v[1], s, v[0]]).sum() * s),
+    "sum-axis": lambda v, s: ((G.as_tensor(np.ones((2, 3))) * v).sum(axis=0) * v).sum() * s,
+}
+
+
+@pytest.mark.parametrize("name", sorted(CASES))
+def test_gradients_match_finite_differences(name):
+    v, s = G.vector("v"), G.scalar("s")
+    cost = CASES[name](v, s)
+    gv, gs = G.grad(cost, [v, s])
+    fn = G.function([v, s], [cost, gv, gs])
+    v0, s0 = np.array([0.3, -1.2, 2.0]), 0.7
+    c, dv, ds = fn(v0, s0)
+    f_cost = G.function([v, s], cost, mode="FAST_COMPILE")
+    np.testing.assert_allclose(dv, _fd(lambda x: float(f_cost(x, s0)), v0), rtol=1e-5, atol=1e-7)
+    np.testing.assert_allclose(ds, _fd(lambda x: float(f_cost(v0, float(x))), np.array(s0)), rtol=1e-5, atol=1e-7)
+    assert np.isfinite(c)
+
+
+def test_grad_of_unused_input_is_zero_and_disconnected_outputs_are_flagged():
+    a, b = G.scalar("a"), G.scalar("b")
+    g = G.grad(a * a, [a, b])
+    fn = G.function([a, b], g)
+    assert [float(x) for x in fn(3.0, 5.0)] == [6.0, 0.0]
+    with pytest.raises(ValueError):
+        G.grad(a * a, [b], disconnected_inputs="raise")
+    with pytest.raises(TypeError):
+        G.grad(G.vector() * 2.0, [a])  # non-scalar cost
+
+
+def test_merge_pass_deduplicates_and_function_graph_validates_inputs():
+    a = G.scalar("a")
+    e1 = G.exp(a * 2.0)
+    e2 = G.exp(a * 2.0)
+    fn = G.function([a], e1 + e2)
+    ops = [type(n.op).__name__ + ":" + getattr(n.op, "name", "") for n in fn.maker.fgraph.toposort()]
+    assert ops.count("Elemwise:exp") == 1  # merged
+    assert float(fn(0.5)) == pytest.approx(2 * np.exp(1.0))
+    b = G.scalar("b")
+    with pytest.raises(ValueError):
+        G.function([a], a + b)  # b is not an input
+    with pytest.raises(TypeError):
+        fn(np.array([1.0, 2.0]))  # wrong ndim
+    with pytest.raises(TypeError):
+        list(a)  # symbolic variables are not iterable
+
+
+def test_replace_validate_rolls_back_on_failure():
+    a, b = G.scalar("a"), G.scalar("b")
+    out = a * 2.0
+    fg = G.FunctionGraph([a], [out], clone=True)
+    fg.attach_feature(G.ReplaceValidate())
+    before = [n.op for n in fg.toposort()]
+    with pytest.raises(ValueError):
+        fg.replace_all_validate([(fg.outputs[0].owner.inputs[0], b)])  # b is foreign -> invalid graph
+    assert [n.op for n in fg.toposort()] == before
