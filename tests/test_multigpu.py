@@ -141,3 +141,32 @@ def test_dead_peer_raises_timeout_instead_of_hanging():
     results = _run(2, "ipc", "dead-peer")
     root = [r for r in results if r[0] == "root"][0]
     assert root[1] == "timeout" and "did not deliver" in root[2]
+
+
+def _build_linreg(rank, world, dev):
+    from pytensor_federated_b200.models import LinregShards
+
+    x, y = _shard_data(rank, 64)
+    return LinregShards([x], [y], [0.7], local_ids=[rank], n_shards_total=world, device=dev)
+
+
+def test_launch_federation_context_manager_on_gpus():
+    """The user-facing launcher: peers are spawned, the caller is the client, nodes are addressable
+    through NodeFederation and the reference's client API."""
+    import scipy.stats
+
+    if torch.cuda.device_count() < 2:
+        pytest.skip("needs 2 GPUs")
+    from pytensor_federated_b200 import LogpGradServiceClient
+    from pytensor_federated_b200.federation import NodeFederation, launch_federation
+
+    with launch_federation(_build_linreg, 2, timeout=30.0) as eng:
+        assert eng.backend == "fused" and eng.world == 2
+        fed = NodeFederation(eng)
+        addresses = fed.register_services("gpu", 0)
+        client = LogpGradServiceClient(*addresses[1])
+        logp, grads = client.evaluate(np.array(0.3), np.array(-0.2))
+        x, y = _shard_data(1, 64)
+        np.testing.assert_allclose(logp, scipy.stats.norm.logpdf(y, 0.3 - 0.2 * x, 0.7).sum(), rtol=1e-11)
+        del client
+        fed.unregister_services()
