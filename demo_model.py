@@ -54,6 +54,28 @@ def run_model(remote_ops, n: int, tune: int, draws: int):
     return res
 
 
+def run_model_pymc(remote_ops, n: int, tune: int, draws: int):
+    """The same model through PyMC (needs PyMC + PyTensor; the Ops are then genuine PyTensor Ops).
+
+    Mirrors ``/root/reference/demo_model.py:28-44``; not executable in the offline B200 image.
+    """
+    import arviz
+    import pymc as pm
+
+    with pm.Model():
+        intercept_mu = pm.Normal("intercept_mu")
+        intercept = pm.Normal("intercept", intercept_mu, sigma=0.1, size=n)
+        slope = pm.Normal("slope")
+        for i, off in enumerate(np.linspace(-n / 2, n / 2, n)):
+            logp, *_ = remote_ops[i](intercept[i] + off, slope)
+            pm.Potential(f"potential_{i}", var=logp)
+        _log.info("Running MAP estimation")
+        print(pm.find_MAP())
+        idata = pm.sample(tune=tune, draws=draws)
+        print(arviz.summary(idata))
+    return idata
+
+
 def remote_ops_grpc(host: str, ports: Sequence[int], n: int, use_async: bool):
     from pytensor_federated_b200 import AsyncLogpGradOp, LogpGradOp, LogpGradServiceClient
 
@@ -86,12 +108,14 @@ if __name__ == "__main__":
     parser.add_argument("--nodes", default=3, type=int, help="remote calls per model evaluation")
     parser.add_argument("--tune", default=500, type=int)
     parser.add_argument("--draws", default=200, type=int)
+    parser.add_argument("--pymc", action="store_true", help="sample with PyMC instead of the in-repo NUTS")
     args, _ = parser.parse_known_args()
+    runner = run_model_pymc if args.pymc else run_model
     if args.fused:
         ops, handle = remote_ops_fused(args.fused)
-        run_model(ops, args.fused, args.tune, args.draws)
+        runner(ops, args.fused, args.tune, args.draws)
         handle.shutdown()
     else:
         ops, handle = remote_ops_grpc(args.host, [int(p) for p in args.ports.split(",")], args.nodes,
                                       args.parallel.lower() == "true")
-        run_model(ops, args.nodes, args.tune, args.draws)
+        runner(ops, args.nodes, args.tune, args.draws)
