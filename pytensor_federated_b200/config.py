@@ -14,6 +14,7 @@ Environment variables (all optional):
 ``B200FED_CONNECT_SLEEP``   ``"lo,hi"`` seconds of the balanced-connect de-synchronisation pause
 ``B200FED_PROBE_TIMEOUT``   seconds to wait for a ``GetLoad`` answer
 ``B200FED_GRAPH_BACKEND``   ``auto`` | ``builtin`` — graph IR of the Op layer
+``B200FED_NVTX``            set to wrap every evaluation in an NVTX range (host-side tracing)
 """
 from __future__ import annotations
 

@@ -99,6 +99,8 @@ class FederatedEngine:
         self.comm_mode = "none"
         self.n_evals = 0
         self._stop_seen = False
+        # host-side tracing: NVTX range per evaluation (B200FED_NVTX=1); device-side phase stamps: trace()
+        self._nvtx = bool(os.environ.get("B200FED_NVTX")) and self.device.type == "cuda"
         if backend == "fused":
             self._init_fused(comm or cfg.comm, grid)
 
@@ -218,15 +220,23 @@ class FederatedEngine:
             raise FederationError("only rank 0 evaluates; other ranks call serve()")
         with self._lock:
             self.n_evals += 1
-            if self.backend == "fused":
-                self.model.pack_theta(inputs, self._stage)
-                rc = self._lib.b200_engine_eval(
-                    self._handle, self._stage_p, self.model.n_theta_words, self._out_p, self.timeout + 5.0
-                )
-                if rc != 0:
-                    self._raise(rc)
-                return self._out
-            return self._collective_eval(inputs)
+            if self._nvtx:
+                import torch
+
+                torch.cuda.nvtx.range_push(f"fed_eval[{self.n_evals}]")
+            try:
+                if self.backend == "fused":
+                    self.model.pack_theta(inputs, self._stage)
+                    rc = self._lib.b200_engine_eval(
+                        self._handle, self._stage_p, self.model.n_theta_words, self._out_p, self.timeout + 5.0
+                    )
+                    if rc != 0:
+                        self._raise(rc)
+                    return self._out
+                return self._collective_eval(inputs)
+            finally:
+                if self._nvtx:
+                    torch.cuda.nvtx.range_pop()
 
     def evaluate(self, *inputs: np.ndarray) -> List[np.ndarray]:
         """``ComputeFunc`` signature: ``(logp, *gradients)`` as fresh NumPy arrays."""
