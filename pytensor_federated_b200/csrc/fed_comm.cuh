@@ -291,6 +291,15 @@ __device__ __forceinline__ void epilogue(const FedComm& c, const Prologue& pro, 
     }
 }
 
+// Order-independent accumulation for values that many threads add to one shared cell (the
+// per-group intercept gradients): 40.24 fixed point in a 64-bit integer.  Integer addition is
+// associative, so the result does not depend on which thread's atomic lands first — unlike
+// floating-point atomics — and evaluations stay bit-reproducible.  Resolution 6e-8, range +-5e11.
+__device__ __forceinline__ void fix_add(unsigned long long* acc, double v) {
+    atomicAdd(acc, (unsigned long long)__double2ll_rn(v * 16777216.0));
+}
+__device__ __forceinline__ double fix_get(unsigned long long a) { return (double)(long long)a * (1.0 / 16777216.0); }
+
 // block-wide sum of doubles; result valid in thread 0.  `buf` needs >= 32 doubles.
 __device__ __forceinline__ double block_sum(double v, double* buf) {
     for (int o = 16; o > 0; o >>= 1) v += __shfl_xor_sync(0xffffffffu, v, o);

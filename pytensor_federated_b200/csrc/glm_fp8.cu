@@ -135,7 +135,7 @@ fed_glm_fp8_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParam
     unsigned char* r_buf = smem + L.off_r;
     float* theta_f = reinterpret_cast<float*>(smem + L.off_theta_f);
     GlmSegment* segs = reinterpret_cast<GlmSegment*>(smem + L.off_segs);
-    double* gi_acc = reinterpret_cast<double*>(smem + L.off_gi);
+    unsigned long long* gi_acc = reinterpret_cast<unsigned long long*>(smem + L.off_gi);  // fixed point (fed::fix_add)
     double* red = reinterpret_cast<double*>(smem + L.off_red);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.off_bars);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L.off_tmem);
@@ -173,7 +173,7 @@ fed_glm_fp8_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParam
 
     if (active) {
         for (int i = threadIdx.x; i < prm.n_segments; i += blockDim.x) segs[i] = segs_g[i];
-        for (int i = threadIdx.x; i < KF * G; i += blockDim.x) gi_acc[i] = 0.0;
+        for (int i = threadIdx.x; i < KF * G; i += blockDim.x) gi_acc[i] = 0ull;
         // ---- theta normalisation per chain: power of two c with max|beta| / c in [128, 256)
         if (warp < KF) {
             float m = 0.f;
@@ -384,7 +384,7 @@ fed_glm_fp8_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParam
                     if (cur_group >= 0) {
 #pragma unroll
                         for (int k = 0; k < KF; ++k) {
-                            atomicAdd(&gi_acc[k * G + cur_group], (double)gi_cur[k]);
+                            fed::fix_add(&gi_acc[k * G + cur_group], (double)gi_cur[k]);
                             gi_cur[k] = 0.f;
                         }
                     }
@@ -455,7 +455,7 @@ fed_glm_fp8_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParam
 #pragma unroll
             for (int k = 0; k < KF; ++k) {
                 ll_total[k] += (double)ll_acc[k];
-                if (cur_group >= 0) atomicAdd(&gi_acc[k * G + cur_group], (double)gi_cur[k]);
+                if (cur_group >= 0) fed::fix_add(&gi_acc[k * G + cur_group], (double)gi_cur[k]);
             }
         }
 
@@ -469,7 +469,7 @@ fed_glm_fp8_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParam
             const double ll_block = fed::block_sum(ll_total[k], red);
             if (threadIdx.x == 0 && k < nch) out[k * (1 + PG)] = ll_block;
         }
-        for (int i = threadIdx.x; i < nch * G; i += blockDim.x) out[(i / G) * (1 + PG) + 1 + (i % G)] = gi_acc[i];
+        for (int i = threadIdx.x; i < nch * G; i += blockDim.x) out[(i / G) * (1 + PG) + 1 + (i % G)] = fed::fix_get(gi_acc[i]);
         for (int pass = 0; pass < 2; ++pass) {  // group A first, then group B adds its periods
             if ((pass == 0 && warp >= 2 && warp <= 5) || (pass == 1 && warp >= 7)) {
                 const int row = (warp & 3) * 32 + lane;

@@ -56,13 +56,13 @@ fed_glm_generic_kernel(FedComm comm, const GlmSegment* __restrict__ segs, GlmPar
     const int G = prm.n_groups;
     float* theta = reinterpret_cast<float*>(smem_raw);                 // [G + P]
     float* g_red = theta + ((comm.n_theta + 3) & ~3);                  // [kWarpsG][J * 32]
-    double* gi_acc = reinterpret_cast<double*>(g_red + kWarpsG * J * 32);
-    double* red = gi_acc + ((G + 1) & ~1);
+    unsigned long long* gi_acc = reinterpret_cast<unsigned long long*>(g_red + kWarpsG * J * 32);  // fixed point
+    double* red = reinterpret_cast<double*>(gi_acc + ((G + 1) & ~1));
 
     fed::Prologue pro = fed::prologue(comm, theta);
     if (!pro.stop && !pro.timed_out) {
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
-        for (int i = threadIdx.x; i < G; i += blockDim.x) gi_acc[i] = 0.0;
+        for (int i = threadIdx.x; i < G; i += blockDim.x) gi_acc[i] = 0ull;
         __syncthreads();
         float beta[J], g[J];
 #pragma unroll
@@ -86,7 +86,7 @@ fed_glm_generic_kernel(FedComm comm, const GlmSegment* __restrict__ segs, GlmPar
         float icpt = theta[seg.group];
         for (; b < b_end; ++b) {
             while (b >= seg.first_tile + ((seg.n_rows + 7) / 8)) {
-                if (lane == 0) atomicAdd(&gi_acc[seg.group], (double)gi);
+                if (lane == 0) fed::fix_add(&gi_acc[seg.group], (double)gi);
                 gi = 0.f;
                 seg = segs[++s];
                 icpt = theta[seg.group];
@@ -122,13 +122,13 @@ fed_glm_generic_kernel(FedComm comm, const GlmSegment* __restrict__ segs, GlmPar
             }
         }
         ll_total += (double)ll_acc;
-        if (lane == 0 && b_end > gw * T8 / W) atomicAdd(&gi_acc[seg.group], (double)gi);
+        if (lane == 0 && b_end > gw * T8 / W) fed::fix_add(&gi_acc[seg.group], (double)gi);
 #pragma unroll
         for (int j = 0; j < J; ++j) g_red[warp * (J * 32) + lane + 32 * j] = g[j];
         const double ll_block = fed::block_sum(ll_total, red);
         double* out = comm.cta_partials + (size_t)blockIdx.x * comm.n_vals;
         if (threadIdx.x == 0) out[0] = ll_block;
-        for (int i = threadIdx.x; i < G; i += blockDim.x) out[1 + i] = gi_acc[i];
+        for (int i = threadIdx.x; i < G; i += blockDim.x) out[1 + i] = fed::fix_get(gi_acc[i]);
         for (int f = threadIdx.x; f < P; f += blockDim.x) {
             double sum = 0.0;
 #pragma unroll

@@ -65,14 +65,14 @@ fed_glm_simt_kernel(FedComm comm, const GlmSegment* __restrict__ segs, GlmParams
     const int G = prm.n_groups;
     float* theta = reinterpret_cast<float*>(smem_raw);                         // [G + P]
     float* g_red = theta + ((comm.n_theta + 3) & ~3);                          // [kWarps][P]
-    double* gi_acc = reinterpret_cast<double*>(g_red + kWarps * NCH * 256);     // [G]
-    double* red = gi_acc + ((G + 1) & ~1);                                      // [32]
+    unsigned long long* gi_acc = reinterpret_cast<unsigned long long*>(g_red + kWarps * NCH * 256);  // [G] fixed point
+    double* red = reinterpret_cast<double*>(gi_acc + ((G + 1) & ~1));                                      // [32]
 
     fed::Prologue pro = fed::prologue(comm, theta);
     if (!pro.stop && !pro.timed_out) {
         const int lane = threadIdx.x & 31;
         const int warp = threadIdx.x >> 5;
-        for (int i = threadIdx.x; i < G; i += blockDim.x) gi_acc[i] = 0.0;
+        for (int i = threadIdx.x; i < G; i += blockDim.x) gi_acc[i] = 0ull;
         __syncthreads();
 
         // this lane's slice of beta
@@ -111,7 +111,7 @@ fed_glm_simt_kernel(FedComm comm, const GlmSegment* __restrict__ segs, GlmParams
             while (b >= seg.first_tile + ((seg.n_rows + kBatch - 1) / kBatch)) {
                 // segment switch: flush the intercept gradient of the finished group
                 gi = warp_sum(gi);  // every row's r sits in 4 lanes -> x0.25
-                if (lane == 0) atomicAdd(&gi_acc[seg.group], (double)gi * 0.25);
+                if (lane == 0) fed::fix_add(&gi_acc[seg.group], (double)gi * 0.25);
                 gi = 0.f;
                 seg = segs[++s];
                 icpt = theta[seg.group];
@@ -189,7 +189,7 @@ fed_glm_simt_kernel(FedComm comm, const GlmSegment* __restrict__ segs, GlmParams
         }
         ll_total += (double)ll_acc;
         gi = warp_sum(gi);
-        if (lane == 0 && b_end > gw * T / W) atomicAdd(&gi_acc[seg.group], (double)gi * 0.25);
+        if (lane == 0 && b_end > gw * T / W) fed::fix_add(&gi_acc[seg.group], (double)gi * 0.25);
 
         // ---- CTA reduction -> cta_partials[blockIdx.x] = [LL, gi[G], g[P]] ----
 #pragma unroll
@@ -199,7 +199,7 @@ fed_glm_simt_kernel(FedComm comm, const GlmSegment* __restrict__ segs, GlmParams
         const double ll_block = fed::block_sum(ll_total * 0.25, red);  // also syncs
         double* out = comm.cta_partials + (size_t)blockIdx.x * comm.n_vals;
         if (threadIdx.x == 0) out[0] = ll_block;
-        for (int i = threadIdx.x; i < G; i += blockDim.x) out[1 + i] = gi_acc[i];
+        for (int i = threadIdx.x; i < G; i += blockDim.x) out[1 + i] = fed::fix_get(gi_acc[i]);
         for (int f = threadIdx.x; f < P; f += blockDim.x) {
             double sum = 0.0;
 #pragma unroll

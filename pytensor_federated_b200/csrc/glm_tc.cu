@@ -112,7 +112,7 @@ fed_glm_tc_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParams
     float* theta_f = reinterpret_cast<float*>(smem + L.off_theta_f);  // valid until the setup barrier only
     float* icpt = reinterpret_cast<float*>(smem + L.off_icpt);        // [KC][G] intercepts
     GlmSegment* segs = reinterpret_cast<GlmSegment*>(smem + L.off_segs);
-    double* gi_acc = reinterpret_cast<double*>(smem + L.off_gi);
+    unsigned long long* gi_acc = reinterpret_cast<unsigned long long*>(smem + L.off_gi);  // fixed point (fed::fix_add)
     double* red = reinterpret_cast<double*>(smem + L.off_red);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.off_bars);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L.off_tmem);
@@ -148,7 +148,7 @@ fed_glm_tc_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParams
         // ---------------- one-time setup ------------------------------------------------------
         for (int i = threadIdx.x; i < prm.n_segments; i += blockDim.x) segs[i] = segs_g[i];
         for (int i = threadIdx.x; i < KC * G; i += blockDim.x) {
-            gi_acc[i] = 0.0;
+            gi_acc[i] = 0ull;
             icpt[i] = (i / G) < nch ? theta_f[(i / G) * (G + P) + (i % G)] : 0.f;
         }
         // Theta^T as the K-major, 128B-swizzled B operand of MMA #1: row n = 3*chain + term
@@ -302,7 +302,7 @@ fed_glm_tc_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParams
                     if (cur_group >= 0) {
 #pragma unroll
                         for (int k = 0; k < KH; ++k) {
-                            atomicAdd(&gi_acc[(k0 + k) * G + cur_group], (double)gi_cur[k]);
+                            fed::fix_add(&gi_acc[(k0 + k) * G + cur_group], (double)gi_cur[k]);
                             gi_cur[k] = 0.f;
                         }
                     }
@@ -387,7 +387,7 @@ fed_glm_tc_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParams
             for (int k = 0; k < KH; ++k) ll_total[k] += (double)ll_acc[k];  // rows since this group's last flush
             if (cur_group >= 0) {
 #pragma unroll
-                for (int k = 0; k < KH; ++k) atomicAdd(&gi_acc[(k0 + k) * G + cur_group], (double)gi_cur[k]);
+                for (int k = 0; k < KH; ++k) fed::fix_add(&gi_acc[(k0 + k) * G + cur_group], (double)gi_cur[k]);
             }
         }
 
@@ -411,7 +411,7 @@ fed_glm_tc_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParams
             const double ll_block = fed::block_sum(mine, red);
             if (threadIdx.x == 0 && k < nch) out[k * (1 + G + P)] = ll_block;
         }
-        for (int i = threadIdx.x; i < nch * G; i += blockDim.x) out[(i / G) * (1 + G + P) + 1 + (i % G)] = gi_acc[i];
+        for (int i = threadIdx.x; i < nch * G; i += blockDim.x) out[(i / G) * (1 + G + P) + 1 + (i % G)] = fed::fix_get(gi_acc[i]);
         // gradient: the two tile-parity groups of a chain each flushed part of the periods
         for (int pass = 0; pass < EGT; ++pass) {
             if (is_epi && my_tp == pass) {

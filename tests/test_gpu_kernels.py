@@ -232,6 +232,26 @@ def test_custom_likelihood_runs_inside_the_fused_kernel(dev):
     np.testing.assert_allclose(d_beta, w[2], rtol=1e-4, atol=5e-3)
 
 
+@pytest.mark.parametrize("kernel", ["tc", "simt", "fp8", "generic"])
+def test_glm_kernels_are_bit_reproducible_with_many_groups(dev, kernel):
+    """Fixed-order reductions + fixed-point intercept accumulation: 10 repeats, identical bits."""
+    torch.manual_seed(13)
+    rows = [40_000, 25_000, 33_333, 128, 19_999]
+    Xs = [torch.randn(n, 256, device=dev) for n in rows]
+    ys = [(torch.rand(n, device=dev) < 0.5).float() for n in rows]
+    if kernel == "fp8":
+        model = Fp8GlmShards.from_dense(Xs, ys, groups=[0, 1, 2, 1, 0], n_groups=3)
+    else:
+        model = GlmShards([X.to(torch.bfloat16) for X in Xs], ys, groups=[0, 1, 2, 1, 0], n_groups=3, kernel=kernel)
+    ic = np.array([0.3, -0.2, 0.1])
+    beta = (np.random.default_rng(1).normal(size=256) * 0.03).astype(np.float32)
+    with FederatedEngine(model) as eng:
+        first = [v.copy() for v in eng.evaluate(ic, beta)]
+        for _ in range(9):
+            for u, v in zip(first, eng.evaluate(ic, beta)):
+                assert np.array_equal(u, v)
+
+
 def test_glm_simt_is_deterministic(dev):
     X, y, _ = synth_logistic_shard(50_000, 256, seed=5, device=dev)
     model = GlmShards([X], [y], kernel="simt")
