@@ -65,6 +65,17 @@ struct FedComm {
     unsigned long long* epoch_counter;             // peers: device-resident epoch (graph replay friendly); may be null
     unsigned long long* done_flag;                 // host-mapped: last finished epoch on this node (peers' serve loop)
     unsigned long long* trace;                     // optional device-timer ring [4 x u64 per epoch % 256] or null
+
+    // --- low-latency ("LL") mode for small results: flag-in-data words, no fences, no flag writes ----
+    // Every 8-byte word carries 32 bits of payload and the low 32 bits of the epoch as its tag, so a
+    // reader that sees the right tag has the data (8-byte accesses are single transactions on NVLink
+    // and PCIe).  theta: one word per 32-bit theta word; results: two words per double.
+    int ll_mode;
+    unsigned long long* ll_theta_local;                  // own theta mailbox      [n_theta]
+    unsigned long long* ll_peer_theta[B200FED_MAX_WORLD]; // root: every node's     [n_theta]
+    unsigned long long* ll_mc_theta;                     // root: multicast alias or null
+    unsigned long long* ll_root_slots;                   // root's slot array      [world][n_vals][2]
+    unsigned long long* ll_host_result;                  // host-mapped            [n_vals][2]
 };
 
 namespace fed {
@@ -103,6 +114,42 @@ __device__ __forceinline__ void multimem_st_f32(float* mc, float v) {
 }
 __device__ __forceinline__ void multimem_st_release_u64(unsigned long long* mc, unsigned long long v) {
     asm volatile("multimem.st.release.sys.global.u64 [%0], %1;" ::"l"(mc), "l"(v) : "memory");
+}
+
+__device__ __forceinline__ void multimem_st_relaxed_u64(unsigned long long* mc, unsigned long long v) {
+    asm volatile("multimem.st.relaxed.sys.global.u64 [%0], %1;" ::"l"(mc), "l"(v) : "memory");
+}
+__device__ __forceinline__ void st_relaxed_sys(unsigned long long* p, unsigned long long v) {
+    asm volatile("st.relaxed.sys.global.u64 [%0], %1;" ::"l"(p), "l"(v) : "memory");
+}
+__device__ __forceinline__ unsigned long long ll_pack(unsigned int payload, unsigned long long epoch) {
+    return (unsigned long long)payload | ((epoch & 0xFFFFFFFFull) << 32);
+}
+// Stores a double as two tagged words.
+__device__ __forceinline__ void ll_store_f64(unsigned long long* dst, double v, unsigned long long epoch) {
+    const unsigned long long bits = (unsigned long long)__double_as_longlong(v);
+    st_relaxed_sys(dst, ll_pack((unsigned int)bits, epoch));
+    st_relaxed_sys(dst + 1, ll_pack((unsigned int)(bits >> 32), epoch));
+}
+// Polls one tagged word.  0 = ok, 1 = timeout, 2 = STOP seen on the (legacy) flag.
+__device__ __forceinline__ int ll_wait_word(const unsigned long long* src, unsigned long long epoch, unsigned long long timeout_ns,
+                                            const unsigned long long* stop_flag, unsigned int* payload) {
+    const unsigned long long want = epoch & 0xFFFFFFFFull;
+    unsigned long long t0 = 0;
+    unsigned int spins = 0;
+    while (true) {
+        const unsigned long long w = ld_relaxed_sys(src);
+        if ((w >> 32) == want) {
+            *payload = (unsigned int)w;
+            return 0;
+        }
+        if ((++spins & 0x3F) == 0) {
+            if (t0 == 0) t0 = globaltimer();
+            if (stop_flag && (ld_acquire_sys(stop_flag) & B200FED_EPOCH_MASK) == B200FED_STOP_EPOCH) return 2;
+            if (timeout_ns && globaltimer() - t0 > timeout_ns) return 1;
+            __nanosleep(32);
+        }
+    }
 }
 
 // Spin until *flag (epoch part) >= epoch.  Returns false on timeout.
@@ -152,6 +199,37 @@ __device__ __forceinline__ Prologue prologue(const FedComm& c, float* theta_smem
         r0.timed_out = false;
         return r0;
     }
+    if (c.ll_mode) {
+        // LL broadcast: tagged theta words, no fence, no flag.  Every thread polls the words it needs.
+        if (c.rank == 0 && blockIdx.x == 0) {
+            for (int i = threadIdx.x; i < c.n_theta; i += blockDim.x) {
+                const unsigned long long w = ll_pack(__float_as_uint(c.theta_src[i]), epoch);
+                if (c.ll_mc_theta) {
+                    multimem_st_relaxed_u64(c.ll_mc_theta + i, w);
+                } else {
+                    for (int p = 0; p < c.world; ++p) st_relaxed_sys(c.ll_peer_theta[p] + i, w);
+                }
+            }
+            if (threadIdx.x == 0 && c.trace) c.trace[(epoch & 255) * 4 + 0] = globaltimer();
+        }
+        if (threadIdx.x == 0) s_ok = 0;
+        __syncthreads();
+        int bad = 0;
+        for (int i = threadIdx.x; i < c.n_theta; i += blockDim.x) {
+            unsigned int payload = 0;
+            const int rc = ll_wait_word(c.ll_theta_local + i, epoch, c.timeout_ns, c.flag_local, &payload);
+            if (rc) bad |= rc;
+            theta_smem[i] = __uint_as_float(payload);
+        }
+        if (bad) atomicOr(&s_ok, bad);
+        __syncthreads();
+        Prologue rl;
+        rl.epoch = epoch;
+        rl.timed_out = (s_ok & 1) != 0;
+        rl.stop = (s_ok & 2) != 0;
+        __syncthreads();
+        return rl;
+    }
     if (c.rank == 0 && blockIdx.x == 0) {
         // theta_src may live in host memory: read it once, fan it out over NVLink.
         for (int i = threadIdx.x; i < c.n_theta; i += blockDim.x) {
@@ -197,6 +275,20 @@ __device__ __forceinline__ void epilogue(const FedComm& c, const Prologue& pro, 
     if (c.world == 1 && gridDim.x == 1) {
         // latency path: the only CTA's partial IS the result
         __syncthreads();
+        if (c.ll_mode) {
+            // tagged words straight to host-mapped memory: no fence, no flag
+            for (int v = threadIdx.x; v < c.n_vals; v += blockDim.x)
+                ll_store_f64(c.ll_host_result + 2 * v, c.cta_partials[v], pro.epoch);
+            if (threadIdx.x == 0) {
+                if (c.trace) {
+                    c.trace[(pro.epoch & 255) * 4 + 1] = globaltimer();
+                    c.trace[(pro.epoch & 255) * 4 + 2] = globaltimer();
+                }
+                if (c.epoch_counter) *c.epoch_counter = pro.epoch;
+                if (c.done_flag) *reinterpret_cast<volatile unsigned long long*>(c.done_flag) = pro.epoch;
+            }
+            return;
+        }
         for (int v = threadIdx.x; v < c.n_vals; v += blockDim.x) c.host_result[v] = c.cta_partials[v];
         __threadfence_system();
         __syncthreads();
@@ -236,6 +328,55 @@ __device__ __forceinline__ void epilogue(const FedComm& c, const Prologue& pro, 
                 __threadfence_system();
                 st_release_sys(c.host_flag, word);
             }
+        }
+        return;
+    }
+
+    if (c.ll_mode) {
+        // LL reduce: each node's last CTA stores tagged words into the root's slot array (NVLink, no
+        // fence, no flag); the root's last CTA polls the words of every node in rank order, sums, and
+        // stores tagged words into host-mapped memory.  Same fixed summation order as below.
+        unsigned long long* my_slot_ll = c.ll_root_slots + (size_t)c.rank * nv * 2;
+        for (int v = threadIdx.x; v < nv; v += blockDim.x) {
+            double s = 0.0;
+            unsigned int b = 0;
+            for (; b + 8 <= gridDim.x; b += 8) {
+                double t[8];
+#pragma unroll
+                for (int j = 0; j < 8; ++j) t[j] = ld_cg_f64(c.cta_partials + (size_t)(b + j) * nv + v);
+#pragma unroll
+                for (int j = 0; j < 8; ++j) s += t[j];
+            }
+            for (; b < gridDim.x; ++b) s += ld_cg_f64(c.cta_partials + (size_t)b * nv + v);
+            if (c.rank != 0) {
+                ll_store_f64(my_slot_ll + 2 * v, s, epoch);
+            } else {
+                double total = s;  // rank 0 first, then the peers in rank order
+                bool ok = true;
+                for (int p = 1; p < c.world && ok; ++p) {
+                    unsigned int lo = 0, hi = 0;
+                    const unsigned long long* src = c.ll_root_slots + ((size_t)p * nv + v) * 2;
+                    ok = ll_wait_word(src, epoch, c.timeout_ns, nullptr, &lo) == 0 &&
+                         ll_wait_word(src + 1, epoch, c.timeout_ns, nullptr, &hi) == 0;
+                    total += __longlong_as_double((long long)(((unsigned long long)hi << 32) | lo));
+                }
+                if (ok) ll_store_f64(c.ll_host_result + 2 * v, total, epoch);
+                else atomicOr(&s_status, B200FED_ERR_PEER_TIMEOUT);
+            }
+        }
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            if (c.trace) {
+                c.trace[(epoch & 255) * 4 + 1] = globaltimer();
+                if (c.rank == 0) c.trace[(epoch & 255) * 4 + 2] = globaltimer();
+            }
+            if (c.rank == 0 && s_status) {  // errors travel on the legacy flag (the tagged words stay incomplete)
+                __threadfence_system();
+                st_release_sys(c.host_flag, epoch | (s_status << B200FED_STATUS_SHIFT));
+            }
+            *c.ticket = 0;
+            if (c.epoch_counter) *c.epoch_counter = epoch;
+            if (c.done_flag) *reinterpret_cast<volatile unsigned long long*>(c.done_flag) = epoch | (s_status << B200FED_STATUS_SHIFT);
         }
         return;
     }

@@ -60,7 +60,7 @@ int fail(const char* what, cudaError_t err) {
     } while (0)
 
 struct CommLayout {
-    size_t off_flag, off_theta, off_slots, off_slot_flags, bytes;
+    size_t off_flag, off_theta, off_slots, off_slot_flags, off_ll_theta, off_ll_slots, bytes;
 };
 CommLayout comm_layout(int world, int n_theta, int n_vals) {
     CommLayout L;
@@ -69,7 +69,10 @@ CommLayout comm_layout(int world, int n_theta, int n_vals) {
     L.off_theta = 256;
     L.off_slots = up(L.off_theta + (size_t)n_theta * 4);
     L.off_slot_flags = up(L.off_slots + (size_t)world * n_vals * 8);
-    L.bytes = up(L.off_slot_flags + (size_t)world * 8);
+    // low-latency mode (flag-in-data): 8 bytes per theta word, 16 bytes per result value
+    L.off_ll_theta = up(L.off_slot_flags + (size_t)world * 8);
+    L.off_ll_slots = up(L.off_ll_theta + (size_t)n_theta * 8);
+    L.bytes = up(L.off_ll_slots + (size_t)world * n_vals * 16);
     return L;
 }
 
@@ -85,7 +88,8 @@ struct Engine {
     // host-mapped
     unsigned char* host_block = nullptr;      // [theta | result | flag | done | trace]
     unsigned char* host_block_dev = nullptr;  // device alias
-    size_t h_off_theta = 0, h_off_result = 0, h_off_flag = 0, h_off_done = 0;
+    size_t h_off_theta = 0, h_off_result = 0, h_off_flag = 0, h_off_done = 0, h_off_ll = 0;
+    bool ll_mode = false;  // small results: tagged words instead of fences + flags (fed_comm.cuh)
     // device-local
     double* cta_partials = nullptr;
     unsigned int* ticket = nullptr;
@@ -135,6 +139,15 @@ void fill_comm(Engine* e, FedComm* c, bool root_uses_explicit_epoch) {
     c->ticket = e->ticket;
     c->trace = e->trace;
     c->done_flag = reinterpret_cast<unsigned long long*>(e->host_block_dev + e->h_off_done);
+    c->ll_mode = e->ll_mode ? 1 : 0;
+    c->ll_theta_local = reinterpret_cast<unsigned long long*>(e->comm_local + L.off_ll_theta);
+    c->ll_root_slots = reinterpret_cast<unsigned long long*>(root_block + L.off_ll_slots);
+    if (e->rank == 0) {
+        for (int p = 0; p < e->world; ++p)
+            c->ll_peer_theta[p] = reinterpret_cast<unsigned long long*>(e->comm_peer[p] + L.off_ll_theta);
+        if (e->comm_mc) c->ll_mc_theta = reinterpret_cast<unsigned long long*>(e->comm_mc + L.off_ll_theta);
+        c->ll_host_result = reinterpret_cast<unsigned long long*>(e->host_block_dev + e->h_off_ll);
+    }
     if (e->rank == 0) {
         c->theta_src = e->theta_from_device ? e->theta_dev
                                             : reinterpret_cast<const float*>(e->host_block_dev + e->h_off_theta);
@@ -286,7 +299,10 @@ void* b200_engine_create(int device, int rank, int world, int n_theta, int n_val
     e->h_off_result = up((size_t)n_theta * 4);
     e->h_off_flag = up(e->h_off_result + (size_t)n_vals * 8);
     e->h_off_done = e->h_off_flag + 256;
-    const size_t hbytes = e->h_off_done + 256;
+    e->h_off_ll = e->h_off_done + 256;
+    const size_t hbytes = e->h_off_ll + up((size_t)n_vals * 16);
+    // LL mode for small messages (latency-bound models); B200FED_NO_LL=1 forces the fence+flag protocol
+    e->ll_mode = n_vals <= 128 && n_theta <= 256 && !getenv("B200FED_NO_LL");
     ok = ok && cudaHostAlloc((void**)&e->host_block, hbytes, cudaHostAllocMapped | cudaHostAllocPortable) == cudaSuccess;
     if (ok) memset(e->host_block, 0, hbytes);
     ok = ok && cudaHostGetDevicePointer((void**)&e->host_block_dev, e->host_block, 0) == cudaSuccess;
@@ -346,6 +362,9 @@ int b200_engine_reset(void* h) {
                                               reinterpret_cast<unsigned long long*>(e->comm_local + L.off_slot_flags),
                                               e->world, e->ticket, e->epoch_counter);
     CK(cudaStreamSynchronize(e->stream));
+    CK(cudaMemset(e->comm_local + L.off_ll_theta, 0, L.bytes - L.off_ll_theta));
+    CK(cudaDeviceSynchronize());
+    memset(e->host_block + e->h_off_ll, 0, (size_t)e->n_vals * 16);
     e->epoch = 0;
     *e->h_flag() = 0;
     *e->h_done() = 0;
@@ -498,6 +517,37 @@ int b200_engine_wait(void* h, unsigned long long epoch, double* out, double time
     const auto t0 = std::chrono::steady_clock::now();
     unsigned long long v;
     unsigned spins = 0;
+    if (e->ll_mode) {
+        // flag-in-data: the result is complete when every word carries this epoch's tag; errors (and
+        // STOP / theta timeouts) still arrive on the legacy flag
+        volatile unsigned long long* words = reinterpret_cast<volatile unsigned long long*>(e->host_block + e->h_off_ll);
+        const unsigned long long want = epoch & 0xFFFFFFFFull;
+        const int n_words = e->n_vals * 2;
+        int next = 0;
+        while (true) {
+            while (next < n_words && (words[next] >> 32) == want) ++next;
+            if (next == n_words) break;
+            v = *flag;
+            if ((v & B200FED_EPOCH_MASK) >= epoch && (v >> B200FED_STATUS_SHIFT) != 0) return (int)(v >> B200FED_STATUS_SHIFT);
+            if ((++spins & 0xFFF) == 0) {
+                const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+                if (dt > timeout_s) {
+                    cudaError_t err = cudaStreamQuery(e->stream);
+                    g_last_error = std::string("timed out waiting for the tagged result words; stream state: ") +
+                                   cudaGetErrorString(err);
+                    return -5;
+                }
+            }
+        }
+        std::atomic_thread_fence(std::memory_order_acquire);
+        if (out) {
+            for (int i = 0; i < e->n_vals; ++i) {
+                const unsigned long long bits = (words[2 * i] & 0xFFFFFFFFull) | ((words[2 * i + 1] & 0xFFFFFFFFull) << 32);
+                memcpy(out + i, &bits, 8);
+            }
+        }
+        return 0;
+    }
     while (true) {
         v = *flag;
         if ((v & B200FED_EPOCH_MASK) >= epoch) break;
