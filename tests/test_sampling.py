@@ -131,3 +131,42 @@ def test_batched_hmc_on_a_multichain_glm_engine():
     assert eng.n_evals == res.n_batched_evals
     post = res.samples.reshape(-1, 5).mean(0)
     np.testing.assert_allclose(post[1:], beta_true, atol=0.35)
+
+
+def test_hierarchical_glm_with_vector_inputs_through_logp_grad_op():
+    """Partial pooling over shard intercepts: vector-valued Op inputs/gradients through the graph IR."""
+    import torch
+
+    from pytensor_federated_b200.models import GlmShards
+
+    torch.manual_seed(2)
+    true_ic = np.array([-0.6, 0.1, 0.8])
+    beta_true = np.array([0.7, -0.4])
+    Xs, ys = [], []
+    for g in range(3):
+        X = torch.randn(600, 2)
+        p = torch.sigmoid(X @ torch.tensor(beta_true, dtype=torch.float32) + true_ic[g])
+        Xs.append(X.to(torch.bfloat16))
+        ys.append((torch.rand(600) < p).float())
+    eng = FederatedEngine(GlmShards(Xs, ys, groups=[0, 1, 2], n_groups=3, kernel="simt"), backend="collective")
+    op = LogpGradOp(eng.logp_grad)
+    m = Model()
+    mu = m.Normal("mu", 0.0, 1.0)
+    ic = m.Normal("intercept", mu, 0.7, size=3)
+    beta = m.Normal("beta", 0.0, 1.0, size=2)
+    logp, *_ = op(ic, beta)
+    m.Potential("likelihood", logp)
+    theta0 = np.zeros(m.dim)
+    lp, g = m.logp_dlogp(theta0)
+    eps = 1e-3  # theta is float32 in the engine's mailbox -> coarse finite differences
+    for i in range(m.dim):
+        d = np.zeros(m.dim)
+        d[i] = eps
+        fd = (m.logp_dlogp(theta0 + d)[0] - m.logp_dlogp(theta0 - d)[0]) / (2 * eps)
+        np.testing.assert_allclose(g[i], fd, rtol=2e-2, atol=0.5)
+    theta_map, info = find_map(m.logp_dlogp, theta0)
+    point = m.point(theta_map)
+    np.testing.assert_allclose(point["beta"], beta_true, atol=0.25)
+    assert np.all(np.diff(point["intercept"]) > 0)  # ordering of the group intercepts is recovered
+    res = nuts_sample(m.logp_dlogp, theta_map, draws=80, tune=80, seed=3)
+    assert res.divergences == 0 and res.accept_rate > 0.6
