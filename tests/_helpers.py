@@ -99,3 +99,20 @@ class ProductTester:
 
     def run(self, n: int) -> bool:
         return run_product_queries(self.client, n)
+
+
+def fork_pool_scenario(port: int) -> None:
+    """Runs in a FRESH interpreter (see test_client_multiprocessing): a picklable client is handed to
+    fork()-ed pool workers before gRPC was ever initialised in the parent."""
+    import multiprocessing
+
+    from pytensor_federated_b200 import service
+
+    ctx = multiprocessing.get_context("fork")
+    client = service.ArraysToArraysServiceClient("127.0.0.1", port)
+    tester = ProductTester(client)
+    with ctx.Pool(processes=3) as pool:
+        assert all(pool.map(run_product_queries, [client] * 4))
+    with ctx.Pool(processes=3) as pool:
+        assert all(pool.map(tester.run, [25] * 4))
+    print("FORK-OK", flush=True)

@@ -163,8 +163,23 @@ def test_load_probes_and_balancing():
 def test_client_multiprocessing(eval_on_main, mp_start_method):
     if mp_start_method == "fork" and eval_on_main:
         pytest.skip("grpc's C core does not survive fork() once initialised in the parent; use spawn")
-    ctx = multiprocessing.get_context(mp_start_method)
     with ServerProcess() as server:
+        if mp_start_method == "fork":
+            # fork() is only safe while gRPC has never been initialised in the parent, which cannot be
+            # guaranteed inside a long pytest session -> run the scenario in a fresh interpreter
+            import os
+            import subprocess
+            import sys
+
+            here = os.path.dirname(os.path.abspath(__file__))
+            env = dict(os.environ, PYTHONPATH=os.pathsep.join([here, os.path.dirname(here)]))
+            res = subprocess.run(
+                [sys.executable, "-c", f"import _helpers; _helpers.fork_pool_scenario({server.port})"],
+                env=env, capture_output=True, text=True, timeout=150,
+            )
+            assert res.returncode == 0 and "FORK-OK" in res.stdout, res.stderr[-2000:]
+            return
+        ctx = multiprocessing.get_context(mp_start_method)
         client = service.ArraysToArraysServiceClient("127.0.0.1", server.port)
         tester = ProductTester(client)
         if eval_on_main:
