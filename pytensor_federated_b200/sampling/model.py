@@ -19,6 +19,7 @@ class Model:
     def __init__(self) -> None:
         self.free: List[Tuple[str, object, Tuple[int, ...]]] = []   # (name, variable, shape)
         self.terms: List[object] = []
+        self.transforms: Dict[str, Tuple[str, object]] = {}   # constrained name -> (free name, back-transform)
         self._compiled = None
 
     # -- building ----------------------------------------------------------------------------
@@ -39,6 +40,17 @@ class Model:
             (-0.5 * z * z - at.log(sigma)).sum() - n * LOG_SQRT_2PI
         )
         self.terms.append(term)
+        return var
+
+    def HalfNormal(self, name: str, sigma=1.0):
+        """Positive scalar with a half-normal prior, sampled on the log scale (Jacobian included).
+        Returns the constrained variable; the free parameter is ``<name>_log__``."""
+        log_var = self._new(f"{name}_log__", None)
+        var = at.exp(log_var)
+        z = var / sigma
+        # log N+(x | sigma) + log |dx / dlog x| = log 2 - log sigma - log sqrt(2 pi) - z^2 / 2 + log x
+        self.terms.append(-0.5 * z * z + log_var + (np.log(2.0) - np.log(sigma) - LOG_SQRT_2PI))
+        self.transforms[name] = (f"{name}_log__", np.exp)
         return var
 
     def Potential(self, name: str, var) -> None:
@@ -85,4 +97,32 @@ class Model:
         return out
 
     def point(self, theta: np.ndarray) -> Dict[str, np.ndarray]:
-        return {name: val for (name, _, _), val in zip(self.free, self.split(theta))}
+        out = {name: val for (name, _, _), val in zip(self.free, self.split(theta))}
+        for name, (free_name, back) in self.transforms.items():
+            out[name] = back(out[free_name])
+        return out
+
+    # -- inference conveniences (what pm.find_MAP / pm.sample are to a pm.Model) ----------------
+    def find_map(self, start: Optional[np.ndarray] = None, **kwargs):
+        from .mcmc import find_map
+
+        theta, info = find_map(self.logp_dlogp, np.zeros(self.dim) if start is None else start, **kwargs)
+        return self.point(theta), info
+
+    def sample(self, draws: int = 200, tune: int = 500, *, start: Optional[np.ndarray] = None, seed: int = 0, **kwargs):
+        """NUTS from ``start`` (default: the MAP); returns ``(SamplerResult, {name: draws})``."""
+        from .mcmc import find_map, nuts_sample
+
+        if start is None:
+            start, _ = find_map(self.logp_dlogp, np.zeros(self.dim))
+        res = nuts_sample(self.logp_dlogp, start, draws=draws, tune=tune, seed=seed, **kwargs)
+        columns = {}
+        pos = 0
+        for name, _, shape in self.free:
+            n = int(np.prod(shape)) if shape else 1
+            block = res.samples[:, pos : pos + n]
+            columns[name] = block[:, 0] if not shape else block
+            pos += n
+        for name, (free_name, back) in self.transforms.items():
+            columns[name] = back(columns[free_name])
+        return res, columns

@@ -170,3 +170,29 @@ def test_hierarchical_glm_with_vector_inputs_through_logp_grad_op():
     assert np.all(np.diff(point["intercept"]) > 0)  # ordering of the group intercepts is recovered
     res = nuts_sample(m.logp_dlogp, theta_map, draws=80, tune=80, seed=3)
     assert res.divergences == 0 and res.accept_rate > 0.6
+
+
+def test_half_normal_and_model_conveniences():
+    """Unknown noise scale with a HalfNormal prior (log transform + Jacobian), Model.find_map / .sample."""
+    from pytensor_federated_b200._graph_backend import at
+
+    rng = np.random.default_rng(0)
+    data = rng.normal(1.5, 0.6, size=400)
+    m = Model()
+    mu = m.Normal("mu", 0.0, 10.0)
+    sigma = m.HalfNormal("sigma", 5.0)
+    z = (at.as_tensor(data) - mu) / sigma
+    m.Potential("lik", (-0.5 * z * z).sum() - 400.0 * at.log(sigma))
+    # gradient of the transformed density vs finite differences
+    theta = np.array([1.0, np.log(0.8)])
+    lp, g = m.logp_dlogp(theta)
+    for i in range(2):
+        d = np.zeros(2)
+        d[i] = 1e-6
+        fd = (m.logp_dlogp(theta + d)[0] - m.logp_dlogp(theta - d)[0]) / 2e-6
+        np.testing.assert_allclose(g[i], fd, rtol=1e-5)
+    point, info = m.find_map()
+    assert info["converged"] and abs(point["mu"] - data.mean()) < 0.05 and abs(point["sigma"] - data.std()) < 0.05
+    res, cols = m.sample(draws=300, tune=300, seed=4)
+    assert set(cols) == {"mu", "sigma_log__", "sigma"} and np.all(cols["sigma"] > 0)
+    assert abs(np.median(cols["sigma"]) - data.std()) < 0.06 and res.divergences == 0
