@@ -201,6 +201,21 @@ int launch_model(Engine* e, const FedComm* c) {
     return 0;
 }
 
+// Releases everything an Engine owns (also the partially constructed one of a failed create).
+void release_engine(Engine* e) {
+    if (!e) return;
+    cudaSetDevice(e->device);
+    if (e->stream) cudaStreamSynchronize(e->stream);
+    if (e->owns_comm && e->comm_local) cudaFree(e->comm_local);
+    if (e->host_block) cudaFreeHost(e->host_block);
+    void* device_ptrs[] = {e->cta_partials, e->ticket,       e->epoch_counter, e->trace,  e->theta_dev,
+                           e->linreg_dev,   e->glm_segs_dev, e->glm_tmaps_dev, e->ode_dev};
+    for (void* p : device_ptrs)
+        if (p) cudaFree(p);
+    if (e->stream) cudaStreamDestroy(e->stream);
+    delete e;
+}
+
 __global__ void fed_stop_kernel(FedComm comm) {
     // root asks every node to drain its pre-enqueued kernels
     if (threadIdx.x < comm.world) fed::st_release_sys(comm.peer_flag[threadIdx.x], B200FED_STOP_EPOCH);
@@ -321,7 +336,7 @@ void* b200_engine_create(int device, int rank, int world, int n_theta, int n_val
     }
     if (!ok) {
         g_last_error = std::string("engine allocation failed: ") + cudaGetErrorString(cudaGetLastError());
-        delete e;
+        release_engine(e);
         return nullptr;
     }
     return e;
@@ -375,7 +390,12 @@ int b200_engine_reset(void* h) {
 void b200_engine_set_timeout(void* h, double seconds) {
     static_cast<Engine*>(h)->timeout_ns = (unsigned long long)(seconds * 1e9);
 }
-void b200_engine_set_grid(void* h, int grid) { static_cast<Engine*>(h)->grid = grid; }
+void b200_engine_set_grid(void* h, int grid) {
+    // the per-CTA partial array holds sm_count * 8 rows; negative values select single-CTA modes
+    Engine* e = static_cast<Engine*>(h);
+    const int max_blocks = e->sm_count * 8;
+    e->grid = grid > max_blocks ? max_blocks : (grid == 0 ? 1 : grid);
+}
 int b200_engine_grid(void* h) { return static_cast<Engine*>(h)->grid; }
 unsigned long long b200_engine_launches(void* h) { return static_cast<Engine*>(h)->launches; }
 unsigned long long b200_engine_epoch(void* h) { return static_cast<Engine*>(h)->epoch; }
@@ -655,24 +675,6 @@ int b200_engine_trace(void* h, unsigned long long epoch, unsigned long long* out
     return 0;
 }
 
-void b200_engine_destroy(void* h) {
-    Engine* e = static_cast<Engine*>(h);
-    if (!e) return;
-    cudaSetDevice(e->device);
-    cudaStreamSynchronize(e->stream);
-    if (e->owns_comm && e->comm_local) cudaFree(e->comm_local);
-    if (e->host_block) cudaFreeHost(e->host_block);
-    cudaFree(e->cta_partials);
-    cudaFree(e->ticket);
-    cudaFree(e->epoch_counter);
-    cudaFree(e->trace);
-    cudaFree(e->theta_dev);
-    if (e->linreg_dev) cudaFree(e->linreg_dev);
-    if (e->glm_segs_dev) cudaFree(e->glm_segs_dev);
-    if (e->glm_tmaps_dev) cudaFree(e->glm_tmaps_dev);
-    if (e->ode_dev) cudaFree(e->ode_dev);
-    cudaStreamDestroy(e->stream);
-    delete e;
-}
+void b200_engine_destroy(void* h) { release_engine(static_cast<Engine*>(h)); }
 
 }  // extern "C"

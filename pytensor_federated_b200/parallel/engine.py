@@ -96,6 +96,7 @@ class FederatedEngine:
         self._closed = False
         self._handle = None
         self._keepalive = []
+        self._ipc_opened: List[int] = []  # peer blocks mapped with cudaIpcOpenMemHandle (closed in shutdown)
         self.comm_mode = "none"
         self.n_evals = 0
         self._stop_seen = False
@@ -203,6 +204,7 @@ class FederatedEngine:
             out = C.c_void_p()
             native.check(lib.b200_ipc_open_handle(self._dev_index, hb, C.byref(out)), f"ipc open rank {r}")
             ptrs.append(out.value)
+            self._ipc_opened.append(out.value)
         native.check(lib.b200_engine_bind_comm(self._handle, ptr, native.void_p_array(ptrs), None), "bind comm")
         self.comm_mode = "ipc"
 
@@ -402,6 +404,10 @@ class FederatedEngine:
                         _dist().barrier(group=self.group)
                     except Exception:  # pragma: no cover
                         pass
+                self._lib.b200_engine_sync(self._handle)
+                for p in self._ipc_opened:
+                    self._lib.b200_ipc_close_handle(C.c_void_p(p))
+                self._ipc_opened = []
                 self._lib.b200_engine_destroy(self._handle)
                 self._handle = None
 
