@@ -317,7 +317,13 @@ void* b200_engine_create(int device, int rank, int world, int n_theta, int n_val
     e->h_off_ll = e->h_off_done + 256;
     const size_t hbytes = e->h_off_ll + up((size_t)n_vals * 16);
     // LL mode for small messages (latency-bound models); B200FED_NO_LL=1 forces the fence+flag protocol
-    e->ll_mode = n_vals <= 128 && n_theta <= 256 && !getenv("B200FED_NO_LL");
+    // (thresholds tunable with B200FED_LL_MAX_VALS / B200FED_LL_MAX_THETA)
+    auto env_int = [](const char* name, int dflt) {
+        const char* v = getenv(name);
+        return v && *v ? atoi(v) : dflt;
+    };
+    e->ll_mode = n_vals <= env_int("B200FED_LL_MAX_VALS", 128) && n_theta <= env_int("B200FED_LL_MAX_THETA", 256) &&
+                 !getenv("B200FED_NO_LL");
     ok = ok && cudaHostAlloc((void**)&e->host_block, hbytes, cudaHostAllocMapped | cudaHostAllocPortable) == cudaSuccess;
     if (ok) memset(e->host_block, 0, hbytes);
     ok = ok && cudaHostGetDevicePointer((void**)&e->host_block_dev, e->host_block, 0) == cudaSuccess;
