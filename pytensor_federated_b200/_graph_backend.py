@@ -21,7 +21,15 @@ if os.environ.get("B200FED_GRAPH_BACKEND", "auto") != "builtin":
         from pytensor.compile.ops import FromFunctionOp
         from pytensor.gradient import DisconnectedType
         from pytensor.graph import FunctionGraph
-        from pytensor.graph.basic import Apply, Variable, apply_depends_on
+        from pytensor.graph.basic import Apply, Variable
+
+        try:
+            from pytensor.graph.basic import apply_depends_on
+        except ImportError:  # newer PyTensor releases moved the traversal helpers
+            try:
+                from pytensor.graph.traversal import apply_depends_on
+            except ImportError:
+                from .graph.core import apply_depends_on  # duck-typed on .inputs / .owner
         from pytensor.graph.features import ReplaceValidate
         from pytensor.graph.op import Op
         from pytensor.graph.rewriting.basic import GraphRewriter
@@ -29,6 +37,11 @@ if os.environ.get("B200FED_GRAPH_BACKEND", "auto") != "builtin":
         BACKEND = "pytensor"
     except ModuleNotFoundError:
         pass
+    except ImportError as _ex:  # an installed PyTensor whose layout we do not know: say so, use the built-in IR
+        import warnings
+
+        warnings.warn(f"PyTensor is installed but could not be used ({_ex}); falling back to the built-in graph IR")
+        BACKEND = "builtin"
 
 if BACKEND == "builtin":
     from .graph import core as at  # tensor namespace: scalar, vector, as_tensor, exp, log, sum ...

@@ -480,7 +480,7 @@ def ancestors_applies(outputs: Iterable[Variable]) -> List[Apply]:
 
 def apply_depends_on(apply: Apply, depends_on: Union[Apply, Sequence[Apply]]) -> bool:
     """True when ``apply`` (transitively) consumes an output of ``depends_on``."""
-    targets = {id(depends_on)} if isinstance(depends_on, Apply) else {id(d) for d in depends_on}
+    targets = {id(depends_on)} if hasattr(depends_on, "inputs") else {id(d) for d in depends_on}
     seen = set()
     todo = [apply]
     while todo:
