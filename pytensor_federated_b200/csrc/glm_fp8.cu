@@ -16,7 +16,12 @@
 //   MMA #2  G[128 feat x 16] += Xq_tile^T[:, row group q] . R           rows m -> feature block
 //           4h + m/32: column 4h + qq holds the scales of (row groups 0..3, feature block 4h+qq),
 //           sf_id = q.
-//   Scale-factor-B is the constant 2^0.
+//   Scale-factor-B is the constant 2^0 for MMA #1 and for the logistic family (|r| <= 1).
+//   Poisson / Gaussian residuals are unbounded: there (template DYN) every 32-row group of R gets
+//   its own UE8M0 scale — warp max -> exponent, exchanged through shared memory, written to the
+//   scale-factor-B columns of the R buffer by the epilogue warps, byte selected by b_sf_id = row
+//   group — so the radix-16 expansion is relative to the block maximum, which is what the
+//   block-scaled MMA is for.
 // Theta and the residuals are themselves e4m3: theta is a 5-term, r a 4-term radix-16 expansion
 // (term k carries weight 16^-k), the terms sit in separate N columns and are recombined in the
 // epilogue in fp32, so the low precision of the operands does not leak into the result.
@@ -113,12 +118,14 @@ __host__ __device__ inline SmemLayoutF smem_layout(int P, int n_theta, int n_gro
     L.off_gi = o; o += (3 * n_groups * 8 + 15) & ~15;
     L.off_red = o; o += 32 * 8;
     L.off_bars = o; o += 320;
-    L.off_tmem = o; o += 64;
+    L.off_tmem = o; o += 128;  // tmem slot, theta norms, residual-exponent exchange (DYN)
     L.total = o + 1024;
     return L;
 }
 
-template <int KF>  // chains per launch: 1 or 3 (3 x 5 theta terms and 3 x 4 residual terms fit the 16 MMA columns)
+// KF = chains per launch: 1 or 3 (3 x 5 theta terms and 3 x 4 residual terms fit the 16 MMA columns);
+// DYN = per-row-group residual scales (families with unbounded residuals)
+template <int KF, bool DYN>
 __global__ void __launch_bounds__(kThreadsF, 1)
 fed_glm_fp8_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParams prm, const CUtensorMap* __restrict__ tmaps) {
     extern __shared__ unsigned char smem_dyn[];
@@ -140,6 +147,7 @@ fed_glm_fp8_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParam
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.off_bars);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L.off_tmem);
     float* theta_norm = reinterpret_cast<float*>(smem + L.off_tmem + 16);  // c: theta = c * sum_k t_k 16^-k
+    uint8_t* r_expo = smem + L.off_tmem + 64;  // [group][tile parity][chain (3)][row group (4)] UE8M0 bytes
     uint64_t* bar_full = bars;            // [6]
     uint64_t* bar_empty = bars + 6;       // [6]
     uint64_t* bar_eta_full = bars + 12;   // [2]
@@ -238,6 +246,7 @@ fed_glm_fp8_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParam
         const uint32_t tmem_sfa1 = tmem_base + 160;             // ring x 8 columns
         const uint32_t tmem_sfa2 = tmem_base + 160 + kSfRing * 8;   // ring x 8 columns
         const uint32_t tmem_sfb = tmem_base + 160 + kSfRing * 16;   // 4 columns of 2^0
+        const uint32_t tmem_sfb_r = tmem_sfb + 4;                   // DYN: 2 R buffers x 4 columns (col 0 used)
 
         if (warp == 0) {
             if (lane == 0) {
@@ -303,8 +312,11 @@ fed_glm_fp8_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParam
                         for (int q = 0; q < 4; ++q) {   // K step = one 32-row group
                             const uint64_t adesc = make_desc(x_addr + h * kPanelB + q * 4 * 1024, kPanelB, 1024, 2);
                             const uint64_t bdesc = make_desc(r_addr + b * L.r_bytes + q * 4 * 128, 128, 128, 0);
-                            umma_fp8_block_scaled(tmem_g + (gb * NH + h) * kN, adesc, bdesc, idesc2 | ((uint32_t)q << 29),
-                                                  (first && q == 0) ? 0u : 1u, tmem_sfa2 + sfb * 8 + h * 4, tmem_sfb);
+                            // DYN: scale-factor-B byte q of the R buffer's column = exponent of row group q
+                            umma_fp8_block_scaled(tmem_g + (gb * NH + h) * kN, adesc, bdesc,
+                                                  idesc2 | ((uint32_t)q << 29) | (DYN ? ((uint32_t)q << 4) : 0u),
+                                                  (first && q == 0) ? 0u : 1u, tmem_sfa2 + sfb * 8 + h * 4,
+                                                  DYN ? tmem_sfb_r + b * 4 : tmem_sfb);
                         }
                     }
                     umma_commit(&bar_empty[st]);
@@ -405,15 +417,27 @@ fed_glm_fp8_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParam
                 tc_fence_before();
                 mbar_arrive(&bar_eta_empty[b]);
                 uint32_t rwords[4] = {0, 0, 0, 0};  // 16 residual bytes of this row: 4 terms per chain
+                uint8_t* expo_slot = r_expo + (eg * 2 + (int)bph) * 12;
 #pragma unroll
                 for (int k = 0; k < KF; ++k) {
                     const float* vk = v + kThetaTerms * k;
                     const float eta = c_theta[k] * (vk[0] + vk[1] * (1.f / 16) + vk[2] * (1.f / 256) + vk[3] * (1.f / 4096) +
                                                     vk[4] * (1.f / 65536)) + theta_f[k * PG + seg.group];
                     float ll = 0.f, r = 0.f;
-                    if (valid && k < nch) link_loglik(0, y, eta, ll, r);
+                    if (valid && k < nch) link_loglik(DYN ? prm.family : 0, y, eta, ll, r);
                     ll_acc[k] += ll;
                     gi_cur[k] += r;
+                    if constexpr (DYN) {
+                        // this 32-row group's scale: 2^e with max|r| / 2^e in [0.5, 1)
+                        float m = fabsf(r);
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+                        int e = 0;
+                        if (m > 0.f) frexpf(m, &e);
+                        e = max(-126, min(126, e));
+                        r *= __uint_as_float((uint32_t)(127 - e) << 23);
+                        if (lane == 0) expo_slot[k * 4 + q4] = (uint8_t)(127 + e);
+                    }
                     uint8_t rt[kResidTerms];
                     expand16<kResidTerms>(r * 256.f, rt);
                     rwords[k] = (uint32_t)rt[0] | ((uint32_t)rt[1] << 8) | ((uint32_t)rt[2] << 16) | ((uint32_t)rt[3] << 24);
@@ -422,6 +446,17 @@ fed_glm_fp8_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParam
                 *reinterpret_cast<uint4*>(r_buf + b * L.r_bytes + (row >> 3) * 128 + (row & 7) * 16) =
                     make_uint4(rwords[0], rwords[1], rwords[2], rwords[3]);
                 fence_proxy_async();
+                if constexpr (DYN) {
+                    // all four row-group exponents of this tile -> one word per chain; B row n = 4 * chain + term
+                    // reads it from lane n of every subpartition
+                    if (eg) asm volatile("bar.sync 2, 128;" ::: "memory");
+                    else asm volatile("bar.sync 1, 128;" ::: "memory");
+                    const int ch = min(lane >> 2, KF - 1);
+                    const uint32_t w = *reinterpret_cast<const uint32_t*>(expo_slot + ch * 4);
+                    tmem_st_x1(tmem_sfb_r + lane_addr + b * 4, w);
+                    tmem_wait_st();
+                    tc_fence_before();
+                }
                 mbar_arrive(&bar_r_full[b]);
 
                 // scales for this group's next tile (it+2): its ring slot was last used by tile it-2,
@@ -509,7 +544,7 @@ EncodeTiledFn8 get_encode8() {
 extern "C" int b200_glm_fp8_prepare(const GlmSegment* segs_host, int n_segments, const GlmParams* prm, void** tmaps_dev) {
     if (prm->n_features != 128 && prm->n_features != 256) return -21;   // NFB <= 8 scale columns per tile
     if (n_segments > fp8::kMaxSegsF) return -22;
-    if (prm->n_chains < 1 || prm->n_chains > 3 || prm->family != 0) return -23;
+    if (prm->n_chains < 1 || prm->n_chains > 3 || prm->family < 0 || prm->family > 2) return -23;
     if (prm->ld % 16 != 0) return -24;
     EncodeTiledFn8 encode = get_encode8();
     if (!encode) return -25;
@@ -537,12 +572,17 @@ extern "C" int b200_launch_glm_fp8(const FedComm* comm, const GlmSegment* segs_d
     const fp8::SmemLayoutF L = fp8::smem_layout(prm->n_features, comm->n_theta, prm->n_groups);
     if (L.stages < 2) return -2;
     const CUtensorMap* maps = reinterpret_cast<const CUtensorMap*>(tmaps);
+#define B200FED_FP8_LAUNCH(KF, DYN)                                                                                       \
+    do {                                                                                                                 \
+        cudaFuncSetAttribute(fp8::fed_glm_fp8_kernel<KF, DYN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total); \
+        fp8::fed_glm_fp8_kernel<KF, DYN><<<grid, fp8::kThreadsF, L.total, stream>>>(*comm, segs_dev, *prm, maps);         \
+    } while (0)
+    const bool dyn = prm->family != 0;  // unbounded residuals: per-row-group scales for the R operand
     if (prm->n_chains == 1) {
-        cudaFuncSetAttribute(fp8::fed_glm_fp8_kernel<1>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total);
-        fp8::fed_glm_fp8_kernel<1><<<grid, fp8::kThreadsF, L.total, stream>>>(*comm, segs_dev, *prm, maps);
+        if (dyn) B200FED_FP8_LAUNCH(1, true); else B200FED_FP8_LAUNCH(1, false);
     } else {
-        cudaFuncSetAttribute(fp8::fed_glm_fp8_kernel<3>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total);
-        fp8::fed_glm_fp8_kernel<3><<<grid, fp8::kThreadsF, L.total, stream>>>(*comm, segs_dev, *prm, maps);
+        if (dyn) B200FED_FP8_LAUNCH(3, true); else B200FED_FP8_LAUNCH(3, false);
     }
+#undef B200FED_FP8_LAUNCH
     return (int)cudaGetLastError();
 }

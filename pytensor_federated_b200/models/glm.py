@@ -287,13 +287,16 @@ class Fp8GlmShards(GlmShards):
 
     The hierarchical-GLM configuration of BASELINE.json: one partial-pooling group (intercept) per
     shard/GPU, e4m3 design matrix with 32 x 32 UE8M0 block scales, evaluated by ``csrc/glm_fp8.cu``
-    (``tcgen05.mma.kind::mxf8f6f4.block_scale``).  Logistic family, up to 3 chains per launch.
+    (``tcgen05.mma.kind::mxf8f6f4.block_scale``).  Up to 3 chains per launch.  The residuals of the
+    Poisson and Gaussian families are unbounded, so the kernel block-scales them too (one UE8M0
+    exponent per 32-row group, written to the MMA's scale-factor-B columns).
     """
 
-    def __init__(self, Xqs, scales, ys, *, groups=None, n_groups: int = 1, n_chains: int = 1) -> None:
+    def __init__(self, Xqs, scales, ys, *, groups=None, n_groups: int = 1, n_chains: int = 1,
+                 family: str = "logistic") -> None:
         if not 1 <= n_chains <= 3:
             raise ValueError("the fp8 kernel batches at most 3 chains per launch")
-        super().__init__(Xqs, ys, groups=groups, n_groups=n_groups, family="logistic", n_chains=n_chains, kernel="fp8",
+        super().__init__(Xqs, ys, groups=groups, n_groups=n_groups, family=family, n_chains=n_chains, kernel="fp8",
                          scales=scales)
 
     @classmethod

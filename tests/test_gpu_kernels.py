@@ -190,6 +190,39 @@ def test_glm_fp8_batches_chains(dev, K):
     np.testing.assert_allclose(d_beta, w[2], rtol=2e-4, atol=2e-4 * np.abs(w[2]).max())
 
 
+@pytest.mark.parametrize("family,K", [("gaussian", 1), ("poisson", 1), ("gaussian", 3), ("poisson", 2)])
+def test_glm_fp8_unbounded_residual_families(dev, family, K):
+    """Poisson / Gaussian on the fp8 kernel: residuals are block-scaled per 32-row group (scale-factor-B)."""
+    torch.manual_seed(11)
+    rows = [128 * 35 + 17, 640]
+    P = 256
+    Xs = [torch.randn(n, P, device=dev) * torch.exp(0.5 * torch.randn(P, device=dev)) for n in rows]
+    beta_true = torch.randn(P, device=dev) * 0.02
+    ys = []
+    for X in Xs:
+        eta = X @ beta_true
+        if family == "poisson":
+            ys.append(torch.poisson(torch.exp(eta.clamp(max=3.0) + 0.5)))
+        else:
+            # residual magnitudes spanning orders of magnitude between row groups
+            noise = torch.exp(2.0 * torch.randn(X.shape[0], device=dev)) * torch.randn(X.shape[0], device=dev)
+            ys.append(40.0 * eta + 25.0 * noise)
+    model = Fp8GlmShards.from_dense(Xs, ys, groups=[0, 1], n_groups=2, n_chains=K, family=family)
+    rng = np.random.default_rng(12)
+    shape = (K,) if K > 1 else ()
+    ic = (rng.normal(size=shape + (2,)) * 0.2).astype(np.float32)
+    beta = (rng.normal(size=shape + (P,)) * 0.02).astype(np.float32)
+    with FederatedEngine(model) as eng:
+        logp, d_ic, d_beta = eng.evaluate(ic, beta)
+        again = eng.evaluate(ic, beta)
+    w = model.unpack_result(model.reference_partial([ic, beta], dtype=torch.float64))
+    np.testing.assert_allclose(logp, w[0], rtol=3e-5)
+    np.testing.assert_allclose(d_ic, w[1], rtol=2e-4, atol=2e-4 * np.abs(w[1]).max())
+    np.testing.assert_allclose(d_beta, w[2], rtol=3e-4, atol=3e-4 * np.abs(w[2]).max())
+    for u, v in zip((logp, d_ic, d_beta), again):
+        assert np.array_equal(u, v)
+
+
 @pytest.mark.parametrize("P,dtype", [(37, torch.float32), (200, torch.bfloat16), (700, torch.float32), (1000, torch.bfloat16)])
 def test_glm_general_shape_fallback(dev, P, dtype):
     """Shapes none of the fast kernels accept (odd P, fp32 X, non-contiguous rows) still run fused."""
