@@ -153,7 +153,8 @@ class GlmShards(ShardModel):
         n = len(self.Xs)
         Xp = native.void_p_array([X.data_ptr() for X in self.Xs])
         yp = native.void_p_array([y.data_ptr() for y in self.ys])
-        sp = native.void_p_array([s.data_ptr() for s in self.scales]) if self.scales else None
+        kernel_scales = getattr(self, "_kernel_scales", None) or self.scales   # fp8: packed per tile
+        sp = native.void_p_array([s.data_ptr() for s in kernel_scales]) if kernel_scales else None
         rows = (C.c_longlong * n)(*[X.shape[0] for X in self.Xs])
         grp = (C.c_int * n)(*self.groups)
         native.check(
@@ -282,6 +283,24 @@ def dequantize_block_fp8(Xq, scales, block: int = 32):
     return Xq.float() * s_full
 
 
+def pack_tile_scales(scales, n_features: int):
+    """Re-orders the UE8M0 block scales ``[4 * tiles, P / 32]`` into the 16 words per 128-row tile that
+    ``csrc/glm_fp8.cu`` copies into the TMEM scale-factor columns: words 0-7 for ``eta = X . Theta^T``
+    (word ``4g + q`` = row group ``q``, feature blocks ``4g..4g+3``), words 8-15 for ``G += X^T . R``
+    (word ``4h + qq`` = row groups 0..3 of feature block ``4h + qq``).  Returns ``uint8 [tiles, 64]``."""
+    import torch
+
+    nfb = n_features // 32
+    if nfb not in (4, 8) or scales.shape[0] % 4 or scales.shape[1] != nfb:
+        raise ValueError("the fp8 kernel takes P in {128, 256} and scales padded to whole 128-row tiles")
+    tiles, g2 = scales.shape[0] // 4, nfb // 4
+    s4 = scales.contiguous().view(tiles, 4, g2, 4)                       # [tile, q, g, j]
+    packed = torch.full((tiles, 2, 2, 4, 4), 127, dtype=torch.uint8, device=scales.device)
+    packed[:, 0, :g2] = s4.permute(0, 2, 1, 3)                           # [tile, g, q, byte j]
+    packed[:, 1, :g2] = s4.permute(0, 2, 3, 1)                           # [tile, h, qq, byte q]
+    return packed.reshape(tiles, 64).contiguous()
+
+
 class Fp8GlmShards(GlmShards):
     """GLM shards whose design matrices are block-scaled FP8 (``quantize_block_fp8``).
 
@@ -298,6 +317,7 @@ class Fp8GlmShards(GlmShards):
             raise ValueError("the fp8 kernel batches at most 3 chains per launch")
         super().__init__(Xqs, ys, groups=groups, n_groups=n_groups, family=family, n_chains=n_chains, kernel="fp8",
                          scales=scales)
+        self._kernel_scales = [pack_tile_scales(s, self.n_features) for s in self.scales]
 
     @classmethod
     def from_dense(cls, Xs, ys, **kw):
@@ -309,7 +329,7 @@ class Fp8GlmShards(GlmShards):
         return dequantize_block_fp8(X, self.scales[idx])
 
     def bytes_per_eval(self) -> int:
-        return int(sum(X.shape[0] * (self.n_features + 4) + s.numel() for X, s in zip(self.Xs, self.scales)))
+        return int(sum(X.shape[0] * (self.n_features + 4) + s.numel() for X, s in zip(self.Xs, self._kernel_scales)))
 
 
 def synth_logistic_shard(n_rows: int, n_features: int, *, seed: int, device, chunk_rows: int = 1 << 20,

@@ -178,3 +178,26 @@ def test_two_rank_gloo_federation_sums_private_shards():
         x, y = rng.normal(size=50), rng.normal(size=50)
         expected += _scipy_linreg(x, y, 0.8, 0.3, -0.2)
     np.testing.assert_allclose(root[0], expected, rtol=1e-12)
+
+
+def test_fp8_tile_scale_packing_matches_tmem_word_order():
+    """pack_tile_scales: words 0-7 feed MMA #1 (row group q, feature blocks 4g..4g+3), words 8-15 MMA #2
+    (row groups 0..3 of feature block 4h+qq); absent blocks are 2^0 (csrc/glm_fp8.cu)."""
+    import torch
+
+    from pytensor_federated_b200.models.glm import pack_tile_scales
+
+    for P in (128, 256):
+        nfb, tiles = P // 32, 3
+        s = torch.randint(100, 150, (4 * tiles, nfb), dtype=torch.uint8)
+        pk = pack_tile_scales(s, P).view(tiles, 16, 4)
+        for t in range(tiles):
+            rows = s[4 * t : 4 * t + 4]
+            for g in range(2):
+                for q in range(4):
+                    want = [int(rows[q, 4 * g + j]) if 4 * g < nfb else 127 for j in range(4)]
+                    assert pk[t, g * 4 + q].tolist() == want
+                    want = [int(rows[j, 4 * g + q]) if 4 * g < nfb else 127 for j in range(4)]
+                    assert pk[t, 8 + g * 4 + q].tolist() == want
+    with pytest.raises(ValueError):
+        pack_tile_scales(torch.zeros(6, 8, dtype=torch.uint8), 256)
