@@ -28,8 +28,8 @@
 // (term k carries weight 16^-k), the terms sit in separate N columns and are recombined in the
 // epilogue in fp32, so the low precision of the operands does not leak into the result.
 //
-// Pipeline/roles as in glm_tc.cu; scale words are written to TMEM two tiles ahead by the
-// epilogue warps (tcgen05.st), 4-deep ring.  Workload: BASELINE.json "hierarchical GLM, 8
+// Pipeline/roles as in glm_tc.cu; scale words are written to TMEM kEG tiles ahead by the
+// epilogue warps (tcgen05.st), 2*kEG-deep ring.  Workload: BASELINE.json "hierarchical GLM, 8
 // partial-pooling groups (one per GPU), fp8 block-scaled design matrix" (groups = intercepts).
 #include <cuda.h>
 #include <cuda_fp8.h>
@@ -45,12 +45,13 @@ using namespace tc;
 constexpr int kTile = 128;            // rows per tile
 constexpr int kPanelF = 128;          // features per 128-byte swizzle span (1 byte / element)
 constexpr int kPanelB = kTile * 128;  // 16 KB
-constexpr int kThreadsF = 352;        // warps: 0 TMA, 1 MMA#1, 2-5 epilogue A (even tiles), 6 MMA#2, 7-10 epilogue B (odd tiles)
+constexpr int kEG = 3;                // epilogue groups; tile t belongs to group t % kEG (own eta / R buffers)
+constexpr int kThreadsF = 32 * (3 + 4 * kEG);  // warps: 0 TMA, 1 MMA#1, 2-5 group 0, 6 MMA#2, 7-10 group 1, 11-14 group 2
 constexpr int kFlushF = 32;
 constexpr int kN = 16;                // MMA N for both GEMMs
 constexpr int kThetaTerms = 5;
 constexpr int kResidTerms = 4;
-constexpr int kSfRing = 4;
+constexpr int kSfRing = 2 * kEG;      // scale words are written kEG tiles ahead
 constexpr int kMaxSegsF = 64;
 
 __device__ __forceinline__ void umma_fp8_block_scaled(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
@@ -107,20 +108,20 @@ __host__ __device__ inline SmemLayoutF smem_layout(int P, int n_theta, int n_gro
     L.stage_bytes = panels * kPanelB;
     L.theta_b_bytes = panels * kN * 128;
     L.r_bytes = kTile * kN;  // 1 byte per element
-    const uint32_t fixed = L.theta_b_bytes + 2 * L.r_bytes + ((n_theta * 4 + 15) & ~15) + kMaxSegsF * (uint32_t)sizeof(GlmSegment) +
+    const uint32_t fixed = L.theta_b_bytes + kEG * L.r_bytes + ((n_theta * 4 + 15) & ~15) + kMaxSegsF * (uint32_t)sizeof(GlmSegment) +
                            ((3 * n_groups * 8 + 15) & ~15) + 32 * 8 + 512 + 1024;
     uint32_t stages = (227u * 1024u - fixed) / L.stage_bytes;
     if (stages > 6) stages = 6;
     L.stages = stages;
     uint32_t o = stages * L.stage_bytes;
     L.off_theta_b = o; o += L.theta_b_bytes;
-    L.off_r = o; o += 2 * L.r_bytes;
+    L.off_r = o; o += kEG * L.r_bytes;
     L.off_theta_f = o; o += (n_theta * 4 + 15) & ~15;
     L.off_segs = o; o += kMaxSegsF * (uint32_t)sizeof(GlmSegment);
     L.off_gi = o; o += (3 * n_groups * 8 + 15) & ~15;
     L.off_red = o; o += 32 * 8;
     L.off_bars = o; o += 320;
-    L.off_tmem = o; o += 128;  // tmem slot, theta norms, residual-exponent exchange (DYN)
+    L.off_tmem = o; o += 192;  // tmem slot, theta norms, residual-exponent exchange (DYN)
     L.total = o + 1024;
     return L;
 }
@@ -152,13 +153,14 @@ fed_glm_fp8_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParam
     uint8_t* r_expo = smem + L.off_tmem + 64;  // [group][tile parity][chain (3)][row group (4)] UE8M0 bytes
     uint64_t* bar_full = bars;            // [6]
     uint64_t* bar_empty = bars + 6;       // [6]
-    uint64_t* bar_eta_full = bars + 12;   // [2]
-    uint64_t* bar_eta_empty = bars + 14;  // [2]
-    uint64_t* bar_r_full = bars + 16;     // [2]
-    uint64_t* bar_r_empty = bars + 18;    // [2]
-    uint64_t* bar_g_full = bars + 20;     // [2]
-    uint64_t* bar_g_empty = bars + 22;    // [2]
-    uint64_t* bar_sf_full = bars + 24;    // [4]
+    uint64_t* bar_eta_full = bars + 12;             // [kEG]
+    uint64_t* bar_eta_empty = bars + 12 + kEG;      // [kEG]
+    uint64_t* bar_r_full = bars + 12 + 2 * kEG;     // [kEG]
+    uint64_t* bar_r_empty = bars + 12 + 3 * kEG;    // [kEG]
+    uint64_t* bar_g_full = bars + 12 + 4 * kEG;     // [2]
+    uint64_t* bar_g_empty = bars + 14 + 4 * kEG;    // [2]
+    uint64_t* bar_sf_full = bars + 16 + 4 * kEG;    // [kSfRing]   (16 + 6 kEG <= 40 barriers = 320 bytes)
+    static_assert(16 + 4 * kEG + kSfRing <= 40, "barrier block too small");
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
@@ -222,16 +224,18 @@ fed_glm_fp8_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParam
             *reinterpret_cast<uint4*>(theta_b + pnl * (kN * 128) + n * 128 + ((j ^ (n & 7)) * 16)) =
                 make_uint4(packed[0], packed[1], packed[2], packed[3]);
         }
-        for (int i = threadIdx.x; i < (int)(2 * L.r_bytes / 16); i += blockDim.x)
+        for (int i = threadIdx.x; i < (int)(kEG * L.r_bytes / 16); i += blockDim.x)
             reinterpret_cast<uint4*>(r_buf)[i] = make_uint4(0, 0, 0, 0);
         fence_proxy_async();
         if (threadIdx.x == 0) {
             for (int i = 0; i < 6; ++i) { mbar_init(&bar_full[i], 1); mbar_init(&bar_empty[i], 1); }
-            for (int i = 0; i < 2; ++i) {
+            for (int i = 0; i < kEG; ++i) {
                 mbar_init(&bar_eta_full[i], 1);
                 mbar_init(&bar_eta_empty[i], 128);
                 mbar_init(&bar_r_full[i], 128);
                 mbar_init(&bar_r_empty[i], 1);
+            }
+            for (int i = 0; i < 2; ++i) {
                 mbar_init(&bar_g_full[i], 1);
                 mbar_init(&bar_g_empty[i], 128);
             }
@@ -243,12 +247,13 @@ fed_glm_fp8_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParam
         __syncthreads();
         tc_fence_after();
         const uint32_t tmem_base = *tmem_slot;
-        const uint32_t tmem_eta = tmem_base;                    // 2 x 16
-        const uint32_t tmem_g = tmem_base + 32;                 // 2 buffers x NH x 16  (<= 128)
-        const uint32_t tmem_sfa1 = tmem_base + 160;             // ring x 8 columns
-        const uint32_t tmem_sfa2 = tmem_base + 160 + kSfRing * 8;   // ring x 8 columns
-        const uint32_t tmem_sfb = tmem_base + 160 + kSfRing * 16;   // 4 columns of 2^0
-        const uint32_t tmem_sfb_r = tmem_sfb + 4;                   // DYN: 2 R buffers x 4 columns (col 0 used)
+        const uint32_t tmem_eta = tmem_base;                         // kEG x 16            (<= 64)
+        const uint32_t tmem_g = tmem_base + 64;                      // 2 buffers x NH x 16 (<= 64)
+        const uint32_t tmem_sfa1 = tmem_base + 128;                  // ring x 8 columns
+        const uint32_t tmem_sfa2 = tmem_sfa1 + kSfRing * 8;          // ring x 8 columns
+        const uint32_t tmem_sfb = tmem_sfa2 + kSfRing * 8;           // 4 columns of 2^0
+        const uint32_t tmem_sfb_r = tmem_sfb + 4;                    // DYN: kEG R buffers x 4 columns (col 0 used)
+        static_assert(128 + kSfRing * 16 + 4 + kEG * 4 <= (int)kTmemCols, "TMEM budget");
 
         if (warp == 0) {
             if (lane == 0) {
@@ -274,8 +279,8 @@ fed_glm_fp8_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParam
                 for (long long it = 0; it < n_it; ++it) {
                     const int st = (int)(it % S);
                     const uint32_t ph = (uint32_t)((it / S) & 1);
-                    const int b = (int)(it & 1);
-                    const uint32_t bph = (uint32_t)((it >> 1) & 1);
+                    const int b = (int)(it % kEG);
+                    const uint32_t bph = (uint32_t)((it / kEG) & 1);
                     const int sfb = (int)(it % kSfRing);
                     mbar_wait(&bar_sf_full[sfb], (uint32_t)((it / kSfRing) & 1));
                     mbar_wait(&bar_eta_empty[b], bph ^ 1);
@@ -298,8 +303,8 @@ fed_glm_fp8_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParam
                 const uint32_t r_addr = smem_u32(r_buf);
                 for (long long j = 0; j < n_it; ++j) {
                     const int st = (int)(j % S);
-                    const int b = (int)(j & 1);
-                    const uint32_t bph = (uint32_t)((j >> 1) & 1);
+                    const int b = (int)(j % kEG);
+                    const uint32_t bph = (uint32_t)((j / kEG) & 1);
                     const long long period = j / kFlushF;
                     const int gb = (int)(period & 1);
                     const bool first = (j % kFlushF) == 0;
@@ -327,11 +332,13 @@ fed_glm_fp8_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParam
                 }
             }
         } else {
-            // ================= epilogue warps: group A = 2..5 (even tiles), group B = 7..10 (odd) =
+            // ================= epilogue warps: group g = warps 2..5 / 7..10 / 11..14 owns tiles t % kEG == g
             // The per-tile epilogue is a long serial chain (barrier wake-up, TMEM load, link maths,
-            // smem store + proxy fence, TMEM scale stores); two groups ping-pong so that two tiles'
-            // chains overlap.  Group g owns eta/R buffer g, so every barrier still sees 128 arrivals.
-            const int eg = warp >= 7 ? 1 : 0;
+            // smem store + proxy fence, TMEM scale stores).  kEG groups rotate over the tiles so that kEG
+            // chains overlap; group g owns eta/R buffer g, so every barrier still sees 128 arrivals.
+            // Measured (8 x 10M x 256): 1 group 269, 2 groups 279 -> 295 with host-packed scale words,
+            // 3 groups 297 evals/s — beyond two groups the group count is no longer the bound.
+            const int eg = warp >= 7 ? (warp - 7) / 4 + 1 : 0;
             const int q4 = warp & 3;
             const int row = q4 * 32 + lane;
             const uint32_t lane_addr = (uint32_t)(q4 * 32) << 16;
@@ -376,7 +383,7 @@ fed_glm_fp8_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParam
 #pragma unroll
             for (int k = 0; k < KF; ++k) ll_acc[k] = gi_cur[k] = 0.f;
             int cur_group = -1;
-            for (long long it = eg; it < n_it; it += 2) {
+            for (long long it = eg; it < n_it; it += kEG) {
                 const long long tile = blockIdx.x + it * gridDim.x;
                 while (s_idx + 1 < prm.n_segments && segs[s_idx + 1].first_tile <= tile) ++s_idx;
                 const GlmSegment& seg = segs[s_idx];
@@ -393,10 +400,10 @@ fed_glm_fp8_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParam
                 const long long grow = (tile - seg.first_tile) * kTile + row;
                 const bool valid = grow < seg.n_rows;
                 const float y = valid ? __ldg(seg.y + grow) : 0.f;
-                const int b = (int)(it & 1);
-                const uint32_t bph = (uint32_t)((it >> 1) & 1);
+                const int b = eg;
+                const uint32_t bph = (uint32_t)((it / kEG) & 1);
                 uint4 next_scales[4];
-                if (it + 2 < n_it) load_scales(it + 2, sf_sidx, next_scales);  // consumed at the end of this iteration
+                if (it + kEG < n_it) load_scales(it + kEG, sf_sidx, next_scales);  // consumed at the end of this iteration
 
                 mbar_wait(&bar_eta_full[b], bph);
                 tc_fence_after();
@@ -437,8 +444,9 @@ fed_glm_fp8_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParam
                 if constexpr (DYN) {
                     // all four row-group exponents of this tile -> one word per chain; B row n = 4 * chain + term
                     // reads it from lane n of every subpartition
-                    if (eg) asm volatile("bar.sync 2, 128;" ::: "memory");
-                    else asm volatile("bar.sync 1, 128;" ::: "memory");
+                    if (eg == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
+                    else if (eg == 1) asm volatile("bar.sync 2, 128;" ::: "memory");
+                    else asm volatile("bar.sync 3, 128;" ::: "memory");
                     const int ch = min(lane >> 2, KF - 1);
                     const uint32_t w = *reinterpret_cast<const uint32_t*>(expo_slot + ch * 4);
                     tmem_st_x1(tmem_sfb_r + lane_addr + b * 4, w);
@@ -447,9 +455,9 @@ fed_glm_fp8_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParam
                 }
                 mbar_arrive(&bar_r_full[b]);
 
-                // scales for this group's next tile (it+2): its ring slot was last used by tile it-2,
-                // whose MMAs are complete (we just passed r_empty of tile it-2 and eta_full of tile it)
-                if (it + 2 < n_it) store_scales(it + 2, next_scales);
+                // scales for this group's next tile (it+kEG): its ring slot was last used by tile it-kEG,
+                // whose MMAs are complete (we just passed r_empty of tile it-kEG and eta_full of tile it)
+                if (it + kEG < n_it) store_scales(it + kEG, next_scales);
 
                 // the gradient accumulator of a period is flushed by whichever group owns its last tile
                 const bool last = (it % kFlushF) == kFlushF - 1 || it == n_it - 1;
@@ -493,8 +501,9 @@ fed_glm_fp8_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParam
             if (threadIdx.x == 0 && k < nch) out[k * (1 + PG)] = ll_block;
         }
         for (int i = threadIdx.x; i < nch * G; i += blockDim.x) out[(i / G) * (1 + PG) + 1 + (i % G)] = fed::fix_get(gi_acc[i]);
-        for (int pass = 0; pass < 2; ++pass) {  // group A first, then group B adds its periods
-            if ((pass == 0 && warp >= 2 && warp <= 5) || (pass == 1 && warp >= 7)) {
+        for (int pass = 0; pass < kEG; ++pass) {  // group 0 first, then the others add their periods
+            const int my_group = (warp >= 2 && warp <= 5) ? 0 : (warp >= 7 ? (warp - 7) / 4 + 1 : -1);
+            if (my_group == pass) {
                 const int row = (warp & 3) * 32 + lane;
                 for (int h = 0; h < NH; ++h)
 #pragma unroll
