@@ -337,7 +337,8 @@ fed_glm_fp8_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParam
             // smem store + proxy fence, TMEM scale stores).  kEG groups rotate over the tiles so that kEG
             // chains overlap; group g owns eta/R buffer g, so every barrier still sees 128 arrivals.
             // Measured (8 x 10M x 256): 1 group 269, 2 groups 279 -> 295 with host-packed scale words,
-            // 3 groups 297 evals/s — beyond two groups the group count is no longer the bound.
+            // 3 groups 297 evals/s — beyond two groups the group count is no longer the bound
+            // (prefetching y one iteration ahead did not move it either: 293).
             const int eg = warp >= 7 ? (warp - 7) / 4 + 1 : 0;
             const int q4 = warp & 3;
             const int row = q4 * 32 + lane;
