@@ -37,7 +37,7 @@ from typing import AsyncIterator, Callable, Dict, List, Optional, Sequence, Tupl
 import numpy as np
 import psutil
 
-from .npproto.utils import ndarray_from_numpy, ndarray_to_numpy
+from .npproto.utils import ndarray_from_numpy, ndarray_to_numpy  # noqa: F401  (importable from here, as in the reference)
 from .rpc import (
     CHANNEL_OPTIONS,
     ROUTE_EVALUATE_STREAM,

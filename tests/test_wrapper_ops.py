@@ -13,7 +13,7 @@ from pytensor_federated_b200 import (
     LogpOp,
     op_async,
 )
-from pytensor_federated_b200._graph_backend import FunctionGraph, at, function, grad
+from pytensor_federated_b200._graph_backend import at, function, grad
 
 
 class _MockClient:
