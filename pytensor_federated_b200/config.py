@@ -47,6 +47,8 @@ def _env_pair(name: str, default: Tuple[float, float]) -> Tuple[float, float]:
 
 @dataclasses.dataclass
 class FederationConfig:
+    """Engine / client knobs with environment overrides (``B200FED_COMM``, ``B200FED_TIMEOUT``, ...)."""
+
     comm: str = "auto"
     multicast: bool = True
     glm_kernel: str = "auto"
@@ -72,4 +74,5 @@ class FederationConfig:
 
 
 def get_config() -> FederationConfig:
+    """The configuration in effect: defaults overridden by ``B200FED_*`` environment variables."""
     return FederationConfig.from_env()

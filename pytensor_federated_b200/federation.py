@@ -99,6 +99,7 @@ class NodeFederation:
 
 
 def free_port() -> int:
+    """An unused TCP port on 127.0.0.1 (rendezvous of a freshly launched federation)."""
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
         return s.getsockname()[1]

@@ -275,6 +275,7 @@ def quantize_block_fp8(X, block: int = 32):
 
 
 def dequantize_block_fp8(Xq, scales, block: int = 32):
+    """Inverse of :func:`quantize_block_fp8` (fp32 result); the oracle of the fp8 kernel tests."""
     import torch
 
     n, P = Xq.shape

@@ -21,6 +21,11 @@ def lv_rhs(u, v, th):
 
 
 class OdeShards(ShardModel):
+    """Lotka–Volterra parameter estimation: every shard holds many observed time series; one evaluation
+    integrates them (RK4 with forward sensitivities, ``csrc/ode.cu``) and returns the Gaussian
+    log-likelihood and its gradient w.r.t. ``theta = (alpha, beta, gamma, delta)``.  The reference only
+    describes this workload in prose (``/root/reference/README.md:39-52``)."""
+
     def __init__(self, ts: Sequence, y0s: Sequence, y_obs: Sequence, sigmas: Sequence[float], substeps: int = 8):
         import torch
 

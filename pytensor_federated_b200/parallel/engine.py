@@ -35,7 +35,7 @@ _STOP = -1.0
 
 
 class FederationError(RuntimeError):
-    pass
+    """The engine was misused or the native runtime reported a failure (message carries the native error)."""
 
 
 class FederationTimeout(TimeoutError):

@@ -21,6 +21,8 @@ BatchFn = Callable[[np.ndarray], Tuple[np.ndarray, np.ndarray]]
 
 @dataclasses.dataclass
 class BatchedResult:
+    """Draws and diagnostics of K lock-step chains (``hmc_sample_batched``)."""
+
     samples: np.ndarray        # [draws, K, D]
     logp: np.ndarray           # [draws, K]
     accept_rate: np.ndarray    # [K]

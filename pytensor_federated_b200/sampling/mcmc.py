@@ -12,6 +12,8 @@ LogpDlogp = Callable[[np.ndarray], Tuple[float, np.ndarray]]
 
 @dataclasses.dataclass
 class SamplerResult:
+    """Draws and diagnostics of one chain (``hmc_sample`` / ``nuts_sample``)."""
+
     samples: np.ndarray            # [draws, dim]
     logp: np.ndarray               # [draws]
     accept_rate: float

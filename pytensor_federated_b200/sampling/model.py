@@ -16,6 +16,10 @@ LOG_SQRT_2PI = 0.91893853320467274178
 
 
 class Model:
+    """Minimal model builder over the graph backend: free variables with priors (``Normal``, ``HalfNormal``),
+    ``Potential`` terms (e.g. the outputs of ``LogpGradOp`` nodes), a compiled ``logp_dlogp(theta)`` and the
+    ``find_map`` / ``sample`` conveniences — what ``pm.Model`` is to the reference's ``demo_model.py:28-44``."""
+
     def __init__(self) -> None:
         self.free: List[Tuple[str, object, Tuple[int, ...]]] = []   # (name, variable, shape)
         self.terms: List[object] = []

@@ -195,6 +195,7 @@ def register_local_node(host: str, port: int, compute_func: ComputeFunc, name: s
 
 
 def unregister_local_node(host: str, port: int) -> None:
+    """Removes an in-process node; clients connected to it get ``StreamTerminatedError`` on their next call."""
     node = _local_nodes.pop((str(host), int(port)), None)
     if node is not None:
         node.alive = False

@@ -58,6 +58,9 @@ class LogpOp(Op):
 
 
 class AsyncLogpOp(AsyncOp, LogpOp):
+    """:class:`LogpOp` whose ``logp_func`` is a coroutine function (e.g. ``LogpServiceClient.evaluate_async``);
+    several of them in one graph are awaited concurrently after the ``fuse_asyncs`` rewrite."""
+
     async def perform_async(self, node: Apply, inputs: Sequence[Any], output_storage: OutputStorageType) -> None:
         output_storage[0][0] = await self._logp_func(*inputs)
 
@@ -100,6 +103,9 @@ class LogpGradOp(Op):
 
 
 class AsyncLogpGradOp(AsyncOp, LogpGradOp):
+    """:class:`LogpGradOp` whose ``logp_grad_func`` is a coroutine function (e.g.
+    ``LogpGradServiceClient.evaluate_async``); fusable into a :class:`ParallelAsyncOp`."""
+
     async def perform_async(self, node: Apply, inputs: Sequence[Any], output_storage: OutputStorageType) -> None:
         self._store(await self._logp_grad_func(*inputs), output_storage)
 
