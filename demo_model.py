@@ -35,8 +35,8 @@ def build_model(remote_ops, n: int):
     return m
 
 
-def run_model(remote_ops, n: int, tune: int, draws: int):
-    from pytensor_federated_b200.sampling import find_map, nuts_sample
+def run_model(remote_ops, n: int, tune: int, draws: int, chains: int = 1):
+    from pytensor_federated_b200.sampling import find_map, nuts_sample, summarize
 
     m = build_model(remote_ops, n)
     m.compile()
@@ -51,6 +51,10 @@ def run_model(remote_ops, n: int, tune: int, draws: int):
     print(f"{res.n_logp_evals} logp+grad evaluations in {dt:.2f} s "
           f"({res.n_logp_evals / dt:.0f} model evals/s, {n * res.n_logp_evals / dt:.0f} node evals/s); "
           f"accept {res.accept_rate:.2f}, divergences {res.divergences}")
+    if chains > 1:  # further chains (the reference's pm.sample runs 4) and the cross-chain diagnostics
+        _, cols = m.sample(draws=draws, tune=tune, chains=chains, start=theta_map, seed=1234)
+        for name, row in summarize(cols).items():
+            print(f"{name:>16s}  mean {row['mean']:8.4f}  sd {row['sd']:7.4f}  ess {row['ess']:7.1f}  rhat {row['rhat']:.3f}")
     return res
 
 
@@ -108,9 +112,10 @@ if __name__ == "__main__":
     parser.add_argument("--nodes", default=3, type=int, help="remote calls per model evaluation")
     parser.add_argument("--tune", default=500, type=int)
     parser.add_argument("--draws", default=200, type=int)
+    parser.add_argument("--chains", default=1, type=int, help="> 1: run further chains and print ESS / R-hat")
     parser.add_argument("--pymc", action="store_true", help="sample with PyMC instead of the in-repo NUTS")
     args, _ = parser.parse_known_args()
-    runner = run_model_pymc if args.pymc else run_model
+    runner = run_model_pymc if args.pymc else (lambda *a: run_model(*a, chains=args.chains))
     if args.fused:
         ops, handle = remote_ops_fused(args.fused)
         runner(ops, args.fused, args.tune, args.draws)

@@ -8,7 +8,9 @@ callable, plus a minimal model builder over the graph IR.  With PyMC installed t
 ``pm.Potential`` exactly as the reference's do.
 """
 from .batched import BatchedResult, glm_batch_fn, hmc_sample_batched
+from .diagnostics import effective_sample_size, split_rhat, summarize
 from .mcmc import SamplerResult, find_map, hmc_sample, nuts_sample
 from .model import Model
 
-__all__ = ["Model", "SamplerResult", "find_map", "hmc_sample", "nuts_sample", "BatchedResult", "hmc_sample_batched", "glm_batch_fn"]
+__all__ = ["Model", "SamplerResult", "find_map", "hmc_sample", "nuts_sample", "BatchedResult", "hmc_sample_batched", "glm_batch_fn",
+           "split_rhat", "effective_sample_size", "summarize"]

@@ -60,22 +60,13 @@ class SamplerResult:
 
 
 def effective_sample_size(x: np.ndarray) -> float:
-    """Geyer initial-positive-sequence ESS of one chain."""
+    """ESS of one chain (or ``[draws, chains]``); see :mod:`.diagnostics`."""
+    from .diagnostics import effective_sample_size as _ess
+
     x = np.asarray(x, dtype=np.float64)
-    n = len(x)
-    if n < 4 or np.var(x) == 0:
-        return float(n)
-    xc = x - x.mean()
-    f = np.fft.rfft(xc, 2 * n)
-    acf = np.fft.irfft(f * np.conj(f))[:n].real
-    acf /= acf[0]
-    s = 0.0
-    for k in range(1, n - 1, 2):
-        pair = acf[k] + acf[k + 1]
-        if pair < 0:
-            break
-        s += pair
-    return float(n / max(1.0, 1.0 + 2.0 * s))
+    if x.shape[0] < 4 or np.var(x) == 0:
+        return float(x.size)
+    return _ess(x)
 
 
 def find_map(logp_dlogp: LogpDlogp, x0: np.ndarray, *, maxiter: int = 500, tol: float = 1e-10):

@@ -113,20 +113,28 @@ class Model:
         theta, info = find_map(self.logp_dlogp, np.zeros(self.dim) if start is None else start, **kwargs)
         return self.point(theta), info
 
-    def sample(self, draws: int = 200, tune: int = 500, *, start: Optional[np.ndarray] = None, seed: int = 0, **kwargs):
-        """NUTS from ``start`` (default: the MAP); returns ``(SamplerResult, {name: draws})``."""
+    def sample(self, draws: int = 200, tune: int = 500, *, chains: int = 1, start: Optional[np.ndarray] = None,
+               seed: int = 0, **kwargs):
+        """NUTS from ``start`` (default: the MAP).  ``chains == 1`` returns ``(SamplerResult, {name: draws})``;
+        ``chains > 1`` runs them one after the other with seeds ``seed, seed + 1, ...`` and returns
+        ``([SamplerResult, ...], {name: draws[draws, chains(, k)]})`` — feed the dict to
+        :func:`~pytensor_federated_b200.sampling.summarize` for ESS / R-hat."""
         from .mcmc import find_map, nuts_sample
 
         if start is None:
             start, _ = find_map(self.logp_dlogp, np.zeros(self.dim))
-        res = nuts_sample(self.logp_dlogp, start, draws=draws, tune=tune, seed=seed, **kwargs)
+        results = [nuts_sample(self.logp_dlogp, start, draws=draws, tune=tune, seed=seed + c, **kwargs)
+                   for c in range(chains)]
+        samples = np.stack([r.samples for r in results], axis=1)          # [draws, chains, dim]
         columns = {}
         pos = 0
         for name, _, shape in self.free:
             n = int(np.prod(shape)) if shape else 1
-            block = res.samples[:, pos : pos + n]
-            columns[name] = block[:, 0] if not shape else block
+            block = samples[:, :, pos : pos + n]
+            columns[name] = block[:, :, 0] if not shape else block
             pos += n
         for name, (free_name, back) in self.transforms.items():
             columns[name] = back(columns[free_name])
-        return res, columns
+        if chains == 1:
+            return results[0], {k: v[:, 0] for k, v in columns.items()}
+        return results, columns

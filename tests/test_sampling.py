@@ -196,3 +196,45 @@ def test_half_normal_and_model_conveniences():
     res, cols = m.sample(draws=300, tune=300, seed=4)
     assert set(cols) == {"mu", "sigma_log__", "sigma"} and np.all(cols["sigma"] > 0)
     assert abs(np.median(cols["sigma"]) - data.std()) < 0.06 and res.divergences == 0
+
+
+def test_diagnostics_on_known_processes():
+    from pytensor_federated_b200.sampling import effective_sample_size, split_rhat, summarize
+
+    rng = np.random.default_rng(0)
+    iid = rng.normal(size=(2000, 4))
+    assert abs(split_rhat(iid) - 1.0) < 0.01
+    assert 6000 < effective_sample_size(iid) < 10000            # ~ number of draws
+    # AR(1) with phi = 0.9: ESS ~ N (1 - phi) / (1 + phi) = N / 19
+    ar = np.zeros((4000, 4))
+    eps = rng.normal(size=ar.shape)
+    for t in range(1, ar.shape[0]):
+        ar[t] = 0.9 * ar[t - 1] + eps[t]
+    ess = effective_sample_size(ar)
+    assert 16000 / 19 / 1.6 < ess < 16000 / 19 * 1.6
+    # chains stuck in different places
+    assert split_rhat(iid + np.array([0.0, 0.0, 3.0, 3.0])) > 1.5
+    # a trend inside every chain is caught by the split
+    assert split_rhat(iid + np.linspace(0, 3, 2000)[:, None]) > 1.2
+    table = summarize({"a": iid, "v": rng.normal(2.0, 0.5, size=(500, 2, 3))})
+    assert set(table) == {"a", "v[0]", "v[1]", "v[2]"}
+    assert abs(table["v[1]"]["mean"] - 2.0) < 0.1 and abs(table["v[1]"]["sd"] - 0.5) < 0.05
+    assert table["a"]["q3"] < -1.5 and table["a"]["q97"] > 1.5
+    with pytest.raises(ValueError):
+        split_rhat(np.zeros((3, 2)))
+
+
+def test_model_sample_multiple_chains_converge():
+    from pytensor_federated_b200._graph_backend import at
+    from pytensor_federated_b200.sampling import summarize
+
+    m = Model()
+    mu = m.Normal("mu", 0.0, 10.0)
+    data = np.random.default_rng(1).normal(0.7, 1.0, size=50)
+    z = at.as_tensor(data) - mu
+    m.Potential("lik", (-0.5 * z * z).sum())
+    results, cols = m.sample(draws=300, tune=300, chains=3, seed=10)
+    assert len(results) == 3 and cols["mu"].shape == (300, 3)
+    row = summarize(cols)["mu"]
+    assert row["rhat"] < 1.03 and row["ess"] > 150
+    assert abs(row["mean"] - data.mean()) < 0.08 and abs(row["sd"] - 1 / np.sqrt(50)) < 0.04
