@@ -11,6 +11,7 @@ from .batched import BatchedResult, glm_batch_fn, hmc_sample_batched
 from .diagnostics import effective_sample_size, split_rhat, summarize
 from .mcmc import SamplerResult, find_map, hmc_sample, nuts_sample
 from .model import Model
+from .parallel import sample_parallel
 
 __all__ = ["Model", "SamplerResult", "find_map", "hmc_sample", "nuts_sample", "BatchedResult", "hmc_sample_batched", "glm_batch_fn",
-           "split_rhat", "effective_sample_size", "summarize"]
+           "split_rhat", "effective_sample_size", "summarize", "sample_parallel"]

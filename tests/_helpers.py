@@ -18,11 +18,30 @@ def free_port() -> int:
         return s.getsockname()[1]
 
 
+def gaussian_logp_grad_func(theta):
+    """ComputeFunc of a N(1, 0.5^2 I) log-density: ``(logp, dlogp/dtheta)``."""
+    z = (np.asarray(theta, dtype=np.float64) - 1.0) / 0.5
+    return [np.asarray(-0.5 * np.sum(z * z)), -z / 0.5]
+
+
+def remote_gaussian_logp_dlogp(hosts_and_ports):
+    """Picklable model factory for sample_parallel: connects (load-balanced) inside the worker."""
+    from pytensor_federated_b200 import LogpGradServiceClient
+
+    client = LogpGradServiceClient(hosts_and_ports=hosts_and_ports)
+
+    def logp_dlogp(theta):
+        logp, (grad,) = client.evaluate(theta)
+        return float(logp), np.asarray(grad, dtype=np.float64)
+
+    return logp_dlogp
+
+
 def _serve(port: int, n_clients: int, func_name: str, ready) -> None:
     from pytensor_federated_b200 import service
     from pytensor_federated_b200.rpc import Server
 
-    func = {"product": product_func}[func_name]
+    func = {"product": product_func, "gaussian": gaussian_logp_grad_func}[func_name]
 
     async def main():
         svc = service.ArraysToArraysService(func)

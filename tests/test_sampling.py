@@ -238,3 +238,29 @@ def test_model_sample_multiple_chains_converge():
     row = summarize(cols)["mu"]
     assert row["rhat"] < 1.03 and row["ess"] > 150
     assert abs(row["mean"] - data.mean()) < 0.08 and abs(row["sd"] - 1 / np.sqrt(50)) < 0.04
+
+
+def test_chains_in_worker_processes_over_replicas(monkeypatch):
+    """Replica parallelism: one chain per process, each with its own balanced connection to a fleet of
+    identical servers (reference: ``pm.sample(cores=...)`` in test_wrapper_ops.py:305-317)."""
+    import functools
+
+    from _helpers import ServerProcess, remote_gaussian_logp_dlogp
+    from pytensor_federated_b200.sampling import sample_parallel, summarize
+
+    monkeypatch.setenv("B200FED_CONNECT_SLEEP", "0,0")
+    servers = [ServerProcess(func="gaussian").start() for _ in range(2)]
+    try:
+        factory = functools.partial(remote_gaussian_logp_dlogp, [("127.0.0.1", s.port) for s in servers])
+        results = sample_parallel(factory, np.zeros(2), chains=2, cores=2, sampler="hmc", draws=150, tune=150, seed=5)
+    finally:
+        for s in servers:
+            s.terminate()
+    assert len(results) == 2 and all(r.samples.shape == (150, 2) for r in results)
+    assert not np.array_equal(results[0].samples, results[1].samples)      # different seeds
+    draws = np.stack([r.samples for r in results], axis=1)                  # [draws, chains, dim]
+    table = summarize({"theta": draws})
+    for row in table.values():
+        assert abs(row["mean"] - 1.0) < 0.15 and abs(row["sd"] - 0.5) < 0.12 and row["rhat"] < 1.1
+    with pytest.raises(ValueError):
+        sample_parallel(factory, np.zeros(2), sampler="gibbs")
