@@ -41,8 +41,9 @@ class LinearModelBlackbox:
         return logp, grads
 
 
-async def run_node_async(*, bind: str, port: int, delay: float, device: str) -> None:
+async def run_node_async(*, bind: str, port: int, delay: float, device: str, metrics_port: int = 0) -> None:
     from pytensor_federated_b200 import ArraysToArraysService, wrap_logp_grad_func
+    from pytensor_federated_b200.metrics import ServiceMetrics
     from pytensor_federated_b200.models import make_demo_data
     from pytensor_federated_b200.rpc import Server
 
@@ -53,26 +54,29 @@ async def run_node_async(*, bind: str, port: int, delay: float, device: str) -> 
     print(scipy.stats.linregress(x, y))
     model_fn = LinearModelBlackbox(x, y, sigma, delay=delay, device=device)
     _log.info("Binding the service to %s on port %i", bind, port)
-    server = Server([ArraysToArraysService(wrap_logp_grad_func(model_fn))])
+    metrics = ServiceMetrics(port=metrics_port) if metrics_port else None   # Prometheus /metrics endpoint
+    server = Server([ArraysToArraysService(wrap_logp_grad_func(model_fn), metrics=metrics)])
     await server.start(bind, port)
     await server.wait_closed()
 
 
-def run_node(args: Tuple[str, int, float, str]) -> None:
-    bind, port, delay, device = args
+def run_node(args: Tuple[str, int, float, str, int]) -> None:
+    bind, port, delay, device, metrics_port = args
     logging.basicConfig(level=logging.INFO)
     try:
-        asyncio.new_event_loop().run_until_complete(run_node_async(bind=bind, port=port, delay=delay, device=device))
+        asyncio.new_event_loop().run_until_complete(
+            run_node_async(bind=bind, port=port, delay=delay, device=device, metrics_port=metrics_port))
     except KeyboardInterrupt:
         pass
 
 
-def run_node_pool(bind: str, ports: Sequence[int], delay: float, device: str) -> None:
+def run_node_pool(bind: str, ports: Sequence[int], delay: float, device: str, metrics_port: int = 0) -> None:
     _log.info("Launching workers on %i subprocesses", len(ports))
     ctx = multiprocessing.get_context("spawn")  # CUDA contexts do not survive fork()
     with ctx.Pool(len(ports)) as pool:
         try:
-            pool.map(run_node, [(bind, p, delay, device) for p in ports])
+            pool.map(run_node, [(bind, p, delay, device, metrics_port + i if metrics_port else 0)
+                                for i, p in enumerate(ports)])
         except KeyboardInterrupt:
             _log.info("Stopping workers...")
             pool.terminate()
@@ -87,5 +91,7 @@ if __name__ == "__main__":
                         help="Port numbers for the ArraysToArrays gRPC service.")
     parser.add_argument("--delay", default=0, type=float, help="Seconds to sleep in each evaluation.")
     parser.add_argument("--device", default="auto", choices=["auto", "cuda", "cpu"])
+    parser.add_argument("--metrics-port", default=0, type=int,
+                        help="Prometheus endpoint of the first worker (worker i serves on this port + i); 0 = off.")
     args, _ = parser.parse_known_args()
-    run_node_pool(args.bind, [int(p) for p in str(args.ports).split(",")], args.delay, args.device)
+    run_node_pool(args.bind, [int(p) for p in str(args.ports).split(",")], args.delay, args.device, args.metrics_port)

@@ -15,6 +15,9 @@ Environment variables (all optional):
 ``B200FED_PROBE_TIMEOUT``   seconds to wait for a ``GetLoad`` answer
 ``B200FED_GRAPH_BACKEND``   ``auto`` | ``builtin`` — graph IR of the Op layer
 ``B200FED_NVTX``            set to wrap every evaluation in an NVTX range (host-side tracing)
+``B200FED_METRICS_PORT``    Prometheus ``/metrics`` port of a node started with ``service.serve`` (``metrics.py``)
+``B200FED_NO_LL``           set to force the fence + flag protocol for small results (default: flag-in-data words)
+``B200FED_LL_MAX_VALS`` / ``B200FED_LL_MAX_THETA``   size thresholds of the flag-in-data protocol (128 / 256)
 """
 from __future__ import annotations
 

@@ -31,6 +31,7 @@ import logging
 import os
 import random
 import threading
+import time
 import uuid
 from typing import AsyncIterator, Callable, Dict, List, Optional, Sequence, Tuple
 
@@ -108,11 +109,13 @@ def gpu_load(gpu_index: int) -> Optional[Tuple[float, float]]:
 class ArraysToArraysService(ArraysToArraysServiceBase):
     """Serves a ``ComputeFunc`` over the ``ArraysToArraysService`` gRPC schema."""
 
-    def __init__(self, compute_func: ComputeFunc, *, offload: bool = False, gpu_index: Optional[int] = None) -> None:
+    def __init__(self, compute_func: ComputeFunc, *, offload: bool = False, gpu_index: Optional[int] = None,
+                 metrics=None) -> None:
         self._compute_func = compute_func
         self._n_clients = 0
         self._offload = offload
         self._gpu_index = gpu_index
+        self._metrics = metrics  # optional metrics.ServiceMetrics (Prometheus counters / latency histogram)
         # psutil's load average needs one priming call to start monitoring.
         self.determine_load()
         super().__init__()
@@ -130,12 +133,28 @@ class ArraysToArraysService(ArraysToArraysServiceBase):
         return result
 
     async def _run(self, input_arrays: InputArrays) -> OutputArrays:
+        if self._metrics is None:
+            return await self._run_unmetered(input_arrays)
+        t0 = time.perf_counter()
+        ok = False
+        try:
+            result = await self._run_unmetered(input_arrays)
+            ok = True
+            return result
+        finally:
+            self._metrics.observe(t0, ok)
+
+    async def _run_unmetered(self, input_arrays: InputArrays) -> OutputArrays:
         if self._offload:
             loop = asyncio.get_running_loop()
             return await loop.run_in_executor(
                 None, _run_compute_func, input_arrays, self._compute_func
             )
         return _run_compute_func(input_arrays, self._compute_func)
+
+    def _clients_changed(self) -> None:
+        if self._metrics is not None:
+            self._metrics.set_clients(self._n_clients)
 
     async def evaluate(self, input_arrays: InputArrays) -> OutputArrays:
         return await self._run(input_arrays)
@@ -145,11 +164,13 @@ class ArraysToArraysService(ArraysToArraysServiceBase):
     ) -> AsyncIterator[OutputArrays]:
         _log.info("Evaluation stream opened")
         self._n_clients += 1
+        self._clients_changed()
         try:
             async for input_arrays in input_arrays_iterator:
                 yield await self._run(input_arrays)
         finally:
             self._n_clients -= 1
+            self._clients_changed()
             _log.info("Evaluation stream closed")
 
     async def get_load(self, get_load_params: GetLoadParams) -> GetLoadResult:
@@ -631,9 +652,10 @@ async def serve(
     ready: Optional[Callable[[int], None]] = None,
 ) -> None:
     """Serves ``compute_func`` until cancelled (helper for node launchers)."""
+    from .metrics import metrics_from_env
     from .rpc import Server
 
-    service = ArraysToArraysService(compute_func, offload=offload)
+    service = ArraysToArraysService(compute_func, offload=offload, metrics=metrics_from_env())
     server = Server([service])
     bound = await server.start(bind, port)
     _log.info("Serving on %s:%i", bind, bound)

@@ -241,3 +241,50 @@ def test_concurrent_async_clients_share_a_loop():
     finally:
         for s in servers:
             s.terminate()
+
+
+def test_prometheus_metrics_of_a_serving_node():
+    """Counters, latency histogram and the client gauge; scraped over HTTP like Prometheus would."""
+    import urllib.request
+
+    pytest.importorskip("prometheus_client")
+    from pytensor_federated_b200.metrics import ServiceMetrics, metrics_from_env
+    from pytensor_federated_b200.rpc import InputArrays
+
+    assert metrics_from_env() is None          # opt-in only
+    metrics = ServiceMetrics(port=0, addr="127.0.0.1")
+    calls = {"n": 0}
+
+    def flaky(a):
+        calls["n"] += 1
+        if calls["n"] == 3:
+            raise RuntimeError("boom")
+        return [a * 2]
+
+    svc = service.ArraysToArraysService(flaky, metrics=metrics)
+    loop = get_useful_event_loop()
+    request = InputArrays.from_arrays([np.arange(3.0)], uuid="u")
+
+    async def drive():
+        async def requests():
+            for _ in range(2):
+                yield request
+
+        gen = svc.evaluate_stream(requests())
+        first = await gen.__anext__()
+        assert svc._n_clients == 1 and "b200fed_clients 1.0" in metrics.render()
+        await gen.__anext__()
+        with pytest.raises(StopAsyncIteration):
+            await gen.__anext__()
+        with pytest.raises(RuntimeError):
+            await svc.evaluate(request)
+        return first
+
+    first = loop.run_until_complete(drive())
+    np.testing.assert_array_equal(first.arrays[0], [0.0, 2.0, 4.0])
+    try:
+        text = urllib.request.urlopen(f"http://127.0.0.1:{metrics.port}/metrics", timeout=5).read().decode()
+    finally:
+        metrics.close()
+    assert "b200fed_evaluations_total 3.0" in text and "b200fed_errors_total 1.0" in text
+    assert "b200fed_clients 0.0" in text and "b200fed_compute_seconds_count 3.0" in text
