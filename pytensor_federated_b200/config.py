@@ -16,6 +16,8 @@ Environment variables (all optional):
 ``B200FED_GRAPH_BACKEND``   ``auto`` | ``builtin`` — graph IR of the Op layer
 ``B200FED_NVTX``            set to wrap every evaluation in an NVTX range (host-side tracing)
 ``B200FED_METRICS_PORT``    Prometheus ``/metrics`` port of a node started with ``service.serve`` (``metrics.py``)
+``B200FED_TLS_CA`` / ``B200FED_TLS_CERT`` / ``B200FED_TLS_KEY`` / ``B200FED_TLS_SERVER_NAME`` / ``B200FED_TLS_MUTUAL``
+                            PEM files that switch the gRPC path to TLS (see :class:`TlsConfig`)
 ``B200FED_NO_LL``           set to force the fence + flag protocol for small results (default: flag-in-data words)
 ``B200FED_LL_MAX_VALS`` / ``B200FED_LL_MAX_THETA``   size thresholds of the flag-in-data protocol (128 / 256)
 """
@@ -23,7 +25,7 @@ from __future__ import annotations
 
 import dataclasses
 import os
-from typing import Tuple
+from typing import Optional, Tuple
 
 
 def _env_float(name: str, default: float) -> float:
@@ -74,6 +76,43 @@ class FederationConfig:
             probe_timeout=_env_float("B200FED_PROBE_TIMEOUT", 5.0),
             graph_backend=os.environ.get("B200FED_GRAPH_BACKEND", "auto"),
         )
+
+
+@dataclasses.dataclass(frozen=True)
+class TlsConfig:
+    """TLS material of the gRPC path (PEM bytes).  The reference only speaks plaintext
+    (``grpclib.client.Channel(host, port)``, ``/root/reference/pytensor_federated/service.py:230``); nodes
+    that hold private data usually sit behind TLS, optionally with client certificates.
+
+    Server: ``cert`` + ``key`` (its identity); ``ca`` + ``mutual=True`` additionally demands client certs.
+    Client: ``ca`` (who signed the server), optionally ``cert`` + ``key`` (its identity for mutual TLS) and
+    ``server_name`` when the certificate was issued for a name other than the dialled host."""
+
+    ca: Optional[bytes] = None
+    cert: Optional[bytes] = None
+    key: Optional[bytes] = None
+    server_name: Optional[str] = None
+    mutual: bool = False
+
+    @classmethod
+    def from_files(cls, ca: Optional[str] = None, cert: Optional[str] = None, key: Optional[str] = None,
+                   server_name: Optional[str] = None, mutual: bool = False) -> "TlsConfig":
+        def read(path):
+            if not path:
+                return None
+            with open(path, "rb") as fh:
+                return fh.read()
+
+        return cls(ca=read(ca), cert=read(cert), key=read(key), server_name=server_name, mutual=mutual)
+
+
+def tls_from_env() -> Optional[TlsConfig]:
+    """``TlsConfig`` from the ``B200FED_TLS_*`` variables (paths to PEM files), or ``None`` = plaintext."""
+    ca, cert, key = (os.environ.get(f"B200FED_TLS_{k}") for k in ("CA", "CERT", "KEY"))
+    if not (ca or cert):
+        return None
+    return TlsConfig.from_files(ca, cert, key, os.environ.get("B200FED_TLS_SERVER_NAME"),
+                                bool(os.environ.get("B200FED_TLS_MUTUAL")))
 
 
 def get_config() -> FederationConfig:

@@ -356,9 +356,12 @@ class Server:
     reference's launchers use (``Server([service]); await start(host, port);
     await wait_closed()`` — ``/root/reference/demo_node.py:76-79``)."""
 
-    def __init__(self, services: Sequence[ArraysToArraysServiceBase]) -> None:
+    def __init__(self, services: Sequence[ArraysToArraysServiceBase], *, tls=None) -> None:
+        """``tls``: a :class:`~pytensor_federated_b200.config.TlsConfig` with ``cert`` + ``key`` (default: the
+        ``B200FED_TLS_*`` environment, else plaintext like the reference)."""
         self._services = list(services)
         self._server = None
+        self._tls = tls
         self.port: Optional[int] = None
 
     async def start(self, host: str = "127.0.0.1", port: int = 0) -> int:
@@ -366,7 +369,19 @@ class Server:
 
         self._server = grpc.aio.server(options=CHANNEL_OPTIONS)
         self._server.add_generic_rpc_handlers(tuple(s.generic_handler() for s in self._services))
-        self.port = self._server.add_insecure_port(f"{host}:{port}")
+        from .config import tls_from_env
+
+        tls = self._tls if self._tls is not None else tls_from_env()
+        if tls is not None and tls.cert and tls.key:
+            import grpc
+
+            credentials = grpc.ssl_server_credentials(
+                [(tls.key, tls.cert)], root_certificates=tls.ca if tls.mutual else None,
+                require_client_auth=bool(tls.mutual and tls.ca),
+            )
+            self.port = self._server.add_secure_port(f"{host}:{port}", credentials)
+        else:
+            self.port = self._server.add_insecure_port(f"{host}:{port}")
         if self.port == 0:
             raise OSError(f"Could not bind {host}:{port}")
         await self._server.start()

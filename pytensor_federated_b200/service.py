@@ -234,6 +234,26 @@ def _lookup_local(host, port) -> Optional[LocalNode]:
 # ---------------------------------------------------------------------------
 
 
+_default_tls = None
+_default_tls_set = False
+
+
+def set_default_tls(tls) -> None:
+    """Process-wide TLS material for outgoing connections (a :class:`~pytensor_federated_b200.config.TlsConfig`
+    with at least ``ca``); ``None`` = plaintext.  Without a call the ``B200FED_TLS_*`` environment decides, so
+    worker processes of a sampler inherit the setting.  Clients stay picklable: no credentials live on them."""
+    global _default_tls, _default_tls_set
+    _default_tls, _default_tls_set = tls, True
+
+
+def _channel_tls():
+    if _default_tls_set:
+        return _default_tls
+    from .config import tls_from_env
+
+    return tls_from_env()
+
+
 class _Channel:
     """``grpc.aio`` channel plus the bookkeeping the reference exposes on its
     channel objects (``_host`` / ``_port``; tests and log lines read them)."""
@@ -243,7 +263,18 @@ class _Channel:
 
         self._host = host
         self._port = port
-        self._channel = grpc.aio.insecure_channel(f"{host}:{port}", options=CHANNEL_OPTIONS)
+        tls = _channel_tls()
+        if tls is not None and tls.ca:
+            import grpc
+
+            credentials = grpc.ssl_channel_credentials(root_certificates=tls.ca, private_key=tls.key,
+                                                       certificate_chain=tls.cert)
+            options = CHANNEL_OPTIONS
+            if tls.server_name:
+                options = options + (("grpc.ssl_target_name_override", tls.server_name),)
+            self._channel = grpc.aio.secure_channel(f"{host}:{port}", credentials, options=options)
+        else:
+            self._channel = grpc.aio.insecure_channel(f"{host}:{port}", options=CHANNEL_OPTIONS)
         self._closed = False
 
     @property
@@ -677,6 +708,7 @@ __all__ = [
     "get_load_async",
     "get_loads_async",
     "register_local_node",
+    "set_default_tls",
     "unregister_local_node",
     "serve",
     "start_bidirectional_stream",
