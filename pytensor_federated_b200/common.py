@@ -84,13 +84,14 @@ class LogpServiceClient(_ClientAdapter):
         """Alias for ``.evaluate(*inputs)``."""
         return self.evaluate(*inputs)
 
-    def evaluate(self, *inputs: np.ndarray, use_stream: bool = True) -> np.ndarray:
-        """Evaluates the federated log-potential; returns the scalar ``logp``."""
-        (logp,) = self._client.evaluate(*inputs, use_stream=use_stream)
+    def evaluate(self, *inputs: np.ndarray, use_stream: bool = True, **kwargs) -> np.ndarray:
+        """Evaluates the federated log-potential; returns the scalar ``logp``
+        (``retries`` / ``timeout`` are passed on to :meth:`ArraysToArraysServiceClient.evaluate_async`)."""
+        (logp,) = self._client.evaluate(*inputs, use_stream=use_stream, **kwargs)
         return logp
 
-    async def evaluate_async(self, *inputs: np.ndarray, use_stream: bool = True) -> np.ndarray:
-        (logp,) = await self._client.evaluate_async(*inputs, use_stream=use_stream)
+    async def evaluate_async(self, *inputs: np.ndarray, use_stream: bool = True, **kwargs) -> np.ndarray:
+        (logp,) = await self._client.evaluate_async(*inputs, use_stream=use_stream, **kwargs)
         return logp
 
 
@@ -102,19 +103,20 @@ class LogpGradServiceClient(_ClientAdapter):
         return self.evaluate(*inputs)
 
     def evaluate(
-        self, *inputs: np.ndarray, use_stream: bool = True
+        self, *inputs: np.ndarray, use_stream: bool = True, **kwargs
     ) -> Tuple[np.ndarray, List[np.ndarray]]:
         """Evaluates the federated log-potential and its gradients.
 
-        Returns ``(logp, gradients)`` with one gradient per input.
+        Returns ``(logp, gradients)`` with one gradient per input
+        (``retries`` / ``timeout`` are passed on to :meth:`ArraysToArraysServiceClient.evaluate_async`).
         """
-        logp, *gradients = self._client.evaluate(*inputs, use_stream=use_stream)
+        logp, *gradients = self._client.evaluate(*inputs, use_stream=use_stream, **kwargs)
         return logp, gradients
 
     async def evaluate_async(
-        self, *inputs: np.ndarray, use_stream: bool = True
+        self, *inputs: np.ndarray, use_stream: bool = True, **kwargs
     ) -> Tuple[np.ndarray, List[np.ndarray]]:
-        logp, *gradients = await self._client.evaluate_async(*inputs, use_stream=use_stream)
+        logp, *gradients = await self._client.evaluate_async(*inputs, use_stream=use_stream, **kwargs)
         return logp, gradients
 
 

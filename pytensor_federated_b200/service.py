@@ -620,7 +620,7 @@ class ArraysToArraysServiceClient:
         return loop.run_until_complete(self.evaluate_async(*inputs, **kwargs))
 
     async def evaluate_async(
-        self, *inputs: np.ndarray, use_stream: bool = True, retries: int = 2
+        self, *inputs: np.ndarray, use_stream: bool = True, retries: int = 2, timeout: Optional[float] = None
     ) -> List[np.ndarray]:
         """Evaluates the federated compute function on ``inputs``.
 
@@ -634,6 +634,10 @@ class ArraysToArraysServiceClient:
         retries
             How many times to re-connect (possibly to another replica) when the
             connection is lost mid-call.
+        timeout
+            Seconds one attempt may take (default: unbounded, like the reference).  A node that accepts
+            the call but never answers is treated like a lost connection: the stream is dropped, the next
+            attempt re-balances, and ``TimeoutError`` is raised when every attempt timed out.
         """
         if retries < 0:
             raise ValueError("Number of retries must be >= 0.")
@@ -653,16 +657,22 @@ class ArraysToArraysServiceClient:
                     return _evaluate_local(priv.local, inputs)
                 if input is None:
                     input = InputArrays.from_arrays([np.asarray(i) for i in inputs], uuid=str(uuid.uuid4()))
-                output = await _connect_evaluate_async(input, cid, hap, use_stream)
+                call = _connect_evaluate_async(input, cid, hap, use_stream)
+                output = await (call if timeout is None else asyncio.wait_for(call, timeout))
                 break
-            except StreamTerminatedError as ex:
+            except (StreamTerminatedError, asyncio.TimeoutError) as ex:
                 last_error = ex
                 cp = _privates.pop(cid, None)
                 if cp is not None:
-                    _log.warning("Lost connection to %s:%s.", cp.channel._host, cp.channel._port)
+                    what = "No answer within the timeout from" if isinstance(ex, asyncio.TimeoutError) else "Lost connection to"
+                    _log.warning("%s %s:%s.", what, cp.channel._host, cp.channel._port)
+                    if cp.stream is not None:
+                        cp.stream._call.cancel()  # a half-finished request must not be answered into the next one
                     cp.close()
 
         if output is None:
+            if isinstance(last_error, asyncio.TimeoutError):
+                raise TimeoutError(f"No answer within {timeout} s in {retries + 1} attempt(s).")
             raise StreamTerminatedError(
                 f"Evaluation failed after {retries + 1} attempt(s): {last_error}"
             )

@@ -18,6 +18,13 @@ def free_port() -> int:
         return s.getsockname()[1]
 
 
+def slow_product_func(a, b):
+    """Like the product, but a == 99 takes a second (a node that accepts a call and then stalls)."""
+    if a == 99:
+        time.sleep(1.0)
+    return [a * b]
+
+
 def gaussian_logp_grad_func(theta):
     """ComputeFunc of a N(1, 0.5^2 I) log-density: ``(logp, dlogp/dtheta)``."""
     z = (np.asarray(theta, dtype=np.float64) - 1.0) / 0.5
@@ -41,7 +48,7 @@ def _serve(port: int, n_clients: int, func_name: str, ready) -> None:
     from pytensor_federated_b200 import service
     from pytensor_federated_b200.rpc import Server
 
-    func = {"product": product_func, "gaussian": gaussian_logp_grad_func}[func_name]
+    func = {"product": product_func, "gaussian": gaussian_logp_grad_func, "slow_product": slow_product_func}[func_name]
 
     async def main():
         svc = service.ArraysToArraysService(func)

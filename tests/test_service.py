@@ -7,12 +7,13 @@ Every "node" is a child process on 127.0.0.1, an unbound port plays a dead node,
 import asyncio
 import multiprocessing
 import pickle
+import time
 from unittest import mock
 
 import numpy as np
 import pytest
 
-from pytensor_federated_b200 import service
+from pytensor_federated_b200 import LogpServiceClient, service
 from pytensor_federated_b200.npproto.utils import ndarray_from_numpy, ndarray_to_numpy
 from pytensor_federated_b200.rpc import GetLoadResult, InputArrays, OutputArrays
 from pytensor_federated_b200.utils import get_useful_event_loop
@@ -288,3 +289,22 @@ def test_prometheus_metrics_of_a_serving_node():
         metrics.close()
     assert "b200fed_evaluations_total 3.0" in text and "b200fed_errors_total 1.0" in text
     assert "b200fed_clients 0.0" in text and "b200fed_compute_seconds_count 3.0" in text
+
+
+def test_per_attempt_timeout_detects_a_stalled_node(monkeypatch):
+    """A node that accepts the call but does not answer: ``timeout`` turns it into ``TimeoutError`` and the
+    stale answer can never be mistaken for the reply to a later request (fresh stream + uuid check)."""
+    monkeypatch.setenv("B200FED_CONNECT_SLEEP", "0,0")
+    with ServerProcess(func="slow_product") as srv:
+        client = service.ArraysToArraysServiceClient("127.0.0.1", srv.port)
+        (out,) = client.evaluate(np.array(3), np.array(4), timeout=5.0)
+        assert out == 12
+        t0 = time.perf_counter()
+        with pytest.raises(TimeoutError):
+            client.evaluate(np.array(99), np.array(2), timeout=0.25, retries=0)
+        assert time.perf_counter() - t0 < 0.9
+        # the node finishes its stalled computation, then serves the next request correctly
+        (out,) = client.evaluate(np.array(5), np.array(6), timeout=10.0)
+        assert out == 30
+        logp_client = LogpServiceClient("127.0.0.1", srv.port)
+        assert logp_client.evaluate(np.array(2), np.array(8), timeout=10.0, retries=1) == 16
