@@ -658,25 +658,43 @@ class ArraysToArraysServiceClient:
                 if input is None:
                     input = InputArrays.from_arrays([np.asarray(i) for i in inputs], uuid=str(uuid.uuid4()))
                 call = _connect_evaluate_async(input, cid, hap, use_stream)
-                output = await (call if timeout is None else asyncio.wait_for(call, timeout))
+                output = await (call if timeout is None else _bounded(call, timeout))
                 break
-            except (StreamTerminatedError, asyncio.TimeoutError) as ex:
+            except (StreamTerminatedError, _AttemptTimedOut) as ex:
                 last_error = ex
                 cp = _privates.pop(cid, None)
                 if cp is not None:
-                    what = "No answer within the timeout from" if isinstance(ex, asyncio.TimeoutError) else "Lost connection to"
+                    what = "No answer within the timeout from" if isinstance(ex, _AttemptTimedOut) else "Lost connection to"
                     _log.warning("%s %s:%s.", what, cp.channel._host, cp.channel._port)
                     if cp.stream is not None:
                         cp.stream._call.cancel()  # a half-finished request must not be answered into the next one
                     cp.close()
 
         if output is None:
-            if isinstance(last_error, asyncio.TimeoutError):
+            if isinstance(last_error, _AttemptTimedOut):
                 raise TimeoutError(f"No answer within {timeout} s in {retries + 1} attempt(s).")
             raise StreamTerminatedError(
                 f"Evaluation failed after {retries + 1} attempt(s): {last_error}"
             )
         return list(output.arrays)
+
+
+class _AttemptTimedOut(Exception):
+    """One evaluation attempt exceeded the caller's ``timeout`` (distinct from the ``TimeoutError`` that
+    ``connect_balanced`` raises when no server answers the load probes)."""
+
+
+async def _bounded(coro, timeout: float):
+    task = asyncio.ensure_future(coro)
+    done, _ = await asyncio.wait({task}, timeout=timeout)
+    if not done:
+        task.cancel()
+        try:
+            await task
+        except BaseException:  # noqa: BLE001 - the cancelled attempt's outcome is irrelevant
+            pass
+        raise _AttemptTimedOut()
+    return task.result()
 
 
 def _evaluate_local(node: LocalNode, inputs) -> List[np.ndarray]:
