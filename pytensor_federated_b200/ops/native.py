@@ -93,14 +93,18 @@ def load(build_if_missing: bool = True) -> C.CDLL:
         _build.build()
     if not LIB_PATH.exists():
         raise NativeError(f"{LIB_PATH} is missing; run `python -m pytensor_federated_b200.build`")
-    try:
-        import torch  # noqa: F401  (loads the libcudart.so.12 that the library links against)
-    except Exception:  # pragma: no cover
-        pass
+    # The library's RUNPATH points at the libcudart.so.12 of the CUDA runtime wheel (build.py), so it loads
+    # on its own; gRPC-only processes (codec users) must not pay a multi-second `import torch` for it.
+    # If that fails (relocated environment) torch is imported first: it brings the same libcudart along.
     try:
         lib = C.CDLL(str(LIB_PATH), mode=os.RTLD_NOW | os.RTLD_LOCAL)
-    except OSError as ex:
-        raise NativeError(f"could not load {LIB_PATH}: {ex}") from ex
+    except OSError:
+        try:
+            import torch  # noqa: F401
+
+            lib = C.CDLL(str(LIB_PATH), mode=os.RTLD_NOW | os.RTLD_LOCAL)
+        except (OSError, ImportError) as ex:
+            raise NativeError(f"could not load {LIB_PATH}: {ex}") from ex
     _declare(lib)
     _lib = lib
     return lib

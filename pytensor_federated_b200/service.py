@@ -118,6 +118,10 @@ class ArraysToArraysService(ArraysToArraysServiceBase):
         self._metrics = metrics  # optional metrics.ServiceMetrics (Prometheus counters / latency histogram)
         # psutil's load average needs one priming call to start monitoring.
         self.determine_load()
+        # Load the message codec now: the first request should not pay for a library load.
+        from .npproto import native_codec
+
+        native_codec.available()
         super().__init__()
 
     def determine_load(self) -> GetLoadResult:
@@ -450,6 +454,10 @@ class ClientPrivates:
         """
         rng = random.Random(random.randint(0, 100_000) ^ os.getpid() ^ threading.get_ident())
         candidates = [(str(h), int(p)) for h, p in hosts_and_ports]
+        # replicas that recently stalled on a call sit out (unless nothing else is left)
+        now = time.monotonic()
+        healthy = [c for c in candidates if _quarantine.get(c, 0.0) <= now]
+        candidates = healthy or candidates
         rng.shuffle(candidates)
 
         lo, hi = _connect_sleep_range()
@@ -489,6 +497,11 @@ class _LocalChannel:
     def close(self) -> None:
         self._closed = True
 
+
+QUARANTINE_SECONDS = 30.0
+_quarantine: Dict[Tuple[str, int], float] = {}
+"""Replicas that exceeded a caller's ``timeout``: (host, port) -> monotonic time until which the balancer
+skips them.  Process-local, like the connection cache."""
 
 _privates: Dict[str, ClientPrivates] = {}
 """Non-reusable connections, keyed by :func:`thread_pid_id`."""
@@ -636,8 +649,9 @@ class ArraysToArraysServiceClient:
             connection is lost mid-call.
         timeout
             Seconds one attempt may take (default: unbounded, like the reference).  A node that accepts
-            the call but never answers is treated like a lost connection: the stream is dropped, the next
-            attempt re-balances, and ``TimeoutError`` is raised when every attempt timed out.
+            the call but never answers is treated like a lost connection: the stream is dropped, the node
+            is skipped by the balancer for ``QUARANTINE_SECONDS``, the next attempt re-balances over the
+            remaining replicas, and ``TimeoutError`` is raised when every attempt timed out.
         """
         if retries < 0:
             raise ValueError("Number of retries must be >= 0.")
@@ -666,6 +680,11 @@ class ArraysToArraysServiceClient:
                 if cp is not None:
                     what = "No answer within the timeout from" if isinstance(ex, _AttemptTimedOut) else "Lost connection to"
                     _log.warning("%s %s:%s.", what, cp.channel._host, cp.channel._port)
+                    if isinstance(ex, _AttemptTimedOut):
+                        try:
+                            _quarantine[(str(cp.channel._host), int(cp.channel._port))] = time.monotonic() + QUARANTINE_SECONDS
+                        except (TypeError, ValueError):  # in-process nodes have symbolic addresses
+                            pass
                     if cp.stream is not None:
                         cp.stream._call.cancel()  # a half-finished request must not be answered into the next one
                     cp.close()

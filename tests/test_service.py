@@ -308,3 +308,27 @@ def test_per_attempt_timeout_detects_a_stalled_node(monkeypatch):
         assert out == 30
         logp_client = LogpServiceClient("127.0.0.1", srv.port)
         assert logp_client.evaluate(np.array(2), np.array(8), timeout=10.0, retries=1) == 16
+
+
+def test_stalled_replica_is_quarantined_and_the_call_fails_over(monkeypatch):
+    monkeypatch.setenv("B200FED_CONNECT_SLEEP", "0,0")
+    service._quarantine.clear()
+    stalling = ServerProcess(func="slow_product", n_clients=0).start()     # preferred by the balancer
+    healthy = ServerProcess(func="product", n_clients=5).start()
+    try:
+        client = service.ArraysToArraysServiceClient(
+            hosts_and_ports=[("127.0.0.1", stalling.port), ("127.0.0.1", healthy.port)])
+        (out,) = client.evaluate(np.array(99), np.array(2), timeout=0.5, retries=1)
+        assert out == 198
+        cid = service.thread_pid_id(client)
+        assert int(service._privates[cid].channel._port) == healthy.port
+        assert ("127.0.0.1", stalling.port) in service._quarantine
+        # with every replica quarantined the balancer falls back to the full list instead of giving up
+        service._quarantine[("127.0.0.1", healthy.port)] = time.monotonic() + 60
+        other = service.ArraysToArraysServiceClient(
+            hosts_and_ports=[("127.0.0.1", stalling.port), ("127.0.0.1", healthy.port)])
+        assert other.evaluate(np.array(2), np.array(2))[0] == 4
+    finally:
+        service._quarantine.clear()
+        stalling.terminate()
+        healthy.terminate()
