@@ -269,12 +269,18 @@ class FederatedEngine:
 
     # device-timed benchmarking hooks (root, fused)
     def launch(self) -> int:
+        """Enqueues one evaluation with the current theta (``set_device_theta`` or the last ``evaluate``)
+        and returns its epoch without waiting.  Results live in ONE host-mapped buffer: with several
+        epochs in flight ``wait`` returns the newest completed result, and models small enough for the
+        flag-in-data protocol (``n_vals <= 128``) must ``wait`` for each epoch before launching the next —
+        their result words are tagged with the exact epoch."""
         rc = self._lib.b200_engine_launch(self._handle)
         if rc != 0:
             self._raise(rc)
         return int(self._lib.b200_engine_epoch(self._handle))
 
     def wait(self, epoch: int) -> np.ndarray:
+        """Spins on the host-mapped completion flag (or tagged result words) of ``epoch``; see :meth:`launch`."""
         rc = self._lib.b200_engine_wait(self._handle, epoch, self._out_p, self.timeout + 5.0)
         if rc != 0:
             self._raise(rc)
