@@ -149,6 +149,10 @@ class ArraysToArraysService(ArraysToArraysServiceBase):
             self._metrics.observe(t0, ok)
 
     async def _run_unmetered(self, input_arrays: InputArrays) -> OutputArrays:
+        if getattr(self._compute_func, "is_coroutine_compute_func", False) or asyncio.iscoroutinefunction(self._compute_func):
+            # coroutine compute functions (e.g. batching.DynamicBatcher) overlap waiting requests
+            outputs = await self._compute_func(*input_arrays.arrays)
+            return OutputArrays.from_arrays([np.asarray(o) for o in outputs], uuid=input_arrays.uuid)
         if self._offload:
             loop = asyncio.get_running_loop()
             return await loop.run_in_executor(
