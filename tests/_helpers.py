@@ -19,9 +19,9 @@ def free_port() -> int:
 
 
 def slow_product_func(a, b):
-    """Like the product, but a == 99 takes a second (a node that accepts a call and then stalls)."""
+    """Like the product, but a == 99 takes two seconds (a node that accepts a call and then stalls)."""
     if a == 99:
-        time.sleep(1.0)
+        time.sleep(2.0)
     return [a * b]
 
 

@@ -302,7 +302,7 @@ def test_per_attempt_timeout_detects_a_stalled_node(monkeypatch):
         t0 = time.perf_counter()
         with pytest.raises(TimeoutError):
             client.evaluate(np.array(99), np.array(2), timeout=0.25, retries=0)
-        assert time.perf_counter() - t0 < 0.9
+        assert time.perf_counter() - t0 < 1.5
         # the node finishes its stalled computation, then serves the next request correctly
         (out,) = client.evaluate(np.array(5), np.array(6), timeout=10.0)
         assert out == 30
@@ -318,7 +318,7 @@ def test_stalled_replica_is_quarantined_and_the_call_fails_over(monkeypatch):
     try:
         client = service.ArraysToArraysServiceClient(
             hosts_and_ports=[("127.0.0.1", stalling.port), ("127.0.0.1", healthy.port)])
-        (out,) = client.evaluate(np.array(99), np.array(2), timeout=0.5, retries=1)
+        (out,) = client.evaluate(np.array(99), np.array(2), timeout=1.0, retries=1)
         assert out == 198
         cid = service.thread_pid_id(client)
         assert int(service._privates[cid].channel._port) == healthy.port
