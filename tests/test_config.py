@@ -13,3 +13,15 @@ def test_defaults_and_env_overrides(monkeypatch):
     monkeypatch.setenv("B200FED_SERVE_AHEAD", "not-a-number")
     cfg = get_config()
     assert (cfg.comm, cfg.timeout, cfg.connect_sleep, cfg.multicast, cfg.serve_ahead) == ("ipc", 3.5, (0.0, 0.0), False, 8)
+
+
+def test_operator_cli_info(capsys):
+    import json
+
+    from pytensor_federated_b200.__main__ import main
+
+    assert main(["info"]) == 0
+    info = json.loads(capsys.readouterr().out)
+    assert info["version"] and info["graph_backend"] in ("builtin", "pytensor")
+    assert set(info["config"]) >= {"comm", "timeout", "serve_ahead"} and info["tls"] is None
+    assert "built" in info["native_library"]
