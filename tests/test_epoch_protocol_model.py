@@ -1,0 +1,184 @@
+"""Executable model of the cross-GPU epoch protocol of csrc/fed_comm.cuh (docs/PROTOCOL.md).
+
+Stores to other GPUs / the host become visible late and out of order: every store goes into a pool and is
+applied at a random later time; only a *release* store is held back until the writer's earlier stores
+have landed (fence + st.release.sys), and a flag-in-data ("LL") word is its own unit.  Kernels of one
+node run back to back (stream order), their CTAs interleave freely with everything else.  The model
+checks, for random interleavings and several epochs, that
+
+* every CTA of every node computes with exactly the theta of its epoch (never a mix of two epochs),
+* the host receives, per epoch, exactly the rank-ordered sum of that epoch's node partials,
+* nothing dead-locks — and that the checks have teeth: dropping the fence is detected.
+"""
+import random
+
+import pytest
+
+N_THETA = 3
+
+
+class World:
+    def __init__(self, nodes, ctas, epochs, rng, ll=False, fence=True):
+        self.n, self.g, self.epochs, self.rng, self.ll, self.fence = nodes, ctas, epochs, rng, ll, fence
+        zero_word = (0.0, 0)
+        self.mail = [{"theta": [zero_word if ll else 0.0] * N_THETA, "flag": 0} for _ in range(nodes)]
+        self.slots = [zero_word if ll else 0.0 for _ in range(nodes)]
+        self.slot_flags = [0] * nodes
+        self.host_theta = [0.0] * N_THETA
+        self.host_result = zero_word if ll else 0.0
+        self.host_flag = 0
+        self.partials = [[0.0] * ctas for _ in range(nodes)]
+        self.ticket = [0] * nodes
+        self.pool = []          # pending remote stores: [writer, seq, is_release, apply]
+        self.seq = 0
+        self.results = {}
+
+    # -- memory ---------------------------------------------------------------------------------------
+    def store(self, writer, apply, release=False):
+        self.seq += 1
+        self.pool.append([writer, self.seq, release, apply])
+
+    def deliverable(self):
+        out = []
+        for item in self.pool:
+            writer, seq, release, _ = item
+            if release and self.fence and any(w == writer and s < seq for w, s, _, _ in self.pool):
+                continue            # a release store waits for the writer's earlier stores
+            out.append(item)
+        return out
+
+    @staticmethod
+    def theta_of(epoch):
+        return [epoch * 10.0 + i for i in range(N_THETA)]
+
+    @staticmethod
+    def partial_of(theta, node, cta):
+        return sum(theta) * (node + 1) + cta
+
+    # -- device code ------------------------------------------------------------------------------------
+    def cta(self, node, c, epoch):
+        root = node == 0
+        writer = ("cta", node, c, epoch)
+        if root and c == 0:                                   # broadcast
+            theta = list(self.host_theta)
+            for peer in range(self.n):
+                for i, v in enumerate(theta):
+                    word = (v, epoch) if self.ll else v
+                    self.store(writer, lambda p=peer, i=i, w=word: self.mail[p]["theta"].__setitem__(i, w))
+                    yield
+                if not self.ll:
+                    self.store(writer, lambda p=peer: self.mail[p].__setitem__("flag", epoch), release=True)
+        got = []
+        if self.ll:                                           # acquire: poll the tagged words
+            for i in range(N_THETA):
+                while self.mail[node]["theta"][i][1] != epoch:
+                    yield
+                got.append(self.mail[node]["theta"][i][0])
+        else:                                                 # acquire: flag, then the data
+            while self.mail[node]["flag"] < epoch:
+                yield
+            for i in range(N_THETA):
+                got.append(self.mail[node]["theta"][i])
+                yield
+        assert got == self.theta_of(epoch), f"node {node} CTA {c} computed epoch {epoch} with theta {got}"
+        self.partials[node][c] = self.partial_of(got, node, c)
+        yield
+        self.ticket[node] += 1                                # atomic
+        if self.ticket[node] != self.g:
+            return
+        self.ticket[node] = 0
+        node_sum = sum(self.partials[node])                   # fixed order
+        word = (node_sum, epoch) if self.ll else node_sum
+        self.store(writer, lambda: self.slots.__setitem__(node, word))
+        if not self.ll:
+            self.store(writer, lambda: self.slot_flags.__setitem__(node, epoch), release=True)
+        if not root:
+            return
+        total = 0.0
+        for rank in range(self.n):                            # rank order
+            if self.ll:
+                while self.slots[rank][1] != epoch:
+                    yield
+                total += self.slots[rank][0]
+            else:
+                while self.slot_flags[rank] < epoch:
+                    yield
+                total += self.slots[rank]
+            yield
+        if self.ll:
+            self.store(writer, lambda: setattr(self, "host_result", (total, epoch)))
+        else:
+            self.store(writer, lambda: setattr(self, "host_result", total))
+            self.store(writer, lambda: setattr(self, "host_flag", epoch), release=True)
+
+    def node_stream(self, node):
+        """Kernels of one node in stream order; the root's are launched by the host, peers' are pre-enqueued."""
+        for epoch in range(1, self.epochs + 1):
+            if node == 0:
+                while self.launched < epoch:
+                    yield
+            ctas = [self.cta(node, c, epoch) for c in range(self.g)]
+            while ctas:
+                c = self.rng.choice(ctas)
+                try:
+                    next(c)
+                except StopIteration:
+                    ctas.remove(c)
+                yield
+
+    def host(self):
+        for epoch in range(1, self.epochs + 1):
+            self.host_theta = self.theta_of(epoch)            # visible to the kernel launched afterwards
+            self.launched = epoch
+            if self.ll:
+                while self.host_result[1] != epoch:
+                    yield
+                self.results[epoch] = self.host_result[0]
+            else:
+                while self.host_flag < epoch:
+                    yield
+                self.results[epoch] = self.host_result
+            yield
+
+    def run(self):
+        self.launched = 0
+        actors = [self.host()] + [self.node_stream(n) for n in range(self.n)]
+        steps = 0
+        while actors:
+            steps += 1
+            assert steps < 200_000, "dead-lock / live-lock"
+            ready = self.deliverable()
+            if ready and (self.rng.random() < 0.5):
+                item = self.rng.choice(ready)
+                self.pool.remove(item)
+                item[3]()
+                continue
+            a = self.rng.choice(actors)
+            try:
+                next(a)
+            except StopIteration:
+                actors.remove(a)
+        for item in list(self.pool):
+            item[3]()
+        return self
+
+    def expected(self, epoch):
+        theta = self.theta_of(epoch)
+        return sum(self.partial_of(theta, n, c) for n in range(self.n) for c in range(self.g))
+
+
+@pytest.mark.parametrize("ll", [False, True], ids=["fence+flag", "flag-in-data"])
+def test_epochs_never_mix_and_results_are_exact(ll):
+    rng = random.Random(99 + ll)
+    for trial in range(60):
+        nodes, ctas, epochs = rng.randint(1, 4), rng.randint(1, 3), rng.randint(1, 5)
+        w = World(nodes, ctas, epochs, random.Random(rng.random()), ll=ll).run()
+        assert w.results == {e: w.expected(e) for e in range(1, epochs + 1)}, (nodes, ctas, epochs)
+
+
+def test_the_model_notices_a_missing_fence():
+    """Without fence + release ordering the flag can overtake theta: some schedule reads a stale word."""
+    rng = random.Random(5)
+    with pytest.raises(AssertionError):
+        for _ in range(300):
+            World(3, 2, 4, random.Random(rng.random()), ll=False, fence=False).run()
