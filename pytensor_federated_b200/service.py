@@ -722,6 +722,8 @@ async def _bounded(coro, timeout: float):
 
 def _evaluate_local(node: LocalNode, inputs) -> List[np.ndarray]:
     outputs = node.compute_func(*[np.asarray(i) for i in inputs])
+    if asyncio.iscoroutine(outputs):  # coroutine compute functions (e.g. a DynamicBatcher) work in-process too
+        outputs = get_useful_event_loop().run_until_complete(outputs)
     return [np.asarray(o) for o in outputs]
 
 

@@ -89,3 +89,15 @@ def test_batching_node_over_grpc_serves_several_clients_with_fewer_launches(monk
         loop.run_until_complete(server.close(None))
     assert len(calls) < 12                      # 12 requests, far fewer launches
     assert batcher.n_requests == 12
+
+
+def test_coroutine_compute_function_behind_an_in_process_node():
+    batcher = DynamicBatcher(lambda reqs: [[r[0] + 1] for r in reqs], max_batch=2, max_delay=0.0)
+    service.register_local_node("batched", 0, batcher)
+    try:
+        client = ArraysToArraysServiceClient("batched", 0)
+        np.testing.assert_array_equal(client.evaluate(np.array([1.0, 2.0]))[0], [2.0, 3.0])
+        np.testing.assert_array_equal(client.evaluate(np.array([5.0]))[0], [6.0])   # cached fast path
+    finally:
+        service.unregister_local_node("batched", 0)
+        get_useful_event_loop().run_until_complete(batcher.close())
