@@ -396,16 +396,17 @@ def zeros_like(x) -> Variable:
 
 
 class Stack(Op):
-    """Stacks scalars into a vector (``at.stack``)."""
+    """Stacks equally shaped tensors (typically scalars) along a new leading axis (``at.stack``)."""
 
     __props__ = ()
 
     def make_node(self, *xs) -> Apply:
         xs = [as_tensor(x) for x in xs]
-        return Apply(self, xs, [TensorType("float64", (None,))()])
+        nd = max(x.type.ndim for x in xs)
+        return Apply(self, xs, [TensorType("float64", (None,) * (nd + 1))()])
 
     def perform(self, node, inputs, output_storage) -> None:
-        output_storage[0][0] = np.asarray([float(np.asarray(x)) for x in inputs])
+        output_storage[0][0] = np.stack([np.asarray(x, dtype=np.float64) for x in inputs], axis=0)
 
     def grad(self, inputs, output_grads):
         (g,) = output_grads
@@ -427,6 +428,95 @@ _sqr = Elemwise("sqr", np.square, lambda ins, out, g: [g * 2.0 * ins[0]])
 _sqrt = Elemwise("sqrt", np.sqrt, lambda ins, out, g: [g / (2.0 * out)], True)
 _sigmoid = Elemwise("sigmoid", lambda x: 1.0 / (1.0 + np.exp(-x)), lambda ins, out, g: [g * out * (1.0 - out)], True)
 _softplus = Elemwise("softplus", lambda x: np.logaddexp(0.0, x), lambda ins, out, g: [g * sigmoid(ins[0])], True)
+
+
+_tanh = Elemwise("tanh", np.tanh, lambda ins, out, g: [g * (1.0 - out * out)], True)
+_log1p = Elemwise("log1p", np.log1p, lambda ins, out, g: [g / (1.0 + ins[0])], True)
+_abs = Elemwise("abs", np.abs, lambda ins, out, g: [g * _sign(ins[0])])
+_sign = Elemwise("sign", np.sign, lambda ins, out, g: [zeros_like(ins[0])])
+_maximum = Elemwise("maximum", np.maximum,
+                    lambda ins, out, g: [g * _ge(ins[0], ins[1]), g * (1.0 - _ge(ins[0], ins[1]))])
+_ge = Elemwise("ge", lambda a, b: (np.asarray(a) >= np.asarray(b)).astype(np.float64),
+               lambda ins, out, g: [zeros_like(ins[0]), zeros_like(ins[1])], True)
+
+
+class Dot(Op):
+    """``dot(a, b)`` for vectors and matrices (NumPy semantics for 1-d / 2-d operands)."""
+
+    __props__ = ()
+
+    def make_node(self, a, b) -> Apply:
+        a, b = as_tensor(a), as_tensor(b)
+        if not (1 <= a.type.ndim <= 2 and 1 <= b.type.ndim <= 2):
+            raise TypeError("dot supports vectors and matrices")
+        nd = a.type.ndim + b.type.ndim - 2
+        return Apply(self, [a, b], [TensorType(np.result_type(a.type.dtype, b.type.dtype), (None,) * nd)()])
+
+    def perform(self, node, inputs, output_storage) -> None:
+        output_storage[0][0] = np.asarray(np.dot(*inputs), dtype=node.outputs[0].type.dtype)
+
+    def grad(self, inputs, output_grads):
+        a, b = inputs
+        (g,) = output_grads
+        na, nb = a.type.ndim, b.type.ndim
+        if na == 1 and nb == 1:
+            return [g * b, g * a]
+        if na == 2 and nb == 1:          # (m,k).(k,) -> (m,)
+            return [ExpandDims(1)(g) * ExpandDims(0)(b), Dot()(Transpose()(a), g)]
+        if na == 1 and nb == 2:          # (k,).(k,n) -> (n,)
+            return [Dot()(b, g), ExpandDims(1)(a) * ExpandDims(0)(g)]
+        return [Dot()(g, Transpose()(b)), Dot()(Transpose()(a), g)]
+
+
+class Transpose(Op):
+    __props__ = ()
+
+    def make_node(self, x) -> Apply:
+        x = as_tensor(x)
+        return Apply(self, [x], [x.type()])
+
+    def perform(self, node, inputs, output_storage) -> None:
+        output_storage[0][0] = np.ascontiguousarray(np.transpose(inputs[0]))
+
+    def grad(self, inputs, output_grads):
+        return [Transpose()(output_grads[0])]
+
+
+def dot(a, b): return Dot()(a, b)
+def transpose(x): return Transpose()(x)
+def tanh(a): return _tanh(a)
+def log1p(a): return _log1p(a)
+def abs(a): return _abs(a)  # noqa: A001 - mirrors pytensor.tensor.abs
+def maximum(a, b): return _maximum(a, b)
+
+
+def mean(x, axis=None):
+    x = as_tensor(x)
+    total = x.sum(axis)
+    return total / _size_like(x, axis)
+
+
+class _SizeAlong(Op):
+    """Number of elements reduced by ``sum(axis)`` as a float scalar (runtime shape)."""
+
+    __props__ = ("axis",)
+
+    def __init__(self, axis=None) -> None:
+        self.axis = axis
+
+    def make_node(self, x) -> Apply:
+        return Apply(self, [as_tensor(x)], [TensorType("float64", ())()])
+
+    def perform(self, node, inputs, output_storage) -> None:
+        shape = np.shape(inputs[0])
+        output_storage[0][0] = np.asarray(float(np.prod(shape) if self.axis is None else shape[self.axis]))
+
+    def grad(self, inputs, output_grads):
+        return [zeros_like(inputs[0])]
+
+
+def _size_like(x, axis):
+    return _SizeAlong(axis)(x)
 
 
 def add(a, b): return _add(a, b)

@@ -78,3 +78,38 @@ def test_replace_validate_rolls_back_on_failure():
     with pytest.raises(ValueError):
         fg.replace_all_validate([(fg.outputs[0].owner.inputs[0], b)])  # b is foreign -> invalid graph
     assert [n.op for n in fg.toposort()] == before
+
+
+def test_dot_transpose_and_more_elementwise_gradients():
+    """dot (all vector/matrix combinations), transpose, tanh, log1p, abs, maximum, mean vs finite differences."""
+    from pytensor_federated_b200.graph import core as at
+
+    rng = np.random.default_rng(0)
+
+    def num_grad(fn, v, eps=1e-6):
+        g = np.zeros_like(v)
+        for idx in np.ndindex(*v.shape):
+            vp, vm = v.copy(), v.copy()
+            vp[idx] += eps
+            vm[idx] -= eps
+            g[idx] = (fn(vp) - fn(vm)) / (2 * eps)
+        return g
+
+    A, B, x, b = at.matrix("A"), at.matrix("B"), at.vector("x"), at.vector("b")
+    cost = (at.sum(at.tanh(at.dot(A, x) + b)) + at.mean(at.log1p(at.abs(x))) + at.sum(at.maximum(x, 0.1))
+            + at.sum(at.sqr(at.dot(A, B))) + at.sum(at.sqr(at.dot(x, B))) + at.dot(x, x) + at.sum(at.transpose(A) * 0.5))
+    f = at.function([A, B, x, b], [cost] + list(at.grad(cost, [A, B, x, b])))
+    vals = [rng.normal(size=(3, 2)), rng.normal(size=(2, 4)), rng.normal(size=2), rng.normal(size=3)]
+    out = f(*vals)
+    for i in range(4):
+        def scalar(v, i=i):
+            args = list(vals)
+            args[i] = v
+            return float(f(*args)[0])
+
+        np.testing.assert_allclose(out[1 + i], num_grad(scalar, vals[i]), atol=2e-5)
+    g = at.function([x], [at.mean(x), at.mean(at.stack([x, x]), axis=0)])
+    m, m0 = g(np.array([1.0, 3.0]))
+    assert m == 2.0 and m0.tolist() == [1.0, 3.0]
+    with pytest.raises(TypeError):
+        at.dot(at.scalar("s"), x)
