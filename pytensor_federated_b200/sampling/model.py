@@ -16,7 +16,8 @@ LOG_SQRT_2PI = 0.91893853320467274178
 
 
 class Model:
-    """Minimal model builder over the graph backend: free variables with priors (``Normal``, ``HalfNormal``),
+    """Minimal model builder over the graph backend: free variables with priors (``Flat``, ``Normal``,
+    ``HalfNormal``, ``Exponential``, ``Uniform`` — constrained ones are sampled on an unconstrained scale),
     ``Potential`` terms (e.g. the outputs of ``LogpGradOp`` nodes), a compiled ``logp_dlogp(theta)`` and the
     ``find_map`` / ``sample`` conveniences — what ``pm.Model`` is to the reference's ``demo_model.py:28-44``."""
 
@@ -55,6 +56,27 @@ class Model:
         # log N+(x | sigma) + log |dx / dlog x| = log 2 - log sigma - log sqrt(2 pi) - z^2 / 2 + log x
         self.terms.append(-0.5 * z * z + log_var + (np.log(2.0) - np.log(sigma) - LOG_SQRT_2PI))
         self.transforms[name] = (f"{name}_log__", np.exp)
+        return var
+
+    def Exponential(self, name: str, lam=1.0):
+        """Positive scalar with density ``lam * exp(-lam x)``, sampled on the log scale."""
+        log_var = self._new(f"{name}_log__", None)
+        var = at.exp(log_var)
+        self.terms.append(np.log(lam) - lam * var + log_var)           # + log |dx / dlog x|
+        self.transforms[name] = (f"{name}_log__", np.exp)
+        return var
+
+    def Uniform(self, name: str, lower=0.0, upper=1.0):
+        """Scalar on ``(lower, upper)`` with a flat prior, sampled on the logit scale."""
+        if not upper > lower:
+            raise ValueError("upper must exceed lower")
+        logit = self._new(f"{name}_interval__", None)
+        unit = at.sigmoid(logit)
+        var = lower + (upper - lower) * unit
+        # density 1 / (upper - lower) times |dx / dlogit| = (upper - lower) * s * (1 - s)
+        # log s + log(1 - s) in the overflow-free form
+        self.terms.append(-(at.softplus(-logit) + at.softplus(logit)))
+        self.transforms[name] = (f"{name}_interval__", lambda z, lo=lower, hi=upper: lo + (hi - lo) / (1.0 + np.exp(-z)))
         return var
 
     def Potential(self, name: str, var) -> None:

@@ -264,3 +264,27 @@ def test_chains_in_worker_processes_over_replicas(monkeypatch):
         assert abs(row["mean"] - 1.0) < 0.15 and abs(row["sd"] - 0.5) < 0.12 and row["rhat"] < 1.1
     with pytest.raises(ValueError):
         sample_parallel(factory, np.zeros(2), sampler="gibbs")
+
+
+def test_constrained_priors_sample_their_own_distribution():
+    """Exponential (log scale) and Uniform (logit scale): with no likelihood the draws follow the prior."""
+    from pytensor_federated_b200.sampling import summarize
+
+    m = Model()
+    m.Exponential("rate", lam=2.0)
+    m.Uniform("u", lower=-1.0, upper=3.0)
+    theta = np.array([0.3, -0.4])
+    lp, g = m.logp_dlogp(theta)
+    for i in range(2):
+        d = np.zeros(2)
+        d[i] = 1e-6
+        fd = (m.logp_dlogp(theta + d)[0] - m.logp_dlogp(theta - d)[0]) / 2e-6
+        np.testing.assert_allclose(g[i], fd, rtol=1e-5, atol=1e-7)
+    _, cols = m.sample(draws=600, tune=400, chains=2, start=np.zeros(2), seed=3)
+    assert set(cols) == {"rate_log__", "u_interval__", "rate", "u"}
+    assert np.all(cols["rate"] > 0) and np.all((cols["u"] > -1.0) & (cols["u"] < 3.0))
+    table = summarize({"rate": cols["rate"], "u": cols["u"]})
+    assert abs(table["rate"]["mean"] - 0.5) < 0.08 and abs(table["rate"]["sd"] - 0.5) < 0.12      # Exp(2)
+    assert abs(table["u"]["mean"] - 1.0) < 0.2 and abs(table["u"]["sd"] - 4 / np.sqrt(12)) < 0.15   # U(-1, 3)
+    with pytest.raises(ValueError):
+        m.Uniform("bad", 1.0, 1.0)
