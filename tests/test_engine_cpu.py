@@ -201,3 +201,46 @@ def test_fp8_tile_scale_packing_matches_tmem_word_order():
                     assert pk[t, 8 + g * 4 + q].tolist() == want
     with pytest.raises(ValueError):
         pack_tile_scales(torch.zeros(6, 8, dtype=torch.uint8), 256)
+
+
+@pytest.mark.parametrize("family", ["logistic", "poisson", "gaussian"])
+def test_glm_shards_agree_with_the_same_model_written_in_the_graph_ir(family):
+    """Two independent implementations of the federated GLM: ``GlmShards`` (eager PyTorch partials summed by
+    the engine) and the likelihood written with ``at.dot`` in the graph IR, differentiated symbolically."""
+    from pytensor_federated_b200._graph_backend import BACKEND, at, function, grad
+
+    if BACKEND != "builtin":
+        pytest.skip("written against the built-in IR's op names")
+    rng = np.random.default_rng(3)
+    P, groups = 5, [0, 1, 1]
+    Xs = [rng.normal(size=(n, P)) for n in (40, 25, 31)]
+    beta_true = rng.normal(size=P) * 0.3
+    ys = []
+    for X in Xs:
+        eta = X @ beta_true
+        ys.append({"logistic": (rng.random(X.shape[0]) < 1 / (1 + np.exp(-eta))).astype(float),
+                   "poisson": rng.poisson(np.exp(eta)).astype(float),
+                   "gaussian": eta + rng.normal(size=X.shape[0])}[family])
+    model = GlmShards([torch.tensor(X) for X in Xs], [torch.tensor(y) for y in ys], groups=groups, n_groups=2, family=family)
+    engine = FederatedEngine(model, backend="collective")
+    ic_v, beta_v = np.array([0.2, -0.1]), rng.normal(size=P) * 0.2
+    logp, d_ic, d_beta = engine.evaluate(ic_v, beta_v)
+    engine.shutdown()
+
+    ic, beta = at.vector("ic"), at.vector("beta")
+    total = None
+    for X, y, g in zip(Xs, ys, groups):
+        eta = at.dot(at.as_tensor(X), beta) + ic[g]
+        yv = at.as_tensor(y)
+        if family == "logistic":
+            ll = yv * eta - at.softplus(eta)
+        elif family == "poisson":
+            ll = yv * eta - at.exp(eta)
+        else:
+            ll = -0.5 * at.sqr(yv - eta) - 0.918938533204672742
+        total = ll.sum() if total is None else total + ll.sum()
+    f = function([ic, beta], [total] + list(grad(total, [ic, beta])))
+    want = f(ic_v, beta_v)
+    np.testing.assert_allclose(logp, want[0], rtol=1e-5)
+    np.testing.assert_allclose(d_ic, want[1], rtol=1e-4, atol=1e-4)
+    np.testing.assert_allclose(d_beta, want[2], rtol=1e-4, atol=1e-4)
