@@ -29,6 +29,14 @@ class BatchedResult:
     step_size: np.ndarray      # [K]
     n_batched_evals: int       # number of fused launches (each evaluates K chains)
 
+    def summary(self, names=None):
+        """Mean / sd / quantiles / ESS / split-R-hat per dimension over all K chains (``diagnostics.summarize``)."""
+        from .diagnostics import summarize
+
+        d = self.samples.shape[2]
+        names = list(names) if names is not None else [f"theta[{i}]" for i in range(d)]
+        return summarize({name: self.samples[:, :, i] for i, name in enumerate(names)})
+
     def rhat(self) -> np.ndarray:
         """Split-free potential scale reduction per dimension (needs K >= 2)."""
         n, k, _ = self.samples.shape
