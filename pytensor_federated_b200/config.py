@@ -18,6 +18,7 @@ Environment variables (all optional):
 ``B200FED_METRICS_PORT``    Prometheus ``/metrics`` port of a node started with ``service.serve`` (``metrics.py``)
 ``B200FED_TLS_CA`` / ``B200FED_TLS_CERT`` / ``B200FED_TLS_KEY`` / ``B200FED_TLS_SERVER_NAME`` / ``B200FED_TLS_MUTUAL``
                             PEM files that switch the gRPC path to TLS (see :class:`TlsConfig`)
+``B200FED_ALLOW_PICKLE``    set to decode object-dtype arrays (unpickles peer data: trusted federations only)
 ``B200FED_NO_LL``           set to force the fence + flag protocol for small results (default: flag-in-data words)
 ``B200FED_LL_MAX_VALS`` / ``B200FED_LL_MAX_THETA``   size thresholds of the flag-in-data protocol (128 / 256)
 """

@@ -11,7 +11,10 @@ Differences on purpose:
   by a reference peer (C-contiguous arrays) decode identically.
 * ``dtype=object`` only "works" in the reference inside one process (raw
   ``PyObject*`` are copied).  Here object arrays are pickled into ``data`` so they
-  survive a process boundary; the dtype string stays ``"object"``.
+  survive a process boundary; the dtype string stays ``"object"``.  **Decoding**
+  them means unpickling bytes that came from a peer, so it is refused unless the
+  receiving process opts in with ``B200FED_ALLOW_PICKLE=1`` (or
+  ``allow_pickle(True)``) — only do that between parties that trust each other.
 """
 from __future__ import annotations
 
@@ -22,6 +25,22 @@ import numpy
 from . import Ndarray
 
 _OBJECT_MAGIC = b"\x93B200OBJ"
+_allow_pickle = None  # None: ask the environment
+
+
+def allow_pickle(flag) -> None:
+    """Lets this process decode object-dtype arrays (``True``), forbids it (``False``) or defers to the
+    ``B200FED_ALLOW_PICKLE`` environment variable (``None``, the default)."""
+    global _allow_pickle
+    _allow_pickle = flag
+
+
+def _pickle_allowed() -> bool:
+    if _allow_pickle is not None:
+        return bool(_allow_pickle)
+    import os
+
+    return os.environ.get("B200FED_ALLOW_PICKLE", "") not in ("", "0")
 
 
 def ndarray_from_numpy(arr: numpy.ndarray) -> Ndarray:
@@ -51,6 +70,11 @@ def ndarray_to_numpy(nda: Ndarray) -> numpy.ndarray:
                 "Received an object-dtype array that was not encoded by this package. "
                 "Object arrays from the reference implementation carry process-local "
                 "pointers and cannot be decoded."
+            )
+        if not _pickle_allowed():
+            raise TypeError(
+                "Refusing to unpickle an object-dtype array received from a peer. Set B200FED_ALLOW_PICKLE=1 "
+                "(or call npproto.utils.allow_pickle(True)) if every party on this federation is trusted."
             )
         items = pickle.loads(data[len(_OBJECT_MAGIC) :])
         result = numpy.empty(shape, dtype=object)

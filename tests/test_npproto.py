@@ -30,7 +30,11 @@ ROUNDTRIP_CASES = [
 
 
 @pytest.mark.parametrize("arr", ROUNDTRIP_CASES, ids=lambda a: f"{np.asarray(a).dtype}-{np.asarray(a).shape}")
-def test_roundtrip_through_bytes(arr):
+def test_roundtrip_through_bytes(arr, monkeypatch):
+    if np.asarray(arr).dtype.hasobject:
+        with pytest.raises(TypeError, match="Refusing to unpickle"):     # opt-in only: bytes from a peer
+            utils.ndarray_to_numpy(utils.ndarray_from_numpy(arr))
+        monkeypatch.setenv("B200FED_ALLOW_PICKLE", "1")
     nda = utils.ndarray_from_numpy(arr)
     enc = bytes(nda)
     dec = npproto.Ndarray().parse(enc)
