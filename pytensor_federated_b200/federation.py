@@ -19,6 +19,7 @@ from __future__ import annotations
 import contextlib
 import os
 import socket
+import threading
 from typing import Callable, Dict, List, Optional, Sequence, Tuple
 
 import numpy as np
@@ -37,21 +38,23 @@ class NodeFederation:
         self.n_nodes = engine.model.n_shards_total
         self._intercepts = np.zeros(self.n_nodes)
         self._slopes = np.zeros(self.n_nodes)
+        self._lock = threading.Lock()   # parameter staging + launch + un-staging of the result form one unit
         self.n_launches = 0
 
     # -- evaluation ----------------------------------------------------------------------------
     def evaluate_nodes(self, requests: Dict[int, Sequence[np.ndarray]]) -> Dict[int, Tuple[np.ndarray, List[np.ndarray]]]:
         """``{node: (intercept, slope)} -> {node: (logp, [d_intercept, d_slope])}``, one launch."""
-        for node, (a, b) in requests.items():
-            self._intercepts[node] = float(np.asarray(a))
-            self._slopes[node] = float(np.asarray(b))
-        raw = self.engine.evaluate_raw([self._intercepts, self._slopes])
-        self.n_launches += 1
-        per = LinregShards.per_shard(raw)
-        return {
-            node: (np.asarray(per[node, 0]), [np.asarray(per[node, 1]), np.asarray(per[node, 2])])
-            for node in requests
-        }
+        with self._lock:
+            for node, (a, b) in requests.items():
+                self._intercepts[node] = float(np.asarray(a))
+                self._slopes[node] = float(np.asarray(b))
+            raw = self.engine.evaluate_raw([self._intercepts, self._slopes])
+            self.n_launches += 1
+            per = LinregShards.per_shard(raw)
+            return {
+                node: (np.array(per[node, 0]), [np.array(per[node, 1]), np.array(per[node, 2])])
+                for node in requests
+            }
 
     def evaluate_node(self, node: int, intercept, slope) -> Tuple[np.ndarray, List[np.ndarray]]:
         return self.evaluate_nodes({node: (intercept, slope)})[node]
