@@ -94,3 +94,34 @@ def test_fixed_point_accumulation_is_order_independent():
     assert abs(sums.pop() / 2.0 ** 24 - vals.sum()) < len(vals) * 2.0 ** -25
     float_sums = {float(np.sum(vals[o].astype(np.float32), dtype=np.float32)) for o in orders}
     assert len(float_sums) > 1                                           # what the integers avoid
+
+
+def test_block_fp8_quantisation_roundtrip_on_cpu():
+    """quantize_block_fp8 / dequantize_block_fp8: per-block power-of-two scales, e4m3 relative error,
+    rows padded to whole 128-row tiles with 2^0, all-zero blocks stay exactly zero."""
+    from pytensor_federated_b200.models.glm import dequantize_block_fp8, quantize_block_fp8
+
+    torch.manual_seed(5)
+    n, P = 300, 128
+    X = torch.randn(n, P) * torch.exp(2 * torch.randn(1, P)) * torch.exp(torch.randn(n, 1))
+    X[64:96, 32:64] = 0.0
+    Xq, scales = quantize_block_fp8(X)
+    assert Xq.dtype == torch.float8_e4m3fn and Xq.shape == (n, P)
+    assert scales.dtype == torch.uint8 and scales.shape == (((n + 127) // 128) * 4, P // 32)
+    assert int(scales[2, 1]) == 127 and torch.all(scales[10:] == 127)          # zero block, padding rows
+    back = dequantize_block_fp8(Xq, scales)
+    assert torch.all(back[64:96, 32:64] == 0)
+    # per 32 x 32 block: the scale is the smallest power of two with amax / scale <= 448 ...
+    for rb in range(0, n // 32):
+        for fb in range(P // 32):
+            blk = X[rb * 32:(rb + 1) * 32, fb * 32:(fb + 1) * 32]
+            amax = blk.abs().max().item()
+            if amax == 0:
+                continue
+            s = 2.0 ** (int(scales[rb, fb]) - 127)
+            assert amax / s <= 448.0 and amax / (s / 2) > 448.0
+            # ... and the element error is e4m3's half-ulp relative to the block's range
+            err = (back[rb * 32:(rb + 1) * 32, fb * 32:(fb + 1) * 32] - blk).abs().max().item()
+            assert err <= amax * 2.0 ** -4
+    with pytest.raises(ValueError):
+        quantize_block_fp8(torch.zeros(4, 48))
