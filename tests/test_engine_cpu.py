@@ -244,3 +244,21 @@ def test_glm_shards_agree_with_the_same_model_written_in_the_graph_ir(family):
     np.testing.assert_allclose(logp, want[0], rtol=1e-5)
     np.testing.assert_allclose(d_ic, want[1], rtol=1e-4, atol=1e-4)
     np.testing.assert_allclose(d_beta, want[2], rtol=1e-4, atol=1e-4)
+
+
+def test_fp8_shards_on_the_cpu_oracle_path_equal_dense_shards_of_the_dequantised_matrix():
+    from pytensor_federated_b200.models import Fp8GlmShards, dequantize_block_fp8
+
+    torch.manual_seed(9)
+    Xs = [torch.randn(n, 128) * torch.exp(torch.randn(1, 128)) for n in (200, 130)]
+    ys = [(torch.rand(n) < 0.4).float() for n in (200, 130)]
+    fp8 = Fp8GlmShards.from_dense(Xs, ys, groups=[0, 1], n_groups=2, family="poisson")
+    assert [tuple(s.shape) for s in fp8._kernel_scales] == [(2, 64), (2, 64)]       # 16 words per 128-row tile
+    dense = GlmShards([dequantize_block_fp8(X, s) for X, s in zip(fp8.Xs, fp8.scales)], ys, groups=[0, 1], n_groups=2,
+                      family="poisson")
+    ic, beta = np.array([0.1, -0.2]), (np.random.default_rng(2).normal(size=128) * 0.01)
+    with FederatedEngine(fp8, backend="collective") as a, FederatedEngine(dense, backend="collective") as b:
+        for u, v in zip(a.evaluate(ic, beta), b.evaluate(ic, beta)):
+            np.testing.assert_allclose(u, v, rtol=1e-6, atol=1e-6)
+    with pytest.raises(ValueError):
+        Fp8GlmShards.from_dense(Xs, ys, n_chains=4)
