@@ -58,7 +58,6 @@ class CustomFamily:
         _CACHE.mkdir(parents=True, exist_ok=True)
         so = _CACHE / f"libb200fed_custom_{self.digest()}.so"
         if not so.exists():
-            body = self.cuda_code.replace("\\", "\\\\").replace('"', '\\"')
             cmd = [
                 native_build.nvcc_path(), *native_build.ARCH, *native_build.NVCC_FLAGS, "-shared", "-I", str(_CSRC),
                 f"-DB200FED_CUSTOM_LINK={self.cuda_code}", "-DB200FED_GENERIC_ENTRY=b200_launch_glm_custom",
@@ -67,7 +66,6 @@ class CustomFamily:
             res = subprocess.run(cmd, capture_output=True, text=True)
             if res.returncode != 0:
                 raise RuntimeError(f"nvcc rejected the custom likelihood:\n{res.stderr[-3000:]}")
-            del body
         self._lib = C.CDLL(str(so))
         return self._lib
 

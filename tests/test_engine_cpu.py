@@ -262,3 +262,36 @@ def test_fp8_shards_on_the_cpu_oracle_path_equal_dense_shards_of_the_dequantised
             np.testing.assert_allclose(u, v, rtol=1e-6, atol=1e-6)
     with pytest.raises(ValueError):
         Fp8GlmShards.from_dense(Xs, ys, n_chains=4)
+
+
+def test_custom_family_compiles_for_sm100a_and_has_a_cpu_oracle_path(tmp_path):
+    """The user's CUDA snippet is cross-compiled here (no GPU needed); the eager oracle runs on the CPU."""
+    import shutil
+
+    from pytensor_federated_b200.models import CustomFamily
+
+    if shutil.which("nvcc") is None and not os.path.exists("/usr/local/cuda/bin/nvcc"):
+        pytest.skip("nvcc not available")
+    student_t = CustomFamily(
+        "const float d = y - eta; ll = -2.5f * log1pf(d * d * 0.25f); r = 5.f * d / (4.f + d * d);",
+        torch_fn=lambda y, eta: (-2.5 * torch.log1p((y - eta) ** 2 / 4), 5 * (y - eta) / (4 + (y - eta) ** 2)),
+    )
+    assert student_t.launcher_address() != 0                      # nvcc -> .so -> symbol
+    assert student_t.compile() is student_t.compile()             # cached
+    with pytest.raises(RuntimeError, match="nvcc rejected"):
+        CustomFamily("ll = this is not CUDA;").compile()
+
+    rng = np.random.default_rng(0)
+    X = torch.tensor(rng.normal(size=(60, 4)), dtype=torch.float32)
+    y = torch.tensor(rng.standard_t(4, size=60), dtype=torch.float32)
+    model = GlmShards([X], [y], family=student_t)
+    with FederatedEngine(model, backend="collective") as eng:
+        beta = rng.normal(size=4) * 0.1
+        logp, d_ic, d_beta = eng.evaluate(np.array([0.05]), beta)
+        eps = 1e-3
+        for j in range(4):
+            bp, bm = beta.copy(), beta.copy()
+            bp[j] += eps
+            bm[j] -= eps
+            fd = (eng.evaluate(np.array([0.05]), bp)[0] - eng.evaluate(np.array([0.05]), bm)[0]) / (2 * eps)
+            np.testing.assert_allclose(d_beta[j], fd, rtol=2e-3, atol=2e-3)
