@@ -28,6 +28,27 @@ class BatchedResult:
     accept_rate: np.ndarray    # [K]
     step_size: np.ndarray      # [K]
     n_batched_evals: int       # number of fused launches (each evaluates K chains)
+    inv_mass: Optional[np.ndarray] = None      # adapted diagonal inverse mass matrix [D]
+    rng_state: Optional[dict] = None           # numpy Generator state after the last draw
+
+    # -- checkpoint / resume, as for single chains (SamplerResult.save / .load) --------------------
+    def save(self, path: str) -> None:
+        import json
+
+        np.savez(path, samples=self.samples, logp=self.logp, accept_rate=self.accept_rate, step_size=self.step_size,
+                 n_batched_evals=self.n_batched_evals,
+                 inv_mass=self.inv_mass if self.inv_mass is not None else np.zeros(0),
+                 rng_state=np.frombuffer(json.dumps(self.rng_state, default=int).encode(), dtype=np.uint8))
+
+    @classmethod
+    def load(cls, path: str) -> "BatchedResult":
+        import json
+
+        z = np.load(path if str(path).endswith(".npz") else str(path) + ".npz")
+        rng_state = json.loads(bytes(z["rng_state"]).decode()) if z["rng_state"].size else None
+        return cls(samples=z["samples"], logp=z["logp"], accept_rate=z["accept_rate"], step_size=z["step_size"],
+                   n_batched_evals=int(z["n_batched_evals"]), inv_mass=z["inv_mass"] if z["inv_mass"].size else None,
+                   rng_state=rng_state)
 
     def summary(self, names=None):
         """Mean / sd / quantiles / ESS / split-R-hat per dimension over all K chains (``diagnostics.summarize``)."""
@@ -48,10 +69,19 @@ class BatchedResult:
 
 def hmc_sample_batched(logp_dlogp_batch: BatchFn, x0: np.ndarray, *, draws: int = 500, tune: int = 500,
                        n_leapfrog: int = 16, step_size: float = 0.1, target_accept: float = 0.8, seed: int = 0,
-                       adapt_mass: bool = True) -> BatchedResult:
+                       adapt_mass: bool = True, resume: Optional[BatchedResult] = None) -> BatchedResult:
     """Static-trajectory HMC on K chains in lock step; per-chain dual-averaging step sizes and
-    diagonal mass matrices (pooled over chains)."""
+    diagonal mass matrices (pooled over chains).
+
+    ``resume=<BatchedResult>`` continues finished / checkpointed chains: starts at their last draws with
+    the adapted step sizes and mass matrix and the saved random state, and skips tuning — the concatenation
+    of the two runs equals one longer run."""
     rng = np.random.default_rng(seed)
+    if resume is not None:
+        x0 = resume.samples[-1]
+        tune = 0
+        if resume.rng_state is not None:
+            rng.bit_generator.state = resume.rng_state
     x = np.array(x0, dtype=np.float64)
     if x.ndim != 2:
         raise ValueError("x0 must be [K, D]")
@@ -61,6 +91,10 @@ def hmc_sample_batched(logp_dlogp_batch: BatchFn, x0: np.ndarray, *, draws: int 
     n_evals = 1
     inv_mass = np.ones(D)
     eps = np.full(K, float(step_size))
+    if resume is not None:
+        eps = np.array(resume.step_size, dtype=np.float64)
+        if resume.inv_mass is not None:
+            inv_mass = np.array(resume.inv_mass, dtype=np.float64)
     # dual averaging state per chain
     mu = np.log(10.0 * eps)
     h_bar = np.zeros(K)
@@ -116,7 +150,8 @@ def hmc_sample_batched(logp_dlogp_batch: BatchFn, x0: np.ndarray, *, draws: int 
             samples[it - tune] = x
             lps[it - tune] = lp
             acc += a
-    return BatchedResult(samples, lps, acc / max(1, draws), eps, n_evals)
+    return BatchedResult(samples, lps, acc / max(1, draws), eps, n_evals, inv_mass=inv_mass,
+                         rng_state=rng.bit_generator.state)
 
 
 def glm_batch_fn(engine, n_groups: int) -> BatchFn:

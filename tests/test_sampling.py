@@ -288,3 +288,22 @@ def test_constrained_priors_sample_their_own_distribution():
     assert abs(table["u"]["mean"] - 1.0) < 0.2 and abs(table["u"]["sd"] - 4 / np.sqrt(12)) < 0.15   # U(-1, 3)
     with pytest.raises(ValueError):
         m.Uniform("bad", 1.0, 1.0)
+
+
+def test_batched_chains_checkpoint_and_resume(tmp_path):
+    """Save after 60 draws, resume for 40 more: identical to one 100-draw run (same adaptation, same RNG stream)."""
+    from pytensor_federated_b200.sampling import BatchedResult, hmc_sample_batched
+
+    def fn(theta):
+        return -0.5 * np.sum(theta * theta / np.array([1.0, 4.0]), axis=1), -theta / np.array([1.0, 4.0])
+
+    x0 = np.zeros((3, 2))
+    full = hmc_sample_batched(fn, x0, draws=100, tune=150, seed=11)
+    first = hmc_sample_batched(fn, x0, draws=60, tune=150, seed=11)
+    first.save(str(tmp_path / "ckpt"))
+    loaded = BatchedResult.load(str(tmp_path / "ckpt"))
+    np.testing.assert_array_equal(loaded.samples, first.samples)
+    np.testing.assert_array_equal(loaded.inv_mass, first.inv_mass)
+    rest = hmc_sample_batched(fn, None, draws=40, resume=loaded)
+    np.testing.assert_allclose(np.concatenate([first.samples, rest.samples]), full.samples, rtol=0, atol=0)
+    np.testing.assert_array_equal(rest.step_size, first.step_size)
