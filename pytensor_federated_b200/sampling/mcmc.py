@@ -135,13 +135,20 @@ def _find_reasonable_step(logp_dlogp, x, lp, g, rng, inv_mass) -> Tuple[float, i
 
 def hmc_sample(logp_dlogp: LogpDlogp, x0: np.ndarray, *, draws: int = 500, tune: int = 500, n_leapfrog: int = 16,
                step_size: Optional[float] = None, target_accept: float = 0.8, seed: int = 0,
-               adapt_mass: bool = True) -> SamplerResult:
-    """Static-trajectory HMC with dual-averaging step size and diagonal mass adaptation."""
+               adapt_mass: bool = True, resume: Optional[SamplerResult] = None) -> SamplerResult:
+    """Static-trajectory HMC with dual-averaging step size and diagonal mass adaptation.
+    ``resume=<SamplerResult>`` continues a finished / checkpointed chain without re-tuning (see ``nuts_sample``)."""
     rng = np.random.default_rng(seed)
+    if resume is not None:
+        x0, tune, step_size = resume.samples[-1], 0, resume.step_size
+        if resume.rng_state is not None:
+            rng.bit_generator.state = resume.rng_state
     x = np.asarray(x0, dtype=np.float64).copy()
     lp, g = logp_dlogp(x)
     n_evals = 1
     inv_mass = np.ones_like(x)
+    if resume is not None and resume.inv_mass is not None:
+        inv_mass = np.asarray(resume.inv_mass, dtype=np.float64).copy()
     if step_size is None:
         step_size, k = _find_reasonable_step(logp_dlogp, x, lp, g, rng, inv_mass)
         n_evals += k
@@ -182,7 +189,8 @@ def hmc_sample(logp_dlogp: LogpDlogp, x0: np.ndarray, *, draws: int = 500, tune:
             samples[it - tune] = x
             lps[it - tune] = lp
             acc_sum += a
-    return SamplerResult(samples, lps, acc_sum / max(1, draws), eps, n_evals)
+    return SamplerResult(samples, lps, acc_sum / max(1, draws), eps, n_evals, inv_mass=inv_mass,
+                         rng_state=rng.bit_generator.state)
 
 
 def nuts_sample(logp_dlogp: LogpDlogp, x0: Optional[np.ndarray] = None, *, draws: int = 200, tune: int = 500,

@@ -307,3 +307,16 @@ def test_batched_chains_checkpoint_and_resume(tmp_path):
     rest = hmc_sample_batched(fn, None, draws=40, resume=loaded)
     np.testing.assert_allclose(np.concatenate([first.samples, rest.samples]), full.samples, rtol=0, atol=0)
     np.testing.assert_array_equal(rest.step_size, first.step_size)
+
+
+def test_hmc_chain_resumes_bit_identically(tmp_path):
+    from pytensor_federated_b200.sampling import SamplerResult
+
+    def fn(theta):
+        return float(-0.5 * np.sum(theta * theta)), -theta
+
+    full = hmc_sample(fn, np.zeros(3), draws=80, tune=120, seed=2)
+    first = hmc_sample(fn, np.zeros(3), draws=50, tune=120, seed=2)
+    first.save(str(tmp_path / "chain"))
+    rest = hmc_sample(fn, None, draws=30, resume=SamplerResult.load(str(tmp_path / "chain")))
+    np.testing.assert_array_equal(np.concatenate([first.samples, rest.samples]), full.samples)
