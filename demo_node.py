@@ -57,6 +57,7 @@ async def run_node_async(*, bind: str, port: int, delay: float, device: str, met
     metrics = ServiceMetrics(port=metrics_port) if metrics_port else None   # Prometheus /metrics endpoint
     server = Server([ArraysToArraysService(wrap_logp_grad_func(model_fn), metrics=metrics)])
     await server.start(bind, port)
+    server.install_signal_handlers()      # SIGTERM / SIGINT: finish the request in flight, then close
     await server.wait_closed()
 
 

@@ -390,6 +390,17 @@ class Server:
     async def wait_closed(self) -> None:
         await self._server.wait_for_termination()
 
+    def install_signal_handlers(self, grace: float = 5.0, signals=None) -> None:
+        """SIGTERM / SIGINT drain the node instead of killing it mid-request: no new calls are accepted,
+        requests in flight get ``grace`` seconds to finish, then the (long-lived) streams are cancelled —
+        clients see ``StreamTerminatedError`` on their next call and fail over.  Call from the running loop."""
+        import asyncio
+        import signal
+
+        loop = asyncio.get_running_loop()
+        for sig in signals or (signal.SIGTERM, signal.SIGINT):
+            loop.add_signal_handler(sig, lambda: loop.create_task(self.close(grace)))
+
     async def close(self, grace: Optional[float] = None) -> None:
         if self._server is not None:
             await self._server.stop(grace)

@@ -742,6 +742,10 @@ async def serve(
     service = ArraysToArraysService(compute_func, offload=offload, metrics=metrics_from_env())
     server = Server([service])
     bound = await server.start(bind, port)
+    try:
+        server.install_signal_handlers()
+    except (NotImplementedError, RuntimeError, ValueError):  # no signal support here (non-main thread, Windows)
+        pass
     _log.info("Serving on %s:%i", bind, bound)
     if ready is not None:
         ready(bound)

@@ -6,6 +6,7 @@ Every "node" is a child process on 127.0.0.1, an unbound port plays a dead node,
 """
 import asyncio
 import multiprocessing
+import os
 import pickle
 import time
 from unittest import mock
@@ -27,6 +28,7 @@ from _helpers import (
     start_fleet,
 )
 
+ROOT_DIR = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
 pytestmark = pytest.mark.timeout(180)
 
 
@@ -332,3 +334,48 @@ def test_stalled_replica_is_quarantined_and_the_call_fails_over(monkeypatch):
         service._quarantine.clear()
         stalling.terminate()
         healthy.terminate()
+
+
+def test_sigterm_drains_the_request_in_flight(tmp_path, monkeypatch):
+    """A node started with service.serve() finishes the running request on SIGTERM, then exits cleanly."""
+    import signal
+    import subprocess
+    import sys
+    import textwrap
+
+    monkeypatch.setenv("B200FED_CONNECT_SLEEP", "0,0")
+    script = tmp_path / "node.py"
+    script.write_text(textwrap.dedent(
+        """
+        import asyncio, sys, time
+        import numpy as np
+        sys.path.insert(0, %r)
+        from pytensor_federated_b200 import service
+
+        def slow_square(a):
+            time.sleep(0.8)
+            return [a * a]
+
+        asyncio.new_event_loop().run_until_complete(
+            service.serve(slow_square, "127.0.0.1", int(sys.argv[1]), offload=True, ready=lambda p: print("ready", flush=True)))
+        """
+    ) % str(ROOT_DIR))
+    port = free_port()
+    proc = subprocess.Popen([sys.executable, str(script), str(port)], stdout=subprocess.PIPE, text=True)
+    try:
+        assert proc.stdout.readline().strip() == "ready"
+        client = service.ArraysToArraysServiceClient("127.0.0.1", port)
+        loop = get_useful_event_loop()
+
+        async def call_and_terminate():
+            task = asyncio.ensure_future(client.evaluate_async(np.array(7.0), retries=0))
+            await asyncio.sleep(0.3)                # the request is being computed now
+            proc.send_signal(signal.SIGTERM)
+            return await task
+
+        (out,) = loop.run_until_complete(call_and_terminate())
+        assert out == 49.0
+        assert proc.wait(timeout=15) == 0
+    finally:
+        if proc.poll() is None:
+            proc.kill()
