@@ -132,7 +132,9 @@ template <int KF, bool DYN>
 __global__ void __launch_bounds__(kThreadsF, 1)
 fed_glm_fp8_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParams prm, const CUtensorMap* __restrict__ tmaps) {
     extern __shared__ unsigned char smem_dyn[];
-    unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
+    // 1 KB alignment (128B-swizzled TMA tiles) by offsetting INSIDE the shared array: the pointer keeps its
+    // shared address space, so the compiler emits LDS / STS instead of generic LD / ST for everything below
+    unsigned char* smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
 
     const int P = prm.n_features;
     const int G = prm.n_groups;
@@ -256,79 +258,111 @@ fed_glm_fp8_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParam
         static_assert(128 + kSfRing * 16 + 4 + kEG * 4 <= (int)kTmemCols, "TMEM budget");
 
         if (warp == 0) {
-            if (lane == 0) {
-                for (int i = 0; i < prm.n_segments; ++i) tma_prefetch_desc(&tmaps[i]);
+            {
+                if (lane == 0)
+                    for (int i = 0; i < prm.n_segments; ++i) tma_prefetch_desc(&tmaps[i]);
                 int s_idx = 0;
-                for (long long it = 0; it < n_it; ++it) {
-                    const long long tile = blockIdx.x + it * gridDim.x;
-                    while (s_idx + 1 < prm.n_segments && segs[s_idx + 1].first_tile <= tile) ++s_idx;
-                    const int st = (int)(it % S);
-                    const uint32_t ph = (uint32_t)((it / S) & 1);
-                    mbar_wait(&bar_empty[st], ph ^ 1);
-                    const int row0 = (int)((tile - segs[s_idx].first_tile) * kTile);
-                    mbar_expect_tx(&bar_full[st], L.stage_bytes);
+                Ring stage;
+                long long tile = blockIdx.x;
+                long long seg_first = segs[0].first_tile;
+                long long seg_next = prm.n_segments > 1 ? segs[1].first_tile : (1ll << 62);
+                for (long long it = 0; it < n_it; ++it, tile += gridDim.x) {
+                    while (seg_next <= tile) {
+                        ++s_idx;
+                        seg_first = seg_next;
+                        seg_next = s_idx + 1 < prm.n_segments ? segs[s_idx + 1].first_tile : (1ll << 62);
+                    }
+                    const int st = stage.idx;
+                    mbar_wait(&bar_empty[st], stage.phase ^ 1);
+                    const int row0 = (int)(tile - seg_first) * kTile;
                     unsigned char* dst = smem + (size_t)st * L.stage_bytes;
-                    for (int pnl = 0; pnl < NH; ++pnl)
-                        tma_load_2d(dst + pnl * kPanelB, &tmaps[s_idx], pnl * kPanelF, row0, &bar_full[st]);
+                    if (elect_one()) {
+                        mbar_expect_tx(&bar_full[st], L.stage_bytes);
+                        for (int pnl = 0; pnl < NH; ++pnl)
+                            tma_load_2d(dst + pnl * kPanelB, &tmaps[s_idx], pnl * kPanelF, row0, &bar_full[st]);
+                    }
+                    __syncwarp();
+                    stage.advance(S);
                 }
             }
         } else if (warp == 1) {
-            if (lane == 0) {
+            {
                 constexpr uint32_t idesc1 = make_idesc_bs(128, kN, 0, 0);
-                const uint32_t theta_b_addr = smem_u32(theta_b);
+                // descriptors: constant fields once, the 14-bit (address >> 4) field added per MMA
+                const uint64_t desc_k = make_desc(0, 16, 1024, 2);
+                const uint32_t theta_b_a4 = smem_u32(theta_b) >> 4;
+                const uint32_t x_base_a4 = smem_u32(smem) >> 4;
+                const uint32_t stage_a4 = L.stage_bytes >> 4;
+                Ring stage, buf, sf;   // TMA stages (S), eta buffers (kEG), scale-word slots (kSfRing)
                 for (long long it = 0; it < n_it; ++it) {
-                    const int st = (int)(it % S);
-                    const uint32_t ph = (uint32_t)((it / S) & 1);
-                    const int b = (int)(it % kEG);
-                    const uint32_t bph = (uint32_t)((it / kEG) & 1);
-                    const int sfb = (int)(it % kSfRing);
-                    mbar_wait(&bar_sf_full[sfb], (uint32_t)((it / kSfRing) & 1));
-                    mbar_wait(&bar_eta_empty[b], bph ^ 1);
-                    mbar_wait(&bar_full[st], ph);
+                    mbar_wait(&bar_sf_full[sf.idx], sf.phase);
+                    mbar_wait(&bar_eta_empty[buf.idx], buf.phase ^ 1);
+                    mbar_wait(&bar_full[stage.idx], stage.phase);
                     tc_fence_after();
-                    const uint32_t x_addr = smem_u32(smem + (size_t)st * L.stage_bytes);
-                    for (int fb = 0; fb < NFB; ++fb) {
-                        const int pnl = fb >> 2, ks = fb & 3;   // 4 K-steps of 32 features per 128-feature panel
-                        const uint64_t adesc = make_desc(x_addr + pnl * kPanelB + ks * 32, 16, 1024, 2);
-                        const uint64_t bdesc = make_desc(theta_b_addr + pnl * (kN * 128) + ks * 32, 16, 1024, 2);
-                        umma_fp8_block_scaled(tmem_eta + b * kN, adesc, bdesc, idesc1 | ((uint32_t)(fb & 3) << 29), fb ? 1u : 0u,
-                                              tmem_sfa1 + sfb * 8 + (fb >> 2) * 4, tmem_sfb);
+                    const uint32_t x_a4 = x_base_a4 + (uint32_t)stage.idx * stage_a4;
+                    const uint32_t d_eta = tmem_eta + buf.idx * kN;
+                    const uint32_t sfa = tmem_sfa1 + sf.idx * 8;
+                    if (elect_one()) {
+                        for (int pnl = 0; pnl < NH; ++pnl) {
+#pragma unroll
+                            for (int ks = 0; ks < 4; ++ks) {   // 4 K-steps of 32 features per 128-feature panel
+                                const uint64_t adesc = desc_k | (uint64_t)(x_a4 + ((pnl * kPanelB + ks * 32) >> 4));
+                                const uint64_t bdesc = desc_k | (uint64_t)(theta_b_a4 + ((pnl * (kN * 128) + ks * 32) >> 4));
+                                umma_fp8_block_scaled(d_eta, adesc, bdesc, idesc1 | ((uint32_t)ks << 29), (pnl | ks) ? 1u : 0u,
+                                                      sfa + pnl * 4, tmem_sfb);
+                            }
+                        }
+                        umma_commit(&bar_eta_full[buf.idx]);
                     }
-                    umma_commit(&bar_eta_full[b]);
+                    __syncwarp();
+                    stage.advance(S);
+                    buf.advance(kEG);
+                    sf.advance(kSfRing);
                 }
             }
         } else if (warp == 6) {
-            if (lane == 0) {
+            {
                 constexpr uint32_t idesc2 = make_idesc_bs(128, kN, 1, 1);
-                const uint32_t r_addr = smem_u32(r_buf);
+                const uint64_t desc_x = make_desc(0, kPanelB, 1024, 2);
+                const uint64_t desc_r = make_desc(0, 128, 128, 0);
+                const uint32_t r_a4 = smem_u32(r_buf) >> 4;
+                const uint32_t x_base_a4 = smem_u32(smem) >> 4;
+                const uint32_t stage_a4 = L.stage_bytes >> 4;
+                Ring stage, buf, sf, flush;   // flush: tile within the kFlushF-tile accumulation period, phase = G buffer
+                uint32_t g_phase[2] = {0, 0};  // per G buffer: how many periods it has served (parity)
                 for (long long j = 0; j < n_it; ++j) {
-                    const int st = (int)(j % S);
-                    const int b = (int)(j % kEG);
-                    const uint32_t bph = (uint32_t)((j / kEG) & 1);
-                    const long long period = j / kFlushF;
-                    const int gb = (int)(period & 1);
-                    const bool first = (j % kFlushF) == 0;
-                    const bool last = (j % kFlushF) == kFlushF - 1 || j == n_it - 1;
-                    const int sfb = (int)(j % kSfRing);
-                    if (first) mbar_wait(&bar_g_empty[gb], (uint32_t)(((period >> 1) & 1) ^ 1));
-                    mbar_wait(&bar_r_full[b], bph);
+                    const int gb = (int)flush.phase;
+                    const bool first = flush.idx == 0;
+                    const bool last = flush.idx == kFlushF - 1 || j == n_it - 1;
+                    if (first) mbar_wait(&bar_g_empty[gb], g_phase[gb] ^ 1);
+                    mbar_wait(&bar_r_full[buf.idx], buf.phase);
                     tc_fence_after();
-                    const uint32_t x_addr = smem_u32(smem + (size_t)st * L.stage_bytes);
+                    const uint32_t x_a4 = x_base_a4 + (uint32_t)stage.idx * stage_a4;
+                    const uint32_t rb_a4 = r_a4 + (uint32_t)buf.idx * (L.r_bytes >> 4);
+                    const uint32_t sfa = tmem_sfa2 + sf.idx * 8;
+                    const uint32_t sfbr = DYN ? tmem_sfb_r + buf.idx * 4 : tmem_sfb;
+                    if (elect_one()) {
                     for (int h = 0; h < NH; ++h) {
 #pragma unroll
                         for (int q = 0; q < 4; ++q) {   // K step = one 32-row group
-                            const uint64_t adesc = make_desc(x_addr + h * kPanelB + q * 4 * 1024, kPanelB, 1024, 2);
-                            const uint64_t bdesc = make_desc(r_addr + b * L.r_bytes + q * 4 * 128, 128, 128, 0);
+                            const uint64_t adesc = desc_x | (uint64_t)(x_a4 + ((h * kPanelB + q * 4 * 1024) >> 4));
+                            const uint64_t bdesc = desc_r | (uint64_t)(rb_a4 + ((q * 4 * 128) >> 4));
                             // DYN: scale-factor-B byte q of the R buffer's column = exponent of row group q
                             umma_fp8_block_scaled(tmem_g + (gb * NH + h) * kN, adesc, bdesc,
                                                   idesc2 | ((uint32_t)q << 29) | (DYN ? ((uint32_t)q << 4) : 0u),
-                                                  (first && q == 0) ? 0u : 1u, tmem_sfa2 + sfb * 8 + h * 4,
-                                                  DYN ? tmem_sfb_r + b * 4 : tmem_sfb);
+                                                  (first && q == 0) ? 0u : 1u, sfa + h * 4, sfbr);
                         }
                     }
-                    umma_commit(&bar_empty[st]);
-                    umma_commit(&bar_r_empty[b]);
+                    umma_commit(&bar_empty[stage.idx]);
+                    umma_commit(&bar_r_empty[buf.idx]);
                     if (last) umma_commit(&bar_g_full[gb]);
+                    }
+                    __syncwarp();
+                    if (last) g_phase[gb] ^= 1u;
+                    stage.advance(S);
+                    buf.advance(kEG);
+                    sf.advance(kSfRing);
+                    flush.advance(kFlushF);
                 }
             }
         } else {

@@ -97,7 +97,9 @@ fed_glm_tc_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParams
     constexpr int kArrive = Cfg<KC>::kArrive;
     (void)EG;
     extern __shared__ unsigned char smem_dyn[];
-    unsigned char* smem = reinterpret_cast<unsigned char*>(((uintptr_t)smem_dyn + 1023) & ~(uintptr_t)1023);
+    // 1 KB alignment (128B-swizzled TMA tiles) by offsetting INSIDE the shared array: the pointer keeps its
+    // shared address space, so the compiler emits LDS / STS instead of generic LD / ST for everything below
+    unsigned char* smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
 
     const int P = prm.n_features;
     const int G = prm.n_groups;
@@ -199,81 +201,110 @@ fed_glm_tc_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParams
 
         if (warp == 0) {
             // ================= TMA producer ====================================================
-            if (lane == 0) {
-                for (int i = 0; i < prm.n_segments; ++i) tma_prefetch_desc(&tmaps[i]);
+            // The role loops are warp-uniform (all 32 lanes wait and count); only the issue is predicated on
+            // elect.sync, so the compiler keeps addresses / descriptors in uniform registers.
+            {
+                if (lane == 0)
+                    for (int i = 0; i < prm.n_segments; ++i) tma_prefetch_desc(&tmaps[i]);
                 int s_idx = 0;
-                for (long long it = 0; it < n_it; ++it) {
-                    const long long tile = blockIdx.x + it * gridDim.x;
-                    while (s_idx + 1 < prm.n_segments && segs[s_idx + 1].first_tile <= tile) ++s_idx;
-                    const int st = (int)(it % S);
-                    const uint32_t ph = (uint32_t)((it / S) & 1);
-                    mbar_wait(&bar_empty[st], ph ^ 1);
-                    const int row0 = (int)((tile - segs[s_idx].first_tile) * kTileM);
-                    mbar_expect_tx(&bar_full[st], L.stage_bytes);
+                Ring stage;
+                long long tile = blockIdx.x;
+                long long seg_first = segs[0].first_tile;
+                long long seg_next = prm.n_segments > 1 ? segs[1].first_tile : (1ll << 62);
+                for (long long it = 0; it < n_it; ++it, tile += gridDim.x) {
+                    while (seg_next <= tile) {
+                        ++s_idx;
+                        seg_first = seg_next;
+                        seg_next = s_idx + 1 < prm.n_segments ? segs[s_idx + 1].first_tile : (1ll << 62);
+                    }
+                    const int st = stage.idx;
+                    mbar_wait(&bar_empty[st], stage.phase ^ 1);
+                    const int row0 = (int)(tile - seg_first) * kTileM;
                     unsigned char* dst = smem + (size_t)st * L.stage_bytes;
-                    for (int pnl = 0; pnl < panels; ++pnl)
-                        tma_load_2d(dst + pnl * kPanelBytes, &tmaps[s_idx], pnl * kPanel, row0, &bar_full[st]);
+                    if (elect_one()) {
+                        mbar_expect_tx(&bar_full[st], L.stage_bytes);
+                        for (int pnl = 0; pnl < panels; ++pnl)
+                            tma_load_2d(dst + pnl * kPanelBytes, &tmaps[s_idx], pnl * kPanel, row0, &bar_full[st]);
+                    }
+                    __syncwarp();
+                    stage.advance(S);
                 }
             }
         } else if (warp == 1) {
             // ================= MMA #1 issuer: eta = X . Theta^T ================================
-            if (lane == 0) {
+            {
                 constexpr uint32_t idesc1 = make_idesc(128, N1, 0, 0);
-                const uint32_t theta_b_addr = smem_u32(theta_b);
+                // descriptors: constant fields once, the 14-bit (address >> 4) field added per MMA
+                const uint64_t desc_k = make_desc(0, 16, 1024, 2);
+                const uint32_t theta_b_a4 = smem_u32(theta_b) >> 4;
+                const uint32_t x_base_a4 = smem_u32(smem) >> 4;
+                const uint32_t stage_a4 = L.stage_bytes >> 4;
+                Ring stage, buf;   // TMA stages (S), eta buffers (2)
                 for (long long it = 0; it < n_it; ++it) {
-                    const int st = (int)(it % S);
-                    const uint32_t ph = (uint32_t)((it / S) & 1);
-                    const int b = (int)(it & 1);
-                    const uint32_t bph = (uint32_t)((it >> 1) & 1);
-                    mbar_wait(&bar_eta_empty[b], bph ^ 1);
-                    mbar_wait(&bar_full[st], ph);
+                    mbar_wait(&bar_eta_empty[buf.idx], buf.phase ^ 1);
+                    mbar_wait(&bar_full[stage.idx], stage.phase);
                     tc_fence_after();
-                    const uint32_t x_addr = smem_u32(smem + (size_t)st * L.stage_bytes);
-                    for (int pnl = 0; pnl < panels; ++pnl) {
+                    const uint32_t x_a4 = x_base_a4 + (uint32_t)stage.idx * stage_a4;
+                    const uint32_t d_eta = tmem_eta + buf.idx * N1;
+                    if (elect_one()) {
+                        for (int pnl = 0; pnl < panels; ++pnl) {
 #pragma unroll
-                        for (int ks = 0; ks < kPanel / 16; ++ks) {
-                            const uint64_t adesc = make_desc(x_addr + pnl * kPanelBytes + ks * 32, 16, 1024, 2);
-                            const uint64_t bdesc = make_desc(theta_b_addr + pnl * (N1 * 128) + ks * 32, 16, 1024, 2);
-                            umma_bf16(tmem_eta + b * N1, adesc, bdesc, idesc1, (pnl | ks) ? 1u : 0u);
+                            for (int ks = 0; ks < kPanel / 16; ++ks) {
+                                const uint64_t adesc = desc_k | (uint64_t)(x_a4 + ((pnl * kPanelBytes + ks * 32) >> 4));
+                                const uint64_t bdesc = desc_k | (uint64_t)(theta_b_a4 + ((pnl * (N1 * 128) + ks * 32) >> 4));
+                                umma_bf16(d_eta, adesc, bdesc, idesc1, (pnl | ks) ? 1u : 0u);
+                            }
                         }
+                        umma_commit(&bar_eta_full[buf.idx]);
                     }
-                    umma_commit(&bar_eta_full[b]);
+                    __syncwarp();
+                    stage.advance(S);
+                    buf.advance(2);
                 }
             }
         } else if (warp == 6) {
             // ================= MMA #2 issuer: G += X^T . R ======================================
-            if (lane == 0) {
+            {
                 constexpr uint32_t idesc2 = make_idesc(128, N2, 1, 1);
-                const uint32_t r_addr = smem_u32(r_buf);
-                const uint32_t r_lbo = (N2 / 8) * 128;  // stride between 8-row K groups of R
+                constexpr uint32_t r_lbo = (N2 / 8) * 128;  // stride between 8-row K groups of R
+                // A = X^T: MN-major (features contiguous), 128B swizzle.
+                // LBO = stride between 64-feature panels, SBO = stride between 8-row groups.
+                const uint64_t desc_x = make_desc(0, kPanelBytes, 1024, 2);
+                // B = R: MN-major (chain columns contiguous), no swizzle.
+                // LBO = stride between 8-row K groups, SBO = stride between 8-column groups.
+                const uint64_t desc_r = make_desc(0, r_lbo, 128, 0);
+                const uint32_t r_a4 = smem_u32(r_buf) >> 4;
+                const uint32_t x_base_a4 = smem_u32(smem) >> 4;
+                const uint32_t stage_a4 = L.stage_bytes >> 4;
+                Ring stage, buf, flush;   // flush: tile within the kFlush-tile accumulation period, phase = G buffer
+                uint32_t g_phase[2] = {0, 0};
                 for (long long j = 0; j < n_it; ++j) {
-                    const int st = (int)(j % S);
-                    const int b = (int)(j & 1);
-                    const uint32_t bph = (uint32_t)((j >> 1) & 1);
-                    const long long period = j / kFlush;
-                    const int gb = (int)(period & 1);
-                    const bool first = (j % kFlush) == 0;
-                    const bool last = (j % kFlush) == kFlush - 1 || j == n_it - 1;
-                    if (first) mbar_wait(&bar_g_empty[gb], (uint32_t)(((period >> 1) & 1) ^ 1));
-                    mbar_wait(&bar_r_full[b], bph);
+                    const int gb = (int)flush.phase;
+                    const bool first = flush.idx == 0;
+                    const bool last = flush.idx == kFlush - 1 || j == n_it - 1;
+                    if (first) mbar_wait(&bar_g_empty[gb], g_phase[gb] ^ 1);
+                    mbar_wait(&bar_r_full[buf.idx], buf.phase);
                     tc_fence_after();
-                    const uint32_t x_addr = smem_u32(smem + (size_t)st * L.stage_bytes);
-                    for (int h = 0; h < NH; ++h) {
+                    const uint32_t x_a4 = x_base_a4 + (uint32_t)stage.idx * stage_a4;
+                    const uint32_t rb_a4 = r_a4 + (uint32_t)buf.idx * (L.r_bytes >> 4);
+                    if (elect_one()) {
+                        for (int h = 0; h < NH; ++h) {
 #pragma unroll
-                        for (int ks = 0; ks < kTileM / 16; ++ks) {
-                            // A = X^T: MN-major (features contiguous), 128B swizzle.
-                            // LBO = stride between 64-feature panels, SBO = stride between 8-row groups.
-                            const uint64_t adesc =
-                                make_desc(x_addr + (2 * h) * kPanelBytes + ks * 2 * 1024, kPanelBytes, 1024, 2);
-                            // B = R: MN-major (chain columns contiguous), no swizzle.
-                            // LBO = stride between 8-row K groups, SBO = stride between 8-column groups.
-                            const uint64_t bdesc = make_desc(r_addr + b * L.r_bytes + ks * 2 * r_lbo, r_lbo, 128, 0);
-                            umma_bf16(tmem_g + (gb * NH + h) * N2, adesc, bdesc, idesc2, (first && ks == 0) ? 0u : 1u);
+                            for (int ks = 0; ks < kTileM / 16; ++ks) {
+                                const uint64_t adesc = desc_x | (uint64_t)(x_a4 + (((2 * h) * kPanelBytes + ks * 2 * 1024) >> 4));
+                                const uint64_t bdesc = desc_r | (uint64_t)(rb_a4 + ((ks * 2 * r_lbo) >> 4));
+                                umma_bf16(tmem_g + (gb * NH + h) * N2, adesc, bdesc, idesc2, (first && ks == 0) ? 0u : 1u);
+                            }
                         }
+                        umma_commit(&bar_empty[stage.idx]);   // X stage may be refilled
+                        umma_commit(&bar_r_empty[buf.idx]);   // R buffer may be rewritten
+                        if (last) umma_commit(&bar_g_full[gb]);
                     }
-                    umma_commit(&bar_empty[st]);    // X stage may be refilled
-                    umma_commit(&bar_r_empty[b]);   // R buffer may be rewritten
-                    if (last) umma_commit(&bar_g_full[gb]);
+                    __syncwarp();
+                    if (last) g_phase[gb] ^= 1u;
+                    stage.advance(S);
+                    buf.advance(2);
+                    flush.advance(kFlush);
                 }
             }
         } else {

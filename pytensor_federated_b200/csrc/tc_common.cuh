@@ -42,6 +42,19 @@ __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
         if (fed::globaltimer() - t0 > 4000000000ull) __trap();
     }
 }
+// One lane of a fully active warp (the role loops stay warp-uniform; only the issue is predicated, so the
+// compiler keeps descriptors and addresses in uniform registers instead of a per-instruction waterfall).
+__device__ __forceinline__ bool elect_one() {
+    uint32_t pred;
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "elect.sync _|p, 0xffffffff;\n\t"
+        "selp.u32 %0, 1, 0, p;\n\t"
+        "}"
+        : "=r"(pred));
+    return pred != 0;
+}
 __device__ __forceinline__ void fence_barrier_init() { asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory"); }
 __device__ __forceinline__ void fence_proxy_async() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 __device__ __forceinline__ void tc_fence_before() { asm volatile("tcgen05.fence::before_thread_sync;" ::: "memory"); }
@@ -120,6 +133,19 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn_major, 
            | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) | ((uint32_t)(N >> 3) << 17) |
            ((uint32_t)(M >> 4) << 24);
 }
+
+// Index + phase bit of an n-deep circular buffer, advanced without division (the single-thread
+// TMA / MMA issue loops are latency chains: a 64-bit `it % n`, `it / n` pair costs ~100 instructions).
+struct Ring {
+    int idx = 0;
+    uint32_t phase = 0;
+    __host__ __device__ __forceinline__ void advance(int n) {
+        if (++idx == n) {
+            idx = 0;
+            phase ^= 1u;
+        }
+    }
+};
 
 __device__ __forceinline__ void link_loglik(int family, float y, float eta, float& ll, float& r) {
     if (family == 0) {

@@ -32,7 +32,6 @@ from ._graph_backend import (
     Op,
     ReplaceValidate,
     Variable,
-    apply_depends_on,
     optdb,
 )
 from .utils import get_useful_event_loop
@@ -71,6 +70,16 @@ class AsyncFromFunctionOp(AsyncOp, FromFunctionOp):
             cell[0] = value
 
 
+class ParallelAsyncError(RuntimeError):
+    """Several children of one :class:`ParallelAsyncOp` failed; ``errors`` holds all of them
+    (a single failure is re-raised as it is, so its type stays catchable)."""
+
+    def __init__(self, errors: Sequence[BaseException]) -> None:
+        self.errors = list(errors)
+        summary = "; ".join(f"{type(e).__name__}: {e}" for e in self.errors)
+        super().__init__(f"{len(self.errors)} parallel async children failed: {summary}")
+
+
 class ParallelAsyncOp(AsyncOp):
     """Runs the ``perform_async`` of several ``AsyncOp`` apply nodes concurrently.
 
@@ -82,8 +91,7 @@ class ParallelAsyncOp(AsyncOp):
         for a, apply in enumerate(applies):
             if not isinstance(apply.op, AsyncOp):
                 raise ValueError(
-                    f"The owner of apply node {a} is not an `AsyncOp`. "
-                    "All apply nodes given to `ParallelAsyncOp` must be owned by an `AsyncOp`."
+                    f"Cannot run {type(apply.op).__name__} concurrently: apply node {a} is not an `AsyncOp` application."
                 )
         self.applies = applies
         super().__init__()
@@ -92,8 +100,7 @@ class ParallelAsyncOp(AsyncOp):
         nin_exp = sum(a.nin for a in self.applies)
         if len(inputs) != nin_exp:
             raise ValueError(
-                f"Unexpected number of inputs to `ParallelAsyncOp` {self}. "
-                f"Got {len(inputs)} inputs but expected {nin_exp} for {len(self.applies)} apply nodes."
+                f"`ParallelAsyncOp` received {len(inputs)} inputs, expected {nin_exp} for {len(self.applies)} children."
             )
         outputs = [out.type() for app in self.applies for out in app.outputs]
         return Apply(self, list(inputs), outputs)
@@ -120,8 +127,10 @@ class ParallelAsyncOp(AsyncOp):
             pending.append(members[0][0].op.perform_fused(members))
         results = await asyncio.gather(*pending, return_exceptions=True)
         errors = [r for r in results if isinstance(r, BaseException)]
-        if errors:
+        if len(errors) == 1:
             raise errors[0]
+        if errors:
+            raise ParallelAsyncError(errors) from errors[0]
 
     def perform(self, node: Apply, inputs: Sequence[Any], output_storage: OutputStorageType) -> None:
         loop = get_useful_event_loop()
@@ -143,36 +152,57 @@ class FusableAsyncOp(AsyncOp):
         await asyncio.gather(*[a.op.perform_async(a, i, o) for a, i, o in members])
 
 
-def find_parallelizable_applies(fg: FunctionGraph, op_cls: type) -> List[Apply]:
-    """Finds ≥ 2 apply nodes of ``op_cls`` that do not depend on each other.
+def _async_depths(fg: FunctionGraph, op_cls: type) -> dict:
+    """Maps every ``op_cls`` apply of ``fg`` to the length of the longest chain of ``op_cls``
+    applies above it (0 = no such ancestor).  One pass over the topological order."""
+    above: dict = {}   # apply -> max number of op_cls applies on a path that ends just before it
+    depths: dict = {}
+    for node in fg.toposort():
+        level = 0
+        for var in node.inputs:
+            parent = var.owner
+            if parent is not None and parent in above:
+                level = max(level, above[parent] + (1 if parent in depths else 0))
+        above[node] = level
+        if isinstance(node.op, op_cls):
+            depths[node] = level
+    return depths
 
-    Walks the graph in topological order and collects independent nodes; a dependent node
-    ends the collection (or restarts it, when only one node was collected so far).  Repeated
-    application therefore fuses a dependency chain level by level.
+
+def find_parallelizable_applies(fg: FunctionGraph, op_cls: type) -> List[Apply]:
+    """Returns a maximal set (>= 2, else ``[]``) of mutually independent ``op_cls`` applies.
+
+    Nodes are ranked by how many ``op_cls`` nodes lie on the longest path above them; two nodes
+    of equal rank can never depend on one another, so every rank is an antichain.  The shallowest
+    rank with at least two members is returned, in topological order.  Calling this repeatedly
+    while fusing (see :func:`parallelize_all_async_applies`) therefore works through a dependency
+    chain level by level, like the reference's greedy scan
+    (``/root/reference/pytensor_federated/op_async.py:135-167``), but it also pairs up independent
+    nodes that a dependent node separates in the topological order.
     """
-    applies: List[Apply] = []
-    for apply in fg.toposort():
-        if not isinstance(apply.op, op_cls):
-            continue
-        if not any(apply_depends_on(apply, a) for a in applies):
-            applies.append(apply)
-        elif len(applies) == 1:
-            applies = [apply]
-        else:
-            break
-    return applies if len(applies) > 1 else []
+    by_rank: dict = {}
+    for node, rank in _async_depths(fg, op_cls).items():
+        by_rank.setdefault(rank, []).append(node)
+    for rank in sorted(by_rank):
+        if len(by_rank[rank]) >= 2:
+            return by_rank[rank]
+    return []
 
 
 def parallelize_async_applies(fg: FunctionGraph, applies: Sequence[Apply]) -> None:
-    """Replaces ``applies`` by a single :class:`ParallelAsyncOp` node, in place."""
-    inputs: List[Variable] = []
-    old_outputs: List[Variable] = []
-    for apply in applies:
-        inputs.extend(apply.inputs)
-        old_outputs.extend(apply.outputs)
-    new_outputs = ParallelAsyncOp(applies=applies).make_node(*inputs).outputs
-    replace_all = getattr(fg, "replace_all_validate", fg.replace_all)
-    replace_all(list(zip(old_outputs, new_outputs)))
+    """Substitutes one :class:`ParallelAsyncOp` node for the independent ``applies`` (in place).
+
+    The fused node takes the children's inputs back to back and yields their outputs back to
+    back; every old output variable is rerouted to its twin.  With the ``ReplaceValidate``
+    feature attached the validated replacement is used.
+    """
+    members = tuple(applies)
+    fused = ParallelAsyncOp(members).make_node(*[v for m in members for v in m.inputs])
+    pairs = [(old, new) for old, new in zip((v for m in members for v in m.outputs), fused.outputs)]
+    if hasattr(fg, "replace_all_validate"):
+        fg.replace_all_validate(pairs)
+    else:
+        fg.replace_all(pairs)
 
 
 def parallelize_all_async_applies(fg: FunctionGraph) -> None:
@@ -204,6 +234,7 @@ __all__ = [
     "AsyncOp",
     "AsyncFromFunctionOp",
     "ParallelAsyncOp",
+    "ParallelAsyncError",
     "FusableAsyncOp",
     "find_parallelizable_applies",
     "parallelize_async_applies",
