@@ -79,6 +79,11 @@ class FederationConfig:
         )
 
 
+class TlsConfigError(ValueError):
+    """TLS was requested (explicitly or through ``B200FED_TLS_*``) but the material is incomplete for the
+    role; the process refuses to fall back to plaintext."""
+
+
 @dataclasses.dataclass(frozen=True)
 class TlsConfig:
     """TLS material of the gRPC path (PEM bytes).  The reference only speaks plaintext
@@ -95,6 +100,25 @@ class TlsConfig:
     server_name: Optional[str] = None
     mutual: bool = False
 
+    def check_server(self) -> "TlsConfig":
+        """A server needs its identity (``cert`` + ``key``) and, for mutual TLS, the ``ca`` that signed the
+        clients.  Anything less raises instead of silently serving private data in cleartext."""
+        missing = [name for name in ("cert", "key") if not getattr(self, name)]
+        if self.mutual and not self.ca:
+            missing.append("ca (mutual TLS)")
+        if missing:
+            raise TlsConfigError(f"incomplete TLS configuration for a server: missing {', '.join(missing)}")
+        return self
+
+    def check_client(self) -> "TlsConfig":
+        """A client needs the ``ca`` it trusts; ``cert`` and ``key`` (mutual TLS) only come as a pair."""
+        missing = [] if self.ca else ["ca"]
+        if bool(self.cert) != bool(self.key):
+            missing.append("key" if self.cert else "cert")
+        if missing:
+            raise TlsConfigError(f"incomplete TLS configuration for a client: missing {', '.join(missing)}")
+        return self
+
     @classmethod
     def from_files(cls, ca: Optional[str] = None, cert: Optional[str] = None, key: Optional[str] = None,
                    server_name: Optional[str] = None, mutual: bool = False) -> "TlsConfig":
@@ -108,9 +132,11 @@ class TlsConfig:
 
 
 def tls_from_env() -> Optional[TlsConfig]:
-    """``TlsConfig`` from the ``B200FED_TLS_*`` variables (paths to PEM files), or ``None`` = plaintext."""
+    """``TlsConfig`` from the ``B200FED_TLS_*`` variables (paths to PEM files), or ``None`` = plaintext (none
+    of them set).  A partially filled environment yields a config whose ``check_server`` / ``check_client``
+    raises :class:`TlsConfigError` — it never degrades to plaintext."""
     ca, cert, key = (os.environ.get(f"B200FED_TLS_{k}") for k in ("CA", "CERT", "KEY"))
-    if not (ca or cert):
+    if not (ca or cert or key or os.environ.get("B200FED_TLS_MUTUAL")):
         return None
     return TlsConfig.from_files(ca, cert, key, os.environ.get("B200FED_TLS_SERVER_NAME"),
                                 bool(os.environ.get("B200FED_TLS_MUTUAL")))

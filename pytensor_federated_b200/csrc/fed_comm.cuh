@@ -65,12 +65,14 @@ struct FedComm {
     unsigned long long* epoch_counter;             // peers: device-resident epoch (graph replay friendly); may be null
     unsigned long long* done_flag;                 // host-mapped: last finished epoch on this node (peers' serve loop)
     unsigned long long* trace;                     // optional device-timer ring [4 x u64 per epoch % 256] or null
+    unsigned long long* cta_trace;                 // optional per-CTA phase stamps [grid][8] of the LAST launch, or null
 
     // --- low-latency ("LL") mode for small results: flag-in-data words, no fences, no flag writes ----
     // Every 8-byte word carries 32 bits of payload and the low 32 bits of the epoch as its tag, so a
     // reader that sees the right tag has the data (8-byte accesses are single transactions on NVLink
     // and PCIe).  theta: one word per 32-bit theta word; results: two words per double.
-    int ll_mode;
+    int ll_mode;                                         // results travel as tagged words (small n_vals)
+    int ll_theta;                                        // theta travels as tagged words (n_theta <= a few thousand)
     unsigned long long* ll_theta_local;                  // own theta mailbox      [n_theta]
     unsigned long long* ll_peer_theta[B200FED_MAX_WORLD]; // root: every node's     [n_theta]
     unsigned long long* ll_mc_theta;                     // root: multicast alias or null
@@ -173,6 +175,31 @@ __device__ __forceinline__ bool wait_epoch(const unsigned long long* flag, unsig
     }
 }
 
+// Per-CTA phase stamp k (0 entry, 1 theta acquired, 2 setup done, 3 first tile landed, 4 last load issued,
+// 5 main loop done, 6 partial stored, 7 exit).  Call from ONE thread; a no-op unless tracing is enabled.
+__device__ __forceinline__ void stamp(const FedComm& c, int k) {
+    if (c.cta_trace) c.cta_trace[(size_t)blockIdx.x * 8 + k] = globaltimer();
+}
+
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+// Lets the next kernel of the stream start occupying SMs that this grid no longer needs.
+__device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
+// Fixed-order (b = 0, 1, 2, ...) sum of value v over the per-CTA partials => bit-reproducible.  The loads
+// are issued kWide at a time: a 148-CTA grid costs 4 dependent L2 round trips instead of 148.
+__device__ __forceinline__ double sum_cta_partials(const double* partials, int nv, int v, unsigned int n_ctas) {
+    constexpr unsigned int kWide = 37;
+    double s = 0.0;
+    for (unsigned int b = 0; b < n_ctas; b += kWide) {
+        double t[kWide];
+#pragma unroll
+        for (unsigned int j = 0; j < kWide; ++j) t[j] = (b + j < n_ctas) ? ld_cg_f64(partials + (size_t)(b + j) * nv + v) : 0.0;
+#pragma unroll
+        for (unsigned int j = 0; j < kWide; ++j) s += t[j];
+    }
+    return s;
+}
+
 struct Prologue {
     unsigned long long epoch;   // resolved epoch of this launch
     bool stop;                  // root asked the nodes to drain
@@ -184,8 +211,14 @@ struct Prologue {
 __device__ __forceinline__ Prologue prologue(const FedComm& c, float* theta_smem) {
     __shared__ unsigned long long s_seen;
     __shared__ int s_ok;
+    // Programmatic dependent launch: a kernel launched with programmatic stream serialization may become
+    // resident while the previous evaluation is still draining (its CTAs called pdl_trigger()); everything
+    // above this line (launch, smem carve-up, parameter loads) overlaps with that tail.  The wait returns
+    // once the previous grid has completed and its memory operations are visible (no-op otherwise).
+    pdl_wait();
     unsigned long long epoch = c.epoch;
     if (c.epoch_counter) epoch = *reinterpret_cast<volatile unsigned long long*>(c.epoch_counter) + 1ull;
+    if (threadIdx.x == 0) stamp(c, 0);
 
     if (c.world == 1 && gridDim.x == 1) {
         // Single node, single CTA (tiny models): no mailbox round trip, no flags — theta goes
@@ -199,7 +232,7 @@ __device__ __forceinline__ Prologue prologue(const FedComm& c, float* theta_smem
         r0.timed_out = false;
         return r0;
     }
-    if (c.ll_mode) {
+    if (c.ll_theta) {
         // LL broadcast: tagged theta words, no fence, no flag.  Every thread polls the words it needs.
         if (c.rank == 0 && blockIdx.x == 0) {
             for (int i = threadIdx.x; i < c.n_theta; i += blockDim.x) {
@@ -228,6 +261,7 @@ __device__ __forceinline__ Prologue prologue(const FedComm& c, float* theta_smem
         rl.timed_out = (s_ok & 1) != 0;
         rl.stop = (s_ok & 2) != 0;
         __syncthreads();
+        if (threadIdx.x == 0) stamp(c, 1);
         return rl;
     }
     if (c.rank == 0 && blockIdx.x == 0) {
@@ -264,6 +298,7 @@ __device__ __forceinline__ Prologue prologue(const FedComm& c, float* theta_smem
         for (int i = threadIdx.x; i < c.n_theta; i += blockDim.x) theta_smem[i] = ld_cg_f32(c.theta_local + i);
     }
     __syncthreads();
+    if (threadIdx.x == 0) stamp(c, 1);
     return r;
 }
 
@@ -311,7 +346,10 @@ __device__ __forceinline__ void epilogue(const FedComm& c, const Prologue& pro, 
         s_status = status_in;
     }
     __syncthreads();
-    if (!s_last) return;
+    if (!s_last) {
+        if (threadIdx.x == 0) stamp(c, 7);
+        return;
+    }
     __threadfence();
     const int nv = c.n_vals;
     const unsigned long long epoch = pro.epoch;
@@ -338,16 +376,7 @@ __device__ __forceinline__ void epilogue(const FedComm& c, const Prologue& pro, 
         // stores tagged words into host-mapped memory.  Same fixed summation order as below.
         unsigned long long* my_slot_ll = c.ll_root_slots + (size_t)c.rank * nv * 2;
         for (int v = threadIdx.x; v < nv; v += blockDim.x) {
-            double s = 0.0;
-            unsigned int b = 0;
-            for (; b + 8 <= gridDim.x; b += 8) {
-                double t[8];
-#pragma unroll
-                for (int j = 0; j < 8; ++j) t[j] = ld_cg_f64(c.cta_partials + (size_t)(b + j) * nv + v);
-#pragma unroll
-                for (int j = 0; j < 8; ++j) s += t[j];
-            }
-            for (; b < gridDim.x; ++b) s += ld_cg_f64(c.cta_partials + (size_t)b * nv + v);
+            const double s = sum_cta_partials(c.cta_partials, nv, v, gridDim.x);
             if (c.rank != 0) {
                 ll_store_f64(my_slot_ll + 2 * v, s, epoch);
             } else {
@@ -383,21 +412,7 @@ __device__ __forceinline__ void epilogue(const FedComm& c, const Prologue& pro, 
 
     // 1) node partial = fixed-order sum over CTAs -> root's slot for this rank (NVLink store for peers)
     double* my_slot = c.root_slots + (size_t)c.rank * nv;
-    for (int v = threadIdx.x; v < nv; v += blockDim.x) {
-        // fixed summation order (b = 0, 1, 2, ...) => bit-reproducible; loads are issued 8 at a time
-        // so that the L2 latencies overlap instead of adding up (148 CTAs x ~0.3 us otherwise)
-        double s = 0.0;
-        unsigned int b = 0;
-        for (; b + 8 <= gridDim.x; b += 8) {
-            double t[8];
-#pragma unroll
-            for (int j = 0; j < 8; ++j) t[j] = ld_cg_f64(c.cta_partials + (size_t)(b + j) * nv + v);
-#pragma unroll
-            for (int j = 0; j < 8; ++j) s += t[j];
-        }
-        for (; b < gridDim.x; ++b) s += ld_cg_f64(c.cta_partials + (size_t)b * nv + v);
-        my_slot[v] = s;
-    }
+    for (int v = threadIdx.x; v < nv; v += blockDim.x) my_slot[v] = sum_cta_partials(c.cta_partials, nv, v, gridDim.x);
     __threadfence_system();
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -429,6 +444,7 @@ __device__ __forceinline__ void epilogue(const FedComm& c, const Prologue& pro, 
         *c.ticket = 0;
         if (c.epoch_counter) *c.epoch_counter = epoch;
         if (c.done_flag) *reinterpret_cast<volatile unsigned long long*>(c.done_flag) = epoch | (s_status << B200FED_STATUS_SHIFT);
+        stamp(c, 7);
     }
 }
 

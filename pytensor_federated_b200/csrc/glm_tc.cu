@@ -130,12 +130,37 @@ fed_glm_tc_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParams
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
 
-    fed::Prologue pro = fed::prologue(comm, theta_f);
-    const bool active = !pro.stop && !pro.timed_out;
-
     const long long T = prm.total_tiles;
     const long long n_it = (T > (long long)blockIdx.x) ? (T - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
     constexpr uint32_t kTmemCols = (2 * N1 + 2 * 4 * N2) <= 128 ? 128 : ((2 * N1 + 2 * 4 * N2) <= 256 ? 256 : 512);
+
+    // ---------------- theta-independent setup: runs BEFORE the dependency wait inside fed::prologue, i.e. it
+    // overlaps with the tail of the previous evaluation when launched with programmatic stream serialization
+    for (int i = threadIdx.x; i < prm.n_segments; i += blockDim.x) segs[i] = segs_g[i];
+    for (int i = threadIdx.x; i < KC * G; i += blockDim.x) gi_acc[i] = 0ull;
+    for (int i = threadIdx.x; i < (int)(2 * L.r_bytes / 16); i += blockDim.x)
+        reinterpret_cast<uint4*>(r_buf)[i] = make_uint4(0, 0, 0, 0);
+    if (threadIdx.x == 0) {
+        for (int i = 0; i < 4; ++i) { mbar_init(&bar_full[i], 1); mbar_init(&bar_empty[i], 1); }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&bar_eta_full[i], 1);
+            mbar_init(&bar_eta_empty[i], kArrive);
+            mbar_init(&bar_r_full[i], kArrive);
+            mbar_init(&bar_r_empty[i], 1);
+            mbar_init(&bar_g_full[i], 1);
+            mbar_init(&bar_g_empty[i], kArrive);
+        }
+        fence_barrier_init();
+    }
+    if (warp == 0 && lane == 0)
+        for (int i = 0; i < prm.n_segments; ++i) tma_prefetch_desc(&tmaps[i]);
+    if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
+    tc_fence_before();
+
+    fed::Prologue pro = fed::prologue(comm, theta_f);   // contains __syncthreads()
+    const bool active = !pro.stop && !pro.timed_out;
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
 
     double ll_total[KH];
 #pragma unroll
@@ -147,12 +172,9 @@ fed_glm_tc_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParams
         for (int k = 0; k < KH; ++k) g_acc[h][k] = 0.0;
 
     if (active) {
-        // ---------------- one-time setup ------------------------------------------------------
-        for (int i = threadIdx.x; i < prm.n_segments; i += blockDim.x) segs[i] = segs_g[i];
-        for (int i = threadIdx.x; i < KC * G; i += blockDim.x) {
-            gi_acc[i] = 0ull;
+        // ---------------- theta-dependent setup --------------------------------------------------
+        for (int i = threadIdx.x; i < KC * G; i += blockDim.x)
             icpt[i] = (i / G) < nch ? theta_f[(i / G) * (G + P) + (i % G)] : 0.f;
-        }
         // Theta^T as the K-major, 128B-swizzled B operand of MMA #1: row n = 3*chain + term
         for (int idx = threadIdx.x; idx < panels * N1 * 8; idx += blockDim.x) {
             const int j = idx & 7;              // 16-byte chunk (8 features) within the 128-byte row
@@ -176,26 +198,9 @@ fed_glm_tc_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParams
             uint4* dst = reinterpret_cast<uint4*>(theta_b + pnl * (N1 * 128) + n * 128 + ((j ^ (n & 7)) * 16));
             *dst = make_uint4(packed[0], packed[1], packed[2], packed[3]);
         }
-        for (int i = threadIdx.x; i < (int)(2 * L.r_bytes / 16); i += blockDim.x)
-            reinterpret_cast<uint4*>(r_buf)[i] = make_uint4(0, 0, 0, 0);
         fence_proxy_async();
-        if (threadIdx.x == 0) {
-            for (int i = 0; i < 4; ++i) { mbar_init(&bar_full[i], 1); mbar_init(&bar_empty[i], 1); }
-            for (int i = 0; i < 2; ++i) {
-                mbar_init(&bar_eta_full[i], 1);
-                mbar_init(&bar_eta_empty[i], kArrive);
-                mbar_init(&bar_r_full[i], kArrive);
-                mbar_init(&bar_r_empty[i], 1);
-                mbar_init(&bar_g_full[i], 1);
-                mbar_init(&bar_g_empty[i], kArrive);
-            }
-            fence_barrier_init();
-        }
-        if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
-        tc_fence_before();
         __syncthreads();
-        tc_fence_after();
-        const uint32_t tmem_base = *tmem_slot;
+        if (threadIdx.x == 0) fed::stamp(comm, 2);
         const uint32_t tmem_eta = tmem_base;                 // 2 buffers x N1 columns
         const uint32_t tmem_g = tmem_base + 2 * N1;          // 2 buffers x NH x N2 columns
 
@@ -204,8 +209,6 @@ fed_glm_tc_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParams
             // The role loops are warp-uniform (all 32 lanes wait and count); only the issue is predicated on
             // elect.sync, so the compiler keeps addresses / descriptors in uniform registers.
             {
-                if (lane == 0)
-                    for (int i = 0; i < prm.n_segments; ++i) tma_prefetch_desc(&tmaps[i]);
                 int s_idx = 0;
                 Ring stage;
                 long long tile = blockIdx.x;
@@ -229,6 +232,7 @@ fed_glm_tc_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParams
                     __syncwarp();
                     stage.advance(S);
                 }
+                if (lane == 0) fed::stamp(comm, 4);
             }
         } else if (warp == 1) {
             // ================= MMA #1 issuer: eta = X . Theta^T ================================
@@ -244,6 +248,7 @@ fed_glm_tc_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParams
                     mbar_wait(&bar_eta_empty[buf.idx], buf.phase ^ 1);
                     mbar_wait(&bar_full[stage.idx], stage.phase);
                     tc_fence_after();
+                    if (it == 0 && lane == 0) fed::stamp(comm, 3);
                     const uint32_t x_a4 = x_base_a4 + (uint32_t)stage.idx * stage_a4;
                     const uint32_t d_eta = tmem_eta + buf.idx * N1;
                     if (elect_one()) {
@@ -426,7 +431,8 @@ fed_glm_tc_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParams
         tc_fence_before();
         __syncthreads();
         tc_fence_after();
-        if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
+        fed::pdl_trigger();   // the next evaluation's CTA may take this SM as soon as we exit
+        if (threadIdx.x == 0) fed::stamp(comm, 5);
         double* out = comm.cta_partials + (size_t)blockIdx.x * comm.n_vals;
         // layout per chain: [LL, gi[G], g[P]]
         const bool is_epi = (warp >= 2 && warp <= 5) || warp >= 7;
@@ -457,7 +463,10 @@ fed_glm_tc_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParams
             }
             __syncthreads();
         }
+        if (threadIdx.x == 0) fed::stamp(comm, 6);
     }
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
     fed::epilogue(comm, pro, 0ull);
 }
 
@@ -520,7 +529,17 @@ extern "C" int b200_launch_glm_tc(const FedComm* comm, const GlmSegment* segs_de
                                                  prm->n_groups, KC);                                               \
         if (L.stages < 2) return -2;                                                                               \
         cudaFuncSetAttribute(tc::fed_glm_tc_kernel<KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total); \
-        tc::fed_glm_tc_kernel<KC><<<grid, tc::Cfg<KC>::kThreads, L.total, stream>>>(*comm, segs_dev, *prm, maps);            \
+        cudaLaunchConfig_t cfg{};                                                                                  \
+        cfg.gridDim = dim3(grid);                                                                                  \
+        cfg.blockDim = dim3(tc::Cfg<KC>::kThreads);                                                                \
+        cfg.dynamicSmemBytes = L.total;                                                                            \
+        cfg.stream = stream;                                                                                       \
+        cudaLaunchAttribute attr[1];                                                                               \
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                                           \
+        attr[0].val.programmaticStreamSerializationAllowed = 1;                                                    \
+        cfg.attrs = attr;                                                                                          \
+        cfg.numAttrs = tc::use_pdl() ? 1 : 0;                                                                      \
+        cudaLaunchKernelEx(&cfg, tc::fed_glm_tc_kernel<KC>, *comm, segs_dev, *prm, maps);                          \
     } while (0)
     if (kc == 1) LAUNCH_TC(1);
     else if (kc == 4) LAUNCH_TC(4);

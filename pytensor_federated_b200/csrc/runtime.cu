@@ -90,11 +90,14 @@ struct Engine {
     unsigned char* host_block_dev = nullptr;  // device alias
     size_t h_off_theta = 0, h_off_result = 0, h_off_flag = 0, h_off_done = 0, h_off_ll = 0;
     bool ll_mode = false;  // small results: tagged words instead of fences + flags (fed_comm.cuh)
+    bool ll_theta = false; // theta as tagged words (no fence, no flag round trip)
     // device-local
     double* cta_partials = nullptr;
     unsigned int* ticket = nullptr;
     unsigned long long* epoch_counter = nullptr;
     unsigned long long* trace = nullptr;
+    unsigned long long* cta_trace = nullptr;   // [max_blocks][8] phase stamps of the last launch (opt-in)
+    bool cta_trace_on = false;
     unsigned long long epoch = 0;  // last launched epoch (root)
     unsigned long long timeout_ns = 20ull * 1000 * 1000 * 1000;
     unsigned long long launches = 0;
@@ -138,8 +141,10 @@ void fill_comm(Engine* e, FedComm* c, bool root_uses_explicit_epoch) {
     c->cta_partials = e->cta_partials;
     c->ticket = e->ticket;
     c->trace = e->trace;
+    c->cta_trace = e->cta_trace_on ? e->cta_trace : nullptr;
     c->done_flag = reinterpret_cast<unsigned long long*>(e->host_block_dev + e->h_off_done);
     c->ll_mode = e->ll_mode ? 1 : 0;
+    c->ll_theta = e->ll_theta ? 1 : 0;
     c->ll_theta_local = reinterpret_cast<unsigned long long*>(e->comm_local + L.off_ll_theta);
     c->ll_root_slots = reinterpret_cast<unsigned long long*>(root_block + L.off_ll_slots);
     if (e->rank == 0) {
@@ -208,7 +213,7 @@ void release_engine(Engine* e) {
     if (e->stream) cudaStreamSynchronize(e->stream);
     if (e->owns_comm && e->comm_local) cudaFree(e->comm_local);
     if (e->host_block) cudaFreeHost(e->host_block);
-    void* device_ptrs[] = {e->cta_partials, e->ticket,       e->epoch_counter, e->trace,  e->theta_dev,
+    void* device_ptrs[] = {e->cta_partials, e->ticket,       e->epoch_counter, e->trace,  e->theta_dev, e->cta_trace,
                            e->linreg_dev,   e->glm_segs_dev, e->glm_tmaps_dev, e->ode_dev};
     for (void* p : device_ptrs)
         if (p) cudaFree(p);
@@ -322,8 +327,8 @@ void* b200_engine_create(int device, int rank, int world, int n_theta, int n_val
         const char* v = getenv(name);
         return v && *v ? atoi(v) : dflt;
     };
-    e->ll_mode = n_vals <= env_int("B200FED_LL_MAX_VALS", 128) && n_theta <= env_int("B200FED_LL_MAX_THETA", 256) &&
-                 !getenv("B200FED_NO_LL");
+    e->ll_theta = n_theta <= env_int("B200FED_LL_MAX_THETA", 4096) && !getenv("B200FED_NO_LL");
+    e->ll_mode = e->ll_theta && n_vals <= env_int("B200FED_LL_MAX_VALS", 128);
     ok = ok && cudaHostAlloc((void**)&e->host_block, hbytes, cudaHostAllocMapped | cudaHostAllocPortable) == cudaSuccess;
     if (ok) memset(e->host_block, 0, hbytes);
     ok = ok && cudaHostGetDevicePointer((void**)&e->host_block_dev, e->host_block, 0) == cudaSuccess;
@@ -332,11 +337,13 @@ void* b200_engine_create(int device, int rank, int world, int n_theta, int n_val
     ok = ok && cudaMalloc((void**)&e->ticket, 256) == cudaSuccess;
     ok = ok && cudaMalloc((void**)&e->epoch_counter, 256) == cudaSuccess;
     ok = ok && cudaMalloc((void**)&e->trace, 256 * 4 * 8) == cudaSuccess;
+    ok = ok && cudaMalloc((void**)&e->cta_trace, (size_t)max_blocks * 8 * 8) == cudaSuccess;
     ok = ok && cudaMalloc((void**)&e->theta_dev, (size_t)(n_theta > 0 ? n_theta : 1) * 4) == cudaSuccess;
     if (ok) {
         cudaMemset(e->ticket, 0, 256);
         cudaMemset(e->epoch_counter, 0, 256);
         cudaMemset(e->trace, 0, 256 * 4 * 8);
+        cudaMemset(e->cta_trace, 0, (size_t)max_blocks * 8 * 8);
         cudaMemset(e->theta_dev, 0, (size_t)(n_theta > 0 ? n_theta : 1) * 4);
         cudaDeviceSynchronize();
     }
@@ -679,6 +686,17 @@ int b200_engine_trace(void* h, unsigned long long epoch, unsigned long long* out
     Engine* e = static_cast<Engine*>(h);
     CK(cudaMemcpy(out4, e->trace + (epoch & 255) * 4, 32, cudaMemcpyDeviceToHost));
     return 0;
+}
+
+// Per-CTA phase stamps (fed::stamp) of the most recent launch: out[grid][8] ns on the %globaltimer clock.
+void b200_engine_enable_cta_trace(void* h, int on) { static_cast<Engine*>(h)->cta_trace_on = on != 0; }
+int b200_engine_cta_trace(void* h, unsigned long long* out, int max_rows) {
+    Engine* e = static_cast<Engine*>(h);
+    CK(cudaSetDevice(e->device));
+    int rows = e->grid > 0 ? e->grid : 1;
+    if (rows > max_rows) rows = max_rows;
+    CK(cudaMemcpy(out, e->cta_trace, (size_t)rows * 64, cudaMemcpyDeviceToHost));
+    return rows;
 }
 
 void b200_engine_destroy(void* h) { release_engine(static_cast<Engine*>(h)); }

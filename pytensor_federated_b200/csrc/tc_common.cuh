@@ -1,6 +1,8 @@
 // tcgen05 / TMEM / TMA / mbarrier PTX wrappers and UMMA descriptor builders shared by the
 // tensor-core GLM kernels (glm_tc.cu: bf16, glm_fp8.cu: block-scaled fp8).  sm_100a only.
 #pragma once
+#include <cstdlib>
+
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
@@ -132,6 +134,15 @@ __host__ __device__ constexpr uint32_t make_idesc(int M, int N, int a_mn_major, 
            | (1u << 10)   // B format: bf16
            | ((uint32_t)a_mn_major << 15) | ((uint32_t)b_mn_major << 16) | ((uint32_t)(N >> 3) << 17) |
            ((uint32_t)(M >> 4) << 24);
+}
+
+// Programmatic dependent launch for back-to-back evaluations (B200FED_NO_PDL=1 disables it for A/B runs).
+inline bool use_pdl() {
+    static const bool on = [] {
+        const char* v = getenv("B200FED_NO_PDL");
+        return !(v && *v && *v != '0');
+    }();
+    return on;
 }
 
 // Index + phase bit of an n-deep circular buffer, advanced without division (the single-thread

@@ -29,12 +29,21 @@ class ShardModel:
     #: number of input arrays of the ArraysToArrays signature
     n_inputs: int = 0
 
-    def pack_theta(self, inputs: Sequence[np.ndarray], out: np.ndarray) -> None:
-        """Writes the inputs into ``out`` (``uint32[n_theta_words]`` view of pinned memory)."""
+    def call_context(self, inputs: Sequence[np.ndarray]):
+        """Whatever :meth:`unpack_result` must know about THIS call's inputs (their shapes).  The
+        engine carries it from ``pack_theta`` to ``unpack_result`` so that concurrent callers never
+        see each other's shapes; it is never stored on the model by the engine path."""
+        return None
+
+    def pack_theta(self, inputs: Sequence[np.ndarray], out: np.ndarray):
+        """Writes the inputs into ``out`` (``uint32[n_theta_words]`` view of pinned memory) and
+        returns :meth:`call_context` of the inputs."""
         raise NotImplementedError
 
-    def unpack_result(self, vals: np.ndarray) -> List[np.ndarray]:
-        """``float64[n_vals]`` → ``[logp, grad_0, grad_1, ...]`` (fresh arrays)."""
+    def unpack_result(self, vals: np.ndarray, ctx=None) -> List[np.ndarray]:
+        """``float64[n_vals]`` → ``[logp, grad_0, grad_1, ...]`` (fresh arrays).  ``ctx`` is the
+        value ``pack_theta`` returned for the same call (``None``: the most recent single-threaded
+        ``pack_theta`` / ``reference_partial`` call, kept for interactive use)."""
         raise NotImplementedError
 
     def attach(self, lib, handle) -> None:
@@ -47,7 +56,7 @@ class ShardModel:
 
     # -- conveniences --------------------------------------------------------------------
     def reference(self, inputs: Sequence[np.ndarray]) -> List[np.ndarray]:
-        return self.unpack_result(self.reference_partial(inputs))
+        return self.unpack_result(self.reference_partial(inputs), self.call_context(inputs))
 
     def bytes_per_eval(self) -> int:
         """Algorithmic HBM bytes one evaluation must move on this node (roofline input)."""

@@ -82,30 +82,39 @@ class GlmShards(ShardModel):
         return int(sum(X.shape[0] for X in self.Xs))
 
     # -- packing ---------------------------------------------------------------------------
-    def pack_theta(self, inputs, out: np.ndarray) -> None:
+    def call_context(self, inputs):
+        """``(batched, intercept shape)`` of one call: a 2-D ``beta`` means one row per chain."""
+        intercept, beta = inputs
+        return (np.ndim(beta) == 2, np.shape(intercept))
+
+    def pack_theta(self, inputs, out: np.ndarray):
         intercept, beta = inputs
         th = out.view(np.float32).reshape(self.n_chains, self.n_params)
         ic = np.asarray(intercept, dtype=np.float32)
         bt = np.asarray(beta, dtype=np.float32)
-        self._note_shapes(inputs)
-        th[:, : self.n_groups] = ic.reshape(self.n_chains, -1) if self._batched else ic.reshape(1, -1)
+        ctx = self._note_shapes(inputs)
+        th[:, : self.n_groups] = ic.reshape(self.n_chains, -1) if ctx[0] else ic.reshape(1, -1)
         th[:, self.n_groups :] = bt.reshape(self.n_chains, self.n_features)
+        return ctx
 
     _batched = False
     _icpt_shape = ()
 
-    def _note_shapes(self, inputs) -> None:
-        intercept, beta = inputs
-        self._batched = np.ndim(beta) == 2
-        self._icpt_shape = np.shape(intercept)
+    def _note_shapes(self, inputs):
+        # single-threaded convenience state (tests call reference_partial then unpack_result);
+        # the engine passes the context explicitly instead
+        ctx = self.call_context(inputs)
+        self._batched, self._icpt_shape = ctx
+        return ctx
 
-    def unpack_result(self, vals: np.ndarray) -> List[np.ndarray]:
+    def unpack_result(self, vals: np.ndarray, ctx=None) -> List[np.ndarray]:
         v = np.asarray(vals, dtype=np.float64).reshape(self.n_chains, 1 + self.n_params)
         G = self.n_groups
-        if self._batched:
-            return [v[:, 0].copy(), v[:, 1 : 1 + G].reshape((self.n_chains,) + tuple(self._icpt_shape[1:])).copy(),
+        batched, icpt_shape = ctx if ctx is not None else (self._batched, self._icpt_shape)
+        if batched:
+            return [v[:, 0].copy(), v[:, 1 : 1 + G].reshape((self.n_chains,) + tuple(icpt_shape[1:])).copy(),
                     v[:, 1 + G :].copy()]
-        return [np.asarray(v[0, 0]), v[0, 1 : 1 + G].reshape(self._icpt_shape).copy(), v[0, 1 + G :].copy()]
+        return [np.asarray(v[0, 0]), v[0, 1 : 1 + G].reshape(icpt_shape).copy(), v[0, 1 + G :].copy()]
 
     # -- native ----------------------------------------------------------------------------
     def use_tensor_cores(self):

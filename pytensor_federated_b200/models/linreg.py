@@ -56,17 +56,22 @@ class LinregShards(ShardModel):
         self.n_vals = 3 * self.n_shards_total
 
     # -- packing ---------------------------------------------------------------------------
-    def pack_theta(self, inputs, out: np.ndarray) -> None:
+    def call_context(self, inputs):
         intercept, slope = inputs
-        self._input_shapes = (np.shape(intercept), np.shape(slope))
+        return (np.shape(intercept), np.shape(slope))
+
+    def pack_theta(self, inputs, out: np.ndarray):
+        intercept, slope = inputs
+        ctx = self._input_shapes = self.call_context(inputs)
         th = out.view(np.float64).reshape(self.n_shards_total, 2)
         th[:, 0] = np.asarray(intercept, dtype=np.float64)  # broadcasts scalars
         th[:, 1] = np.asarray(slope, dtype=np.float64)
+        return ctx
 
-    def unpack_result(self, vals: np.ndarray) -> List[np.ndarray]:
+    def unpack_result(self, vals: np.ndarray, ctx=None) -> List[np.ndarray]:
         """``[logp_total, d/d intercept, d/d slope]``; per-shard values via :meth:`per_shard`."""
         v = np.asarray(vals, dtype=np.float64).reshape(self.n_shards_total, 3)
-        shape_a, shape_b = self._input_shapes
+        shape_a, shape_b = ctx if ctx is not None else self._input_shapes
         da = v[:, 1].copy() if shape_a != () else np.asarray(v[:, 1].sum())
         db = v[:, 2].copy() if shape_b != () else np.asarray(v[:, 2].sum())
         return [np.asarray(v[:, 0].sum()), da, db]

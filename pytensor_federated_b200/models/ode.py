@@ -39,11 +39,12 @@ class OdeShards(ShardModel):
         self.n_theta_words = 4
         self.n_vals = 5
 
-    def pack_theta(self, inputs, out: np.ndarray) -> None:
+    def pack_theta(self, inputs, out: np.ndarray):
         (theta,) = inputs
         out.view(np.float32)[:4] = np.asarray(theta, dtype=np.float32).reshape(4)
+        return None
 
-    def unpack_result(self, vals: np.ndarray) -> List[np.ndarray]:
+    def unpack_result(self, vals: np.ndarray, ctx=None) -> List[np.ndarray]:
         v = np.asarray(vals, dtype=np.float64)
         return [np.asarray(v[0]), v[1:5].copy()]
 

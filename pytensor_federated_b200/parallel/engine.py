@@ -213,36 +213,48 @@ class FederatedEngine:
     def is_root(self) -> bool:
         return self.rank == 0
 
-    def evaluate_raw(self, inputs: Sequence[np.ndarray]) -> np.ndarray:
-        """Root: one federated evaluation, returns the reduced ``float64[n_vals]`` (a view that
-        is overwritten by the next call)."""
+    def _evaluate_locked(self, inputs: Sequence[np.ndarray]):
+        """One evaluation with ``self._lock`` held by the caller: returns ``(vals, ctx)`` where ``vals``
+        is the engine's shared ``float64[n_vals]`` buffer (valid until the lock is released) and
+        ``ctx`` the model's per-call context for ``unpack_result``."""
         if self._closed:
             raise FederationError("engine is shut down")
         if not self.is_root:
             raise FederationError("only rank 0 evaluates; other ranks call serve()")
-        with self._lock:
-            self.n_evals += 1
-            if self._nvtx:
-                import torch
+        self.n_evals += 1
+        if self._nvtx:
+            import torch
 
-                torch.cuda.nvtx.range_push(f"fed_eval[{self.n_evals}]")
-            try:
-                if self.backend == "fused":
-                    self.model.pack_theta(inputs, self._stage)
-                    rc = self._lib.b200_engine_eval(
-                        self._handle, self._stage_p, self.model.n_theta_words, self._out_p, self.timeout + 5.0
-                    )
-                    if rc != 0:
-                        self._raise(rc)
-                    return self._out
-                return self._collective_eval(inputs)
-            finally:
-                if self._nvtx:
-                    torch.cuda.nvtx.range_pop()
+            torch.cuda.nvtx.range_push(f"fed_eval[{self.n_evals}]")
+        try:
+            if self.backend == "fused":
+                ctx = self.model.pack_theta(inputs, self._stage)
+                rc = self._lib.b200_engine_eval(
+                    self._handle, self._stage_p, self.model.n_theta_words, self._out_p, self.timeout + 5.0
+                )
+                if rc != 0:
+                    self._raise(rc)
+                return self._out, ctx
+            return self._collective_eval(inputs), self.model.call_context(inputs)
+        finally:
+            if self._nvtx:
+                torch.cuda.nvtx.range_pop()
+
+    def evaluate_raw(self, inputs: Sequence[np.ndarray]) -> np.ndarray:
+        """Root: one federated evaluation, returns a fresh copy of the reduced ``float64[n_vals]``."""
+        with self._lock:
+            vals, _ = self._evaluate_locked(inputs)
+            return np.array(vals, dtype=np.float64, copy=True)
 
     def evaluate(self, *inputs: np.ndarray) -> List[np.ndarray]:
-        """``ComputeFunc`` signature: ``(logp, *gradients)`` as fresh NumPy arrays."""
-        return self.model.unpack_result(self.evaluate_raw(inputs))
+        """``ComputeFunc`` signature: ``(logp, *gradients)`` as fresh NumPy arrays.
+
+        Thread-safe: packing, the launch and the unpacking of the shared result buffer happen
+        under one lock, and the shapes of THIS call's inputs travel with the call (several service
+        streams or a ``DynamicBatcher`` may call this concurrently)."""
+        with self._lock:
+            vals, ctx = self._evaluate_locked(inputs)
+            return self.model.unpack_result(vals, ctx)
 
     __call__ = evaluate
 
@@ -311,6 +323,21 @@ class FederatedEngine:
         buf = (C.c_ulonglong * 4)()
         self._lib.b200_engine_trace(self._handle, epoch, buf)
         return int(buf[0]), int(buf[1]), int(buf[2])
+
+    def enable_cta_trace(self, on: bool = True) -> None:
+        """Per-CTA phase stamps (``fed::stamp`` in the kernels) for the following launches."""
+        self._lib.b200_engine_enable_cta_trace(self._handle, int(on))
+
+    def cta_trace(self) -> np.ndarray:
+        """``uint64[grid, 8]`` device-timer stamps (ns) of the most recent launch on this rank:
+        0 entry, 1 theta acquired, 2 setup done, 3 first tile landed, 4 last load issued, 5 main loop
+        done, 6 partial stored, 7 exit.  Zero where a kernel has no such phase."""
+        rows = int(self._lib.b200_engine_max_blocks(self._handle))
+        buf = np.zeros((rows, 8), dtype=np.uint64)
+        n = int(self._lib.b200_engine_cta_trace(self._handle, buf.ctypes.data_as(C.POINTER(C.c_ulonglong)), rows))
+        if n < 0:
+            raise FederationError("cta_trace failed")
+        return buf[:n].copy()
 
     # ------------------------------------------------------------------ collective backend
     def _collective_eval(self, inputs) -> np.ndarray:

@@ -357,8 +357,10 @@ class Server:
     await wait_closed()`` — ``/root/reference/demo_node.py:76-79``)."""
 
     def __init__(self, services: Sequence[ArraysToArraysServiceBase], *, tls=None) -> None:
-        """``tls``: a :class:`~pytensor_federated_b200.config.TlsConfig` with ``cert`` + ``key`` (default: the
-        ``B200FED_TLS_*`` environment, else plaintext like the reference)."""
+        """``tls``: a :class:`~pytensor_federated_b200.config.TlsConfig` with ``cert`` + ``key`` (+ ``ca`` when
+        ``mutual``); ``None`` = the ``B200FED_TLS_*`` environment, else plaintext like the reference;
+        ``False`` = plaintext no matter what the environment says.  An incomplete configuration raises
+        :class:`~pytensor_federated_b200.config.TlsConfigError` at ``start`` — it never degrades to plaintext."""
         self._services = list(services)
         self._server = None
         self._tls = tls
@@ -371,13 +373,14 @@ class Server:
         self._server.add_generic_rpc_handlers(tuple(s.generic_handler() for s in self._services))
         from .config import tls_from_env
 
-        tls = self._tls if self._tls is not None else tls_from_env()
-        if tls is not None and tls.cert and tls.key:
+        tls = None if self._tls is False else (self._tls if self._tls is not None else tls_from_env())
+        if tls is not None:
             import grpc
 
+            tls.check_server()
             credentials = grpc.ssl_server_credentials(
                 [(tls.key, tls.cert)], root_certificates=tls.ca if tls.mutual else None,
-                require_client_auth=bool(tls.mutual and tls.ca),
+                require_client_auth=bool(tls.mutual),
             )
             self.port = self._server.add_secure_port(f"{host}:{port}", credentials)
         else:

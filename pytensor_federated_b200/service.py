@@ -272,8 +272,10 @@ class _Channel:
         self._host = host
         self._port = port
         tls = _channel_tls()
-        if tls is not None and tls.ca:
+        if tls is not None:
             import grpc
+
+            tls.check_client()  # incomplete material raises: a client never falls back to plaintext
 
             credentials = grpc.ssl_channel_credentials(root_certificates=tls.ca, private_key=tls.key,
                                                        certificate_chain=tls.cert)
@@ -312,6 +314,34 @@ class _Channel:
             coro.close()
 
 
+class RemoteComputeError(Exception):
+    """The node answered the call with an application error (its compute function raised, or it
+    rejected the request): re-running the same call would fail the same way, so it is reported once,
+    with the server's status and message, instead of being retried like a lost connection."""
+
+    def __init__(self, code, details: str) -> None:
+        self.code = code
+        self.details = details
+        super().__init__(f"Remote evaluation failed ({getattr(code, 'name', code)}): {details}")
+
+
+def _translate_rpc_error(ex) -> Exception:
+    """``grpc.aio.AioRpcError`` -> connection loss (retry elsewhere) or application error (report)."""
+    import grpc
+
+    code = ex.code() if hasattr(ex, "code") else None
+    sc = grpc.StatusCode
+    # Codes a *handler* produces (a raised exception arrives as UNKNOWN; the others are explicit aborts).
+    # Transport-level trouble — UNAVAILABLE, CANCELLED, DEADLINE_EXCEEDED, but also the INTERNAL
+    # "error from Core" of a write to a peer that just died — means the connection is gone: retry elsewhere.
+    application = (sc.UNKNOWN, sc.INVALID_ARGUMENT, sc.NOT_FOUND, sc.ALREADY_EXISTS, sc.PERMISSION_DENIED,
+                   sc.FAILED_PRECONDITION, sc.OUT_OF_RANGE, sc.UNIMPLEMENTED, sc.UNAUTHENTICATED)
+    if code not in application:
+        return StreamTerminatedError(str(ex))
+    details = ex.details() if hasattr(ex, "details") else str(ex)
+    return RemoteComputeError(code, details or str(ex))
+
+
 class EvaluationStream:
     """Bidirectional ``EvaluateStream`` call with grpclib-like method names."""
 
@@ -323,8 +353,10 @@ class EvaluationStream:
 
         try:
             await self._call.write(message)
-        except (grpc.aio.AioRpcError, asyncio.InvalidStateError) as ex:
+        except asyncio.InvalidStateError as ex:
             raise StreamTerminatedError(str(ex)) from ex
+        except grpc.aio.AioRpcError as ex:
+            raise _translate_rpc_error(ex) from ex
 
     async def recv_message(self) -> Optional[OutputArrays]:
         import grpc
@@ -332,7 +364,7 @@ class EvaluationStream:
         try:
             response = await self._call.read()
         except grpc.aio.AioRpcError as ex:
-            raise StreamTerminatedError(str(ex)) from ex
+            raise _translate_rpc_error(ex) from ex
         if response is grpc.aio.EOF:
             raise StreamTerminatedError("The evaluation stream was closed by the server.")
         return response
@@ -536,9 +568,7 @@ async def _connect_evaluate_async(
         try:
             output = await priv.client.evaluate(input)
         except grpc.aio.AioRpcError as ex:
-            if ex.code() in (grpc.StatusCode.UNAVAILABLE, grpc.StatusCode.CANCELLED):
-                raise StreamTerminatedError(str(ex)) from ex
-            raise
+            raise _translate_rpc_error(ex) from ex
     if output.uuid != input.uuid:
         raise Exception("Response does not correspond to the request.")
     return output
@@ -678,6 +708,12 @@ class ArraysToArraysServiceClient:
                 call = _connect_evaluate_async(input, cid, hap, use_stream)
                 output = await (call if timeout is None else _bounded(call, timeout))
                 break
+            except RemoteComputeError:
+                # the stream died with the failed call; the next evaluation reconnects, this one reports
+                cp = _privates.pop(cid, None)
+                if cp is not None:
+                    cp.close()
+                raise
             except (StreamTerminatedError, _AttemptTimedOut) as ex:
                 last_error = ex
                 cp = _privates.pop(cid, None)
@@ -761,6 +797,7 @@ __all__ = [
     "ClientPrivates",
     "EvaluationStream",
     "LocalNode",
+    "RemoteComputeError",
     "StreamTerminatedError",
     "get_load_async",
     "get_loads_async",

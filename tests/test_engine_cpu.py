@@ -48,6 +48,44 @@ def test_linreg_per_shard_parameters():
     np.testing.assert_allclose(logp, expected, rtol=1e-12)
 
 
+def test_concurrent_evaluate_keeps_every_callers_shapes_and_values():
+    """``evaluate`` is called from several service threads (``offload=True``, ``DynamicBatcher``): packing,
+    evaluation and unpacking of the shared buffers must be atomic and the input shapes per call."""
+    import threading
+
+    rng = np.random.default_rng(5)
+    xs = [rng.normal(size=30) for _ in range(4)]
+    ys = [rng.normal(size=30) for _ in range(4)]
+    model = LinregShards(xs, ys, [1.0] * 4)
+    eng = FederatedEngine(model, backend="collective")
+    vec = np.array([0.1, 0.2, 0.3, 0.4])
+    want_scalar = [np.array(v) for v in eng.evaluate(np.array(0.5), np.array(0.25))]
+    want_vector = [np.array(v) for v in eng.evaluate(vec, vec[::-1].copy())]
+    assert want_scalar[1].shape == () and want_vector[1].shape == (4,)
+    errors = []
+
+    def worker(scalar: bool):
+        try:
+            for _ in range(150):
+                got = eng.evaluate(np.array(0.5), np.array(0.25)) if scalar else eng.evaluate(vec, vec[::-1].copy())
+                want = want_scalar if scalar else want_vector
+                for g, w in zip(got, want):
+                    assert g.shape == w.shape
+                    np.testing.assert_array_equal(g, w)
+        except Exception as ex:  # noqa: BLE001 - reported by the main thread
+            errors.append(ex)
+
+    threads = [threading.Thread(target=worker, args=(i % 2 == 0,)) for i in range(4)]
+    for t in threads:
+        t.start()
+    for t in threads:
+        t.join()
+    assert not errors, errors[0]
+    raw = eng.evaluate_raw([vec, vec])
+    raw2 = eng.evaluate_raw([np.array(0.0), np.array(0.0)])
+    assert raw is not raw2 and not np.array_equal(raw, raw2)   # fresh copies, not views of one buffer
+
+
 def test_glm_reference_gradient_matches_autograd():
     torch.manual_seed(0)
     X = torch.randn(300, 16).to(torch.bfloat16)

@@ -70,7 +70,7 @@ def test_parallel_async_op_validation_and_concurrency():
     with pytest.raises(ValueError, match="not an `AsyncOp`"):
         op_async.ParallelAsyncOp([a1, (x + y).owner])
     pop = op_async.ParallelAsyncOp([a1, a2])
-    with pytest.raises(ValueError, match="Unexpected number of inputs"):
+    with pytest.raises(ValueError, match="expected 2 for 2"):
         pop.make_node(x)
     node = pop.make_node(x, y)
     assert len(node.outputs) == 2

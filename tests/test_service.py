@@ -16,7 +16,7 @@ import pytest
 
 from pytensor_federated_b200 import LogpServiceClient, service
 from pytensor_federated_b200.npproto.utils import ndarray_from_numpy, ndarray_to_numpy
-from pytensor_federated_b200.rpc import GetLoadResult, InputArrays, OutputArrays
+from pytensor_federated_b200.rpc import GetLoadResult, InputArrays, OutputArrays, Server
 from pytensor_federated_b200.utils import get_useful_event_loop
 
 from _helpers import (
@@ -226,6 +226,36 @@ def test_single_dead_server_raises_after_retries():
     client = service.ArraysToArraysServiceClient("127.0.0.1", free_port())
     with pytest.raises(service.StreamTerminatedError):
         client.evaluate(np.array(1), retries=0)
+
+
+def test_a_failing_compute_function_is_reported_once_not_retried():
+    """A compute function that raises on the node is an application error: the client must surface it
+    (with the server's message) after ONE execution, not treat it as a lost connection and re-run it."""
+    calls = []
+
+    def picky(a):
+        calls.append(float(a))
+        if a < 0:
+            raise ValueError("negative input rejected")
+        return [np.sqrt(a)]
+
+    loop = get_useful_event_loop()
+    server = Server([service.ArraysToArraysService(picky)])
+    port = loop.run_until_complete(server.start("127.0.0.1", 0))
+    client = service.ArraysToArraysServiceClient("127.0.0.1", port)
+    try:
+        assert client.evaluate(np.array(4.0))[0] == 2.0
+        for use_stream in (True, False):
+            calls.clear()
+            with pytest.raises(service.RemoteComputeError, match="negative input rejected") as err:
+                loop.run_until_complete(client.evaluate_async(np.array(-1.0), use_stream=use_stream, retries=2))
+            assert calls == [-1.0]
+            assert not isinstance(err.value, service.StreamTerminatedError)
+            # the connection is re-established transparently for the next (valid) call
+            assert client.evaluate(np.array(9.0))[0] == 3.0
+    finally:
+        del client
+        loop.run_until_complete(server.close(None))
 
 
 def test_concurrent_async_clients_share_a_loop():

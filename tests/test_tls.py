@@ -105,3 +105,39 @@ def test_tls_from_env_reads_pem_files(pki, tmp_path, monkeypatch):
     monkeypatch.setenv("B200FED_TLS_SERVER_NAME", "localhost")
     cfg = tls_from_env()
     assert cfg.ca == pki["ca"] and cfg.cert is None and cfg.server_name == "localhost" and not cfg.mutual
+
+
+def test_incomplete_tls_material_fails_closed(pki, tmp_path, monkeypatch):
+    """Partial TLS material must raise for the role, never degrade to plaintext (server and client)."""
+    import asyncio
+
+    from pytensor_federated_b200.config import TlsConfigError
+    from pytensor_federated_b200.rpc import Server
+
+    cert, key = pki["server"]
+    # server: certificate without key, and mutual TLS without a CA
+    for bad in (TlsConfig(cert=cert), TlsConfig(ca=pki["ca"]), TlsConfig(cert=cert, key=key, mutual=True)):
+        with pytest.raises(TlsConfigError, match="server"):
+            asyncio.new_event_loop().run_until_complete(Server([], tls=bad).start("127.0.0.1", 0))
+    # the environment counts: a lone B200FED_TLS_CERT is a request for TLS
+    (tmp_path / "c.pem").write_bytes(cert)
+    monkeypatch.setenv("B200FED_TLS_CERT", str(tmp_path / "c.pem"))
+    with pytest.raises(TlsConfigError, match="key"):
+        asyncio.new_event_loop().run_until_complete(Server([]).start("127.0.0.1", 0))
+    # ... unless plaintext is asked for explicitly
+    loop = asyncio.new_event_loop()
+    srv = Server([], tls=False)
+    assert loop.run_until_complete(srv.start("127.0.0.1", 0)) > 0
+    loop.run_until_complete(srv.close())
+    monkeypatch.delenv("B200FED_TLS_CERT")
+    # client: identity without the CA, or half an identity
+    with pytest.raises(TlsConfigError, match="client"):
+        TlsConfig(cert=cert, key=key).check_client()
+    with pytest.raises(TlsConfigError, match="key"):
+        TlsConfig(ca=pki["ca"], cert=cert).check_client()
+    service.set_default_tls(TlsConfig(cert=cert, key=key))
+    try:
+        with pytest.raises(TlsConfigError):
+            service._Channel("127.0.0.1", 1)
+    finally:
+        service.set_default_tls(None)
