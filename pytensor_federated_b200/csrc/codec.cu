@@ -145,8 +145,9 @@ static bool parse_int64s(const unsigned char*& p, const unsigned char* end, int 
     return true;
 }
 
-// Returns the number of items (may exceed max_items: call again with a larger array), or -1 on
-// malformed input.  Offsets are relative to `buf`.
+// Returns the number of items (may exceed max_items: call again with a larger array), -1 on malformed
+// input, or -2 for a well-formed message this fast path does not cover (an array with more than 16
+// dimensions): the caller falls back to the general decoder.  Offsets are relative to `buf`.
 long long b200_pb_decode_arrays(const unsigned char* buf, long long len, B200PbItem* items, int max_items,
                                 long long* uuid_off, long long* uuid_len) {
     const unsigned char* p = buf;
@@ -183,7 +184,7 @@ long long b200_pb_decode_arrays(const unsigned char* buf, long long len, B200PbI
                     return -1;
                 }
             }
-            if (it.ndim > 16 || it.n_strides > 16) return -1;
+            if (it.ndim > 16 || it.n_strides > 16) return -2;   // valid, but more dimensions than B200PbItem holds
             if (n < max_items) items[n] = it;
             ++n;
             p = qe;

@@ -36,6 +36,7 @@
 #define B200FED_EPOCH_MASK 0x00FFFFFFFFFFFFFFull
 #define B200FED_ERR_THETA_TIMEOUT 1ull
 #define B200FED_ERR_PEER_TIMEOUT 2ull
+#define B200FED_ERR_PIPELINE 4ull      // a tensor-core kernel's mbarrier pipeline stalled (tc_common.cuh)
 #define B200FED_STOP_EPOCH 0x00FFFFFFFFFFFFFFull
 
 struct FedComm {
@@ -61,7 +62,8 @@ struct FedComm {
     double* root_slots;                            // root's slot array [world][n_vals]   (peer memory)
     unsigned long long* root_slot_flags;           // root's slot flags [world]             (peer memory)
     double* cta_partials;                          // local scratch [grid][n_vals]
-    unsigned int* ticket;                          // local "last CTA" counter
+    double* group_partials;                        // local scratch of the two-level reduction [grid/16][n_vals] (x2 for pairs)
+    unsigned int* ticket;                          // [0]: groups finished; [1 + g]: CTAs of group g finished
     unsigned long long* epoch_counter;             // peers: device-resident epoch (graph replay friendly); may be null
     unsigned long long* done_flag;                 // host-mapped: last finished epoch on this node (peers' serve loop)
     unsigned long long* trace;                     // optional device-timer ring [4 x u64 per epoch % 256] or null
@@ -185,21 +187,6 @@ __device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;"
 // Lets the next kernel of the stream start occupying SMs that this grid no longer needs.
 __device__ __forceinline__ void pdl_trigger() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
 
-// Fixed-order (b = 0, 1, 2, ...) sum of value v over the per-CTA partials => bit-reproducible.  The loads
-// are issued kWide at a time: a 148-CTA grid costs 4 dependent L2 round trips instead of 148.
-__device__ __forceinline__ double sum_cta_partials(const double* partials, int nv, int v, unsigned int n_ctas) {
-    constexpr unsigned int kWide = 37;
-    double s = 0.0;
-    for (unsigned int b = 0; b < n_ctas; b += kWide) {
-        double t[kWide];
-#pragma unroll
-        for (unsigned int j = 0; j < kWide; ++j) t[j] = (b + j < n_ctas) ? ld_cg_f64(partials + (size_t)(b + j) * nv + v) : 0.0;
-#pragma unroll
-        for (unsigned int j = 0; j < kWide; ++j) s += t[j];
-    }
-    return s;
-}
-
 struct Prologue {
     unsigned long long epoch;   // resolved epoch of this launch
     bool stop;                  // root asked the nodes to drain
@@ -302,18 +289,73 @@ __device__ __forceinline__ Prologue prologue(const FedComm& c, float* theta_smem
     return r;
 }
 
-// Every CTA has stored its partial into c.cta_partials[blockIdx.x * n_vals ...].
-// `scratch` is shared memory for at least 1 int.  Must be called by all threads.
-__device__ __forceinline__ void epilogue(const FedComm& c, const Prologue& pro, unsigned long long status_in) {
+// ---- double-double partial sums --------------------------------------------------------------------------
+// Kernels that hand out work dynamically (csrc/glm_tc.cu) cannot fix WHICH CTA sums which chunk of rows, so
+// they keep every running sum as an unevaluated pair (hi, lo) with |lo| <= ulp(hi)/2 (Knuth TwoSum).  Every
+// chunk contributes a value that depends on the chunk only; pairs make the additions exact to ~2^-100, so the
+// total — rounded to a double exactly once, at the very end — does not depend on the assignment of chunks to
+// CTAs (bit-reproducible except when the exact sum sits within 2^-100 of a rounding boundary).
+__device__ __forceinline__ void dd_add(double& hi, double& lo, double xh, double xl) {
+    const double s = hi + xh;
+    const double bb = s - hi;
+    const double err = (hi - (s - bb)) + (xh - bb);
+    hi = s;
+    lo += err + xl;
+}
+__device__ __forceinline__ double2 ld_cg_f64x2(const double* p) {
+    double2 v;
+    asm volatile("ld.global.cg.v2.f64 {%0, %1}, [%2];" : "=d"(v.x), "=d"(v.y) : "l"(p) : "memory");
+    return v;
+}
+
+constexpr unsigned int kReduceGroup = 16;   // CTAs per level-1 reduction group
+
+// Fixed-order sum of value v over rows [first, first + count) of a partial array with `stride` doubles per
+// row.  DD: rows hold (hi, lo) pairs and the result is a pair; otherwise plain doubles (lo stays 0).
+template <bool DD>
+__device__ __forceinline__ void sum_rows(const double* rows, size_t stride, int v, unsigned int first, unsigned int count,
+                                         double& hi, double& lo) {
+    constexpr unsigned int kWide = DD ? 16 : 37;   // loads in flight per thread
+    hi = 0.0;
+    lo = 0.0;
+    for (unsigned int b = 0; b < count; b += kWide) {
+        if constexpr (DD) {
+            double2 t[kWide];
+#pragma unroll
+            for (unsigned int j = 0; j < kWide; ++j)
+                t[j] = (b + j < count) ? ld_cg_f64x2(rows + (size_t)(first + b + j) * stride + 2 * (size_t)v) : make_double2(0.0, 0.0);
+#pragma unroll
+            for (unsigned int j = 0; j < kWide; ++j) dd_add(hi, lo, t[j].x, t[j].y);
+        } else {
+            double t[kWide];
+#pragma unroll
+            for (unsigned int j = 0; j < kWide; ++j)
+                t[j] = (b + j < count) ? ld_cg_f64(rows + (size_t)(first + b + j) * stride + v) : 0.0;
+#pragma unroll
+            for (unsigned int j = 0; j < kWide; ++j) hi += t[j];
+        }
+    }
+}
+
+// Every CTA has stored its partial into row blockIdx.x of c.cta_partials (`row_stride` doubles per row; DD:
+// (hi, lo) pairs).  Two-level, fixed-shape reduction: the last CTA to finish within a group of kReduceGroup
+// consecutive CTAs sums the group's rows into `group_buf[group]` (groups that finish early reduce early, off
+// the critical path); the last group to finish sums the group partials, exchanges the node partial with the
+// root over NVLink, and the root publishes the result to the host.  Returns true in the one CTA that ran the
+// final stage (it may reset per-launch kernel state such as work counters).  Must be called by all threads.
+template <bool DD>
+__device__ __forceinline__ bool epilogue_t(const FedComm& c, const Prologue& pro, unsigned long long status_in,
+                                           size_t row_stride, double* group_buf) {
     __shared__ int s_last;
     __shared__ unsigned long long s_status;
+    const int nv = c.n_vals;
     if (c.world == 1 && gridDim.x == 1) {
         // latency path: the only CTA's partial IS the result
         __syncthreads();
+        auto value = [&](int v) { return DD ? c.cta_partials[2 * v] + c.cta_partials[2 * v + 1] : c.cta_partials[v]; };
         if (c.ll_mode) {
             // tagged words straight to host-mapped memory: no fence, no flag
-            for (int v = threadIdx.x; v < c.n_vals; v += blockDim.x)
-                ll_store_f64(c.ll_host_result + 2 * v, c.cta_partials[v], pro.epoch);
+            for (int v = threadIdx.x; v < nv; v += blockDim.x) ll_store_f64(c.ll_host_result + 2 * v, value(v), pro.epoch);
             if (threadIdx.x == 0) {
                 if (c.trace) {
                     c.trace[(pro.epoch & 255) * 4 + 1] = globaltimer();
@@ -321,10 +363,11 @@ __device__ __forceinline__ void epilogue(const FedComm& c, const Prologue& pro, 
                 }
                 if (c.epoch_counter) *c.epoch_counter = pro.epoch;
                 if (c.done_flag) *reinterpret_cast<volatile unsigned long long*>(c.done_flag) = pro.epoch;
+                stamp(c, 7);
             }
-            return;
+            return true;
         }
-        for (int v = threadIdx.x; v < c.n_vals; v += blockDim.x) c.host_result[v] = c.cta_partials[v];
+        for (int v = threadIdx.x; v < nv; v += blockDim.x) c.host_result[v] = value(v);
         __threadfence_system();
         __syncthreads();
         if (threadIdx.x == 0) {
@@ -335,26 +378,61 @@ __device__ __forceinline__ void epilogue(const FedComm& c, const Prologue& pro, 
             st_release_sys(c.host_flag, pro.epoch | (status_in << B200FED_STATUS_SHIFT));
             if (c.epoch_counter) *c.epoch_counter = pro.epoch;
             if (c.done_flag) *reinterpret_cast<volatile unsigned long long*>(c.done_flag) = pro.epoch;
+            stamp(c, 7);
         }
-        return;
+        return true;
     }
+    const bool computed = !(pro.stop || pro.timed_out);
+    const unsigned int n_groups = (gridDim.x + kReduceGroup - 1) / kReduceGroup;
+    const unsigned int grp = blockIdx.x / kReduceGroup;
+    const unsigned int grp_first = grp * kReduceGroup;
+    const unsigned int grp_size = min(kReduceGroup, gridDim.x - grp_first);
+    constexpr int kW = DD ? 2 : 1;
+
+    // ---- level 1: last CTA of the group -> group partial ------------------------------------------------
+    if (threadIdx.x == 0 && status_in) atomicOr(c.ticket + 255, (unsigned int)status_in);   // any CTA's fault reaches the host
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) {
-        unsigned int t = atomicAdd(c.ticket, 1u);
-        s_last = (t == gridDim.x - 1) ? 1 : 0;
+        const unsigned int t = atomicAdd(c.ticket + 1 + grp, 1u);
+        s_last = (t == grp_size - 1) ? 1 : 0;
+        if (s_last) c.ticket[1 + grp] = 0;   // nobody touches this group's ticket again in this launch
         s_status = status_in;
     }
     __syncthreads();
     if (!s_last) {
         if (threadIdx.x == 0) stamp(c, 7);
-        return;
+        return false;
     }
     __threadfence();
-    const int nv = c.n_vals;
+    if (computed) {
+        for (int v = threadIdx.x; v < nv; v += blockDim.x) {
+            double hi, lo;
+            sum_rows<DD>(c.cta_partials, row_stride, v, grp_first, grp_size, hi, lo);
+            group_buf[((size_t)grp * nv + v) * kW] = hi;
+            if constexpr (DD) group_buf[((size_t)grp * nv + v) * kW + 1] = lo;
+        }
+    }
+    // ---- level 2: last group -> node partial ------------------------------------------------------------
+    __threadfence();
+    __syncthreads();
+    if (threadIdx.x == 0) {
+        const unsigned int t = atomicAdd(c.ticket, 1u);
+        s_last = (t == n_groups - 1) ? 1 : 0;
+    }
+    __syncthreads();
+    if (!s_last) {
+        if (threadIdx.x == 0) stamp(c, 7);
+        return false;
+    }
+    __threadfence();
     const unsigned long long epoch = pro.epoch;
+    if (threadIdx.x == 0) {
+        s_status |= (unsigned long long)atomicExch(c.ticket + 255, 0u);
+    }
+    __syncthreads();
 
-    if (pro.stop || pro.timed_out) {
+    if (!computed) {
         // nothing was computed: just report and drain
         if (threadIdx.x == 0) {
             *c.ticket = 0;
@@ -367,16 +445,21 @@ __device__ __forceinline__ void epilogue(const FedComm& c, const Prologue& pro, 
                 st_release_sys(c.host_flag, word);
             }
         }
-        return;
+        return true;
     }
+    auto node_value = [&](int v) {
+        double hi, lo;
+        sum_rows<DD>(group_buf, (size_t)nv * kW, v, 0u, n_groups, hi, lo);
+        return hi + lo;   // DD: the one rounding of this node's partial
+    };
 
     if (c.ll_mode) {
-        // LL reduce: each node's last CTA stores tagged words into the root's slot array (NVLink, no
-        // fence, no flag); the root's last CTA polls the words of every node in rank order, sums, and
-        // stores tagged words into host-mapped memory.  Same fixed summation order as below.
+        // LL reduce: each node's last CTA stores tagged words into the root's slot array (NVLink, no fence,
+        // no flag); the root polls the words of every node in rank order, sums, and stores tagged words into
+        // host-mapped memory.
         unsigned long long* my_slot_ll = c.ll_root_slots + (size_t)c.rank * nv * 2;
         for (int v = threadIdx.x; v < nv; v += blockDim.x) {
-            const double s = sum_cta_partials(c.cta_partials, nv, v, gridDim.x);
+            const double s = node_value(v);
             if (c.rank != 0) {
                 ll_store_f64(my_slot_ll + 2 * v, s, epoch);
             } else {
@@ -406,32 +489,56 @@ __device__ __forceinline__ void epilogue(const FedComm& c, const Prologue& pro, 
             *c.ticket = 0;
             if (c.epoch_counter) *c.epoch_counter = epoch;
             if (c.done_flag) *reinterpret_cast<volatile unsigned long long*>(c.done_flag) = epoch | (s_status << B200FED_STATUS_SHIFT);
+            stamp(c, 7);
         }
-        return;
+        return true;
     }
 
-    // 1) node partial = fixed-order sum over CTAs -> root's slot for this rank (NVLink store for peers)
-    double* my_slot = c.root_slots + (size_t)c.rank * nv;
-    for (int v = threadIdx.x; v < nv; v += blockDim.x) my_slot[v] = sum_cta_partials(c.cta_partials, nv, v, gridDim.x);
-    __threadfence_system();
-    __syncthreads();
-    if (threadIdx.x == 0) {
-        if (c.trace) c.trace[(epoch & 255) * 4 + 1] = globaltimer();
-        st_release_sys(c.root_slot_flags + c.rank, epoch);
-    }
-
-    // 2) root: gather the nodes, ordered sum, publish to the host
-    if (c.rank == 0) {
-        if (threadIdx.x < c.world) {
+    if (c.rank != 0) {
+        // peer: node partial -> root's slot for this rank (NVLink stores), then the slot flag
+        double* my_slot = c.root_slots + (size_t)c.rank * nv;
+        for (int v = threadIdx.x; v < nv; v += blockDim.x) my_slot[v] = node_value(v);
+        __threadfence_system();
+        __syncthreads();
+        if (threadIdx.x == 0) {
+            if (c.trace) c.trace[(epoch & 255) * 4 + 1] = globaltimer();
+            st_release_sys(c.root_slot_flags + c.rank, epoch);
+        }
+    } else {
+        // root: own partial stays in registers; gather the peers, ordered sum (rank 0, 1, 2, ...), publish
+        if (threadIdx.x == 0 && c.trace) c.trace[(epoch & 255) * 4 + 1] = globaltimer();
+        constexpr int kOwn = 4;   // values per thread kept in registers across the wait for the peers
+        double own[kOwn];
+        const bool cached = nv <= kOwn * (int)blockDim.x;
+        if (cached) {
+#pragma unroll
+            for (int i = 0; i < kOwn; ++i) {
+                const int v = threadIdx.x + i * blockDim.x;
+                own[i] = v < nv ? node_value(v) : 0.0;
+            }
+        }
+        if (threadIdx.x >= 1 && threadIdx.x < c.world) {
             unsigned long long seen;
             bool ok = wait_epoch(c.root_slot_flags + threadIdx.x, epoch, c.timeout_ns, &seen);
             if (!ok) atomicOr(&s_status, B200FED_ERR_PEER_TIMEOUT);
         }
         __syncthreads();
-        for (int v = threadIdx.x; v < nv; v += blockDim.x) {
-            double s = 0.0;
-            for (int p = 0; p < c.world; ++p) s += ld_cg_f64(c.root_slots + (size_t)p * nv + v);
-            c.host_result[v] = s;
+        if (cached) {
+#pragma unroll
+            for (int i = 0; i < kOwn; ++i) {
+                const int v = threadIdx.x + i * blockDim.x;
+                if (v < nv) {
+                    double s = own[i];
+                    for (int p = 1; p < c.world; ++p) s += ld_cg_f64(c.root_slots + (size_t)p * nv + v);
+                    c.host_result[v] = s;
+                }
+            }
+        } else {
+            for (int v = threadIdx.x; v < nv; v += blockDim.x) {
+                double s = node_value(v);
+                for (int p = 1; p < c.world; ++p) s += ld_cg_f64(c.root_slots + (size_t)p * nv + v);
+                c.host_result[v] = s;
+            }
         }
         __threadfence_system();
         __syncthreads();
@@ -446,6 +553,12 @@ __device__ __forceinline__ void epilogue(const FedComm& c, const Prologue& pro, 
         if (c.done_flag) *reinterpret_cast<volatile unsigned long long*>(c.done_flag) = epoch | (s_status << B200FED_STATUS_SHIFT);
         stamp(c, 7);
     }
+    return true;
+}
+
+// Plain-double partials, one row of n_vals per CTA (every kernel except the dynamically scheduled GLM).
+__device__ __forceinline__ bool epilogue(const FedComm& c, const Prologue& pro, unsigned long long status_in) {
+    return epilogue_t<false>(c, pro, status_in, (size_t)c.n_vals, c.group_partials);
 }
 
 // Order-independent accumulation for values that many threads add to one shared cell (the

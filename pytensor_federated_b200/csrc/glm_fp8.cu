@@ -230,6 +230,7 @@ fed_glm_fp8_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParam
             reinterpret_cast<uint4*>(r_buf)[i] = make_uint4(0, 0, 0, 0);
         fence_proxy_async();
         if (threadIdx.x == 0) {
+            *pipeline_fault() = 0;
             for (int i = 0; i < 6; ++i) { mbar_init(&bar_full[i], 1); mbar_init(&bar_empty[i], 1); }
             for (int i = 0; i < kEG; ++i) {
                 mbar_init(&bar_eta_full[i], 1);
@@ -551,7 +552,7 @@ fed_glm_fp8_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParam
             __syncthreads();
         }
     }
-    fed::epilogue(comm, pro, 0ull);
+    fed::epilogue(comm, pro, (active && *pipeline_fault()) ? B200FED_ERR_PIPELINE : 0ull);
 }
 
 }  // namespace fp8

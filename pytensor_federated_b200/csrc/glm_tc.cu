@@ -19,6 +19,8 @@
 //
 // Workload: BASELINE.json "federated logistic GLM, 10M rows x 256 features per shard, bf16".
 // Nothing comparable exists in the reference (its model is /root/reference/demo_node.py:31-43).
+#include <vector>
+
 #include <cuda.h>
 #include <cuda_bf16.h>
 #include <cuda_runtime.h>
@@ -33,11 +35,14 @@ constexpr int kTileM = 128;          // rows per tile (UMMA M for MMA #1, UMMA K
 constexpr int kPanel = 64;           // features per 128-byte swizzle span
 constexpr int kPanelBytes = kTileM * 128;  // 16 KB
 // warps: 0 TMA, 1 MMA#1 issuer, 2-5 epilogue group 0, 6 MMA#2 issuer, 7.. further epilogue groups
-constexpr int kFlush = 32;           // tiles between TMEM -> fp64 flushes of the gradient
+constexpr int kMaxChunk = 32;        // tiles per chunk at most (= tiles accumulated in TMEM in fp32 before a flush)
+constexpr int kMinChunk = 4;
 constexpr int kMaxSegs = 64;
+constexpr int kRing = 32;            // published chunks the consumers may lag behind (needs only ~3)
+constexpr int kLLRows = 16;          // epilogue warps at most (per-warp log-likelihood slots)
 
 struct SmemLayout {
-    uint32_t stages, stage_bytes, off_theta_b, theta_b_bytes, off_r, r_bytes, off_theta_f, off_icpt, off_segs, off_gi, off_red,
+    uint32_t stages, stage_bytes, off_theta_b, theta_b_bytes, off_r, r_bytes, off_theta_f, off_icpt, off_segs, off_gi, off_ring,
         off_bars, off_tmem, total;
 };
 __host__ __device__ inline SmemLayout smem_layout(int P, int n1, int n2, int n_theta, int n_groups, int chains) {
@@ -49,7 +54,7 @@ __host__ __device__ inline SmemLayout smem_layout(int P, int n1, int n2, int n_t
     // theta (fp32) is staged inside the (not yet used) TMA stage ring and is dead once the bf16 B operand
     // and the intercept table are built, so it costs no shared memory of its own.
     const uint32_t fixed = L.theta_b_bytes + 2 * L.r_bytes + ((chains * n_groups * 4 + 15) & ~15) +
-                           kMaxSegs * (uint32_t)sizeof(GlmSegment) + ((chains * n_groups * 8 + 15) & ~15) + 32 * 8 + 256 +
+                           kMaxSegs * (uint32_t)sizeof(GlmSegment) + ((chains * n_groups * 8 + 15) & ~15) + kRing * 16 + 16 + 192 + 64 +
                            1024 /*alignment slack*/;
     uint32_t stages = (227u * 1024u - fixed) / L.stage_bytes;
     if (stages > 4) stages = 4;
@@ -61,7 +66,7 @@ __host__ __device__ inline SmemLayout smem_layout(int P, int n1, int n2, int n_t
     L.off_icpt = o; o += (chains * n_groups * 4 + 15) & ~15;
     L.off_segs = o; o += kMaxSegs * (uint32_t)sizeof(GlmSegment);
     L.off_gi = o; o += (chains * n_groups * 8 + 15) & ~15;
-    L.off_red = o; o += 32 * 8;
+    L.off_ring = o; o += kRing * 16 + 16;   // published chunks + the publication counter
     L.off_bars = o; o += 192;
     L.off_tmem = o; o += 64;
     L.total = o + 1024;
@@ -85,17 +90,44 @@ struct Cfg {
     static constexpr int kThreads = 224 + (EG - 1) * 128;
 };
 
+// doubles per CTA row of the partial array: (hi, lo) pairs of the n_vals outputs, then the per-warp
+// log-likelihood slots [kLLRows][KC]
+__host__ __device__ constexpr size_t partial_row_doubles(int n_vals, int kc) { return 2 * ((size_t)n_vals + (size_t)kLLRows * kc); }
+
+__device__ __forceinline__ uint32_t ld_acquire_shared(const uint32_t* p) {
+    uint32_t v;
+    asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
+    return v;
+}
+__device__ __forceinline__ void st_release_shared(uint32_t* p, uint32_t v) {
+    asm volatile("st.release.cta.shared::cta.u32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
+}
+// (hi, lo) += x on a pair that only this thread touches during the launch
+__device__ __forceinline__ void dd_accumulate(double* slot, double x) {
+    double2 cur = *reinterpret_cast<double2*>(slot);
+    fed::dd_add(cur.x, cur.y, x, 0.0);
+    *reinterpret_cast<double2*>(slot) = cur;
+}
+
+// Work is handed out in CHUNKS of consecutive tiles of one segment (host-built table: 32 tiles while much
+// work is left, shrinking to 4 towards the end; always an even number, a segment with an odd tile count
+// gets one empty tile).  The TMA warp claims chunks from a global counter and publishes them to the other
+// roles through a small shared-memory ring, so CTAs on faster SMs simply take more chunks: no CTA waits on
+// a statically assigned straggler.  Everything a chunk contributes (fp32 TMEM accumulation over its tiles,
+// per-thread fp32 sums) depends on the chunk alone, and chunk results are combined as double-double pairs
+// (fed::dd_add), so the evaluation stays reproducible although the assignment is not.
 template <int KC>
 __global__ void __launch_bounds__(Cfg<KC>::kThreads, 1)
-fed_glm_tc_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParams prm, const CUtensorMap* __restrict__ tmaps) {
+fed_glm_tc_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParams prm, const CUtensorMap* __restrict__ tmaps,
+                  const GlmChunk* __restrict__ chunks, int n_chunks, unsigned int* __restrict__ work_counter) {
     constexpr int N1 = Cfg<KC>::N1;
     constexpr int N2 = Cfg<KC>::N2;
     constexpr int EG = Cfg<KC>::EG;
     constexpr int KH = Cfg<KC>::KH;
     constexpr int EGC = Cfg<KC>::EGC;
-    constexpr int EGT = Cfg<KC>::EGT;
     constexpr int kArrive = Cfg<KC>::kArrive;
-    (void)EG;
+    static_assert(Cfg<KC>::EGT == 2, "tile parity <-> eta / R buffer");
+    static_assert(EG * 4 <= kLLRows, "per-warp LL slots");
     extern __shared__ unsigned char smem_dyn[];
     // 1 KB alignment (128B-swizzled TMA tiles) by offsetting INSIDE the shared array: the pointer keeps its
     // shared address space, so the compiler emits LDS / STS instead of generic LD / ST for everything below
@@ -108,6 +140,7 @@ fed_glm_tc_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParams
     const SmemLayout L = smem_layout(P, N1, N2, comm.n_theta, G, KC);
     const int S = (int)L.stages;
     const int nch = prm.n_chains < KC ? prm.n_chains : KC;  // chains actually present in theta
+    const int NV1 = 1 + G + P;        // outputs per chain: [LL, gi[G], g[P]]
 
     unsigned char* theta_b = smem + L.off_theta_b;
     unsigned char* r_buf = smem + L.off_r;
@@ -115,7 +148,8 @@ fed_glm_tc_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParams
     float* icpt = reinterpret_cast<float*>(smem + L.off_icpt);        // [KC][G] intercepts
     GlmSegment* segs = reinterpret_cast<GlmSegment*>(smem + L.off_segs);
     unsigned long long* gi_acc = reinterpret_cast<unsigned long long*>(smem + L.off_gi);  // fixed point (fed::fix_add)
-    double* red = reinterpret_cast<double*>(smem + L.off_red);
+    int4* ring = reinterpret_cast<int4*>(smem + L.off_ring);          // (segment or -1, first row, tiles, -)
+    uint32_t* n_published = reinterpret_cast<uint32_t*>(smem + L.off_ring + kRing * 16);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.off_bars);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L.off_tmem);
     uint64_t* bar_full = bars;            // [4]
@@ -129,9 +163,6 @@ fed_glm_tc_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParams
 
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
-
-    const long long T = prm.total_tiles;
-    const long long n_it = (T > (long long)blockIdx.x) ? (T - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
     constexpr uint32_t kTmemCols = (2 * N1 + 2 * 4 * N2) <= 128 ? 128 : ((2 * N1 + 2 * 4 * N2) <= 256 ? 256 : 512);
 
     // ---------------- theta-independent setup: runs BEFORE the dependency wait inside fed::prologue, i.e. it
@@ -141,6 +172,8 @@ fed_glm_tc_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParams
     for (int i = threadIdx.x; i < (int)(2 * L.r_bytes / 16); i += blockDim.x)
         reinterpret_cast<uint4*>(r_buf)[i] = make_uint4(0, 0, 0, 0);
     if (threadIdx.x == 0) {
+        *pipeline_fault() = 0;
+        *n_published = 0u;
         for (int i = 0; i < 4; ++i) { mbar_init(&bar_full[i], 1); mbar_init(&bar_empty[i], 1); }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&bar_eta_full[i], 1);
@@ -161,18 +194,13 @@ fed_glm_tc_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParams
     const bool active = !pro.stop && !pro.timed_out;
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-
-    double ll_total[KH];
-#pragma unroll
-    for (int k = 0; k < KH; ++k) ll_total[k] = 0.0;
-    double g_acc[4][KH];  // [half][own chain] for feature (half*128 + row); epilogue threads only
-#pragma unroll
-    for (int h = 0; h < 4; ++h)
-#pragma unroll
-        for (int k = 0; k < KH; ++k) g_acc[h][k] = 0.0;
+    const size_t row_doubles = partial_row_doubles(comm.n_vals, KC);
+    double* out = comm.cta_partials + (size_t)blockIdx.x * row_doubles;   // this CTA's running sums, (hi, lo) pairs
+    double* ll_slots = out + 2 * (size_t)comm.n_vals;                     // [kLLRows][KC] pairs
 
     if (active) {
         // ---------------- theta-dependent setup --------------------------------------------------
+        for (size_t i = threadIdx.x; i < row_doubles / 2; i += blockDim.x) reinterpret_cast<double2*>(out)[i] = make_double2(0.0, 0.0);
         for (int i = threadIdx.x; i < KC * G; i += blockDim.x)
             icpt[i] = (i / G) < nch ? theta_f[(i / G) * (G + P) + (i % G)] : 0.f;
         // Theta^T as the K-major, 128B-swizzled B operand of MMA #1: row n = 3*chain + term
@@ -204,51 +232,65 @@ fed_glm_tc_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParams
         const uint32_t tmem_eta = tmem_base;                 // 2 buffers x N1 columns
         const uint32_t tmem_g = tmem_base + 2 * N1;          // 2 buffers x NH x N2 columns
 
+        // Consumers: the j-th chunk of this CTA, or x < 0 when the producer found the work counter exhausted.
+        auto next_chunk = [&](int j) -> int4 {
+            while (ld_acquire_shared(n_published) <= (uint32_t)j) {
+            }
+            return ring[j & (kRing - 1)];
+        };
+
         if (warp == 0) {
-            // ================= TMA producer ====================================================
+            // ================= TMA producer + chunk scheduler ==================================
             // The role loops are warp-uniform (all 32 lanes wait and count); only the issue is predicated on
             // elect.sync, so the compiler keeps addresses / descriptors in uniform registers.
-            {
-                int s_idx = 0;
-                Ring stage;
-                long long tile = blockIdx.x;
-                long long seg_first = segs[0].first_tile;
-                long long seg_next = prm.n_segments > 1 ? segs[1].first_tile : (1ll << 62);
-                for (long long it = 0; it < n_it; ++it, tile += gridDim.x) {
-                    while (seg_next <= tile) {
-                        ++s_idx;
-                        seg_first = seg_next;
-                        seg_next = s_idx + 1 < prm.n_segments ? segs[s_idx + 1].first_tile : (1ll << 62);
-                    }
+            Ring stage;
+            unsigned int claim = 0, ahead = 0;
+            if (lane == 0) claim = atomicAdd(work_counter, 1u);
+            claim = __shfl_sync(0xffffffffu, claim, 0);
+            for (int j = 0;; ++j) {
+                const bool have = claim < (unsigned int)n_chunks;
+                GlmChunk ch{};
+                if (have) ch = chunks[claim];
+                if (lane == 0) {
+                    ring[j & (kRing - 1)] = have ? make_int4(ch.seg, ch.first_tile * kTileM, ch.n_tiles, 0) : make_int4(-1, 0, 0, 0);
+                    st_release_shared(n_published, (uint32_t)j + 1u);
+                    if (have) ahead = atomicAdd(work_counter, 1u);   // next claim: the round trip hides behind this chunk
+                }
+                __syncwarp();
+                if (!have) break;
+                for (int t = 0; t < ch.n_tiles; ++t) {
                     const int st = stage.idx;
                     mbar_wait(&bar_empty[st], stage.phase ^ 1);
-                    const int row0 = (int)(tile - seg_first) * kTileM;
+                    if (j == 0 && t == 0 && lane == 0) fed::stamp(comm, 3);
+                    const int row0 = (ch.first_tile + t) * kTileM;
                     unsigned char* dst = smem + (size_t)st * L.stage_bytes;
                     if (elect_one()) {
                         mbar_expect_tx(&bar_full[st], L.stage_bytes);
                         for (int pnl = 0; pnl < panels; ++pnl)
-                            tma_load_2d(dst + pnl * kPanelBytes, &tmaps[s_idx], pnl * kPanel, row0, &bar_full[st]);
+                            tma_load_2d(dst + pnl * kPanelBytes, &tmaps[ch.seg], pnl * kPanel, row0, &bar_full[st]);
                     }
                     __syncwarp();
                     stage.advance(S);
                 }
-                if (lane == 0) fed::stamp(comm, 4);
+                claim = __shfl_sync(0xffffffffu, ahead, 0);
             }
+            if (lane == 0) fed::stamp(comm, 4);
         } else if (warp == 1) {
             // ================= MMA #1 issuer: eta = X . Theta^T ================================
-            {
-                constexpr uint32_t idesc1 = make_idesc(128, N1, 0, 0);
-                // descriptors: constant fields once, the 14-bit (address >> 4) field added per MMA
-                const uint64_t desc_k = make_desc(0, 16, 1024, 2);
-                const uint32_t theta_b_a4 = smem_u32(theta_b) >> 4;
-                const uint32_t x_base_a4 = smem_u32(smem) >> 4;
-                const uint32_t stage_a4 = L.stage_bytes >> 4;
-                Ring stage, buf;   // TMA stages (S), eta buffers (2)
-                for (long long it = 0; it < n_it; ++it) {
+            constexpr uint32_t idesc1 = make_idesc(128, N1, 0, 0);
+            // descriptors: constant fields once, the 14-bit (address >> 4) field added per MMA
+            const uint64_t desc_k = make_desc(0, 16, 1024, 2);
+            const uint32_t theta_b_a4 = smem_u32(theta_b) >> 4;
+            const uint32_t x_base_a4 = smem_u32(smem) >> 4;
+            const uint32_t stage_a4 = L.stage_bytes >> 4;
+            Ring stage, buf;   // TMA stages (S), eta buffers (2)
+            for (int j = 0;; ++j) {
+                const int4 ch = next_chunk(j);
+                if (ch.x < 0) break;
+                for (int t = 0; t < ch.z; ++t) {
                     mbar_wait(&bar_eta_empty[buf.idx], buf.phase ^ 1);
                     mbar_wait(&bar_full[stage.idx], stage.phase);
                     tc_fence_after();
-                    if (it == 0 && lane == 0) fed::stamp(comm, 3);
                     const uint32_t x_a4 = x_base_a4 + (uint32_t)stage.idx * stage_a4;
                     const uint32_t d_eta = tmem_eta + buf.idx * N1;
                     if (elect_one()) {
@@ -269,25 +311,25 @@ fed_glm_tc_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParams
             }
         } else if (warp == 6) {
             // ================= MMA #2 issuer: G += X^T . R ======================================
-            {
-                constexpr uint32_t idesc2 = make_idesc(128, N2, 1, 1);
-                constexpr uint32_t r_lbo = (N2 / 8) * 128;  // stride between 8-row K groups of R
-                // A = X^T: MN-major (features contiguous), 128B swizzle.
-                // LBO = stride between 64-feature panels, SBO = stride between 8-row groups.
-                const uint64_t desc_x = make_desc(0, kPanelBytes, 1024, 2);
-                // B = R: MN-major (chain columns contiguous), no swizzle.
-                // LBO = stride between 8-row K groups, SBO = stride between 8-column groups.
-                const uint64_t desc_r = make_desc(0, r_lbo, 128, 0);
-                const uint32_t r_a4 = smem_u32(r_buf) >> 4;
-                const uint32_t x_base_a4 = smem_u32(smem) >> 4;
-                const uint32_t stage_a4 = L.stage_bytes >> 4;
-                Ring stage, buf, flush;   // flush: tile within the kFlush-tile accumulation period, phase = G buffer
-                uint32_t g_phase[2] = {0, 0};
-                for (long long j = 0; j < n_it; ++j) {
-                    const int gb = (int)flush.phase;
-                    const bool first = flush.idx == 0;
-                    const bool last = flush.idx == kFlush - 1 || j == n_it - 1;
-                    if (first) mbar_wait(&bar_g_empty[gb], g_phase[gb] ^ 1);
+            constexpr uint32_t idesc2 = make_idesc(128, N2, 1, 1);
+            constexpr uint32_t r_lbo = (N2 / 8) * 128;  // stride between 8-row K groups of R
+            // A = X^T: MN-major (features contiguous), 128B swizzle.
+            // LBO = stride between 64-feature panels, SBO = stride between 8-row groups.
+            const uint64_t desc_x = make_desc(0, kPanelBytes, 1024, 2);
+            // B = R: MN-major (chain columns contiguous), no swizzle.
+            // LBO = stride between 8-row K groups, SBO = stride between 8-column groups.
+            const uint64_t desc_r = make_desc(0, r_lbo, 128, 0);
+            const uint32_t r_a4 = smem_u32(r_buf) >> 4;
+            const uint32_t x_base_a4 = smem_u32(smem) >> 4;
+            const uint32_t stage_a4 = L.stage_bytes >> 4;
+            Ring stage, buf, gbuf;   // gbuf: TMEM gradient accumulator of the current chunk (2, alternating)
+            for (int j = 0;; ++j) {
+                const int4 ch = next_chunk(j);
+                if (ch.x < 0) break;
+                const int gb = gbuf.idx;
+                mbar_wait(&bar_g_empty[gb], gbuf.phase ^ 1);   // the epilogue has drained this accumulator
+                for (int t = 0; t < ch.z; ++t) {
+                    const bool last = t == ch.z - 1;
                     mbar_wait(&bar_r_full[buf.idx], buf.phase);
                     tc_fence_after();
                     const uint32_t x_a4 = x_base_a4 + (uint32_t)stage.idx * stage_a4;
@@ -298,7 +340,7 @@ fed_glm_tc_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParams
                             for (int ks = 0; ks < kTileM / 16; ++ks) {
                                 const uint64_t adesc = desc_x | (uint64_t)(x_a4 + (((2 * h) * kPanelBytes + ks * 2 * 1024) >> 4));
                                 const uint64_t bdesc = desc_r | (uint64_t)(rb_a4 + ((ks * 2 * r_lbo) >> 4));
-                                umma_bf16(tmem_g + (gb * NH + h) * N2, adesc, bdesc, idesc2, (first && ks == 0) ? 0u : 1u);
+                                umma_bf16(tmem_g + (gb * NH + h) * N2, adesc, bdesc, idesc2, (t == 0 && ks == 0) ? 0u : 1u);
                             }
                         }
                         umma_commit(&bar_empty[stage.idx]);   // X stage may be refilled
@@ -306,168 +348,163 @@ fed_glm_tc_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParams
                         if (last) umma_commit(&bar_g_full[gb]);
                     }
                     __syncwarp();
-                    if (last) g_phase[gb] ^= 1u;
                     stage.advance(S);
                     buf.advance(2);
-                    flush.advance(kFlush);
                 }
+                gbuf.advance(2);
             }
         } else {
             // ================= epilogue warps: group 0 = warps 2-5, group g >= 1 = warps 7+4(g-1) .. =====
             const int eg = warp <= 5 ? 0 : (warp - 7) / 4 + 1;
+            const int ew = eg * 4 + (warp <= 5 ? warp - 2 : (warp - 7) % 4);   // epilogue warp ordinal: LL slot row
             const int cg = eg % EGC;                // which chains
-            const int tp = eg / EGC;                // which tile parity
+            const int tp = eg / EGC;                // which tile parity (chunks are even => also this group's eta/R buffer)
             const int q = warp & 3;                 // TMEM lane quarter this warp may access
             const int row = q * 32 + lane;          // row of the tile == TMEM lane
             const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
             const int k0 = cg * KH;                 // first chain of this group
-            int s_idx = 0;
-            float ll_acc[KH];
-            float gi_cur[KH];
-#pragma unroll
-            for (int k = 0; k < KH; ++k) ll_acc[k] = gi_cur[k] = 0.f;
-            int cur_group = -1;
             const uint32_t r_lbo = (N2 / 8) * 128;
             constexpr int kEtaLoads = (3 * KH + 3) / 4;
             constexpr int kGLoads = (2 * KH + 3) / 4;
-            for (long long it = tp; it < n_it; it += EGT) {
-                const long long tile = blockIdx.x + it * gridDim.x;
-                while (s_idx + 1 < prm.n_segments && segs[s_idx + 1].first_tile <= tile) ++s_idx;
-                const GlmSegment& seg = segs[s_idx];
-                if (seg.group != cur_group) {
-                    if (cur_group >= 0) {
+            const int b = tp;                       // eta / R buffer of this group's tiles
+            uint32_t bph = 0;                       // its phase: flips after every tile of this group
+            Ring gbuf;
+            for (int j = 0;; ++j) {
+                const int4 ch = next_chunk(j);
+                if (ch.x < 0) break;
+                const GlmSegment& seg = segs[ch.x];
+                float ll_acc[KH], gi_cur[KH];
 #pragma unroll
-                        for (int k = 0; k < KH; ++k) {
-                            fed::fix_add(&gi_acc[(k0 + k) * G + cur_group], (double)gi_cur[k]);
-                            gi_cur[k] = 0.f;
-                        }
-                    }
-                    cur_group = seg.group;
-                }
-                const long long grow = (tile - seg.first_tile) * kTileM + row;
-                const bool valid = grow < seg.n_rows;
-                const float y = valid ? __ldg(seg.y + grow) : 0.f;
-                const int b = (int)(it & 1);
-                const uint32_t bph = (uint32_t)((it >> 1) & 1);
+                for (int k = 0; k < KH; ++k) ll_acc[k] = gi_cur[k] = 0.f;
+                for (int t = tp; t < ch.z; t += 2) {
+                    const long long grow = (long long)ch.y + (long long)t * kTileM + row;
+                    const bool valid = grow < seg.n_rows;
+                    const float y = valid ? __ldg(seg.y + grow) : 0.f;
 
-                mbar_wait(&bar_eta_full[b], bph);
-                tc_fence_after();
-                float ev[kEtaLoads * 4];
-#pragma unroll
-                for (int i = 0; i < kEtaLoads; ++i) {
-                    float v[4];
-                    tmem_ld_x4(tmem_eta + lane_addr + b * N1 + 3 * k0 + 4 * i, v);
-                    ev[4 * i + 0] = v[0]; ev[4 * i + 1] = v[1]; ev[4 * i + 2] = v[2]; ev[4 * i + 3] = v[3];
-                }
-                tc_fence_before();
-                mbar_arrive(&bar_eta_empty[b]);
-
-                // link, likelihood, residual -> (hi, lo) bf16 columns of R
-                uint32_t rpk[KH];
-#pragma unroll
-                for (int k = 0; k < KH; ++k) {
-                    const float eta = (ev[3 * k] + ev[3 * k + 1]) + ev[3 * k + 2];
-                    float ll = 0.f, r = 0.f;
-                    if (valid && (k0 + k) < nch)
-                        link_loglik(prm.family, y, eta + icpt[(k0 + k) * G + seg.group], ll, r);
-                    ll_acc[k] += ll;
-                    gi_cur[k] += r;
-                    const __nv_bfloat16 hi = __float2bfloat16_rn(r);
-                    const __nv_bfloat16 lo = __float2bfloat16_rn(r - __bfloat162float(hi));
-                    rpk[k] = (uint32_t)__bfloat16_as_ushort(hi) | ((uint32_t)__bfloat16_as_ushort(lo) << 16);
-                }
-                mbar_wait(&bar_r_empty[b], bph ^ 1);
-                {
-                    // chain k owns columns (2k, 2k+1): 4 bytes at (k / 4) * 128 + (k % 4) * 4 of the row
-                    unsigned char* rrow = r_buf + b * L.r_bytes + (row >> 3) * r_lbo + (row & 7) * 16;
-                    if constexpr (KH == 8) {
-                        *reinterpret_cast<uint4*>(rrow + (k0 / 4) * 128) = make_uint4(rpk[0], rpk[1], rpk[2], rpk[3]);
-                        *reinterpret_cast<uint4*>(rrow + (k0 / 4 + 1) * 128) = make_uint4(rpk[4], rpk[5], rpk[6], rpk[7]);
-                    } else if constexpr (KH == 4) {
-                        *reinterpret_cast<uint4*>(rrow + (k0 / 4) * 128) = make_uint4(rpk[0], rpk[1], rpk[2], rpk[3]);
-                    } else if constexpr (KH == 2) {
-                        *reinterpret_cast<uint2*>(rrow + (k0 / 4) * 128 + (k0 % 4) * 4) = make_uint2(rpk[0], rpk[1]);
-                    } else {
-                        *reinterpret_cast<uint32_t*>(rrow + (k0 / 4) * 128 + (k0 % 4) * 4) = rpk[0];
-                    }
-                }
-                fence_proxy_async();
-                mbar_arrive(&bar_r_full[b]);
-
-                // gradient flush: TMEM accumulator -> fp64 registers once per period
-                const bool last = (it % kFlush) == kFlush - 1 || it == n_it - 1;
-                if (last) {
-                    const long long period = it / kFlush;
-                    const int gb = (int)(period & 1);
-                    mbar_wait(&bar_g_full[gb], (uint32_t)((period >> 1) & 1));
+                    mbar_wait(&bar_eta_full[b], bph);
                     tc_fence_after();
-                    for (int h = 0; h < NH; ++h) {
+                    float ev[kEtaLoads * 4];
 #pragma unroll
-                        for (int i = 0; i < kGLoads; ++i) {
-                            float v[4];
-                            tmem_ld_x4(tmem_g + lane_addr + (gb * NH + h) * N2 + 2 * k0 + 4 * i, v);
-                            if (2 * i < KH) g_acc[h][2 * i] += (double)v[0] + (double)v[1];
-                            if (2 * i + 1 < KH) g_acc[h][2 * i + 1] += (double)v[2] + (double)v[3];
-                        }
+                    for (int i = 0; i < kEtaLoads; ++i) {
+                        float v[4];
+                        tmem_ld_x4(tmem_eta + lane_addr + b * N1 + 3 * k0 + 4 * i, v);
+                        ev[4 * i + 0] = v[0]; ev[4 * i + 1] = v[1]; ev[4 * i + 2] = v[2]; ev[4 * i + 3] = v[3];
                     }
                     tc_fence_before();
-                    mbar_arrive(&bar_g_empty[gb]);
+                    mbar_arrive(&bar_eta_empty[b]);
+
+                    // link, likelihood, residual -> (hi, lo) bf16 columns of R
+                    uint32_t rpk[KH];
 #pragma unroll
                     for (int k = 0; k < KH; ++k) {
-                        ll_total[k] += (double)ll_acc[k];
-                        ll_acc[k] = 0.f;
+                        const float eta = (ev[3 * k] + ev[3 * k + 1]) + ev[3 * k + 2];
+                        float ll = 0.f, r = 0.f;
+                        if (valid && (k0 + k) < nch)
+                            link_loglik(prm.family, y, eta + icpt[(k0 + k) * G + seg.group], ll, r);
+                        ll_acc[k] += ll;
+                        gi_cur[k] += r;
+                        const __nv_bfloat16 hi = __float2bfloat16_rn(r);
+                        const __nv_bfloat16 lo = __float2bfloat16_rn(r - __bfloat162float(hi));
+                        rpk[k] = (uint32_t)__bfloat16_as_ushort(hi) | ((uint32_t)__bfloat16_as_ushort(lo) << 16);
+                    }
+                    mbar_wait(&bar_r_empty[b], bph ^ 1);
+                    {
+                        // chain k owns columns (2k, 2k+1): 4 bytes at (k / 4) * 128 + (k % 4) * 4 of the row
+                        unsigned char* rrow = r_buf + b * L.r_bytes + (row >> 3) * r_lbo + (row & 7) * 16;
+                        if constexpr (KH == 8) {
+                            *reinterpret_cast<uint4*>(rrow + (k0 / 4) * 128) = make_uint4(rpk[0], rpk[1], rpk[2], rpk[3]);
+                            *reinterpret_cast<uint4*>(rrow + (k0 / 4 + 1) * 128) = make_uint4(rpk[4], rpk[5], rpk[6], rpk[7]);
+                        } else if constexpr (KH == 4) {
+                            *reinterpret_cast<uint4*>(rrow + (k0 / 4) * 128) = make_uint4(rpk[0], rpk[1], rpk[2], rpk[3]);
+                        } else if constexpr (KH == 2) {
+                            *reinterpret_cast<uint2*>(rrow + (k0 / 4) * 128 + (k0 % 4) * 4) = make_uint2(rpk[0], rpk[1]);
+                        } else {
+                            *reinterpret_cast<uint32_t*>(rrow + (k0 / 4) * 128 + (k0 % 4) * 4) = rpk[0];
+                        }
+                    }
+                    fence_proxy_async();
+                    mbar_arrive(&bar_r_full[b]);
+                    bph ^= 1u;
+                }
+                // ---- end of the chunk for this group: fold its sums into the CTA's running pairs ----------
+                // per-thread fp32 sums over the chunk's tiles -> fixed butterfly over the warp (double) ->
+                // lane 0 adds the warp's value to its own slot: every step depends on the chunk only
+#pragma unroll
+                for (int k = 0; k < KH; ++k) {
+                    double l = (double)ll_acc[k], gsum = (double)gi_cur[k];
+#pragma unroll
+                    for (int o = 16; o > 0; o >>= 1) {
+                        l += __shfl_xor_sync(0xffffffffu, l, o);
+                        gsum += __shfl_xor_sync(0xffffffffu, gsum, o);
+                    }
+                    if (lane == 0 && (k0 + k) < nch) {
+                        dd_accumulate(ll_slots + 2 * ((size_t)ew * KC + k0 + k), l);
+                        fed::fix_add(&gi_acc[(k0 + k) * G + seg.group], gsum);
                     }
                 }
-            }
+                // gradient: the group that handled the chunk's last tile (odd index) drains the TMEM accumulator
+                if (tp == 1) {
+                    const int gb = gbuf.idx;
+                    mbar_wait(&bar_g_full[gb], gbuf.phase);
+                    tc_fence_after();
+                    float gv[4][kGLoads * 4];
 #pragma unroll
-            for (int k = 0; k < KH; ++k) ll_total[k] += (double)ll_acc[k];  // rows since this group's last flush
-            if (cur_group >= 0) {
+                    for (int h = 0; h < 4; ++h)
+                        if (h < NH) {
 #pragma unroll
-                for (int k = 0; k < KH; ++k) fed::fix_add(&gi_acc[(k0 + k) * G + cur_group], (double)gi_cur[k]);
+                            for (int i = 0; i < kGLoads; ++i) {
+                                float v[4];
+                                tmem_ld_x4(tmem_g + lane_addr + (gb * NH + h) * N2 + 2 * k0 + 4 * i, v);
+                                gv[h][4 * i + 0] = v[0]; gv[h][4 * i + 1] = v[1]; gv[h][4 * i + 2] = v[2]; gv[h][4 * i + 3] = v[3];
+                            }
+                        }
+                    tc_fence_before();
+                    mbar_arrive(&bar_g_empty[gb]);   // MMA #2 may start the chunk after next in this buffer
+                    // running pairs live in this CTA's row of the partial array (L2): one thread owns each of them
+#pragma unroll
+                    for (int h = 0; h < 4; ++h)
+                        if (h < NH) {
+                            double2 cur[KH];
+#pragma unroll
+                            for (int k = 0; k < KH; ++k)
+                                cur[k] = *reinterpret_cast<const double2*>(out + 2 * ((size_t)(k0 + k) * NV1 + 1 + G + h * 128 + row));
+#pragma unroll
+                            for (int k = 0; k < KH; ++k) {
+                                fed::dd_add(cur[k].x, cur[k].y, (double)gv[h][2 * k] + (double)gv[h][2 * k + 1], 0.0);
+                                if ((k0 + k) < nch)
+                                    *reinterpret_cast<double2*>(out + 2 * ((size_t)(k0 + k) * NV1 + 1 + G + h * 128 + row)) = cur[k];
+                            }
+                        }
+                }
+                gbuf.advance(2);
             }
         }
 
-        // ---------------- CTA partial -> global scratch ------------------------------------------
+        // ---------------- CTA partial: fold the per-warp LL slots and the intercept gradients ----------
         tc_fence_before();
         __syncthreads();
         tc_fence_after();
         fed::pdl_trigger();   // the next evaluation's CTA may take this SM as soon as we exit
         if (threadIdx.x == 0) fed::stamp(comm, 5);
-        double* out = comm.cta_partials + (size_t)blockIdx.x * comm.n_vals;
-        // layout per chain: [LL, gi[G], g[P]]
-        const bool is_epi = (warp >= 2 && warp <= 5) || warp >= 7;
-        const int my_g = warp <= 5 ? 0 : (warp - 7) / 4 + 1;
-        const int my_k0 = (my_g % EGC) * KH;
-        const int my_tp = my_g / EGC;
-#pragma unroll
-        for (int k = 0; k < KC; ++k) {
-            double mine = 0.0;
-#pragma unroll
-            for (int kk = 0; kk < KH; ++kk)
-                if (is_epi && my_k0 + kk == k) mine = ll_total[kk];
-            const double ll_block = fed::block_sum(mine, red);
-            if (threadIdx.x == 0 && k < nch) out[k * (1 + G + P)] = ll_block;
+        // layout per chain: [LL, gi[G], g[P]] as (hi, lo) pairs; g[] was accumulated in place
+        if (threadIdx.x < nch) {
+            const int k = threadIdx.x;
+            double hi = 0.0, lo = 0.0;
+            for (int w = 0; w < EG * 4; ++w) fed::dd_add(hi, lo, ll_slots[2 * ((size_t)w * KC + k)], ll_slots[2 * ((size_t)w * KC + k) + 1]);
+            out[2 * ((size_t)k * NV1)] = hi;
+            out[2 * ((size_t)k * NV1) + 1] = lo;
         }
-        for (int i = threadIdx.x; i < nch * G; i += blockDim.x) out[(i / G) * (1 + G + P) + 1 + (i % G)] = fed::fix_get(gi_acc[i]);
-        // gradient: the two tile-parity groups of a chain each flushed part of the periods
-        for (int pass = 0; pass < EGT; ++pass) {
-            if (is_epi && my_tp == pass) {
-                const int row = (warp & 3) * 32 + lane;
-                for (int h = 0; h < NH; ++h)
-#pragma unroll
-                    for (int kk = 0; kk < KH; ++kk)
-                        if (my_k0 + kk < nch) {
-                            double* dst = &out[(my_k0 + kk) * (1 + G + P) + 1 + G + h * 128 + row];
-                            *dst = pass == 0 ? g_acc[h][kk] : *dst + g_acc[h][kk];
-                        }
-            }
-            __syncthreads();
+        for (int i = threadIdx.x; i < nch * G; i += blockDim.x) {
+            out[2 * ((size_t)(i / G) * NV1 + 1 + (i % G))] = fed::fix_get(gi_acc[i]);
+            out[2 * ((size_t)(i / G) * NV1 + 1 + (i % G)) + 1] = 0.0;
         }
         if (threadIdx.x == 0) fed::stamp(comm, 6);
     }
     __syncthreads();
     if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
-    fed::epilogue(comm, pro, 0ull);
+    const unsigned long long status = *pipeline_fault() ? B200FED_ERR_PIPELINE : 0ull;
+    const bool fin = fed::epilogue_t<true>(comm, pro, status, row_doubles, comm.group_partials);
+    if (fin && threadIdx.x == 0) *work_counter = 0u;   // every CTA has stopped claiming: ready for the next launch
 }
 
 }  // namespace tc
@@ -491,14 +528,44 @@ EncodeTiledFn get_encode() {
 int chains_bucket(int k) { return k <= 1 ? 1 : (k <= 4 ? 4 : (k <= 8 ? 8 : (k <= 16 ? 16 : 0))); }
 }  // namespace
 
-// Builds one TMA descriptor per segment ([n_rows, P] bf16, box = 64 features x 128 rows, 128B swizzle).
-extern "C" int b200_glm_tc_prepare(const GlmSegment* segs_host, int n_segments, const GlmParams* prm, void** tmaps_dev) {
+// Chunk table of the dynamic scheduler: consecutive tiles of one segment, an even number of them (a segment
+// with an odd tile count ends in one empty tile), kMaxChunk tiles while plenty of work is left and shrinking
+// towards kMinChunk as the remaining work approaches two chunks per SM (guided self-scheduling), so the
+// last chunks that are handed out are the small ones.
+static std::vector<GlmChunk> build_chunks(const GlmSegment* segs, int n_segments, int sm_count) {
+    std::vector<GlmChunk> out;
+    long long remaining = 0;
+    for (int s = 0; s < n_segments; ++s) remaining += (segs[s].n_rows + tc::kTileM - 1) / tc::kTileM;
+    const int min_chunk = remaining <= 8ll * sm_count ? 2 : tc::kMinChunk;
+    for (int s = 0; s < n_segments; ++s) {
+        const long long ts = (segs[s].n_rows + tc::kTileM - 1) / tc::kTileM;
+        long long t = 0;
+        while (t < ts) {
+            long long want = (remaining / (2ll * sm_count)) & ~1ll;
+            if (want < min_chunk) want = min_chunk;
+            if (want > tc::kMaxChunk) want = tc::kMaxChunk;
+            long long real = want < ts - t ? want : ts - t;
+            long long n = real + (real & 1);
+            out.push_back(GlmChunk{s, (int)t, (int)n, 0});
+            t += real;
+            remaining -= real;
+        }
+    }
+    return out;
+}
+
+// Builds one TMA descriptor per segment ([n_rows, P] bf16, box = 64 features x 128 rows, 128B swizzle) and
+// the chunk table.
+extern "C" int b200_glm_tc_prepare(const GlmSegment* segs_host, int n_segments, const GlmParams* prm, int sm_count,
+                                   void** tmaps_dev, void** chunks_dev, int* n_chunks) {
     if (prm->n_features % 128 != 0 || prm->n_features > 384 || prm->n_features < 128) return -11;
     if (n_segments > tc::kMaxSegs) return -12;
     if (chains_bucket(prm->n_chains) == 0) return -13;
     if ((prm->ld * 2) % 16 != 0) return -14;
     EncodeTiledFn encode = get_encode();
     if (!encode) return -15;
+    for (int s = 0; s < n_segments; ++s)
+        if (segs_host[s].n_rows + tc::kTileM >= (1ll << 31)) return -18;   // row coordinates are 32-bit
     CUtensorMap* host = new CUtensorMap[n_segments];
     for (int s = 0; s < n_segments; ++s) {
         if (((uintptr_t)segs_host[s].X & 15) != 0) { delete[] host; return -16; }
@@ -515,11 +582,37 @@ extern "C" int b200_glm_tc_prepare(const GlmSegment* segs_host, int n_segments, 
     cudaError_t e = cudaMalloc(tmaps_dev, sizeof(CUtensorMap) * n_segments);
     if (e == cudaSuccess) e = cudaMemcpy(*tmaps_dev, host, sizeof(CUtensorMap) * n_segments, cudaMemcpyHostToDevice);
     delete[] host;
+    if (e != cudaSuccess) return (int)e;
+    const std::vector<GlmChunk> chunks = build_chunks(segs_host, n_segments, sm_count > 0 ? sm_count : 148);
+    if (*chunks_dev) cudaFree(*chunks_dev);
+    e = cudaMalloc(chunks_dev, sizeof(GlmChunk) * (chunks.size() + 1));
+    if (e == cudaSuccess) e = cudaMemcpy(*chunks_dev, chunks.data(), sizeof(GlmChunk) * chunks.size(), cudaMemcpyHostToDevice);
+    *n_chunks = (int)chunks.size();
     return e == cudaSuccess ? 0 : (int)e;
 }
 
+// The chunk table for given segment sizes (host only; tests/test_chunk_schedule.py).  Writes up to max_chunks
+// triples (seg, first_tile, n_tiles) and returns the number of chunks.
+extern "C" int b200_glm_tc_chunk_table(const long long* n_rows, int n_segments, int sm_count, int* out, int max_chunks) {
+    std::vector<GlmSegment> segs(n_segments);
+    for (int s = 0; s < n_segments; ++s) segs[s].n_rows = n_rows[s];
+    const std::vector<GlmChunk> chunks = build_chunks(segs.data(), n_segments, sm_count);
+    for (size_t i = 0; i < chunks.size() && (int)i < max_chunks; ++i) {
+        out[3 * i + 0] = chunks[i].seg;
+        out[3 * i + 1] = chunks[i].first_tile;
+        out[3 * i + 2] = chunks[i].n_tiles;
+    }
+    return (int)chunks.size();
+}
+
+// doubles in the partial array of the tensor-core kernel: one row of (hi, lo) pairs + per-warp LL slots per CTA
+extern "C" size_t b200_glm_tc_partial_row_doubles(int n_vals, int n_chains) {
+    return tc::partial_row_doubles(n_vals, chains_bucket(n_chains));
+}
+
 extern "C" int b200_launch_glm_tc(const FedComm* comm, const GlmSegment* segs_dev, const GlmParams* prm, const void* tmaps,
-                                  int grid, cudaStream_t stream) {
+                                  const void* chunks_dev, int n_chunks, unsigned int* work_counter, int grid,
+                                  cudaStream_t stream) {
     const int kc = chains_bucket(prm->n_chains);
     if (kc == 0) return -1;
     const CUtensorMap* maps = reinterpret_cast<const CUtensorMap*>(tmaps);
@@ -539,7 +632,8 @@ extern "C" int b200_launch_glm_tc(const FedComm* comm, const GlmSegment* segs_de
         attr[0].val.programmaticStreamSerializationAllowed = 1;                                                    \
         cfg.attrs = attr;                                                                                          \
         cfg.numAttrs = tc::use_pdl() ? 1 : 0;                                                                      \
-        cudaLaunchKernelEx(&cfg, tc::fed_glm_tc_kernel<KC>, *comm, segs_dev, *prm, maps);                          \
+        cudaLaunchKernelEx(&cfg, tc::fed_glm_tc_kernel<KC>, *comm, segs_dev, *prm, maps,                           \
+                           reinterpret_cast<const GlmChunk*>(chunks_dev), n_chunks, work_counter);                 \
     } while (0)
     if (kc == 1) LAUNCH_TC(1);
     else if (kc == 4) LAUNCH_TC(4);

@@ -32,6 +32,15 @@ struct GlmParams {
     long long total_tiles;
 };
 
+// Unit of work of the dynamically scheduled tensor-core GLM kernel: n_tiles consecutive 128-row tiles of one
+// segment starting at tile first_tile (n_tiles is even; the last one may lie past the segment's rows).
+struct GlmChunk {
+    int seg;
+    int first_tile;
+    int n_tiles;
+    int _pad;
+};
+
 // Lotka-Volterra parameter estimation: every series i starts from its own (known) state
 // y0[:, i] and is observed at the shared time grid t[0..n_t).
 struct OdeShard {

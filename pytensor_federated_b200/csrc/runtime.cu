@@ -34,9 +34,11 @@ extern "C" {
 int b200_launch_linreg(const FedComm*, const LinregShard*, int, int, int, cudaStream_t);
 int b200_launch_glm_simt(const FedComm*, const GlmSegment*, const GlmParams*, int, cudaStream_t);
 size_t b200_glm_simt_smem(int, int, int);
-int b200_launch_glm_tc(const FedComm*, const GlmSegment*, const GlmParams*, const void* tmaps, int grid,
-                       cudaStream_t);
-int b200_glm_tc_prepare(const GlmSegment* segs_host, int n_segments, const GlmParams* prm, void** tmaps_dev);
+int b200_launch_glm_tc(const FedComm*, const GlmSegment*, const GlmParams*, const void* tmaps, const void* chunks,
+                       int n_chunks, unsigned int* work_counter, int grid, cudaStream_t);
+int b200_glm_tc_prepare(const GlmSegment* segs_host, int n_segments, const GlmParams* prm, int sm_count, void** tmaps_dev,
+                        void** chunks_dev, int* n_chunks);
+size_t b200_glm_tc_partial_row_doubles(int n_vals, int n_chains);
 int b200_launch_ode(const FedComm*, const OdeShard*, int, int, cudaStream_t);
 int b200_launch_glm_fp8(const FedComm*, const GlmSegment*, const GlmParams*, const void* tmaps, int grid, cudaStream_t);
 int b200_glm_fp8_prepare(const GlmSegment* segs_host, int n_segments, const GlmParams* prm, void** tmaps_dev);
@@ -112,6 +114,11 @@ struct Engine {
     GlmSegment* glm_segs_dev = nullptr;
     GlmParams glm{};
     void* glm_tmaps_dev = nullptr;
+    void* glm_chunks_dev = nullptr;      // tensor-core kernel: chunk table of the dynamic scheduler
+    int glm_n_chunks = 0;
+    unsigned int* work_counter = nullptr;
+    double* tc_partials = nullptr;       // its partial array: rows of (hi, lo) pairs, then the group partials
+    size_t tc_row_doubles = 0;
     int glm_elem_bytes = 2;
     // launcher of a user-compiled likelihood (models/custom.py); null = built-in families
     int (*custom_launcher)(const FedComm*, const GlmSegment*, const GlmParams*, int, int, cudaStream_t) = nullptr;
@@ -139,6 +146,7 @@ void fill_comm(Engine* e, FedComm* c, bool root_uses_explicit_epoch) {
     c->root_slots = reinterpret_cast<double*>(root_block + L.off_slots);
     c->root_slot_flags = reinterpret_cast<unsigned long long*>(root_block + L.off_slot_flags);
     c->cta_partials = e->cta_partials;
+    c->group_partials = e->cta_partials + (size_t)e->sm_count * 8 * e->n_vals;   // behind the max_blocks rows
     c->ticket = e->ticket;
     c->trace = e->trace;
     c->cta_trace = e->cta_trace_on ? e->cta_trace : nullptr;
@@ -181,9 +189,14 @@ int launch_model(Engine* e, const FedComm* c) {
         case MODEL_GLM_SIMT:
             rc = b200_launch_glm_simt(c, e->glm_segs_dev, &e->glm, e->grid, e->stream);
             break;
-        case MODEL_GLM_TC:
-            rc = b200_launch_glm_tc(c, e->glm_segs_dev, &e->glm, e->glm_tmaps_dev, e->grid, e->stream);
+        case MODEL_GLM_TC: {
+            FedComm ct = *c;   // double-double rows + group partials of the dynamically scheduled kernel
+            ct.cta_partials = e->tc_partials;
+            ct.group_partials = e->tc_partials + (size_t)e->sm_count * e->tc_row_doubles;
+            rc = b200_launch_glm_tc(&ct, e->glm_segs_dev, &e->glm, e->glm_tmaps_dev, e->glm_chunks_dev, e->glm_n_chunks,
+                                    e->work_counter, e->grid, e->stream);
             break;
+        }
         case MODEL_ODE:
             rc = b200_launch_ode(c, e->ode_dev, (int)e->ode.size(), e->grid, e->stream);
             break;
@@ -214,6 +227,7 @@ void release_engine(Engine* e) {
     if (e->owns_comm && e->comm_local) cudaFree(e->comm_local);
     if (e->host_block) cudaFreeHost(e->host_block);
     void* device_ptrs[] = {e->cta_partials, e->ticket,       e->epoch_counter, e->trace,  e->theta_dev, e->cta_trace,
+                           e->glm_chunks_dev, e->work_counter, e->tc_partials,
                            e->linreg_dev,   e->glm_segs_dev, e->glm_tmaps_dev, e->ode_dev};
     for (void* p : device_ptrs)
         if (p) cudaFree(p);
@@ -227,11 +241,12 @@ __global__ void fed_stop_kernel(FedComm comm) {
 }
 
 __global__ void fed_reset_kernel(unsigned long long* flag, unsigned long long* slot_flags, int world,
-                                 unsigned int* ticket, unsigned long long* epoch_counter) {
+                                 unsigned int* ticket, unsigned long long* epoch_counter, unsigned int* work_counter) {
+    for (int i = threadIdx.x; i < 256; i += blockDim.x) ticket[i] = 0;
     if (threadIdx.x == 0) {
         *flag = 0;
-        *ticket = 0;
         *epoch_counter = 0;
+        *work_counter = 0;
     }
     if (threadIdx.x < world) slot_flags[threadIdx.x] = 0;
 }
@@ -328,19 +343,23 @@ void* b200_engine_create(int device, int rank, int world, int n_theta, int n_val
         return v && *v ? atoi(v) : dflt;
     };
     e->ll_theta = n_theta <= env_int("B200FED_LL_MAX_THETA", 4096) && !getenv("B200FED_NO_LL");
-    e->ll_mode = e->ll_theta && n_vals <= env_int("B200FED_LL_MAX_VALS", 128);
+    e->ll_mode = e->ll_theta && n_vals <= env_int("B200FED_LL_MAX_VALS", 2048);
     ok = ok && cudaHostAlloc((void**)&e->host_block, hbytes, cudaHostAllocMapped | cudaHostAllocPortable) == cudaSuccess;
     if (ok) memset(e->host_block, 0, hbytes);
     ok = ok && cudaHostGetDevicePointer((void**)&e->host_block_dev, e->host_block, 0) == cudaSuccess;
     const int max_blocks = e->sm_count * 8;
-    ok = ok && cudaMalloc((void**)&e->cta_partials, (size_t)max_blocks * n_vals * 8) == cudaSuccess;
-    ok = ok && cudaMalloc((void**)&e->ticket, 256) == cudaSuccess;
+    // per-CTA partial rows, then the group partials of the two-level reduction (fed::epilogue_t)
+    const size_t partial_rows = (size_t)max_blocks + max_blocks / 16 + 2;
+    ok = ok && cudaMalloc((void**)&e->cta_partials, partial_rows * n_vals * 8) == cudaSuccess;
+    ok = ok && cudaMalloc((void**)&e->ticket, 1024) == cudaSuccess;
+    ok = ok && cudaMalloc((void**)&e->work_counter, 256) == cudaSuccess;
     ok = ok && cudaMalloc((void**)&e->epoch_counter, 256) == cudaSuccess;
     ok = ok && cudaMalloc((void**)&e->trace, 256 * 4 * 8) == cudaSuccess;
     ok = ok && cudaMalloc((void**)&e->cta_trace, (size_t)max_blocks * 8 * 8) == cudaSuccess;
     ok = ok && cudaMalloc((void**)&e->theta_dev, (size_t)(n_theta > 0 ? n_theta : 1) * 4) == cudaSuccess;
     if (ok) {
-        cudaMemset(e->ticket, 0, 256);
+        cudaMemset(e->ticket, 0, 1024);
+        cudaMemset(e->work_counter, 0, 256);
         cudaMemset(e->epoch_counter, 0, 256);
         cudaMemset(e->trace, 0, 256 * 4 * 8);
         cudaMemset(e->cta_trace, 0, (size_t)max_blocks * 8 * 8);
@@ -388,7 +407,7 @@ int b200_engine_reset(void* h) {
     const CommLayout& L = e->layout;
     fed_reset_kernel<<<1, 32, 0, e->stream>>>(reinterpret_cast<unsigned long long*>(e->comm_local + L.off_flag),
                                               reinterpret_cast<unsigned long long*>(e->comm_local + L.off_slot_flags),
-                                              e->world, e->ticket, e->epoch_counter);
+                                              e->world, e->ticket, e->epoch_counter, e->work_counter);
     CK(cudaStreamSynchronize(e->stream));
     CK(cudaMemset(e->comm_local + L.off_ll_theta, 0, L.bytes - L.off_ll_theta));
     CK(cudaDeviceSynchronize());
@@ -406,7 +425,7 @@ void b200_engine_set_timeout(void* h, double seconds) {
 void b200_engine_set_grid(void* h, int grid) {
     // the per-CTA partial array holds sm_count * 8 rows; negative values select single-CTA modes
     Engine* e = static_cast<Engine*>(h);
-    const int max_blocks = e->sm_count * 8;
+    const int max_blocks = e->kind == MODEL_GLM_TC ? e->sm_count : e->sm_count * 8;   // rows of the partial array
     e->grid = grid > max_blocks ? max_blocks : (grid == 0 ? 1 : grid);
 }
 int b200_engine_grid(void* h) { return static_cast<Engine*>(h)->grid; }
@@ -478,13 +497,20 @@ int b200_engine_set_glm(void* h, int n_segments, const void** X, const float** y
         e->kind = MODEL_GLM_FP8;
         e->grid = e->sm_count;
     } else if (use_tensor_cores) {
-        int rc = b200_glm_tc_prepare(e->glm_segs.data(), n_segments, &e->glm, &e->glm_tmaps_dev);
+        int rc = b200_glm_tc_prepare(e->glm_segs.data(), n_segments, &e->glm, e->sm_count, &e->glm_tmaps_dev,
+                                     &e->glm_chunks_dev, &e->glm_n_chunks);
         if (rc != 0) {
             g_last_error = "tensor-core GLM path rejected this shape (rc=" + std::to_string(rc) + ")";
             return rc;
         }
+        e->tc_row_doubles = b200_glm_tc_partial_row_doubles(e->n_vals, n_chains);
+        if (e->tc_partials) cudaFree(e->tc_partials);
+        const size_t tc_doubles = (size_t)e->sm_count * e->tc_row_doubles + ((size_t)e->sm_count / 16 + 2) * e->n_vals * 2;
+        CK(cudaMalloc((void**)&e->tc_partials, tc_doubles * 8));
+        CK(cudaMemset(e->tc_partials, 0, tc_doubles * 8));
         e->kind = MODEL_GLM_TC;
         e->grid = e->sm_count;
+        if (e->glm_n_chunks > 0 && e->grid > e->glm_n_chunks) e->grid = e->glm_n_chunks;
     } else {
         e->kind = MODEL_GLM_SIMT;
         e->grid = e->sm_count * 2;

@@ -36,12 +36,25 @@ __device__ __forceinline__ bool mbar_try_wait(uint64_t* bar, uint32_t parity) {
         : "memory");
     return ok != 0;
 }
-// Bounded wait: a pipeline bug must surface as a launch failure, never as a hung GPU.
+// CTA-wide "the mbarrier pipeline stalled" flag.  A wait that exceeds 4 s raises it instead of trapping (a
+// trap poisons the whole CUDA context: engine, torch and all); once it is up every wait returns at once, so the
+// roles run off the end of their loops, the CTA reports B200FED_ERR_PIPELINE through fed::epilogue and the host
+// raises an ordinary exception with the context intact.  Results of such a launch are garbage by definition.
+__device__ __forceinline__ volatile int* pipeline_fault() {
+    __shared__ int fault;
+    return &fault;
+}
+// Bounded wait: a pipeline bug must surface as an error status, never as a hung GPU.
 __device__ __forceinline__ void mbar_wait(uint64_t* bar, uint32_t parity) {
     if (mbar_try_wait(bar, parity)) return;
     const unsigned long long t0 = fed::globaltimer();
+    volatile int* fault = pipeline_fault();
     while (!mbar_try_wait(bar, parity)) {
-        if (fed::globaltimer() - t0 > 4000000000ull) __trap();
+        if (*fault) return;
+        if (fed::globaltimer() - t0 > 4000000000ull) {
+            *fault = 1;
+            return;
+        }
     }
 }
 // One lane of a fully active warp (the role loops stay warp-uniform; only the issue is predicated, so the

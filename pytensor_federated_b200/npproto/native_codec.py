@@ -95,6 +95,8 @@ def decode_arrays(message: bytes) -> Tuple[List[np.ndarray], str]:
     while True:
         items = (_PbItem * cap)()
         n = lib.b200_pb_decode_arrays(message, len(message), items, cap, C.byref(uuid_off), C.byref(uuid_len))
+        if n == -2:
+            raise TypeError("arrays with more than 16 dimensions are handled by the Python codec")
         if n < 0:
             raise ValueError("malformed ArraysToArrays message")
         if n <= cap:
@@ -107,6 +109,12 @@ def decode_arrays(message: bytes) -> Tuple[List[np.ndarray], str]:
             raise TypeError("object arrays are handled by the Python codec")
         shape = tuple(it.shape[: it.ndim])
         strides = tuple(it.strides[: it.n_strides]) if it.n_strides == it.ndim else None
-        out.append(np.ndarray(shape=shape, dtype=dtype, buffer=message, offset=int(it.data_off), strides=strides))
+        # the view is built over the item's OWN data field, so NumPy checks shape x strides against its length
+        # (a short or inconsistent `data` raises instead of reading the neighbouring fields of the message)
+        field = memoryview(message)[int(it.data_off) : int(it.data_off) + int(it.data_len)]
+        try:
+            out.append(np.ndarray(shape=shape, dtype=dtype, buffer=field, strides=strides))
+        except (TypeError, ValueError) as ex:   # "buffer is too small" / "strides is incompatible with ... size of buffer"
+            raise ValueError(f"malformed ndarray item: {ex}") from ex
     uuid = message[uuid_off.value : uuid_off.value + uuid_len.value].decode()
     return out, uuid

@@ -265,6 +265,11 @@ class FederatedEngine:
     def _raise(self, rc: int) -> None:
         from ..ops import native
 
+        if rc > 0 and rc & 4:
+            raise FederationError(
+                "a tensor-core kernel's mbarrier pipeline stalled (internal error; the CUDA context is intact, "
+                "the evaluation's result is invalid)"
+            )
         if rc > 0:
             which = []
             if rc & 1:

@@ -66,3 +66,28 @@ def test_fuzz_against_python_codec(arrays, uuid):
     assert got_uuid == uuid
     for got, want in zip(decoded, arrays):
         np.testing.assert_array_equal(got, want)
+
+
+def test_short_data_field_is_rejected_not_read_from_neighbouring_fields():
+    from pytensor_federated_b200 import _pb
+    from pytensor_federated_b200.npproto import Ndarray
+
+    # shape says 4 float64 (32 bytes), the data field holds 8: must not decode the dtype/shape bytes behind it
+    item = Ndarray(data=np.arange(1.0, 2.0).tobytes(), dtype="float64", shape=[4], strides=[8])
+    message = _pb.enc_len_field(1, bytes(item)) + _pb.enc_len_field(2, b"u")
+    with pytest.raises(ValueError, match="malformed"):
+        native_codec.decode_arrays(message)
+    with pytest.raises(Exception):
+        ndarray_to_numpy(item)   # the Python codec agrees
+
+
+def test_more_than_16_dimensions_round_trip_through_the_fallback():
+    a = np.arange(2.0**18).reshape((2,) * 18)
+    wire = bytes(InputArrays.from_arrays([a], uuid="deep"))
+    with pytest.raises(TypeError):          # the fast path declines ...
+        native_codec.decode_arrays(wire)
+    parsed = InputArrays.FromString(wire)   # ... and the message class falls back to the general decoder
+    assert parsed.uuid == "deep"
+    (got,) = parsed.arrays
+    assert got.shape == a.shape
+    np.testing.assert_array_equal(got, a)
