@@ -24,7 +24,7 @@ ROOT = os.path.dirname(os.path.abspath(__file__))
 if ROOT not in sys.path:
     sys.path.insert(0, ROOT)
 
-METRIC = "logp+grad evals/sec for 8-shard federated GLM"
+METRIC = "logp+grad evals/sec for 8-shard federated GLM"   # the headline; the other configs: CONFIGS
 
 
 def parse_args():
@@ -38,6 +38,13 @@ def parse_args():
     p.add_argument("--shards", type=int, default=8)
     p.add_argument("--kernel", default=os.environ.get("B200FED_GLM_KERNEL", "auto"), choices=["auto", "simt", "tc", "fp8"])
     p.add_argument("--chains", type=int, default=1)
+    p.add_argument("--config", default="glm", choices=["glm", "fp8", "ode", "linreg"],
+                   help="BASELINE.json configuration (glm = the headline; --kernel fp8 is an alias of --config fp8)")
+    p.add_argument("--series", type=int, default=20_000, help="ode: time series per shard")
+    p.add_argument("--timepoints", type=int, default=32, help="ode: observations per series")
+    p.add_argument("--min-seconds", type=float, default=0.5,
+                   help="the S-step block is repeated until the timed region lasts this long; the median block counts")
+    p.add_argument("--nuts-draws", type=int, default=200, help="linreg: draws (= tune) of the NUTS run")
     p.add_argument("--out", default=None, help="also append the JSON line to this file")
     return p.parse_args()
 
@@ -158,12 +165,90 @@ class ClockSampler:
         }
 
 
+CONFIGS = {
+    # name: (metric, model description)
+    "glm": ("logp+grad evals/sec for 8-shard federated GLM", "federated logistic GLM (logp + gradient)"),
+    "fp8": ("logp+grad evals/sec for hierarchical GLM, fp8 block-scaled design matrix",
+            "hierarchical logistic GLM, one group intercept per shard (logp + gradient)"),
+    "ode": ("logp+grad evals/sec for federated ODE parameter estimation",
+            "Lotka-Volterra ODE, RK4 x8 with forward sensitivities, Gaussian likelihood (logp + gradient)"),
+    "linreg": ("logp+grad evals/sec for federated Bayesian linear regression",
+               "the reference's demo model (demo_node.py): Gaussian linear regression, 10 rows per shard"),
+}
+
+
+def build_workload(args, world, rank, dev):
+    """This rank's shard model of the chosen BASELINE.json configuration, a theta sampler and descriptive keys."""
+    import numpy as np
+    import torch
+
+    from pytensor_federated_b200.models import (
+        Fp8GlmShards, GlmShards, LinregShards, OdeShards, make_demo_data, synth_logistic_shard,
+        synth_logistic_shard_fp8, synth_lv_shard,
+    )
+
+    rng = np.random.default_rng(7)
+    K = args.chains
+    my_shards = [s for s in range(args.shards) if s % world == rank]
+    if args.config in ("glm", "fp8"):
+        P = args.features
+        Xs, ys, scs = [], [], []
+        for s in my_shards:
+            if args.config == "fp8":
+                X, sc, y = synth_logistic_shard_fp8(args.rows, P, seed=1000 + s, device=dev)
+                scs.append(sc)
+            else:
+                X, y, _ = synth_logistic_shard(args.rows, P, seed=1000 + s, device=dev)
+            Xs.append(X)
+            ys.append(y)
+        torch.cuda.synchronize()
+        if args.config == "fp8":  # hierarchical config: one partial-pooling group (intercept) per shard
+            n_groups = args.shards
+            model = Fp8GlmShards(Xs, scs, ys, groups=my_shards, n_groups=n_groups, n_chains=K)
+        else:
+            n_groups = 1
+            model = GlmShards(Xs, ys, n_groups=1, family="logistic", n_chains=K, kernel=args.kernel)
+
+        def draw_theta():
+            ic = rng.normal(size=(K, n_groups) if K > 1 else (n_groups,)).astype(np.float32) * 0.1
+            beta = rng.normal(size=(K, P) if K > 1 else (P,)).astype(np.float32) * 0.02
+            return ic, beta
+
+        keys = {"rows_per_shard": args.rows, "features": P, "global_batch": args.shards * args.rows, "seq_len": P,
+                "l2_policy": "inputs (>= 2.5 GB per GPU) are larger than the 126 MB L2; no flush needed"}
+    elif args.config == "ode":
+        shards = [synth_lv_shard(args.series, args.timepoints, seed=s, device=dev) for s in my_shards]
+        model = OdeShards([s[0] for s in shards], [s[1] for s in shards], [s[2] for s in shards], [s[3] for s in shards])
+
+        def draw_theta():
+            return (np.array([1.0, 0.4, 0.8, 0.2]) + 0.01 * rng.normal(size=4),)
+
+        keys = {"series_per_shard": args.series, "timepoints": args.timepoints, "global_batch": args.shards * args.series,
+                "seq_len": args.timepoints,
+                "l2_policy": "compute-bound (RK4 + sensitivities in registers); inputs fit in L2 and are re-read every "
+                             "evaluation by design, theta changes every step"}
+    else:  # linreg
+        xs, ys_, sg = [], [], []
+        for s in my_shards:
+            x, y, sigma = make_demo_data(seed=123 + s)
+            xs.append(x)
+            ys_.append(y)
+            sg.append(sigma)
+        model = LinregShards(xs, ys_, sg, local_ids=my_shards, n_shards_total=args.shards, device=dev)
+
+        def draw_theta():
+            return rng.normal(size=args.shards), np.asarray(rng.normal())
+
+        keys = {"rows_per_shard": 10, "global_batch": args.shards * 10, "seq_len": 1,
+                "l2_policy": "latency-bound: 10 rows per shard; theta changes every step"}
+    return model, draw_theta, keys
+
+
 def run_b200(args):
     import numpy as np
     import torch
     import torch.distributed as dist
 
-    from pytensor_federated_b200.models import Fp8GlmShards, GlmShards, synth_logistic_shard, synth_logistic_shard_fp8
     from pytensor_federated_b200.parallel import FederatedEngine
 
     world = int(os.environ.get("WORLD_SIZE", "1"))
@@ -178,112 +263,142 @@ def run_b200(args):
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
 
-    # ---- data: this rank's share of the 8 shards -------------------------------------------
-    my_shards = [s for s in range(args.shards) if s % world == rank]
-    Xs, ys, scs = [], [], []
-    for s in my_shards:
-        if args.kernel == "fp8":
-            X, sc, y = synth_logistic_shard_fp8(args.rows, args.features, seed=1000 + s, device=dev)
-            scs.append(sc)
-        else:
-            X, y, _ = synth_logistic_shard(args.rows, args.features, seed=1000 + s, device=dev)
-        Xs.append(X)
-        ys.append(y)
-    torch.cuda.synchronize()
+    if args.kernel == "fp8":
+        args.config = "fp8"
+    model, draw_theta, cfg_keys = build_workload(args, world, rank, dev)
     backend = "fused" if args.impl == "b200" else "collective"
-    n_groups = 1
-    if args.kernel == "fp8":  # hierarchical config: one partial-pooling group (intercept) per shard
-        n_groups = args.shards
-        model = Fp8GlmShards(Xs, scs, ys, groups=my_shards, n_groups=n_groups, n_chains=args.chains)
-    else:
-        model = GlmShards(Xs, ys, n_groups=1, family="logistic", n_chains=args.chains, kernel=args.kernel)
     eng = FederatedEngine(model, backend=backend, timeout=120.0)
-
-    rng = np.random.default_rng(7)
-    P, K = args.features, args.chains
-
-    def draw_theta():
-        ic = rng.normal(size=(K, n_groups) if K > 1 else (n_groups,)).astype(np.float32) * 0.1
-        beta = rng.normal(size=(K, P) if K > 1 else (P,)).astype(np.float32) * 0.02
-        return ic, beta
-
-    thetas = [draw_theta() for _ in range(args.steps + args.warmup)]
-    W, S = args.warmup, args.steps
+    W, S, K = args.warmup, args.steps, args.chains
+    n_verify = 2
 
     def barrier():
         if world > 1:
             dist.barrier()
         torch.cuda.synchronize()
 
+    def share(n: int) -> int:
+        """The root decides how many evaluations a phase has; the peers serve exactly that many."""
+        if world == 1:
+            return n
+        t = torch.tensor([n], device=dev, dtype=torch.int64)
+        dist.broadcast(t, src=0)
+        return int(t.item())
+
+    def oracle_sum(inputs):
+        """fp64 oracle of the same evaluation: every rank evaluates ITS shards with stock PyTorch, NCCL sums."""
+        import inspect
+
+        kw = {"dtype": torch.float64} if "dtype" in inspect.signature(model.reference_partial).parameters else {}
+        part = torch.from_numpy(np.asarray(model.reference_partial(inputs, **kw), dtype=np.float64)).to(dev)
+        if world > 1:
+            dist.all_reduce(part, op=dist.ReduceOp.SUM)
+        return part.cpu().numpy()
+
+    # ---- every rank draws the same thetas (same seed) so the peers can evaluate the oracle too -------------
+    verify_thetas = [draw_theta() for _ in range(n_verify)]
     result = {}
-    sampler = None
     if rank == 0:
-        # ---- warm-up through the public API -------------------------------------------------
+        # ---- correctness first: fused result vs the fp64 oracle on the same shards, at this N -------------
+        got = [np.array(eng.evaluate_raw(th)) for th in verify_thetas]
+        barrier()
+        max_rel = 0.0
+        for th, g in zip(verify_thetas, got):
+            want = oracle_sum(th)
+            v = np.asarray(want).reshape(K, -1) if args.config in ("glm", "fp8") else np.asarray(want).reshape(1, -1)
+            gg = g.reshape(v.shape)
+            # logp: relative; gradient block: relative to its largest entry (entries near zero carry no signal)
+            if args.config == "linreg":
+                scale = np.maximum(np.abs(v), 1e-9)
+                err = float(np.max(np.abs(gg - v) / np.maximum(scale, np.abs(v).max() * 1e-6)))
+            else:
+                e_lp = np.abs(gg[:, 0] - v[:, 0]) / np.maximum(np.abs(v[:, 0]), 1e-30)
+                e_gr = np.abs(gg[:, 1:] - v[:, 1:]).max(axis=1) / np.maximum(np.abs(v[:, 1:]).max(axis=1), 1e-30)
+                err = float(max(e_lp.max(), e_gr.max()))
+            max_rel = max(max_rel, err)
+        tol = {"glm": 2e-4, "fp8": 3e-3, "ode": 2e-3, "linreg": 1e-9}[args.config]
+        verified = bool(max_rel <= tol)
+        if not verified:
+            print(json.dumps({"error": "verification failed", "max_rel_err": max_rel, "tolerance": tol, "n_gpus": world}),
+                  flush=True)
+        thetas = [draw_theta() for _ in range(W + S)]
+        # ---- warm-up through the public API, and a first estimate of the step time --------------------------
+        share(W)
+        t0 = time.perf_counter()
         for i in range(W):
             eng.evaluate(*thetas[i])
+        est = max((time.perf_counter() - t0) / max(W, 1), 1e-6)
         barrier()
+        # the timed regions last at least --min-seconds: the S-step block is repeated, the MEDIAN block is reported
+        blocks = max(1, int(np.ceil(args.min_seconds / (est * S)))) if args.min_seconds > 0 else 1
+        blocks = min(blocks, 2000)
+        share(blocks * S)
         sampler = ClockSampler(local_rank).start()
-        # ---- device-timed region: K back-to-back fused evaluations --------------------------
+        # ---- device-timed region: `blocks` x S back-to-back fused evaluations --------------------------------
+        block_ms = []
         if backend == "fused":
             stream = eng.torch_stream()
             eng.set_device_theta(thetas[W], enable=True)
             launches0 = eng.kernel_launches
-            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            ev0.record(stream)
+            events = [torch.cuda.Event(enable_timing=True) for _ in range(blocks + 1)]
+            events[0].record(stream)
             last = 0
-            for _ in range(S):
-                last = eng.launch()
-            ev1.record(stream)
+            for bi in range(blocks):
+                for _ in range(S):
+                    last = eng.launch()
+                events[bi + 1].record(stream)
             eng.wait(last)
-            ev1.synchronize()
-            dev_ms = ev0.elapsed_time(ev1)
-            launches = eng.kernel_launches - launches0
+            events[-1].synchronize()
+            block_ms = [events[i].elapsed_time(events[i + 1]) for i in range(blocks)]
+            launches = (eng.kernel_launches - launches0) // blocks
             eng.set_device_theta(thetas[W], enable=False)
         else:
-            ev0, ev1 = torch.cuda.Event(enable_timing=True), torch.cuda.Event(enable_timing=True)
-            ev0.record()
-            for i in range(S):
-                eng.evaluate_raw(thetas[W + i])
-            ev1.record()
-            ev1.synchronize()
-            dev_ms = ev0.elapsed_time(ev1)
+            events = [torch.cuda.Event(enable_timing=True) for _ in range(blocks + 1)]
+            events[0].record()
+            for bi in range(blocks):
+                for i in range(S):
+                    eng.evaluate_raw(thetas[W + i])
+                events[bi + 1].record()
+            events[-1].synchronize()
+            block_ms = [events[i].elapsed_time(events[i + 1]) for i in range(blocks)]
             launches = 0
         barrier()
-        # ---- end-to-end region: public API, pinned H2D of theta + D2H of the result each step
+        # ---- end-to-end region: public API, pinned H2D of theta + D2H of the result each step -----------------
+        e2e_steps = share(blocks * S)
         t0 = time.perf_counter()
         checksum = 0.0
-        for i in range(S):
-            logp, d_ic, d_beta = eng.evaluate(*thetas[W + i])
-            checksum += float(np.sum(logp))
+        for i in range(e2e_steps):
+            out = eng.evaluate(*thetas[W + i % S])
+            if i < S:
+                checksum += float(np.sum(out[0]))
         torch.cuda.synchronize()
         e2e_s = time.perf_counter() - t0
         barrier()
         clocks = sampler.stop()
-        result = dict(dev_ms=dev_ms, e2e_s=e2e_s, launches=launches, checksum=checksum, clocks=clocks)
+        result = dict(block_ms=block_ms, e2e_s=e2e_s, e2e_steps=e2e_steps, launches=launches, checksum=checksum,
+                      clocks=clocks, verified=verified, max_rel_err=max_rel, blocks=blocks)
     else:
-        # peers: each phase serves exactly as many epochs as the root evaluates; their kernels wait
-        # on the device for the root's epoch flag, the host only keeps the queue filled
-        eng.serve(max_epochs=W)
+        # peers: each phase serves exactly as many epochs as the root evaluates; their kernels wait on the
+        # device for the root's theta, the host only keeps the queue filled
+        eng.serve(max_epochs=n_verify)
         barrier()
-        eng.serve(max_epochs=S)
+        for th in verify_thetas:
+            oracle_sum(th)
+        eng.serve(max_epochs=share(0))
         barrier()
-        eng.serve(max_epochs=S)
+        eng.serve(max_epochs=share(0))
+        barrier()
+        eng.serve(max_epochs=share(0))
         barrier()
 
-    # max over ranks of the device-timed region (the root's kernels cannot finish before every
-    # peer delivered its partial, so the root time already dominates; reduce anyway)
-    if world > 1:
-        t = torch.tensor([result.get("dev_ms", 0.0)], device=dev, dtype=torch.float64)
-        dist.all_reduce(t, op=dist.ReduceOp.MAX)
-        if rank == 0:
-            result["dev_ms"] = float(t.item())
-        peer_launches = torch.tensor([float(eng.kernel_launches if backend == "fused" else 0)], device=dev,
-                                     dtype=torch.float64)
-        dist.all_reduce(peer_launches, op=dist.ReduceOp.SUM)
+    # max over ranks of the device-timed region (the root's kernels cannot finish before every peer delivered
+    # its partial, so the root time already dominates; reduce anyway)
     comm_mode = eng.comm_mode
     bytes_per_eval = model.bytes_per_eval()
     flops_per_eval = model.flops_per_eval()
     n_theta_words, n_vals = model.n_theta_words, model.n_vals
+    extra = {}
+    if rank == 0 and args.config == "linreg" and backend == "fused":
+        extra = linreg_nuts(eng, args)   # NUTS driving FederatedLogpGradOp over the live federation
     eng.shutdown()
     if world > 1:
         dist.barrier()
@@ -291,17 +406,46 @@ def run_b200(args):
     if rank != 0:
         return
 
-    ms_per_step = result["dev_ms"] / S
+    block_ms = sorted(result["block_ms"])
+    med_ms = block_ms[len(block_ms) // 2]
+    ms_per_step = med_ms / S
     value = 1000.0 / ms_per_step * K
-    e2e_value = S / result["e2e_s"] * K
+    e2e_value = result["e2e_steps"] / result["e2e_s"] * K
     peaks = {}
     try:
         peaks = json.load(open(os.path.join(ROOT, "MEASURED_PEAKS.json")))
     except Exception:
         pass
     hbm = peaks.get("hbm_gbs", 6650.0)
+    metric, model_name = CONFIGS[args.config]
+    config = {
+        "model": model_name,
+        "shards": args.shards,
+        "chains_per_eval": K,
+        **cfg_keys,
+        "parallelism": f"shard-parallel x{world} ({args.shards // world} shards/GPU)",
+        "kernel": args.kernel if args.config == "glm" else args.config,
+        "backend": backend,
+        "comm": comm_mode,
+        "timed_blocks": result["blocks"],
+        "timed_seconds": sum(result["block_ms"]) / 1e3,
+        "block_ms_min_med_max": [block_ms[0], med_ms, block_ms[-1]],
+        "hbm_bytes_per_eval_per_gpu": bytes_per_eval,
+    }
+    if bytes_per_eval:
+        config["hbm_roofline_frac_of_measured"] = (bytes_per_eval / (ms_per_step * 1e-3)) / (hbm * 1e9)
+    if args.config in ("glm", "fp8"):
+        # three-term roofline of the fused broadcast->compute->reduce kernel (seconds per eval per GPU):
+        # HBM stream of the shard, tensor-core time of the two skinny GEMMs (N padded to 16 columns each),
+        # NVLink bytes (theta in, partial out) at the measured 770 GB/s peer bandwidth
+        config["roofline_s"] = {
+            "hbm": bytes_per_eval / (hbm * 1e9),
+            "tensor": flops_per_eval * (32.0 / max(1, 4 * K)) / (peaks.get("bf16_tflops", 1590.0) * 1e12),
+            "nvlink": (n_theta_words * 4 + n_vals * 8) / 770e9,
+            "bound": "hbm",
+        }
     line = {
-        "metric": METRIC,
+        "metric": metric,
         "value": value,
         "unit": "evals/s",
         "n_gpus": world,
@@ -311,44 +455,23 @@ def run_b200(args):
         "higher_is_better": True,
         "scaling": "strong",
         "vs_baseline": None,
-        "dtype": "fp8-e4m3 block-scaled (32x32 UE8M0)" if args.kernel == "fp8" else "bf16",
+        "dtype": {"glm": "bf16", "fp8": "fp8-e4m3 block-scaled (32x32 UE8M0)", "ode": "fp32", "linreg": "fp64"}[args.config],
         "data": "synthetic",
         "impl": args.impl,
-        "config": {
-            "model": "hierarchical logistic GLM, one group intercept per shard (logp + gradient)" if args.kernel == "fp8"
-            else "federated logistic GLM (logp + gradient)",
-            "shards": args.shards,
-            "rows_per_shard": args.rows,
-            "features": args.features,
-            "chains_per_eval": K,
-            "global_batch": args.shards * args.rows,
-            "seq_len": args.features,
-            "parallelism": f"shard-parallel x{world} ({args.shards // world} shards/GPU)",
-            "kernel": args.kernel,
-            "backend": backend,
-            "comm": comm_mode,
-            "l2_policy": "inputs (>= 5 GB per GPU) are larger than the 126 MB L2; no flush needed",
-            "hbm_bytes_per_eval_per_gpu": bytes_per_eval,
-            "hbm_roofline_frac_of_measured": (bytes_per_eval / (ms_per_step * 1e-3)) / (hbm * 1e9),
-            # three-term roofline of the fused broadcast->compute->reduce kernel (seconds per eval per GPU):
-            # HBM stream of the shard, tensor-core time of the two skinny GEMMs (N padded to 16 columns each),
-            # NVLink bytes (theta in, partial out) at the measured 770 GB/s peer bandwidth
-            "roofline_s": {
-                "hbm": bytes_per_eval / (hbm * 1e9),
-                "tensor": flops_per_eval * (32.0 / max(1, 4 * K)) / (peaks.get("bf16_tflops", 1590.0) * 1e12),
-                "nvlink": (n_theta_words * 4 + n_vals * 8) / 770e9,
-                "bound": "hbm",
-            },
-        },
+        "config": config,
+        "verified": result["verified"],
+        "max_rel_err": result["max_rel_err"],
         "clocks": result["clocks"],
         "e2e": {
             "value": e2e_value,
             "unit": "evals/s",
+            "steps": result["e2e_steps"],
             "h2d_bytes_per_step": n_theta_words * 4,
             "d2h_bytes_per_step": n_vals * 8 + 8,
         },
         "gpu_launches": int(result["launches"]) * world if backend == "fused" else 0,
         "checksum": result["checksum"],
+        **extra,
     }
     out = json.dumps(line)
     print(out, flush=True)
@@ -356,6 +479,34 @@ def run_b200(args):
         os.makedirs(os.path.dirname(os.path.abspath(args.out)), exist_ok=True)
         with open(args.out, "a") as fh:
             fh.write(out + "\n")
+    if not result["verified"]:
+        raise SystemExit(3)
+
+
+def linreg_nuts(eng, args):
+    """BASELINE.json config 2: the sampler drives one federated Op per node; all of them are answered by ONE
+    fused launch per model evaluation (the peers serve without bound until the root shuts down)."""
+    import numpy as np
+
+    from pytensor_federated_b200.federation import NodeFederation
+    from pytensor_federated_b200.sampling import Model, nuts_sample
+
+    fed = NodeFederation(eng)
+    ops = fed.node_ops()
+    m = Model()
+    mu = m.Normal("intercept_mu", 0.0, 1.0)
+    icpt = m.Normal("intercept", mu, 0.1, size=args.shards)
+    slope = m.Normal("slope", 0.0, 1.0)
+    for i, off in enumerate(np.linspace(-4, 4, args.shards)):
+        logp, *_ = ops[i](icpt[i] + off, slope)
+        m.Potential(f"p{i}", logp)
+    m.compile()
+    t0 = time.perf_counter()
+    res = nuts_sample(m.logp_dlogp, np.zeros(m.dim), draws=args.nuts_draws, tune=args.nuts_draws, seed=1)
+    dt = time.perf_counter() - t0
+    return {"nuts": {"draws": args.nuts_draws, "tune": args.nuts_draws, "seconds": dt, "n_logp_evals": res.n_logp_evals,
+                     "model_evals_per_s": res.n_logp_evals / dt, "node_evals_per_s": args.shards * res.n_logp_evals / dt,
+                     "fused_launches": fed.n_launches, "divergences": int(res.divergences)}}
 
 
 def run_reference(args):

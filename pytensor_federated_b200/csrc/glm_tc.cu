@@ -37,15 +37,16 @@ constexpr int kPanelBytes = kTileM * 128;  // 16 KB
 // warps: 0 TMA, 1 MMA#1 issuer, 2-5 epilogue group 0, 6 MMA#2 issuer, 7.. further epilogue groups
 constexpr int kMaxChunk = 32;        // tiles per chunk at most (= tiles accumulated in TMEM in fp32 before a flush)
 constexpr int kMinChunk = 4;
-constexpr int kMaxSegs = 64;
 constexpr int kRing = 32;            // published chunks the consumers may lag behind (needs only ~3)
 constexpr int kLLRows = 16;          // epilogue warps at most (per-warp log-likelihood slots)
 
 struct SmemLayout {
-    uint32_t stages, stage_bytes, off_theta_b, theta_b_bytes, off_r, r_bytes, off_theta_f, off_icpt, off_segs, off_gi, off_ring,
+    uint32_t stages, stage_bytes, off_theta_b, theta_b_bytes, off_r, r_bytes, off_theta_f, off_icpt, off_gi, off_ring,
         off_bars, off_tmem, total;
 };
-__host__ __device__ inline SmemLayout smem_layout(int P, int n1, int n2, int n_theta, int n_groups, int chains) {
+// r_bufs: residual (R) buffers between the epilogue and MMA #2 — 2 normally; 1 for 16 chains, where the 8 KB
+// buy the third TMA stage (the epilogue of 16 chains is long enough to hide the short MMA #2 it then waits for)
+__host__ __device__ inline SmemLayout smem_layout(int P, int n1, int n2, int n_theta, int n_groups, int chains, int r_bufs) {
     SmemLayout L;
     const uint32_t panels = P / kPanel;
     L.stage_bytes = panels * kPanelBytes;
@@ -53,18 +54,16 @@ __host__ __device__ inline SmemLayout smem_layout(int P, int n1, int n2, int n_t
     L.r_bytes = kTileM * n2 * 2;
     // theta (fp32) is staged inside the (not yet used) TMA stage ring and is dead once the bf16 B operand
     // and the intercept table are built, so it costs no shared memory of its own.
-    const uint32_t fixed = L.theta_b_bytes + 2 * L.r_bytes + ((chains * n_groups * 4 + 15) & ~15) +
-                           kMaxSegs * (uint32_t)sizeof(GlmSegment) + ((chains * n_groups * 8 + 15) & ~15) + kRing * 16 + 16 + 192 + 64 +
-                           1024 /*alignment slack*/;
+    const uint32_t fixed = L.theta_b_bytes + r_bufs * L.r_bytes + ((chains * n_groups * 4 + 15) & ~15) +
+                           ((chains * n_groups * 8 + 15) & ~15) + kRing * 16 + 16 + 192 + 64 + 1024 /*alignment slack*/;
     uint32_t stages = (227u * 1024u - fixed) / L.stage_bytes;
     if (stages > 4) stages = 4;
     L.stages = stages;
     uint32_t o = stages * L.stage_bytes;
     L.off_theta_b = o; o += L.theta_b_bytes;
-    L.off_r = o; o += 2 * L.r_bytes;
+    L.off_r = o; o += r_bufs * L.r_bytes;
     L.off_theta_f = 0;  // aliases stage 0.. (needs n_theta * 4 <= stages * stage_bytes)
     L.off_icpt = o; o += (chains * n_groups * 4 + 15) & ~15;
-    L.off_segs = o; o += kMaxSegs * (uint32_t)sizeof(GlmSegment);
     L.off_gi = o; o += (chains * n_groups * 8 + 15) & ~15;
     L.off_ring = o; o += kRing * 16 + 16;   // published chunks + the publication counter
     L.off_bars = o; o += 192;
@@ -88,6 +87,7 @@ struct Cfg {
     static constexpr int KH = KC / EGC;                 // chains per group
     static constexpr int kArrive = 128 * EGC;           // arrivals per eta/R/G barrier phase
     static constexpr int kThreads = 224 + (EG - 1) * 128;
+    static constexpr int RB = KC >= 16 ? 1 : 2;         // R buffers (see smem_layout)
 };
 
 // doubles per CTA row of the partial array: (hi, lo) pairs of the n_vals outputs, then the per-warp
@@ -126,6 +126,7 @@ fed_glm_tc_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParams
     constexpr int KH = Cfg<KC>::KH;
     constexpr int EGC = Cfg<KC>::EGC;
     constexpr int kArrive = Cfg<KC>::kArrive;
+    constexpr int RB = Cfg<KC>::RB;
     static_assert(Cfg<KC>::EGT == 2, "tile parity <-> eta / R buffer");
     static_assert(EG * 4 <= kLLRows, "per-warp LL slots");
     extern __shared__ unsigned char smem_dyn[];
@@ -137,7 +138,7 @@ fed_glm_tc_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParams
     const int G = prm.n_groups;
     const int NH = P / 128;           // 128-feature halves (UMMA M of MMA #2)
     const int panels = P / kPanel;
-    const SmemLayout L = smem_layout(P, N1, N2, comm.n_theta, G, KC);
+    const SmemLayout L = smem_layout(P, N1, N2, comm.n_theta, G, KC, RB);
     const int S = (int)L.stages;
     const int nch = prm.n_chains < KC ? prm.n_chains : KC;  // chains actually present in theta
     const int NV1 = 1 + G + P;        // outputs per chain: [LL, gi[G], g[P]]
@@ -146,7 +147,6 @@ fed_glm_tc_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParams
     unsigned char* r_buf = smem + L.off_r;
     float* theta_f = reinterpret_cast<float*>(smem + L.off_theta_f);  // valid until the setup barrier only
     float* icpt = reinterpret_cast<float*>(smem + L.off_icpt);        // [KC][G] intercepts
-    GlmSegment* segs = reinterpret_cast<GlmSegment*>(smem + L.off_segs);
     unsigned long long* gi_acc = reinterpret_cast<unsigned long long*>(smem + L.off_gi);  // fixed point (fed::fix_add)
     int4* ring = reinterpret_cast<int4*>(smem + L.off_ring);          // (segment or -1, first row, tiles, -)
     uint32_t* n_published = reinterpret_cast<uint32_t*>(smem + L.off_ring + kRing * 16);
@@ -167,9 +167,8 @@ fed_glm_tc_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParams
 
     // ---------------- theta-independent setup: runs BEFORE the dependency wait inside fed::prologue, i.e. it
     // overlaps with the tail of the previous evaluation when launched with programmatic stream serialization
-    for (int i = threadIdx.x; i < prm.n_segments; i += blockDim.x) segs[i] = segs_g[i];
     for (int i = threadIdx.x; i < KC * G; i += blockDim.x) gi_acc[i] = 0ull;
-    for (int i = threadIdx.x; i < (int)(2 * L.r_bytes / 16); i += blockDim.x)
+    for (int i = threadIdx.x; i < (int)(RB * L.r_bytes / 16); i += blockDim.x)
         reinterpret_cast<uint4*>(r_buf)[i] = make_uint4(0, 0, 0, 0);
     if (threadIdx.x == 0) {
         *pipeline_fault() = 0;
@@ -344,12 +343,16 @@ fed_glm_tc_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParams
                             }
                         }
                         umma_commit(&bar_empty[stage.idx]);   // X stage may be refilled
-                        umma_commit(&bar_r_empty[buf.idx]);   // R buffer may be rewritten
+                        // R may be rewritten.  Two buffers: one barrier per buffer.  One buffer: the tiles of
+                        // the two epilogue groups alternate in it, and each group waits for the OTHER group's
+                        // tile to be consumed — one barrier per tile parity, so that a group can never be two
+                        // phases ahead of the barrier it waits on (parity waits alias after two phases).
+                        umma_commit(&bar_r_empty[RB == 2 ? buf.idx : (t & 1)]);
                         if (last) umma_commit(&bar_g_full[gb]);
                     }
                     __syncwarp();
                     stage.advance(S);
-                    buf.advance(2);
+                    buf.advance(RB);
                 }
                 gbuf.advance(2);
             }
@@ -364,32 +367,30 @@ fed_glm_tc_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParams
             const uint32_t lane_addr = (uint32_t)(q * 32) << 16;
             const int k0 = cg * KH;                 // first chain of this group
             const uint32_t r_lbo = (N2 / 8) * 128;
-            constexpr int kEtaLoads = (3 * KH + 3) / 4;
-            constexpr int kGLoads = (2 * KH + 3) / 4;
+            // columns fetched per request (power-of-two shapes; the surplus columns are allocated TMEM, ignored)
+            constexpr int kEtaCols = KH == 1 ? 4 : (KH == 2 ? 8 : (KH == 4 ? 16 : 24));
+            constexpr int kGCols = KH <= 2 ? 4 : (KH == 4 ? 8 : 16);
             const int b = tp;                       // eta / R buffer of this group's tiles
             uint32_t bph = 0;                       // its phase: flips after every tile of this group
             Ring gbuf;
             for (int j = 0;; ++j) {
                 const int4 ch = next_chunk(j);
                 if (ch.x < 0) break;
-                const GlmSegment& seg = segs[ch.x];
+                const float* __restrict__ seg_y = segs_g[ch.x].y;   // segment table: global, read once per chunk
+                const long long seg_rows = segs_g[ch.x].n_rows;
+                const int seg_group = segs_g[ch.x].group;
                 float ll_acc[KH], gi_cur[KH];
 #pragma unroll
                 for (int k = 0; k < KH; ++k) ll_acc[k] = gi_cur[k] = 0.f;
                 for (int t = tp; t < ch.z; t += 2) {
                     const long long grow = (long long)ch.y + (long long)t * kTileM + row;
-                    const bool valid = grow < seg.n_rows;
-                    const float y = valid ? __ldg(seg.y + grow) : 0.f;
+                    const bool valid = grow < seg_rows;
+                    const float y = valid ? __ldg(seg_y + grow) : 0.f;
 
                     mbar_wait(&bar_eta_full[b], bph);
                     tc_fence_after();
-                    float ev[kEtaLoads * 4];
-#pragma unroll
-                    for (int i = 0; i < kEtaLoads; ++i) {
-                        float v[4];
-                        tmem_ld_x4(tmem_eta + lane_addr + b * N1 + 3 * k0 + 4 * i, v);
-                        ev[4 * i + 0] = v[0]; ev[4 * i + 1] = v[1]; ev[4 * i + 2] = v[2]; ev[4 * i + 3] = v[3];
-                    }
+                    float ev[kEtaCols];
+                    tmem_ld_cols<kEtaCols>(tmem_eta + lane_addr + b * N1 + 3 * k0, ev);   // one TMEM round trip
                     tc_fence_before();
                     mbar_arrive(&bar_eta_empty[b]);
 
@@ -400,17 +401,25 @@ fed_glm_tc_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParams
                         const float eta = (ev[3 * k] + ev[3 * k + 1]) + ev[3 * k + 2];
                         float ll = 0.f, r = 0.f;
                         if (valid && (k0 + k) < nch)
-                            link_loglik(prm.family, y, eta + icpt[(k0 + k) * G + seg.group], ll, r);
+                            link_loglik(prm.family, y, eta + icpt[(k0 + k) * G + seg_group], ll, r);
                         ll_acc[k] += ll;
                         gi_cur[k] += r;
                         const __nv_bfloat16 hi = __float2bfloat16_rn(r);
                         const __nv_bfloat16 lo = __float2bfloat16_rn(r - __bfloat162float(hi));
                         rpk[k] = (uint32_t)__bfloat16_as_ushort(hi) | ((uint32_t)__bfloat16_as_ushort(lo) << 16);
                     }
-                    mbar_wait(&bar_r_empty[b], bph ^ 1);
+                    // R buffer of this tile: with two buffers the group's own; with one, every tile of the CTA uses it
+                    const int rb = RB == 2 ? b : 0;
+                    if constexpr (RB == 2) {
+                        mbar_wait(&bar_r_empty[b], bph ^ 1);
+                    } else {
+                        // wait until MMA #2 has consumed the previous tile (the other group's): for group 0 that is
+                        // the (m)-th commit on the odd barrier before its m-th tile, for group 1 the (m+1)-th on the even
+                        mbar_wait(&bar_r_empty[tp ^ 1], tp == 0 ? (bph ^ 1) : bph);
+                    }
                     {
                         // chain k owns columns (2k, 2k+1): 4 bytes at (k / 4) * 128 + (k % 4) * 4 of the row
-                        unsigned char* rrow = r_buf + b * L.r_bytes + (row >> 3) * r_lbo + (row & 7) * 16;
+                        unsigned char* rrow = r_buf + rb * L.r_bytes + (row >> 3) * r_lbo + (row & 7) * 16;
                         if constexpr (KH == 8) {
                             *reinterpret_cast<uint4*>(rrow + (k0 / 4) * 128) = make_uint4(rpk[0], rpk[1], rpk[2], rpk[3]);
                             *reinterpret_cast<uint4*>(rrow + (k0 / 4 + 1) * 128) = make_uint4(rpk[4], rpk[5], rpk[6], rpk[7]);
@@ -423,7 +432,7 @@ fed_glm_tc_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParams
                         }
                     }
                     fence_proxy_async();
-                    mbar_arrive(&bar_r_full[b]);
+                    mbar_arrive(&bar_r_full[rb]);
                     bph ^= 1u;
                 }
                 // ---- end of the chunk for this group: fold its sums into the CTA's running pairs ----------
@@ -439,7 +448,7 @@ fed_glm_tc_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParams
                     }
                     if (lane == 0 && (k0 + k) < nch) {
                         dd_accumulate(ll_slots + 2 * ((size_t)ew * KC + k0 + k), l);
-                        fed::fix_add(&gi_acc[(k0 + k) * G + seg.group], gsum);
+                        fed::fix_add(&gi_acc[(k0 + k) * G + seg_group], gsum);
                     }
                 }
                 // gradient: the group that handled the chunk's last tile (odd index) drains the TMEM accumulator
@@ -447,30 +456,24 @@ fed_glm_tc_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParams
                     const int gb = gbuf.idx;
                     mbar_wait(&bar_g_full[gb], gbuf.phase);
                     tc_fence_after();
-                    float gv[4][kGLoads * 4];
+                    // one 128-feature half at a time keeps 16 values live instead of 64; the running pairs live in
+                    // this CTA's row of the partial array (L2): one thread owns each of them
 #pragma unroll
                     for (int h = 0; h < 4; ++h)
                         if (h < NH) {
-#pragma unroll
-                            for (int i = 0; i < kGLoads; ++i) {
-                                float v[4];
-                                tmem_ld_x4(tmem_g + lane_addr + (gb * NH + h) * N2 + 2 * k0 + 4 * i, v);
-                                gv[h][4 * i + 0] = v[0]; gv[h][4 * i + 1] = v[1]; gv[h][4 * i + 2] = v[2]; gv[h][4 * i + 3] = v[3];
+                            float gv[kGCols];
+                            tmem_ld_cols<kGCols>(tmem_g + lane_addr + (gb * NH + h) * N2 + 2 * k0, gv);
+                            if (h == NH - 1) {
+                                tc_fence_before();
+                                mbar_arrive(&bar_g_empty[gb]);   // MMA #2 may start the chunk after next in this buffer
                             }
-                        }
-                    tc_fence_before();
-                    mbar_arrive(&bar_g_empty[gb]);   // MMA #2 may start the chunk after next in this buffer
-                    // running pairs live in this CTA's row of the partial array (L2): one thread owns each of them
-#pragma unroll
-                    for (int h = 0; h < 4; ++h)
-                        if (h < NH) {
                             double2 cur[KH];
 #pragma unroll
                             for (int k = 0; k < KH; ++k)
                                 cur[k] = *reinterpret_cast<const double2*>(out + 2 * ((size_t)(k0 + k) * NV1 + 1 + G + h * 128 + row));
 #pragma unroll
                             for (int k = 0; k < KH; ++k) {
-                                fed::dd_add(cur[k].x, cur[k].y, (double)gv[h][2 * k] + (double)gv[h][2 * k + 1], 0.0);
+                                fed::dd_add(cur[k].x, cur[k].y, (double)gv[2 * k] + (double)gv[2 * k + 1], 0.0);
                                 if ((k0 + k) < nch)
                                     *reinterpret_cast<double2*>(out + 2 * ((size_t)(k0 + k) * NV1 + 1 + G + h * 128 + row)) = cur[k];
                             }
@@ -559,7 +562,6 @@ static std::vector<GlmChunk> build_chunks(const GlmSegment* segs, int n_segments
 extern "C" int b200_glm_tc_prepare(const GlmSegment* segs_host, int n_segments, const GlmParams* prm, int sm_count,
                                    void** tmaps_dev, void** chunks_dev, int* n_chunks) {
     if (prm->n_features % 128 != 0 || prm->n_features > 384 || prm->n_features < 128) return -11;
-    if (n_segments > tc::kMaxSegs) return -12;
     if (chains_bucket(prm->n_chains) == 0) return -13;
     if ((prm->ld * 2) % 16 != 0) return -14;
     EncodeTiledFn encode = get_encode();
@@ -619,7 +621,7 @@ extern "C" int b200_launch_glm_tc(const FedComm* comm, const GlmSegment* segs_de
 #define LAUNCH_TC(KC)                                                                                              \
     do {                                                                                                           \
         const tc::SmemLayout L = tc::smem_layout(prm->n_features, tc::Cfg<KC>::N1, tc::Cfg<KC>::N2, comm->n_theta,  \
-                                                 prm->n_groups, KC);                                               \
+                                                 prm->n_groups, KC, tc::Cfg<KC>::RB);                              \
         if (L.stages < 2) return -2;                                                                               \
         cudaFuncSetAttribute(tc::fed_glm_tc_kernel<KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total); \
         cudaLaunchConfig_t cfg{};                                                                                  \

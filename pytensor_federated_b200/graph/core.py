@@ -210,6 +210,14 @@ def as_tensor(x, name: Optional[str] = None, dtype: Optional[str] = None) -> Var
 as_tensor_variable = as_tensor
 
 
+def constant(x, name: Optional[str] = None, dtype: Optional[str] = None) -> Variable:
+    """``pytensor.tensor.constant``: a literal in the graph (the reference's gradient-free test pins the
+    intercept with ``at.constant(0.5)``)."""
+    if isinstance(x, Variable):
+        raise TypeError("constant() takes a number or an array, not a graph variable")
+    return as_tensor(x, name, dtype)
+
+
 def scalar(name: Optional[str] = None, dtype: str = "float64") -> Variable:
     return TensorType(dtype, ())(name)
 

@@ -142,7 +142,7 @@ class GlmShards(ShardModel):
         # TMA streaming + the X tile reused from smem for both GEMMs), then SIMT, then the general kernel
         bf16 = X0.dtype == torch.bfloat16
         tc_ok = (bf16 and self.n_features % 128 == 0 and 128 <= self.n_features <= 384 and self.n_chains <= 16
-                 and len(self.Xs) <= 64 and all(X.data_ptr() % 16 == 0 for X in self.Xs) and self.ld % 8 == 0)
+                 and all(X.data_ptr() % 16 == 0 for X in self.Xs) and self.ld % 8 == 0)
         if tc_ok:
             return 1
         if self.n_chains > 1:
@@ -177,7 +177,10 @@ class GlmShards(ShardModel):
             lib.b200_engine_set_custom_launcher(handle, C.c_void_p(self.family.launcher_address()))
 
     # -- eager oracle (also the compute step of the NCCL baseline) ---------------------------
-    def reference_partial(self, inputs, *, dtype=None) -> np.ndarray:
+    def reference_partial(self, inputs, *, dtype=None, chunk_rows: int = 1 << 20) -> np.ndarray:
+        """This node's partial with stock PyTorch ops (oracle of the kernels, compute step of the CPU / gloo
+        path).  Rows are processed ``chunk_rows`` at a time (a multiple of 128), so an fp64 oracle of a
+        10M-row shard needs 2 GB of scratch, not 20."""
         import torch
 
         dtype = dtype or torch.float32
@@ -185,31 +188,38 @@ class GlmShards(ShardModel):
         self._note_shapes(inputs)
         ic = torch.as_tensor(np.asarray(intercept, dtype=np.float64)).reshape(self.n_chains, -1)
         bt = torch.as_tensor(np.asarray(beta, dtype=np.float64)).reshape(self.n_chains, self.n_features)
-        out = torch.zeros(self.n_chains, 1 + self.n_params, dtype=torch.float64)
-        for X, y, g in zip(self.Xs, self.ys, self.groups):
-            Xf = self._dequant(X).to(dtype)
-            B = bt.to(self.device, dtype)                          # [K, P]
-            eta = Xf @ B.T + ic[:, g].to(self.device, dtype)        # [n, K]
-            yy = y.to(dtype).unsqueeze(1)
-            if hasattr(self.family, "code_id"):
-                if self.family.torch_fn is None:
-                    raise ValueError("this CustomFamily has no torch_fn oracle")
-                ll, r = self.family.torch_fn(yy, eta)
-            elif self.family == "logistic":
-                ll = yy * eta - torch.nn.functional.softplus(eta)
-                r = yy - torch.sigmoid(eta)
-            elif self.family == "poisson":
-                mu = torch.exp(eta)
-                ll = yy * eta - mu
-                r = yy - mu
-            else:
-                d = yy - eta
-                ll = -0.5 * d * d - 0.918938533204672742
-                r = d
-            out[:, 0] += ll.double().sum(0).cpu()
-            out[:, 1 + g] += r.double().sum(0).cpu()
-            out[:, 1 + self.n_groups :] += (r.T @ Xf).double().cpu()
-        return out.reshape(-1).numpy()
+        out = torch.zeros(self.n_chains, 1 + self.n_params, dtype=torch.float64, device=self.device)
+        B = bt.to(self.device, dtype)                              # [K, P]
+        for si, (X, y, g) in enumerate(zip(self.Xs, self.ys, self.groups)):
+            icg = ic[:, g].to(self.device, dtype)
+            for r0 in range(0, X.shape[0], chunk_rows):
+                r1 = min(X.shape[0], r0 + chunk_rows)
+                Xf = self._dequant_rows(si, r0, r1).to(dtype)
+                eta = Xf @ B.T + icg                                # [n, K]
+                yy = y[r0:r1].to(dtype).unsqueeze(1)
+                if hasattr(self.family, "code_id"):
+                    if self.family.torch_fn is None:
+                        raise ValueError("this CustomFamily has no torch_fn oracle")
+                    ll, r = self.family.torch_fn(yy, eta)
+                elif self.family == "logistic":
+                    ll = yy * eta - torch.nn.functional.softplus(eta)
+                    r = yy - torch.sigmoid(eta)
+                elif self.family == "poisson":
+                    mu = torch.exp(eta)
+                    ll = yy * eta - mu
+                    r = yy - mu
+                else:
+                    d = yy - eta
+                    ll = -0.5 * d * d - 0.918938533204672742
+                    r = d
+                out[:, 0] += ll.double().sum(0)
+                out[:, 1 + g] += r.double().sum(0)
+                out[:, 1 + self.n_groups :] += (r.T @ Xf).double()
+        return out.reshape(-1).cpu().numpy()
+
+    def _dequant_rows(self, seg: int, r0: int, r1: int):
+        """Rows ``[r0, r1)`` of segment ``seg`` as stored values (dense kernels: the matrix itself)."""
+        return self.Xs[seg][r0:r1]
 
     def _dequant(self, X):
         return X
@@ -337,6 +347,11 @@ class Fp8GlmShards(GlmShards):
     def _dequant(self, X):
         idx = next(i for i, Xi in enumerate(self.Xs) if Xi is X)
         return dequantize_block_fp8(X, self.scales[idx])
+
+    def _dequant_rows(self, seg: int, r0: int, r1: int):
+        if r0 % 32:
+            raise ValueError("row chunks of block-scaled matrices start on a 32-row boundary")
+        return dequantize_block_fp8(self.Xs[seg][r0:r1], self.scales[seg][r0 // 32 : (r1 + 31) // 32])
 
     def bytes_per_eval(self) -> int:
         return int(sum(X.shape[0] * (self.n_features + 4) + s.numel() for X, s in zip(self.Xs, self._kernel_scales)))

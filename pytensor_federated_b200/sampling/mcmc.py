@@ -306,3 +306,88 @@ def nuts_sample(logp_dlogp: LogpDlogp, x0: Optional[np.ndarray] = None, *, draws
             acc_total += a
     return SamplerResult(samples, lps, acc_total / max(1, draws), eps, counter["n"], depths, counter["div"],
                          inv_mass=inv_mass.copy(), rng_state=rng.bit_generator.state)
+
+
+def metropolis_sample(
+    logp: Callable[[np.ndarray], float],
+    x0: Optional[np.ndarray] = None,
+    *,
+    draws: int = 1000,
+    tune: int = 1000,
+    seed: int = 0,
+    scale: float = 1.0,
+    tune_interval: int = 100,
+    resume: Optional[SamplerResult] = None,
+) -> SamplerResult:
+    """Random-walk Metropolis for gradient-free potentials (``LogpOp`` / ``LogpServiceClient``).
+
+    The reference samples its gradient-free black box with ``pm.Metropolis()``
+    (``/root/reference/pytensor_federated/test_wrapper_ops.py:68-118``); this is the in-repo counterpart:
+    all coordinates are proposed jointly from ``N(0, (scale * s)^2)`` with a per-coordinate ``s``; during
+    ``tune`` the global scale is adapted every ``tune_interval`` steps from the acceptance rate of the
+    interval (the schedule PyMC uses: shrink below 20 % / 5 % / 0.1 %, grow above 50 % / 75 % / 95 %) and
+    ``s`` follows the running standard deviation of the chain.  One ``logp`` call per step.
+    ``resume`` continues a finished run with its proposal and random state (no further tuning).
+    """
+    if resume is not None:
+        x = np.array(resume.samples[-1], dtype=np.float64)
+        rng = np.random.default_rng()
+        if resume.rng_state is not None:
+            rng.bit_generator.state = resume.rng_state
+        step = float(resume.step_size)
+        spread = np.ones_like(x) if resume.inv_mass is None else np.sqrt(np.asarray(resume.inv_mass, dtype=np.float64))
+        tune = 0
+    else:
+        if x0 is None:
+            raise ValueError("x0 is required unless resuming")
+        x = np.atleast_1d(np.asarray(x0, dtype=np.float64)).copy()
+        rng = np.random.default_rng(seed)
+        step = float(scale)
+        spread = np.ones_like(x)
+    cur = float(logp(x))
+    if not np.isfinite(cur):
+        raise ValueError("Metropolis needs a finite log-probability at the starting point")
+    n_evals = 1
+    samples = np.empty((draws, x.size))
+    logps = np.empty(draws)
+    accepted_interval = 0
+    accepted_draws = 0
+    # Welford running moments of the tuning phase -> per-coordinate proposal spread
+    n_seen, mean, m2 = 0, np.zeros_like(x), np.zeros_like(x)
+    for it in range(tune + draws):
+        proposal = x + step * spread * rng.normal(size=x.size)
+        new = float(logp(proposal))
+        n_evals += 1
+        accept = np.isfinite(new) and np.log(rng.uniform()) < new - cur
+        if accept:
+            x, cur = proposal, new
+        if it < tune:
+            accepted_interval += int(accept)
+            n_seen += 1
+            delta = x - mean
+            mean += delta / n_seen
+            m2 += delta * (x - mean)
+            if (it + 1) % tune_interval == 0:
+                rate = accepted_interval / tune_interval
+                for bound, factor in ((0.001, 0.1), (0.05, 0.5), (0.2, 0.9)):
+                    if rate < bound:
+                        step *= factor
+                        break
+                else:
+                    for bound, factor in ((0.95, 10.0), (0.75, 2.0), (0.5, 1.1)):
+                        if rate > bound:
+                            step *= factor
+                            break
+                accepted_interval = 0
+                if n_seen >= 2 * tune_interval and x.size > 1:
+                    sd = np.sqrt(m2 / (n_seen - 1))
+                    if np.all(sd > 0):
+                        spread = sd / np.exp(np.mean(np.log(sd)))   # shape only; `step` keeps the overall size
+        else:
+            samples[it - tune] = x
+            logps[it - tune] = cur
+            accepted_draws += int(accept)
+    return SamplerResult(
+        samples=samples, logp=logps, accept_rate=accepted_draws / max(draws, 1), step_size=step, n_logp_evals=n_evals,
+        inv_mass=spread**2, rng_state=rng.bit_generator.state,
+    )

@@ -102,6 +102,18 @@ class Model:
         self._compiled = fn
         return fn
 
+    def compile_logp(self, mode=None):
+        """The joint log-probability WITHOUT gradients — all a model with gradient-free potentials
+        (``LogpOp`` / ``AsyncLogpOp``, which define no ``grad``) can offer; Metropolis consumes it."""
+        fn = function([v for _, v, _ in self.free], [self._total()], mode=mode)
+        self._compiled_logp = fn
+        return fn
+
+    def logp(self, theta: np.ndarray) -> float:
+        fn = getattr(self, "_compiled_logp", None) or self.compile_logp()
+        (total,) = fn(*self.split(np.atleast_1d(theta)))
+        return float(total)
+
     def split(self, theta: np.ndarray) -> List[np.ndarray]:
         out, pos = [], 0
         for _, _, shape in self.free:
@@ -135,18 +147,18 @@ class Model:
         theta, info = find_map(self.logp_dlogp, np.zeros(self.dim) if start is None else start, **kwargs)
         return self.point(theta), info
 
-    def sample(self, draws: int = 200, tune: int = 500, *, chains: int = 1, start: Optional[np.ndarray] = None,
-               seed: int = 0, **kwargs):
-        """NUTS from ``start`` (default: the MAP).  ``chains == 1`` returns ``(SamplerResult, {name: draws})``;
-        ``chains > 1`` runs them one after the other with seeds ``seed, seed + 1, ...`` and returns
-        ``([SamplerResult, ...], {name: draws[draws, chains(, k)]})`` — feed the dict to
-        :func:`~pytensor_federated_b200.sampling.summarize` for ESS / R-hat."""
-        from .mcmc import find_map, nuts_sample
+    def sample_metropolis(self, draws: int = 1000, tune: int = 1000, *, chains: int = 1,
+                          start: Optional[np.ndarray] = None, seed: int = 0, **kwargs):
+        """Random-walk Metropolis on :meth:`logp` — the sampler for models whose potentials have no gradient
+        (what ``pm.sample(step=pm.Metropolis())`` is to the reference's ``LogpOp`` test).  Returns like
+        :meth:`sample`."""
+        from .mcmc import metropolis_sample
 
-        if start is None:
-            start, _ = find_map(self.logp_dlogp, np.zeros(self.dim))
-        results = [nuts_sample(self.logp_dlogp, start, draws=draws, tune=tune, seed=seed + c, **kwargs)
-                   for c in range(chains)]
+        start = np.zeros(self.dim) if start is None else np.asarray(start, dtype=np.float64)
+        results = [metropolis_sample(self.logp, start, draws=draws, tune=tune, seed=seed + c, **kwargs) for c in range(chains)]
+        return self._columns(results, chains)
+
+    def _columns(self, results, chains: int):
         samples = np.stack([r.samples for r in results], axis=1)          # [draws, chains, dim]
         columns = {}
         pos = 0
@@ -160,3 +172,17 @@ class Model:
         if chains == 1:
             return results[0], {k: v[:, 0] for k, v in columns.items()}
         return results, columns
+
+    def sample(self, draws: int = 200, tune: int = 500, *, chains: int = 1, start: Optional[np.ndarray] = None,
+               seed: int = 0, **kwargs):
+        """NUTS from ``start`` (default: the MAP).  ``chains == 1`` returns ``(SamplerResult, {name: draws})``;
+        ``chains > 1`` runs them one after the other with seeds ``seed, seed + 1, ...`` and returns
+        ``([SamplerResult, ...], {name: draws[draws, chains(, k)]})`` — feed the dict to
+        :func:`~pytensor_federated_b200.sampling.summarize` for ESS / R-hat."""
+        from .mcmc import find_map, nuts_sample
+
+        if start is None:
+            start, _ = find_map(self.logp_dlogp, np.zeros(self.dim))
+        results = [nuts_sample(self.logp_dlogp, start, draws=draws, tune=tune, seed=seed + c, **kwargs)
+                   for c in range(chains)]
+        return self._columns(results, chains)

@@ -13,11 +13,11 @@ from typing import Callable, List, Optional
 
 import numpy as np
 
-from .mcmc import LogpDlogp, SamplerResult, hmc_sample, nuts_sample
+from .mcmc import LogpDlogp, SamplerResult, hmc_sample, metropolis_sample, nuts_sample
 
 __all__ = ["sample_parallel"]
 
-_SAMPLERS = {"nuts": nuts_sample, "hmc": hmc_sample}
+_SAMPLERS = {"nuts": nuts_sample, "hmc": hmc_sample, "metropolis": metropolis_sample}
 
 
 def _run_chain(job) -> SamplerResult:
@@ -39,6 +39,7 @@ def sample_parallel(
 ) -> List[SamplerResult]:
     """Runs ``chains`` chains on ``cores`` worker processes; chain ``c`` uses seed ``seed + c``.
 
+    ``sampler="metropolis"`` is the gradient-free driver: the factory then returns ``logp(theta) -> float``.
     ``make_logp_dlogp`` is called once per chain *in the worker* and must be picklable (a module-level
     function or a ``functools.partial`` of one).  ``spawn`` is the default start method: a forked child
     inherits neither CUDA contexts nor gRPC channels safely.  Remaining keyword arguments go to the

@@ -44,11 +44,44 @@ def remote_gaussian_logp_dlogp(hosts_and_ports):
     return logp_dlogp
 
 
+def straight_line_blackbox(intercept, slope):
+    """Gradient-free black box: log-likelihood of y = 2 x + 0.5 (+ noise, sd 0.1) at 15 points.
+
+    The fixture of the reference's gradient-free end-to-end test
+    (``/root/reference/pytensor_federated/test_wrapper_ops.py:55-65``): same data-generating recipe, so the
+    golden value of that test, ``logp(0.4, 1.2) = -1511.41423640139``, must come out here too."""
+    import scipy.stats
+
+    x = np.linspace(-3.0, 3.0, num=15)
+    y = np.random.RandomState(42).normal(loc=2.0 * x + 0.5, scale=0.1)
+    return np.asarray(scipy.stats.norm(loc=intercept + slope * x, scale=0.1).logpdf(y).sum())
+
+
+def slope_posterior_logp(port: int, use_async: bool):
+    """Picklable model factory for ``sample_parallel(sampler="metropolis")``: builds, INSIDE the worker, the
+    model of the reference test — fixed intercept 0.5, ``slope ~ N(0, 2)``, the remote black box as a
+    ``Potential`` through ``LogpOp`` / ``AsyncLogpOp`` — and returns its gradient-free ``logp(theta)``."""
+    from pytensor_federated_b200 import AsyncLogpOp, LogpOp, LogpServiceClient
+    from pytensor_federated_b200._graph_backend import at
+    from pytensor_federated_b200.sampling import Model
+
+    client = LogpServiceClient("127.0.0.1", port)
+    op = AsyncLogpOp(client.evaluate_async) if use_async else LogpOp(client)
+    m = Model()
+    slope = m.Normal("slope", 0.0, 2.0)
+    m.Potential("L", op(at.constant(0.5), slope))
+    m._client = client   # keeps the connection alive as long as the model
+    return m.logp
+
+
 def _serve(port: int, n_clients: int, func_name: str, ready) -> None:
     from pytensor_federated_b200 import service
     from pytensor_federated_b200.rpc import Server
 
-    func = {"product": product_func, "gaussian": gaussian_logp_grad_func, "slow_product": slow_product_func}[func_name]
+    from pytensor_federated_b200 import wrap_logp_func
+
+    func = {"product": product_func, "gaussian": gaussian_logp_grad_func, "slow_product": slow_product_func,
+            "blackbox_logp": wrap_logp_func(straight_line_blackbox)}[func_name]
 
     async def main():
         svc = service.ArraysToArraysService(func)

@@ -1,4 +1,6 @@
-"""Fused broadcast -> compute -> reduce across GPUs (needs >= 2 B200s; run with gpurun --gpus 2)."""
+"""Fused broadcast -> compute -> reduce across GPUs (needs >= 2 B200s; run with gpurun --gpus N).
+
+Every scenario runs at world = 2, 4 and 8; a world larger than the number of visible GPUs is skipped."""
 import os
 import socket
 
@@ -14,6 +16,9 @@ def _free_port():
     with socket.socket() as s:
         s.bind(("127.0.0.1", 0))
         return s.getsockname()[1]
+
+
+WORLDS = [2, 4, 8]
 
 
 def _shard_data(rank, n=5000):
@@ -51,19 +56,32 @@ def _worker(rank, world, port, comm, scenario, q):
                 q.put(("peer", served))
                 eng.shutdown()
         elif scenario.startswith("glm"):
+            from pytensor_federated_b200.models import Fp8GlmShards
+
             kernel = scenario.split("-")[1]
+            chains = int(scenario.split("-")[2]) if scenario.count("-") >= 2 else 1
             X, y, _ = synth_logistic_shard(30_000 + 17 * rank, 256, seed=50 + rank, device=dev)
-            model = GlmShards([X], [y], groups=[rank % 2], n_groups=2, kernel=kernel)
+            if kernel == "fp8":
+                model = Fp8GlmShards.from_dense([X], [y], groups=[rank % 2], n_groups=2, n_chains=chains)
+            else:
+                model = GlmShards([X], [y], groups=[rank % 2], n_groups=2, kernel=kernel, n_chains=chains)
             eng = FederatedEngine(model, comm=comm, timeout=20.0)
-            ic = np.array([0.2, -0.1])
-            beta = (np.random.default_rng(1).normal(size=256) * 0.03).astype(np.float32)
+            rng = np.random.default_rng(1)
+            if chains == 1:
+                ic = np.array([0.2, -0.1])
+                beta = (rng.normal(size=256) * 0.03).astype(np.float32)
+            else:
+                ic = rng.normal(size=(chains, 2)) * 0.1
+                beta = (rng.normal(size=(chains, 256)) * 0.03).astype(np.float32)
             local = model.reference_partial([ic, beta], dtype=torch.float64)
             gathered = [None] * world
             dist.all_gather_object(gathered, local)
             if rank == 0:
                 got = eng.evaluate(ic, beta)
-                want = model.unpack_result(np.sum(gathered, axis=0))
-                q.put(("root", eng.comm_mode, [np.asarray(g).tolist() for g in got], [np.asarray(w).tolist() for w in want]))
+                again = eng.evaluate(ic, beta)   # dynamic work distribution, same bits
+                same = all(np.array_equal(np.asarray(a), np.asarray(b)) for a, b in zip(got, again))
+                want = model.unpack_result(np.sum(gathered, axis=0), model.call_context([ic, beta]))
+                q.put(("root", eng.comm_mode, [np.asarray(g).tolist() for g in got], [np.asarray(w).tolist() for w in want], same))
                 eng.shutdown()
             else:
                 eng.serve()
@@ -81,10 +99,18 @@ def _worker(rank, world, port, comm, scenario, q):
                     q.put(("root", "timeout", str(ex)))
                 dist.barrier()
                 eng.shutdown()
-            else:
+            elif rank == world - 1:
                 dist.barrier()  # fault injection: this node never serves
                 eng.shutdown()
                 q.put(("peer", 0))
+            else:
+                try:
+                    eng.serve(max_epochs=1)  # the healthy nodes answer; the root still misses one partial
+                except Exception:
+                    pass
+                dist.barrier()
+                eng.shutdown()
+                q.put(("peer", 1))
     finally:
         dist.destroy_process_group()
 
@@ -105,17 +131,18 @@ def _run(world, comm, scenario):
     return results
 
 
+@pytest.mark.parametrize("world", WORLDS)
 @pytest.mark.parametrize("comm", ["ipc", "symm", "auto"])
-def test_two_gpu_linreg_matches_numpy(comm):
+def test_linreg_across_gpus_matches_numpy(comm, world):
     import scipy.stats
 
-    results = _run(2, comm, "linreg")
+    results = _run(world, comm, "linreg")
     root = [r for r in results if r[0] == "root"][0]
-    peer = [r for r in results if r[0] == "peer"][0]
-    assert peer[1] == 4  # 4 evaluations served
+    peers = [r for r in results if r[0] == "peer"]
+    assert len(peers) == world - 1 and all(p[1] == 4 for p in peers)  # 4 evaluations served by every node
     for (a, b), got in zip([(0.3, -0.2), (1.0, 0.5), (0.0, 0.0)], root[2]):
         want_lp, want_da, want_db = 0.0, 0.0, 0.0
-        for rank in range(2):
+        for rank in range(world):
             x, y = _shard_data(rank)
             want_lp += scipy.stats.norm.logpdf(y, a + b * x, 0.7).sum()
             r = y - (a + b * x)
@@ -123,22 +150,29 @@ def test_two_gpu_linreg_matches_numpy(comm):
             want_db += (r * x).sum() / 0.49
         np.testing.assert_allclose(got, [want_lp, want_da, want_db], rtol=1e-11)
     per = np.asarray(root[3])
-    assert per.shape == (2, 3) and np.all(per[:, 0] < 0)
+    assert per.shape == (world, 3) and np.all(per[:, 0] < 0)
     print("comm mode:", root[1])
 
 
-@pytest.mark.parametrize("kernel", ["simt", "tc"])
-def test_two_gpu_glm_matches_reference(kernel):
-    results = _run(2, "auto", f"glm-{kernel}")
+@pytest.mark.parametrize("world", WORLDS)
+@pytest.mark.parametrize("kernel", ["simt", "tc", "tc-4", "tc-16", "fp8"])
+def test_glm_across_gpus_matches_reference(kernel, world):
+    results = _run(world, "auto", f"glm-{kernel}")
     root = [r for r in results if r[0] == "root"][0]
-    got, want = root[2], root[3]
+    got, want, same = root[2], root[3], root[4]
+    assert same, "two evaluations of the same theta must agree bit for bit"
+    if kernel == "fp8":
+        np.testing.assert_allclose(got[0], want[0], rtol=2e-5)
+        np.testing.assert_allclose(got[2], want[2], rtol=2e-4, atol=2e-4 * np.abs(want[2]).max())
+        return
     np.testing.assert_allclose(got[0], want[0], rtol=2e-5)
     np.testing.assert_allclose(got[1], want[1], rtol=1e-4, atol=2e-3)
     np.testing.assert_allclose(got[2], want[2], rtol=1e-4, atol=0.5)
 
 
-def test_dead_peer_raises_timeout_instead_of_hanging():
-    results = _run(2, "ipc", "dead-peer")
+@pytest.mark.parametrize("world", WORLDS)
+def test_dead_peer_raises_timeout_instead_of_hanging(world):
+    results = _run(world, "ipc", "dead-peer")
     root = [r for r in results if r[0] == "root"][0]
     assert root[1] == "timeout" and "did not deliver" in root[2]
 
