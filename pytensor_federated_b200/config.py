@@ -9,7 +9,8 @@ Environment variables (all optional):
 ``B200FED_COMM``            ``auto`` | ``symm`` | ``ipc`` — how peers' comm blocks are mapped
 ``B200FED_NO_MULTICAST``    set to disable NVSwitch multicast stores (P2P stores instead)
 ``B200FED_GLM_KERNEL``      ``auto`` | ``tc`` | ``simt`` | ``fp8``
-``B200FED_TIMEOUT``         seconds a node may stay silent before ``FederationTimeout``
+``B200FED_TIMEOUT``         seconds ONE evaluation may take before ``FederationTimeout`` (dead peer, lost theta)
+``B200FED_IDLE_TIMEOUT``    seconds a peer keeps waiting between evaluations (0 = for ever; it re-arms its kernels)
 ``B200FED_SERVE_AHEAD``     kernels a peer keeps pre-enqueued
 ``B200FED_CONNECT_SLEEP``   ``"lo,hi"`` seconds of the balanced-connect de-synchronisation pause
 ``B200FED_PROBE_TIMEOUT``   seconds to wait for a ``GetLoad`` answer
@@ -59,6 +60,7 @@ class FederationConfig:
     multicast: bool = True
     glm_kernel: str = "auto"
     timeout: float = 20.0
+    idle_timeout: float = 0.0     # peers: give up after this long without an evaluation (0 = never)
     serve_ahead: int = 8
     connect_sleep: Tuple[float, float] = (0.2, 2.0)
     probe_timeout: float = 5.0
@@ -72,6 +74,7 @@ class FederationConfig:
             multicast=not os.environ.get("B200FED_NO_MULTICAST"),
             glm_kernel=os.environ.get("B200FED_GLM_KERNEL", "auto"),
             timeout=_env_float("B200FED_TIMEOUT", 20.0),
+            idle_timeout=_env_float("B200FED_IDLE_TIMEOUT", 0.0),
             serve_ahead=_env_int("B200FED_SERVE_AHEAD", 8),
             connect_sleep=_env_pair("B200FED_CONNECT_SLEEP", (0.2, 2.0)),
             probe_timeout=_env_float("B200FED_PROBE_TIMEOUT", 5.0),

@@ -66,6 +66,7 @@ struct FedComm {
     unsigned int* ticket;                          // [0]: groups finished; [1 + g]: CTAs of group g finished
     unsigned long long* epoch_counter;             // peers: device-resident epoch (graph replay friendly); may be null
     unsigned long long* done_flag;                 // host-mapped: last finished epoch on this node (peers' serve loop)
+    unsigned long long* idle_ticks;                // host-mapped: launches that gave up waiting for theta (peers re-arm)
     unsigned long long* trace;                     // optional device-timer ring [4 x u64 per epoch % 256] or null
     unsigned long long* cta_trace;                 // optional per-CTA phase stamps [grid][8] of the LAST launch, or null
 
@@ -433,12 +434,20 @@ __device__ __forceinline__ bool epilogue_t(const FedComm& c, const Prologue& pro
     __syncthreads();
 
     if (!computed) {
-        // nothing was computed: just report and drain
+        // nothing was computed: just report and drain.  A PEER whose wait for theta expired has merely been idle
+        // (the client paused between evaluations): it leaves the epoch where it was and counts an idle tick, so
+        // the serve loop re-arms it instead of taking the federation down.
         if (threadIdx.x == 0) {
+            const bool idle = pro.timed_out && !pro.stop && c.rank != 0;
+            const unsigned long long done_epoch = idle ? epoch - 1ull : epoch;
             *c.ticket = 0;
-            if (c.epoch_counter) *c.epoch_counter = epoch;
-            unsigned long long st = pro.timed_out ? B200FED_ERR_THETA_TIMEOUT : 0ull;
-            unsigned long long word = (pro.stop ? B200FED_STOP_EPOCH : epoch) | (st << B200FED_STATUS_SHIFT);
+            if (c.epoch_counter) *c.epoch_counter = done_epoch;
+            unsigned long long st = (pro.timed_out && !idle) ? B200FED_ERR_THETA_TIMEOUT : 0ull;
+            unsigned long long word = (pro.stop ? B200FED_STOP_EPOCH : done_epoch) | (st << B200FED_STATUS_SHIFT);
+            if (idle && c.idle_ticks) {
+                volatile unsigned long long* ticks = c.idle_ticks;
+                *ticks = *ticks + 1ull;
+            }
             if (c.done_flag) { *reinterpret_cast<volatile unsigned long long*>(c.done_flag) = word; }
             if (c.rank == 0 && c.host_flag) {
                 __threadfence_system();

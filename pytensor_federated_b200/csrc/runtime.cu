@@ -130,6 +130,8 @@ struct Engine {
     double* h_result() { return reinterpret_cast<double*>(host_block + h_off_result); }
     volatile unsigned long long* h_flag() { return reinterpret_cast<volatile unsigned long long*>(host_block + h_off_flag); }
     volatile unsigned long long* h_done() { return reinterpret_cast<volatile unsigned long long*>(host_block + h_off_done); }
+    volatile unsigned long long* h_idle() { return reinterpret_cast<volatile unsigned long long*>(host_block + h_off_done + 64); }
+    double idle_timeout_s = 0.0;   // peers: give up after this long without an evaluation (0 = keep waiting)
 };
 
 void fill_comm(Engine* e, FedComm* c, bool root_uses_explicit_epoch) {
@@ -151,6 +153,7 @@ void fill_comm(Engine* e, FedComm* c, bool root_uses_explicit_epoch) {
     c->trace = e->trace;
     c->cta_trace = e->cta_trace_on ? e->cta_trace : nullptr;
     c->done_flag = reinterpret_cast<unsigned long long*>(e->host_block_dev + e->h_off_done);
+    c->idle_ticks = reinterpret_cast<unsigned long long*>(e->host_block_dev + e->h_off_done + 64);
     c->ll_mode = e->ll_mode ? 1 : 0;
     c->ll_theta = e->ll_theta ? 1 : 0;
     c->ll_theta_local = reinterpret_cast<unsigned long long*>(e->comm_local + L.off_ll_theta);
@@ -415,6 +418,7 @@ int b200_engine_reset(void* h) {
     e->epoch = 0;
     *e->h_flag() = 0;
     *e->h_done() = 0;
+    *e->h_idle() = 0;
     e->stop_serving = 0;
     return 0;
 }
@@ -422,6 +426,9 @@ int b200_engine_reset(void* h) {
 void b200_engine_set_timeout(void* h, double seconds) {
     static_cast<Engine*>(h)->timeout_ns = (unsigned long long)(seconds * 1e9);
 }
+// Peers: how long serve() keeps re-arming kernels without seeing an evaluation (0 = for ever).  The per-launch
+// wait for theta stays the evaluation timeout; a launch that expires counts an idle tick and is replaced.
+void b200_engine_set_idle_timeout(void* h, double seconds) { static_cast<Engine*>(h)->idle_timeout_s = seconds; }
 void b200_engine_set_grid(void* h, int grid) {
     // the per-CTA partial array holds sm_count * 8 rows; negative values select single-CTA modes
     Engine* e = static_cast<Engine*>(h);
@@ -584,7 +591,9 @@ int b200_engine_wait(void* h, unsigned long long epoch, double* out, double time
         const int n_words = e->n_vals * 2;
         int next = 0;
         while (true) {
-            while (next < n_words && (words[next] >> 32) == want) ++next;
+            // a word tagged with this epoch OR A LATER ONE is complete for our purposes (like the epoch flag: with
+            // several launches in flight an older epoch can still be waited for); signed 32-bit tag distance
+            while (next < n_words && (int32_t)((uint32_t)(words[next] >> 32) - (uint32_t)want) >= 0) ++next;
             if (next == n_words) break;
             v = *flag;
             if ((v & B200FED_EPOCH_MASK) >= epoch && (v >> B200FED_STATUS_SHIFT) != 0) return (int)(v >> B200FED_STATUS_SHIFT);
@@ -651,28 +660,44 @@ long long b200_engine_serve(void* h, int ahead, long long max_epochs) {
     // epochs are absolute (device-resident counter); this call serves [base+1, base+max_epochs]
     const unsigned long long base = *e->h_done() & B200FED_EPOCH_MASK;
     if (base == B200FED_STOP_EPOCH) return 0;
-    unsigned long long launched = base;
+    const unsigned long long idle_base = *e->h_idle();
+    unsigned long long enqueued = 0;      // kernels launched by this call
+    unsigned long long idle_seen = 0;     // ... of which gave up waiting for theta (re-armed below)
+    double idle_s = 0.0;                  // time spent idle since the last served evaluation
+    unsigned long long last_done = base;
     long long served = 0;
     while (!e->stop_serving.load()) {
         const unsigned long long word = *e->h_done();
         const unsigned long long done = word & B200FED_EPOCH_MASK;
-        const unsigned long long status = word >> B200FED_STATUS_SHIFT;
         if (done == B200FED_STOP_EPOCH) break;
-        if (status & B200FED_ERR_THETA_TIMEOUT) {
-            g_last_error = "idle timeout: no theta arrived from the root";
-            cudaStreamSynchronize(e->stream);
-            return -7;
+        const unsigned long long idle_now = *e->h_idle() - idle_base;
+        if (done != last_done) {
+            last_done = done;
+            idle_s = 0.0;
+        }
+        if (idle_now != idle_seen) {
+            idle_s += (double)(idle_now - idle_seen) * (double)e->timeout_ns * 1e-9;
+            idle_seen = idle_now;
+            if (e->idle_timeout_s > 0.0 && idle_s > e->idle_timeout_s) {
+                g_last_error = "idle timeout: no theta arrived from the root";
+                cudaStreamSynchronize(e->stream);
+                return -7;
+            }
         }
         served = (long long)(done - base);
-        if (max_epochs > 0 && (long long)(launched - base) >= max_epochs) {
-            if (done >= launched) break;
-            std::this_thread::yield();
+        const unsigned long long finished = (done - base) + idle_seen;
+        const unsigned long long in_flight = enqueued - finished;
+        if (max_epochs > 0 && served >= max_epochs) {
+            if (in_flight == 0) break;
+            std::this_thread::yield();   // surplus kernels cannot exist: in_flight <= max_epochs - served below
             continue;
         }
-        if (launched - done < (unsigned long long)ahead) {
+        const bool room = in_flight < (unsigned long long)ahead &&
+                          (max_epochs <= 0 || (long long)(served + in_flight) < max_epochs);
+        if (room) {
             int rc = launch_model(e, &c);
             if (rc != 0) return -8;
-            launched++;
+            enqueued++;
         } else {
             std::this_thread::yield();
         }

@@ -64,6 +64,7 @@ class FederatedEngine:
         group=None,
         device=None,
         timeout: Optional[float] = None,
+        idle_timeout: Optional[float] = None,
         comm: Optional[str] = None,
         grid: Optional[int] = None,
     ) -> None:
@@ -73,6 +74,10 @@ class FederatedEngine:
 
         cfg = get_config()
         timeout = cfg.timeout if timeout is None else timeout
+        # ``timeout`` bounds ONE evaluation (a dead peer / lost theta inside an evaluation in flight).  A client
+        # that merely pauses between evaluations is not a failure: peers re-arm their waiting kernels for as long
+        # as ``idle_timeout`` allows (0 = for ever; B200FED_IDLE_TIMEOUT)
+        self.idle_timeout = float(cfg.idle_timeout if idle_timeout is None else idle_timeout)
         self._serve_ahead = cfg.serve_ahead
 
         self.model = model
@@ -125,6 +130,7 @@ class FederatedEngine:
         if grid:
             lib.b200_engine_set_grid(self._handle, int(grid))
         lib.b200_engine_set_timeout(self._handle, self.timeout)
+        lib.b200_engine_set_idle_timeout(self._handle, self.idle_timeout)
         self._bootstrap_comm(comm)
         native.check(lib.b200_engine_reset(self._handle), "engine reset")
         if self.world > 1:
