@@ -20,7 +20,7 @@ CSRC = PKG / "csrc"
 BUILD = CSRC / "build"
 LIB = PKG / "libb200fed.so"
 
-SOURCES = ["runtime.cu", "linreg.cu", "glm_simt.cu", "glm_tc.cu", "glm_fp8.cu", "glm_generic.cu", "ode.cu", "codec.cu"]
+SOURCES = ["runtime.cu", "linreg.cu", "glm_simt.cu", "glm_tc.cu", "glm_fp8.cu", "glm_generic.cu", "ode.cu", "ode_generic.cu", "codec.cu"]
 ARCH = ["-gencode", "arch=compute_100a,code=sm_100a"]
 NVCC_FLAGS = ["-O3", "-std=c++17", "-lineinfo", "-Xcompiler", "-fPIC", "--expt-relaxed-constexpr"]
 

@@ -124,6 +124,8 @@ struct Engine {
     int (*custom_launcher)(const FedComm*, const GlmSegment*, const GlmParams*, int, int, cudaStream_t) = nullptr;
     std::vector<OdeShard> ode;
     OdeShard* ode_dev = nullptr;
+    // launcher of a user-supplied ODE system (models/ode.py: OdeSystem); null = the built-in Lotka-Volterra kernel
+    int (*ode_launcher)(const FedComm*, const OdeShard*, int, int, cudaStream_t) = nullptr;
     std::atomic<int> stop_serving{0};
 
     float* h_theta() { return reinterpret_cast<float*>(host_block + h_off_theta); }
@@ -201,7 +203,7 @@ int launch_model(Engine* e, const FedComm* c) {
             break;
         }
         case MODEL_ODE:
-            rc = b200_launch_ode(c, e->ode_dev, (int)e->ode.size(), e->grid, e->stream);
+            rc = (e->ode_launcher ? e->ode_launcher : b200_launch_ode)(c, e->ode_dev, (int)e->ode.size(), e->grid, e->stream);
             break;
         case MODEL_GLM_FP8:
             rc = b200_launch_glm_fp8(c, e->glm_segs_dev, &e->glm, e->glm_tmaps_dev, e->grid, e->stream);
@@ -530,6 +532,12 @@ int b200_engine_set_glm(void* h, int n_segments, const void** X, const float** y
 void b200_engine_set_custom_launcher(void* h, void* fn) {
     static_cast<Engine*>(h)->custom_launcher =
         reinterpret_cast<int (*)(const FedComm*, const GlmSegment*, const GlmParams*, int, int, cudaStream_t)>(fn);
+}
+
+// Installs the launcher of a separately compiled ODE system (same signature as b200_launch_ode).
+void b200_engine_set_ode_launcher(void* h, void* fn) {
+    static_cast<Engine*>(h)->ode_launcher =
+        reinterpret_cast<int (*)(const FedComm*, const OdeShard*, int, int, cudaStream_t)>(fn);
 }
 
 int b200_engine_set_ode(void* h, int n_shards, const float** t, const float** y0, const float** y_obs, const int* n_series,

@@ -3,7 +3,7 @@ from .base import ShardModel
 from .custom import CustomFamily
 from .glm import Fp8GlmShards, GlmShards, dequantize_block_fp8, quantize_block_fp8, synth_logistic_shard, synth_logistic_shard_fp8
 from .linreg import LinregShards, make_demo_data
-from .ode import OdeShards, synth_lv_shard
+from .ode import LOTKA_VOLTERRA, OdeShards, OdeSystem, synth_lv_shard, synth_ode_shard
 
 __all__ = [
     "ShardModel",
@@ -17,5 +17,8 @@ __all__ = [
     "synth_logistic_shard",
     "synth_logistic_shard_fp8",
     "OdeShards",
+    "OdeSystem",
+    "LOTKA_VOLTERRA",
+    "synth_ode_shard",
     "synth_lv_shard",
 ]

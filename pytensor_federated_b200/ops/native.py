@@ -71,6 +71,7 @@ def _declare(lib: C.CDLL) -> None:
         c_int_p, c_float_p, c_int_p,
     )
     sig("b200_engine_set_custom_launcher", None, C.c_void_p, C.c_void_p)
+    sig("b200_engine_set_ode_launcher", None, C.c_void_p, C.c_void_p)
     sig("b200_engine_launch", C.c_int, C.c_void_p)
     sig("b200_engine_set_device_theta", C.c_int, C.c_void_p, C.c_void_p, C.c_int, C.c_int)
     sig("b200_engine_wait", C.c_int, C.c_void_p, C.c_ulonglong, C.c_void_p, C.c_double)

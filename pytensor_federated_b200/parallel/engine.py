@@ -484,5 +484,5 @@ def default_inputs_from_words(model: ShardModel, words: np.ndarray):
             return th[0, : model.n_groups].copy(), th[0, model.n_groups :].copy()
         return th[:, : model.n_groups].copy(), th[:, model.n_groups :].copy()
     if isinstance(model, OdeShards):
-        return (words.view(np.float32)[:4].copy(),)
+        return model.inputs_from_words(words)
     raise FederationError(f"{type(model).__name__} must implement inputs_from_words()")
