@@ -389,6 +389,8 @@ def run_b200(args):
         barrier()
         eng.serve(max_epochs=share(0))
         barrier()
+        if args.config == "linreg" and backend == "fused":
+            eng.serve()   # the NUTS run of the root: as many evaluations as the sampler asks for, until it shuts down
 
     # max over ranks of the device-timed region (the root's kernels cannot finish before every peer delivered
     # its partial, so the root time already dominates; reduce anyway)

@@ -41,7 +41,7 @@ constexpr int kRing = 32;            // published chunks the consumers may lag b
 constexpr int kLLRows = 16;          // epilogue warps at most (per-warp log-likelihood slots)
 
 struct SmemLayout {
-    uint32_t stages, stage_bytes, off_theta_b, theta_b_bytes, off_r, r_bytes, off_theta_f, off_icpt, off_gi, off_ring,
+    uint32_t stages, stage_bytes, off_theta_b, theta_b_bytes, off_r, r_bytes, off_theta_f, off_icpt, off_ring,
         off_bars, off_tmem, total;
 };
 // r_bufs: residual (R) buffers between the epilogue and MMA #2 — 2 normally; 1 for 16 chains, where the 8 KB
@@ -54,8 +54,8 @@ __host__ __device__ inline SmemLayout smem_layout(int P, int n1, int n2, int n_t
     L.r_bytes = kTileM * n2 * 2;
     // theta (fp32) is staged inside the (not yet used) TMA stage ring and is dead once the bf16 B operand
     // and the intercept table are built, so it costs no shared memory of its own.
-    const uint32_t fixed = L.theta_b_bytes + r_bufs * L.r_bytes + ((chains * n_groups * 4 + 15) & ~15) +
-                           ((chains * n_groups * 8 + 15) & ~15) + kRing * 16 + 16 + 192 + 64 + 1024 /*alignment slack*/;
+    const uint32_t fixed = L.theta_b_bytes + r_bufs * L.r_bytes + ((chains * n_groups * 4 + 15) & ~15) + kRing * 16 + 16 + 192 +
+                           64 + 1024 /*alignment slack*/;
     uint32_t stages = (227u * 1024u - fixed) / L.stage_bytes;
     if (stages > 4) stages = 4;
     L.stages = stages;
@@ -64,7 +64,6 @@ __host__ __device__ inline SmemLayout smem_layout(int P, int n1, int n2, int n_t
     L.off_r = o; o += r_bufs * L.r_bytes;
     L.off_theta_f = 0;  // aliases stage 0.. (needs n_theta * 4 <= stages * stage_bytes)
     L.off_icpt = o; o += (chains * n_groups * 4 + 15) & ~15;
-    L.off_gi = o; o += (chains * n_groups * 8 + 15) & ~15;
     L.off_ring = o; o += kRing * 16 + 16;   // published chunks + the publication counter
     L.off_bars = o; o += 192;
     L.off_tmem = o; o += 64;
@@ -90,9 +89,12 @@ struct Cfg {
     static constexpr int RB = KC >= 16 ? 1 : 2;         // R buffers (see smem_layout)
 };
 
-// doubles per CTA row of the partial array: (hi, lo) pairs of the n_vals outputs, then the per-warp
-// log-likelihood slots [kLLRows][KC]
-__host__ __device__ constexpr size_t partial_row_doubles(int n_vals, int kc) { return 2 * ((size_t)n_vals + (size_t)kLLRows * kc); }
+// doubles per CTA row of the partial array: (hi, lo) pairs of the n_vals outputs, then the per-warp slots of
+// the values that a whole warp contributes to — [kLLRows][n_out][KC][1 + G]: log-likelihood and the G
+// intercept gradients of every (output block, chain)
+__host__ __device__ constexpr size_t partial_row_doubles(int n_vals, int kc, int n_out, int n_groups) {
+    return 2 * ((size_t)n_vals + (size_t)kLLRows * n_out * kc * (1 + n_groups));
+}
 
 __device__ __forceinline__ uint32_t ld_acquire_shared(const uint32_t* p) {
     uint32_t v;
@@ -147,7 +149,6 @@ fed_glm_tc_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParams
     unsigned char* r_buf = smem + L.off_r;
     float* theta_f = reinterpret_cast<float*>(smem + L.off_theta_f);  // valid until the setup barrier only
     float* icpt = reinterpret_cast<float*>(smem + L.off_icpt);        // [KC][G] intercepts
-    unsigned long long* gi_acc = reinterpret_cast<unsigned long long*>(smem + L.off_gi);  // fixed point (fed::fix_add)
     int4* ring = reinterpret_cast<int4*>(smem + L.off_ring);          // (segment or -1, first row, tiles, -)
     uint32_t* n_published = reinterpret_cast<uint32_t*>(smem + L.off_ring + kRing * 16);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.off_bars);
@@ -167,7 +168,6 @@ fed_glm_tc_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParams
 
     // ---------------- theta-independent setup: runs BEFORE the dependency wait inside fed::prologue, i.e. it
     // overlaps with the tail of the previous evaluation when launched with programmatic stream serialization
-    for (int i = threadIdx.x; i < KC * G; i += blockDim.x) gi_acc[i] = 0ull;
     for (int i = threadIdx.x; i < (int)(RB * L.r_bytes / 16); i += blockDim.x)
         reinterpret_cast<uint4*>(r_buf)[i] = make_uint4(0, 0, 0, 0);
     if (threadIdx.x == 0) {
@@ -193,9 +193,11 @@ fed_glm_tc_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParams
     const bool active = !pro.stop && !pro.timed_out;
     tc_fence_after();
     const uint32_t tmem_base = *tmem_slot;
-    const size_t row_doubles = partial_row_doubles(comm.n_vals, KC);
+    const int NOUT = prm.n_out;       // output blocks (1 = everything summed; else one per node)
+    const int NS1 = 1 + G;            // warp-level values per (block, chain): LL and the G intercept gradients
+    const size_t row_doubles = partial_row_doubles(comm.n_vals, KC, NOUT, G);
     double* out = comm.cta_partials + (size_t)blockIdx.x * row_doubles;   // this CTA's running sums, (hi, lo) pairs
-    double* ll_slots = out + 2 * (size_t)comm.n_vals;                     // [kLLRows][KC] pairs
+    double* ll_slots = out + 2 * (size_t)comm.n_vals;                     // [kLLRows][NOUT][KC][1 + G] pairs
 
     if (active) {
         // ---------------- theta-dependent setup --------------------------------------------------
@@ -379,6 +381,7 @@ fed_glm_tc_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParams
                 const float* __restrict__ seg_y = segs_g[ch.x].y;   // segment table: global, read once per chunk
                 const long long seg_rows = segs_g[ch.x].n_rows;
                 const int seg_group = segs_g[ch.x].group;
+                const int og = segs_g[ch.x].out_group;               // output block of this chunk's segment
                 float ll_acc[KH], gi_cur[KH];
 #pragma unroll
                 for (int k = 0; k < KH; ++k) ll_acc[k] = gi_cur[k] = 0.f;
@@ -447,8 +450,9 @@ fed_glm_tc_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParams
                         gsum += __shfl_xor_sync(0xffffffffu, gsum, o);
                     }
                     if (lane == 0 && (k0 + k) < nch) {
-                        dd_accumulate(ll_slots + 2 * ((size_t)ew * KC + k0 + k), l);
-                        fed::fix_add(&gi_acc[(k0 + k) * G + seg_group], gsum);
+                        double* slot = ll_slots + 2 * ((((size_t)ew * NOUT + og) * KC + k0 + k) * NS1);
+                        dd_accumulate(slot, l);
+                        dd_accumulate(slot + 2 * (1 + seg_group), gsum);
                     }
                 }
                 // gradient: the group that handled the chunk's last tile (odd index) drains the TMEM accumulator
@@ -470,12 +474,14 @@ fed_glm_tc_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParams
                             double2 cur[KH];
 #pragma unroll
                             for (int k = 0; k < KH; ++k)
-                                cur[k] = *reinterpret_cast<const double2*>(out + 2 * ((size_t)(k0 + k) * NV1 + 1 + G + h * 128 + row));
+                                cur[k] = (k0 + k) < nch
+                                             ? *reinterpret_cast<const double2*>(out + 2 * (((size_t)og * nch + k0 + k) * NV1 + 1 + G + h * 128 + row))
+                                             : make_double2(0.0, 0.0);
 #pragma unroll
                             for (int k = 0; k < KH; ++k) {
                                 fed::dd_add(cur[k].x, cur[k].y, (double)gv[2 * k] + (double)gv[2 * k + 1], 0.0);
                                 if ((k0 + k) < nch)
-                                    *reinterpret_cast<double2*>(out + 2 * ((size_t)(k0 + k) * NV1 + 1 + G + h * 128 + row)) = cur[k];
+                                    *reinterpret_cast<double2*>(out + 2 * (((size_t)og * nch + k0 + k) * NV1 + 1 + G + h * 128 + row)) = cur[k];
                             }
                         }
                 }
@@ -489,17 +495,17 @@ fed_glm_tc_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParams
         tc_fence_after();
         fed::pdl_trigger();   // the next evaluation's CTA may take this SM as soon as we exit
         if (threadIdx.x == 0) fed::stamp(comm, 5);
-        // layout per chain: [LL, gi[G], g[P]] as (hi, lo) pairs; g[] was accumulated in place
-        if (threadIdx.x < nch) {
-            const int k = threadIdx.x;
+        // layout per (output block, chain): [LL, gi[G], g[P]] as (hi, lo) pairs; g[] was accumulated in place,
+        // LL and gi[] are the per-warp slots summed in warp order
+        for (int i = threadIdx.x; i < NOUT * nch * NS1; i += blockDim.x) {
+            const int j = i % NS1, k = (i / NS1) % nch, o = i / (NS1 * nch);
             double hi = 0.0, lo = 0.0;
-            for (int w = 0; w < EG * 4; ++w) fed::dd_add(hi, lo, ll_slots[2 * ((size_t)w * KC + k)], ll_slots[2 * ((size_t)w * KC + k) + 1]);
-            out[2 * ((size_t)k * NV1)] = hi;
-            out[2 * ((size_t)k * NV1) + 1] = lo;
-        }
-        for (int i = threadIdx.x; i < nch * G; i += blockDim.x) {
-            out[2 * ((size_t)(i / G) * NV1 + 1 + (i % G))] = fed::fix_get(gi_acc[i]);
-            out[2 * ((size_t)(i / G) * NV1 + 1 + (i % G)) + 1] = 0.0;
+            for (int w = 0; w < EG * 4; ++w) {
+                const double* slot = ll_slots + 2 * ((((size_t)w * NOUT + o) * KC + k) * NS1 + j);
+                fed::dd_add(hi, lo, slot[0], slot[1]);
+            }
+            out[2 * (((size_t)o * nch + k) * NV1 + j)] = hi;
+            out[2 * (((size_t)o * nch + k) * NV1 + j) + 1] = lo;
         }
         if (threadIdx.x == 0) fed::stamp(comm, 6);
     }
@@ -608,8 +614,8 @@ extern "C" int b200_glm_tc_chunk_table(const long long* n_rows, int n_segments, 
 }
 
 // doubles in the partial array of the tensor-core kernel: one row of (hi, lo) pairs + per-warp LL slots per CTA
-extern "C" size_t b200_glm_tc_partial_row_doubles(int n_vals, int n_chains) {
-    return tc::partial_row_doubles(n_vals, chains_bucket(n_chains));
+extern "C" size_t b200_glm_tc_partial_row_doubles(int n_vals, int n_chains, int n_out, int n_groups) {
+    return tc::partial_row_doubles(n_vals, chains_bucket(n_chains), n_out > 0 ? n_out : 1, n_groups);
 }
 
 extern "C" int b200_launch_glm_tc(const FedComm* comm, const GlmSegment* segs_dev, const GlmParams* prm, const void* tmaps,

@@ -19,7 +19,7 @@ struct GlmSegment {
     long long n_rows;
     long long first_tile; // prefix sum over segments of ceil(n_rows / tile_rows)
     int group;            // which intercept this segment uses
-    int _pad;
+    int out_group;        // which output block this segment's [LL, grads] go to (0 unless per-node outputs are kept)
 };
 
 struct GlmParams {
@@ -30,6 +30,8 @@ struct GlmParams {
     int n_chains;         // K parameter vectors evaluated per launch (theta is [K][G+P])
     int family;           // 0 = logistic (Bernoulli), 1 = Poisson (log link), 2 = Gaussian (identity, unit variance)
     long long total_tiles;
+    int n_out;            // output blocks: 1 = everything summed; > 1 = one [K][1+G+P] block per node (tensor-core kernel)
+    int _pad;
 };
 
 // Unit of work of the dynamically scheduled tensor-core GLM kernel: n_tiles consecutive 128-row tiles of one
@@ -51,4 +53,6 @@ struct OdeShard {
     int n_t;
     float sigma;          // observation noise (Gaussian)
     int substeps;         // RK4 steps between consecutive observation times
+    int theta_offset;     // first float of this shard's parameter vector in theta (per-node parameters)
+    int out_offset;       // first double of this shard's [LL, dLL/dtheta] block in the result
 };

@@ -63,15 +63,24 @@ __device__ __forceinline__ void rk4_step(State& s, const float th[4], float h) {
     }
 }
 
+constexpr int kMaxTheta = 1024;   // floats of theta staged in shared memory (nodes x 4)
+
+// theta holds one (alpha, beta, gamma, delta) per node and the result one [LL, dLL/dtheta] block per node:
+// every shard names its own (theta_offset, out_offset), so the client may give each node its own parameters
+// and weight / sum the node results itself (the reference's one-Op-per-node pattern), still in ONE launch.
 __global__ void __launch_bounds__(128) fed_ode_kernel(FedComm comm, const OdeShard* __restrict__ shards, int n_shards) {
-    __shared__ float theta[8];
+    __shared__ float theta[kMaxTheta];
     __shared__ double red[32];
     fed::Prologue pro = fed::prologue(comm, theta);
     if (!pro.stop && !pro.timed_out) {
-        float th[4] = {theta[0], theta[1], theta[2], theta[3]};
-        double acc[5] = {0, 0, 0, 0, 0};  // LL, dLL/dtheta[4]
+        double* out = comm.cta_partials + (size_t)blockIdx.x * comm.n_vals;
+        for (int i = threadIdx.x; i < comm.n_vals; i += blockDim.x) out[i] = 0.0;
+        __syncthreads();
         for (int sidx = 0; sidx < n_shards; ++sidx) {
             const OdeShard sh = shards[sidx];
+            const float th[4] = {theta[sh.theta_offset], theta[sh.theta_offset + 1], theta[sh.theta_offset + 2],
+                                 theta[sh.theta_offset + 3]};
+            double acc[5] = {0, 0, 0, 0, 0};  // LL, dLL/dtheta[4]
             const float inv_var = 1.f / (sh.sigma * sh.sigma);
             const float log_norm = -__logf(sh.sigma) - 0.918938533204672742f;
             for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < sh.n_series; i += gridDim.x * blockDim.x) {
@@ -98,12 +107,11 @@ __global__ void __launch_bounds__(128) fed_ode_kernel(FedComm comm, const OdeSha
 #pragma unroll
                 for (int k = 0; k < 4; ++k) acc[1 + k] += (double)g[k];
             }
-        }
-        double* out = comm.cta_partials + (size_t)blockIdx.x * comm.n_vals;
 #pragma unroll
-        for (int k = 0; k < 5; ++k) {
-            const double v = fed::block_sum(acc[k], red);
-            if (threadIdx.x == 0) out[k] = v;
+            for (int k = 0; k < 5; ++k) {
+                const double v = fed::block_sum(acc[k], red);
+                if (threadIdx.x == 0) out[sh.out_offset + k] += v;
+            }
         }
     }
     fed::epilogue(comm, pro, 0ull);
@@ -113,7 +121,7 @@ __global__ void __launch_bounds__(128) fed_ode_kernel(FedComm comm, const OdeSha
 
 extern "C" int b200_launch_ode(const FedComm* comm, const OdeShard* shards_dev, int n_shards, int grid,
                                cudaStream_t stream) {
-    if (comm->n_theta != 4 || comm->n_vals != 5) return -1;
+    if (comm->n_theta % 4 != 0 || comm->n_theta > kMaxTheta || comm->n_vals % 5 != 0) return -1;
     fed_ode_kernel<<<grid, 128, 0, stream>>>(*comm, shards_dev, n_shards);
     return (int)cudaGetLastError();
 }

@@ -35,6 +35,7 @@ namespace odeg {
 
 constexpr int NS = B200FED_ODE_NS;
 constexpr int NP = B200FED_ODE_NP;
+constexpr int kMaxTheta = 1024;   // floats of theta staged in shared memory (nodes x NP)
 
 // ---- forward-mode dual number: v + sum_k d[k] eps_k ------------------------------------------------------
 struct Dual {
@@ -128,21 +129,25 @@ __device__ __forceinline__ void rk4_step(State& s, const Dual (&th)[NP], float t
 
 // Data layout (models/ode.py): y0 [NS, n_series], y_obs [n_t, NS, n_series] (series index fastest).
 __global__ void __launch_bounds__(128) fed_ode_generic_kernel(FedComm comm, const OdeShard* __restrict__ shards, int n_shards) {
-    __shared__ float theta[NP + 4];
+    __shared__ float theta[kMaxTheta];
     __shared__ double red[32];
     fed::Prologue pro = fed::prologue(comm, theta);
     if (!pro.stop && !pro.timed_out) {
-        Dual th[NP];
-#pragma unroll
-        for (int k = 0; k < NP; ++k) {
-            th[k] = make_const(theta[k]);
-            th[k].d[k] = 1.f;
-        }
-        double acc[1 + NP];
-#pragma unroll
-        for (int k = 0; k <= NP; ++k) acc[k] = 0.0;
+        double* out = comm.cta_partials + (size_t)blockIdx.x * comm.n_vals;
+        for (int i = threadIdx.x; i < comm.n_vals; i += blockDim.x) out[i] = 0.0;
+        __syncthreads();
         for (int sidx = 0; sidx < n_shards; ++sidx) {
             const OdeShard sh = shards[sidx];
+            // per-node parameters and result block (see csrc/ode.cu)
+            Dual th[NP];
+#pragma unroll
+            for (int k = 0; k < NP; ++k) {
+                th[k] = make_const(theta[sh.theta_offset + k]);
+                th[k].d[k] = 1.f;
+            }
+            double acc[1 + NP];
+#pragma unroll
+            for (int k = 0; k <= NP; ++k) acc[k] = 0.0;
             const float inv_var = 1.f / (sh.sigma * sh.sigma);
             const float log_norm = -__logf(sh.sigma) - 0.918938533204672742f;
             for (int i = blockIdx.x * blockDim.x + threadIdx.x; i < sh.n_series; i += gridDim.x * blockDim.x) {
@@ -170,12 +175,11 @@ __global__ void __launch_bounds__(128) fed_ode_generic_kernel(FedComm comm, cons
 #pragma unroll
                 for (int k = 0; k < NP; ++k) acc[1 + k] += (double)g[k];
             }
-        }
-        double* out = comm.cta_partials + (size_t)blockIdx.x * comm.n_vals;
 #pragma unroll
-        for (int k = 0; k <= NP; ++k) {
-            const double v = fed::block_sum(acc[k], red);
-            if (threadIdx.x == 0) out[k] = v;
+            for (int k = 0; k <= NP; ++k) {
+                const double v = fed::block_sum(acc[k], red);
+                if (threadIdx.x == 0) out[sh.out_offset + k] += v;
+            }
         }
     }
     fed::epilogue(comm, pro, 0ull);
@@ -184,7 +188,7 @@ __global__ void __launch_bounds__(128) fed_ode_generic_kernel(FedComm comm, cons
 }  // namespace odeg
 
 extern "C" int B200FED_ODE_ENTRY(const FedComm* comm, const OdeShard* shards_dev, int n_shards, int grid, cudaStream_t stream) {
-    if (comm->n_theta != odeg::NP || comm->n_vals != 1 + odeg::NP) return -1;
+    if (comm->n_theta % odeg::NP != 0 || comm->n_theta > odeg::kMaxTheta || comm->n_vals % (1 + odeg::NP) != 0) return -1;
     odeg::fed_ode_generic_kernel<<<grid, 128, 0, stream>>>(*comm, shards_dev, n_shards);
     return (int)cudaGetLastError();
 }

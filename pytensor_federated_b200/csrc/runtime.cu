@@ -38,7 +38,7 @@ int b200_launch_glm_tc(const FedComm*, const GlmSegment*, const GlmParams*, cons
                        int n_chunks, unsigned int* work_counter, int grid, cudaStream_t);
 int b200_glm_tc_prepare(const GlmSegment* segs_host, int n_segments, const GlmParams* prm, int sm_count, void** tmaps_dev,
                         void** chunks_dev, int* n_chunks);
-size_t b200_glm_tc_partial_row_doubles(int n_vals, int n_chains);
+size_t b200_glm_tc_partial_row_doubles(int n_vals, int n_chains, int n_out, int n_groups);
 int b200_launch_ode(const FedComm*, const OdeShard*, int, int, cudaStream_t);
 int b200_launch_glm_fp8(const FedComm*, const GlmSegment*, const GlmParams*, const void* tmaps, int grid, cudaStream_t);
 int b200_glm_fp8_prepare(const GlmSegment* segs_host, int n_segments, const GlmParams* prm, void** tmaps_dev);
@@ -472,7 +472,7 @@ int b200_engine_set_linreg(void* h, int n_shards, const void** x, const void** y
 
 int b200_engine_set_glm(void* h, int n_segments, const void** X, const float** y, const void** scales,
                         const long long* n_rows, const int* groups, int n_features, int ld, int n_groups,
-                        int n_chains, int family, int use_tensor_cores) {
+                        int n_chains, int family, int use_tensor_cores, const int* out_groups, int n_out) {
     Engine* e = static_cast<Engine*>(h);
     CK(cudaSetDevice(e->device));
     const int tile_rows = (use_tensor_cores == 1 || use_tensor_cores == 2) ? 128 : 8;
@@ -486,10 +486,23 @@ int b200_engine_set_glm(void* h, int n_segments, const void** X, const float** y
         g.n_rows = n_rows[s];
         g.first_tile = tiles;
         g.group = groups[s];
+        g.out_group = out_groups ? out_groups[s] : 0;
+        if (g.out_group < 0 || g.out_group >= (n_out > 0 ? n_out : 1)) {
+            g_last_error = "segment output block out of range";
+            return -31;
+        }
         e->glm_segs[s] = g;
         tiles += (n_rows[s] + tile_rows - 1) / tile_rows;
     }
-    e->glm = GlmParams{n_segments, n_features, ld, n_groups, n_chains, family, tiles};
+    e->glm = GlmParams{n_segments, n_features, ld, n_groups, n_chains, family, tiles, n_out > 0 ? n_out : 1, 0};
+    if (e->glm.n_out > 1 && use_tensor_cores != 1) {
+        g_last_error = "per-node outputs need the tensor-core GLM kernel (kernel='tc')";
+        return -32;
+    }
+    if ((long long)e->glm.n_out * n_chains * (1 + n_groups + n_features) != e->n_vals) {
+        g_last_error = "n_vals does not match n_out x n_chains x (1 + n_groups + n_features)";
+        return -33;
+    }
     if (e->glm_segs_dev) cudaFree(e->glm_segs_dev);
     CK(cudaMalloc((void**)&e->glm_segs_dev, sizeof(GlmSegment) * (n_segments > 0 ? n_segments : 1)));
     CK(cudaMemcpy(e->glm_segs_dev, e->glm_segs.data(), sizeof(GlmSegment) * n_segments, cudaMemcpyHostToDevice));
@@ -512,7 +525,7 @@ int b200_engine_set_glm(void* h, int n_segments, const void** X, const float** y
             g_last_error = "tensor-core GLM path rejected this shape (rc=" + std::to_string(rc) + ")";
             return rc;
         }
-        e->tc_row_doubles = b200_glm_tc_partial_row_doubles(e->n_vals, n_chains);
+        e->tc_row_doubles = b200_glm_tc_partial_row_doubles(e->n_vals, n_chains, e->glm.n_out, n_groups);
         if (e->tc_partials) cudaFree(e->tc_partials);
         const size_t tc_doubles = (size_t)e->sm_count * e->tc_row_doubles + ((size_t)e->sm_count / 16 + 2) * e->n_vals * 2;
         CK(cudaMalloc((void**)&e->tc_partials, tc_doubles * 8));
@@ -541,13 +554,15 @@ void b200_engine_set_ode_launcher(void* h, void* fn) {
 }
 
 int b200_engine_set_ode(void* h, int n_shards, const float** t, const float** y0, const float** y_obs, const int* n_series,
-                        const int* n_t, const float* sigma, const int* substeps) {
+                        const int* n_t, const float* sigma, const int* substeps, const int* theta_offset,
+                        const int* out_offset) {
     Engine* e = static_cast<Engine*>(h);
     CK(cudaSetDevice(e->device));
     e->ode.resize(n_shards);
     long long series = 0;
     for (int s = 0; s < n_shards; ++s) {
-        e->ode[s] = OdeShard{t[s], y0[s], y_obs[s], n_series[s], n_t[s], sigma[s], substeps[s]};
+        e->ode[s] = OdeShard{t[s], y0[s], y_obs[s], n_series[s], n_t[s], sigma[s], substeps[s],
+                             theta_offset ? theta_offset[s] : 0, out_offset ? out_offset[s] : 0};
         series += n_series[s];
     }
     if (e->ode_dev) cudaFree(e->ode_dev);

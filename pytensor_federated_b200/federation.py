@@ -29,45 +29,112 @@ from .parallel.engine import FederatedEngine, FederationError
 
 
 class NodeFederation:
-    """Per-node access to an engine whose model keeps per-shard results (``LinregShards``)."""
+    """Per-node access to an engine whose model keeps per-node results.
+
+    * ``LinregShards`` — node = shard; inputs ``(intercept, slope)``.
+    * ``OdeShards(..., node_ids=, n_nodes=)`` — node = the shards with that node id; input ``(theta,)``; every
+      node may be given its own parameter vector.
+    * ``GlmShards(..., node_ids=, n_nodes=)`` — node = the segments with that node id; inputs
+      ``(intercepts[G], beta[P])``.  Nodes that are given the same parameters (the usual federated GLM)
+      share a chain; *distinct* parameter vectors occupy one chain each, so the model must have been built
+      with ``n_chains >=`` the number of distinct vectors of a call.
+
+    Whatever the model, one call of :meth:`evaluate_nodes` is ONE fused launch per GPU.
+    """
 
     def __init__(self, engine: FederatedEngine) -> None:
-        if not isinstance(engine.model, LinregShards):
-            raise FederationError("NodeFederation needs a model with per-shard outputs (LinregShards)")
+        from .models.glm import GlmShards
+        from .models.ode import OdeShards
+
+        m = engine.model
+        if isinstance(m, LinregShards):
+            self._kind = "linreg"
+            self.n_nodes = m.n_shards_total
+            self._intercepts = np.zeros(self.n_nodes)
+            self._slopes = np.zeros(self.n_nodes)
+        elif isinstance(m, OdeShards) and m.node_ids is not None:
+            self._kind = "ode"
+            self.n_nodes = m.n_nodes
+            self._theta = np.zeros((m.n_nodes, m.n_params))
+        elif isinstance(m, GlmShards) and m.node_ids is not None:
+            self._kind = "glm"
+            self.n_nodes = m.n_nodes
+        else:
+            raise FederationError(
+                "NodeFederation needs a model that keeps per-node results: LinregShards, or OdeShards / GlmShards "
+                "built with node_ids= and n_nodes="
+            )
         self.engine = engine
-        self.n_nodes = engine.model.n_shards_total
-        self._intercepts = np.zeros(self.n_nodes)
-        self._slopes = np.zeros(self.n_nodes)
         self._lock = threading.Lock()   # parameter staging + launch + un-staging of the result form one unit
         self.n_launches = 0
 
     # -- evaluation ----------------------------------------------------------------------------
     def evaluate_nodes(self, requests: Dict[int, Sequence[np.ndarray]]) -> Dict[int, Tuple[np.ndarray, List[np.ndarray]]]:
-        """``{node: (intercept, slope)} -> {node: (logp, [d_intercept, d_slope])}``, one launch."""
+        """``{node: inputs} -> {node: (logp, [gradients])}``, one launch."""
+        for node in requests:
+            if not 0 <= int(node) < self.n_nodes:
+                raise FederationError(f"node {node} does not exist (the federation has {self.n_nodes})")
         with self._lock:
-            for node, (a, b) in requests.items():
-                self._intercepts[node] = float(np.asarray(a))
-                self._slopes[node] = float(np.asarray(b))
-            raw = self.engine.evaluate_raw([self._intercepts, self._slopes])
             self.n_launches += 1
-            per = LinregShards.per_shard(raw)
-            return {
-                node: (np.array(per[node, 0]), [np.array(per[node, 1]), np.array(per[node, 2])])
-                for node in requests
-            }
+            return getattr(self, f"_evaluate_{self._kind}")(requests)
 
-    def evaluate_node(self, node: int, intercept, slope) -> Tuple[np.ndarray, List[np.ndarray]]:
-        return self.evaluate_nodes({node: (intercept, slope)})[node]
+    def _evaluate_linreg(self, requests):
+        for node, (a, b) in requests.items():
+            self._intercepts[node] = float(np.asarray(a))
+            self._slopes[node] = float(np.asarray(b))
+        per = LinregShards.per_shard(self.engine.evaluate_raw([self._intercepts, self._slopes]))
+        return {node: (np.array(per[node, 0]), [np.array(per[node, 1]), np.array(per[node, 2])]) for node in requests}
+
+    def _evaluate_ode(self, requests):
+        m = self.engine.model
+        for node, inputs in requests.items():
+            (theta,) = inputs
+            self._theta[node] = np.asarray(theta, dtype=np.float64).reshape(m.n_params)
+        per = m.per_node(self.engine.evaluate_raw([self._theta]))
+        return {node: (np.array(per[node, 0]), [per[node, 1:].copy()]) for node in requests}
+
+    def _evaluate_glm(self, requests):
+        m = self.engine.model
+        G, K = m.n_groups, m.n_chains
+        chains: Dict[bytes, int] = {}      # distinct parameter vector -> chain
+        rows: List[np.ndarray] = []
+        chain_of: Dict[int, int] = {}
+        shapes: Dict[int, tuple] = {}
+        for node, (intercept, beta) in requests.items():
+            ic = np.asarray(intercept, dtype=np.float32)
+            vec = np.concatenate([ic.reshape(G), np.asarray(beta, dtype=np.float32).reshape(m.n_features)])
+            key = vec.tobytes()
+            if key not in chains:
+                if len(rows) == K:
+                    raise FederationError(
+                        f"{len(rows) + 1} distinct parameter vectors in one call but the model evaluates {K} chain(s) per "
+                        "launch: build GlmShards with n_chains >= the number of nodes that get their own parameters"
+                    )
+                chains[key] = len(rows)
+                rows.append(vec)
+            chain_of[node] = chains[key]
+            shapes[node] = ic.shape
+        theta = np.stack(rows + [rows[0]] * (K - len(rows)))                       # unused chains repeat the first
+        inputs = [theta[:, :G], theta[:, G:]] if K > 1 else [theta[0, :G], theta[0, G:]]
+        per = m.per_node(self.engine.evaluate_raw(inputs))                         # [n_nodes, K, 1 + G + P]
+        out = {}
+        for node in requests:
+            v = per[node, chain_of[node]]
+            out[node] = (np.array(v[0]), [v[1 : 1 + G].reshape(shapes[node]).copy(), v[1 + G :].copy()])
+        return out
+
+    def evaluate_node(self, node: int, *inputs) -> Tuple[np.ndarray, List[np.ndarray]]:
+        return self.evaluate_nodes({node: inputs})[node]
 
     def logp_grad_func(self, node: int) -> Callable:
         """The node as a plain ``LogpGradFunc`` (usable with the generic ``LogpGradOp``)."""
-        return lambda intercept, slope: self.evaluate_node(node, intercept, slope)
+        return lambda *inputs: self.evaluate_node(node, *inputs)
 
     def compute_func(self, node: int) -> Callable:
-        """The node as a ``ComputeFunc``: ``(logp, d_intercept, d_slope)``."""
+        """The node as a ``ComputeFunc``: ``(logp, *gradients)``."""
 
-        def compute(intercept, slope):
-            logp, grads = self.evaluate_node(node, intercept, slope)
+        def compute(*inputs):
+            logp, grads = self.evaluate_node(node, *inputs)
             return (logp, *grads)
 
         return compute

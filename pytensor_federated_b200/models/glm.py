@@ -39,6 +39,12 @@ class GlmShards(ShardModel):
         Parameter vectors evaluated per call (K).  ``K > 1`` needs the tensor-core kernel.
     kernel
         ``"simt"`` (one chain, any P % 8 == 0 up to 512), ``"tc"`` (tcgen05 + TMA) or ``"auto"``.
+    node_ids, n_nodes
+        Keep the result PER NODE instead of summed: segment ``s`` is (part of) node ``node_ids[s]`` of
+        an ``n_nodes`` federation and the reduced vector holds one ``[K][1 + G + P]`` block per node
+        (tensor-core kernel only).  ``evaluate`` still returns the sum; :meth:`per_node` and
+        :class:`~pytensor_federated_b200.federation.NodeFederation` expose the blocks — the reference's
+        one-Op-per-node pattern (``/root/reference/demo_model.py:28-36``) answered by one launch.
     """
 
     def __init__(
@@ -52,6 +58,8 @@ class GlmShards(ShardModel):
         n_chains: int = 1,
         kernel: str = "auto",
         scales: Optional[Sequence] = None,
+        node_ids: Optional[Sequence[int]] = None,
+        n_nodes: Optional[int] = None,
     ) -> None:
         import torch
 
@@ -75,7 +83,13 @@ class GlmShards(ShardModel):
         self.n_inputs = 2
         self.n_params = self.n_groups + self.n_features
         self.n_theta_words = self.n_chains * self.n_params
-        self.n_vals = self.n_chains * (1 + self.n_params)
+        if (node_ids is None) != (n_nodes is None):
+            raise ValueError("node_ids and n_nodes come together")
+        self.node_ids = list(node_ids) if node_ids is not None else None
+        self.n_nodes = int(n_nodes) if n_nodes is not None else 1
+        if self.node_ids is not None and (len(self.node_ids) != len(self.Xs) or not all(0 <= i < self.n_nodes for i in self.node_ids)):
+            raise ValueError("node_ids needs one node index in [0, n_nodes) per segment")
+        self.n_vals = self.n_nodes * self.n_chains * (1 + self.n_params)
 
     @property
     def n_rows(self) -> int:
@@ -107,8 +121,12 @@ class GlmShards(ShardModel):
         self._batched, self._icpt_shape = ctx
         return ctx
 
+    def per_node(self, vals: np.ndarray) -> np.ndarray:
+        """The reduced vector as ``[n_nodes, n_chains, 1 + G + P]`` (``[LL, d intercepts, d beta]`` per block)."""
+        return np.asarray(vals, dtype=np.float64).reshape(self.n_nodes, self.n_chains, 1 + self.n_params)
+
     def unpack_result(self, vals: np.ndarray, ctx=None) -> List[np.ndarray]:
-        v = np.asarray(vals, dtype=np.float64).reshape(self.n_chains, 1 + self.n_params)
+        v = self.per_node(vals).sum(axis=0) if self.n_nodes > 1 else np.asarray(vals, dtype=np.float64).reshape(self.n_chains, 1 + self.n_params)
         G = self.n_groups
         batched, icpt_shape = ctx if ctx is not None else (self._batched, self._icpt_shape)
         if batched:
@@ -166,10 +184,11 @@ class GlmShards(ShardModel):
         sp = native.void_p_array([s.data_ptr() for s in kernel_scales]) if kernel_scales else None
         rows = (C.c_longlong * n)(*[X.shape[0] for X in self.Xs])
         grp = (C.c_int * n)(*self.groups)
+        out_grp = (C.c_int * n)(*self.node_ids) if self.node_ids is not None else None
         native.check(
             lib.b200_engine_set_glm(
                 handle, n, Xp, yp, sp, rows, grp, self.n_features, self.ld, self.n_groups,
-                self.n_chains, _family_code(self.family), int(self.use_tensor_cores()),
+                self.n_chains, _family_code(self.family), int(self.use_tensor_cores()), out_grp, self.n_nodes,
             ),
             "set_glm",
         )
@@ -188,9 +207,10 @@ class GlmShards(ShardModel):
         self._note_shapes(inputs)
         ic = torch.as_tensor(np.asarray(intercept, dtype=np.float64)).reshape(self.n_chains, -1)
         bt = torch.as_tensor(np.asarray(beta, dtype=np.float64)).reshape(self.n_chains, self.n_features)
-        out = torch.zeros(self.n_chains, 1 + self.n_params, dtype=torch.float64, device=self.device)
+        full = torch.zeros(self.n_nodes, self.n_chains, 1 + self.n_params, dtype=torch.float64, device=self.device)
         B = bt.to(self.device, dtype)                              # [K, P]
         for si, (X, y, g) in enumerate(zip(self.Xs, self.ys, self.groups)):
+            out = full[self.node_ids[si] if self.node_ids is not None else 0]
             icg = ic[:, g].to(self.device, dtype)
             for r0 in range(0, X.shape[0], chunk_rows):
                 r1 = min(X.shape[0], r0 + chunk_rows)
@@ -215,7 +235,7 @@ class GlmShards(ShardModel):
                 out[:, 0] += ll.double().sum(0)
                 out[:, 1 + g] += r.double().sum(0)
                 out[:, 1 + self.n_groups :] += (r.T @ Xf).double()
-        return out.reshape(-1).cpu().numpy()
+        return full.reshape(-1).cpu().numpy()
 
     def _dequant_rows(self, seg: int, r0: int, r1: int):
         """Rows ``[r0, r1)`` of segment ``seg`` as stored values (dense kernels: the matrix itself)."""

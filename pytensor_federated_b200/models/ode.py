@@ -111,9 +111,17 @@ class OdeShards(ShardModel):
     workload in prose (``/root/reference/README.md:39-52``)."""
 
     def __init__(self, ts: Sequence, y0s: Sequence, y_obs: Sequence, sigmas: Sequence[float], substeps: int = 8,
-                 system: Optional[OdeSystem] = None):
+                 system: Optional[OdeSystem] = None, node_ids: Optional[Sequence[int]] = None,
+                 n_nodes: Optional[int] = None):
+        """``node_ids`` / ``n_nodes``: shard ``s`` is node ``node_ids[s]`` of an ``n_nodes`` federation; theta then
+        holds one parameter vector PER NODE (a single vector is broadcast) and the result one
+        ``[LL, dLL/dtheta]`` block per node — what ``NodeFederation`` needs to give every node its own Op."""
         import torch
 
+        if (node_ids is None) != (n_nodes is None):
+            raise ValueError("node_ids and n_nodes come together")
+        self.node_ids = list(node_ids) if node_ids is not None else None
+        self.n_nodes = int(n_nodes) if n_nodes is not None else 1
         self.system = system
         self.n_states = system.n_states if system is not None else 2
         self.n_params = system.n_params if system is not None else 4
@@ -126,21 +134,38 @@ class OdeShards(ShardModel):
         self.sigmas = [float(s) for s in sigmas]
         self.substeps = int(substeps)
         self.device = self.ts[0].device
+        if self.node_ids is not None and (len(self.node_ids) != len(self.ts) or not all(0 <= i < self.n_nodes for i in self.node_ids)):
+            raise ValueError("node_ids needs one node index in [0, n_nodes) per shard")
+        if self.n_nodes * self.n_params > 1024:
+            raise ValueError("theta of all nodes must fit 1024 floats")
         self.n_inputs = 1
-        self.n_theta_words = self.n_params
-        self.n_vals = 1 + self.n_params
+        self.n_theta_words = self.n_nodes * self.n_params
+        self.n_vals = self.n_nodes * (1 + self.n_params)
+
+    def call_context(self, inputs):
+        (theta,) = inputs
+        return np.ndim(theta) == 2        # one parameter vector per node?
 
     def pack_theta(self, inputs, out: np.ndarray):
         (theta,) = inputs
-        out.view(np.float32)[: self.n_params] = np.asarray(theta, dtype=np.float32).reshape(self.n_params)
-        return None
+        th = np.asarray(theta, dtype=np.float32)
+        rows = out.view(np.float32)[: self.n_nodes * self.n_params].reshape(self.n_nodes, self.n_params)
+        rows[:] = th.reshape(-1, self.n_params)    # [n_nodes, NP], or one vector broadcast to every node
+        return th.ndim == 2
+
+    def per_node(self, vals: np.ndarray) -> np.ndarray:
+        """The reduced vector as ``[n_nodes, 1 + n_params]`` (``[LL, dLL/dtheta]`` per node)."""
+        return np.asarray(vals, dtype=np.float64).reshape(self.n_nodes, 1 + self.n_params)
 
     def unpack_result(self, vals: np.ndarray, ctx=None) -> List[np.ndarray]:
-        v = np.asarray(vals, dtype=np.float64)
-        return [np.asarray(v[0]), v[1 : 1 + self.n_params].copy()]
+        v = self.per_node(vals)
+        if ctx:   # per-node parameters in, per-node gradients out
+            return [np.asarray(v[:, 0].sum()), v[:, 1:].copy()]
+        return [np.asarray(v[:, 0].sum()), v[:, 1:].sum(axis=0)]
 
     def inputs_from_words(self, words: np.ndarray):
-        return (words.view(np.float32)[: self.n_params].copy(),)
+        rows = words.view(np.float32)[: self.n_nodes * self.n_params].reshape(self.n_nodes, self.n_params).copy()
+        return (rows,)
 
     def attach(self, lib, handle) -> None:
         from ..ops import native
@@ -156,17 +181,30 @@ class OdeShards(ShardModel):
                 (C.c_int * n)(*[t.numel() for t in self.ts]),
                 (C.c_float * n)(*self.sigmas),
                 (C.c_int * n)(*([self.substeps] * n)),
+                (C.c_int * n)(*[self._node(s) * self.n_params for s in range(n)]),
+                (C.c_int * n)(*[self._node(s) * (1 + self.n_params) for s in range(n)]),
             ),
             "set_ode",
         )
         if self.system is not None:
             lib.b200_engine_set_ode_launcher(handle, C.c_void_p(self.system.launcher_address()))
 
+    def _node(self, s: int) -> int:
+        return self.node_ids[s] if self.node_ids is not None else 0
+
     # -- eager oracle: same RK4 discretisation, autograd for the gradient, float64 -----------
     def reference_partial(self, inputs) -> np.ndarray:
+        """``[n_nodes, 1 + n_params]`` flattened: every local shard evaluated at its node's parameters."""
+        (theta,) = inputs
+        rows = np.broadcast_to(np.asarray(theta, dtype=np.float64).reshape(-1, self.n_params), (self.n_nodes, self.n_params))
+        out = np.zeros((self.n_nodes, 1 + self.n_params))
+        for s in range(len(self.ts)):
+            out[self._node(s)] += self._shard_partial(s, rows[self._node(s)])
+        return out.reshape(-1)
+
+    def _shard_partial(self, s: int, theta) -> np.ndarray:
         import torch
 
-        (theta,) = inputs
         th = torch.tensor(np.asarray(theta, dtype=np.float64).reshape(self.n_params), device=self.device, requires_grad=True)
         if self.system is None:
             f = lambda y, t: lv_rhs(y[0], y[1], th)
@@ -175,7 +213,7 @@ class OdeShards(ShardModel):
                 raise ValueError("this OdeSystem has no rhs_torch oracle")
             f = lambda y, t: self.system.rhs_torch(y, th, t)
         total = torch.zeros((), dtype=torch.float64, device=self.device)
-        for t, y0, yo, sigma in zip(self.ts, self.y0s, self.y_obs, self.sigmas):
+        for t, y0, yo, sigma in [(self.ts[s], self.y0s[s], self.y_obs[s], self.sigmas[s])]:
             y = [y0[c].double() for c in range(self.n_states)]
             t_prev = 0.0
             for j in range(t.numel()):

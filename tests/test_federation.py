@@ -100,3 +100,94 @@ def test_launch_federation_spawns_peer_nodes():
         np.testing.assert_allclose(per[rank][0], lp, rtol=1e-12)
         want += lp
     np.testing.assert_allclose(logp, want, rtol=1e-12)
+
+
+def _glm_nodes(n_chains=1, n_nodes=3):
+    import torch
+
+    from pytensor_federated_b200.models import GlmShards
+
+    torch.manual_seed(4)
+    Xs = [torch.randn(150 + 20 * i, 8).to(torch.bfloat16) for i in range(n_nodes)]
+    ys = [(torch.rand(X.shape[0]) < 0.45).float() for X in Xs]
+    per_node = GlmShards(Xs, ys, groups=[0, 1, 0][:n_nodes], n_groups=2, n_chains=n_chains, node_ids=list(range(n_nodes)),
+                         n_nodes=n_nodes, kernel="tc")
+    return Xs, ys, per_node
+
+
+def test_glm_nodes_keep_their_own_outputs_and_parameters():
+    """One Op per GLM node (reference pattern) on a model that keeps per-node output blocks: shared parameters
+    use one chain, distinct parameters one chain each, all in one launch."""
+    from pytensor_federated_b200.models import GlmShards
+    from pytensor_federated_b200.parallel import FederationError
+
+    Xs, ys, model = _glm_nodes(n_chains=3)
+    fed = NodeFederation(FederatedEngine(model, backend="collective"))
+    assert fed.n_nodes == 3
+    rng = np.random.default_rng(0)
+    ic, beta = rng.normal(size=2) * 0.2, rng.normal(size=8) * 0.3
+    # (1) every node at the same parameters == the node's own single-shard model; their sum == the pooled model
+    res = fed.evaluate_nodes({i: (ic, beta) for i in range(3)})
+    assert fed.n_launches == 1
+    total = 0.0
+    for i in range(3):
+        single = FederatedEngine(GlmShards([Xs[i]], [ys[i]], groups=[[0, 1, 0][i]], n_groups=2, kernel="simt"), backend="collective")
+        want = single.logp_grad(ic, beta)
+        np.testing.assert_allclose(res[i][0], want[0], rtol=2e-6)
+        np.testing.assert_allclose(res[i][1][0], want[1][0], rtol=2e-5, atol=1e-4)
+        np.testing.assert_allclose(res[i][1][1], want[1][1], rtol=2e-5, atol=1e-4)
+        total += float(want[0])
+    pooled = FederatedEngine(GlmShards(Xs, ys, groups=[0, 1, 0], n_groups=2, kernel="simt"), backend="collective")
+    np.testing.assert_allclose(pooled.evaluate(ic, beta)[0], total, rtol=2e-6)
+    # (2) three different parameter vectors -> three chains, still one launch
+    betas = [beta, beta * 0.5, -beta]
+    res = fed.evaluate_nodes({i: (ic, betas[i]) for i in range(3)})
+    assert fed.n_launches == 2
+    for i in range(3):
+        single = FederatedEngine(GlmShards([Xs[i]], [ys[i]], groups=[[0, 1, 0][i]], n_groups=2, kernel="simt"), backend="collective")
+        np.testing.assert_allclose(res[i][0], single.logp_grad(ic, betas[i])[0], rtol=2e-6)
+    # (3) more distinct vectors than chains is an error, not a silent re-launch
+    _, _, small = _glm_nodes(n_chains=1)
+    fed1 = NodeFederation(FederatedEngine(small, backend="collective"))
+    with pytest.raises(FederationError, match="n_chains"):
+        fed1.evaluate_nodes({0: (ic, beta), 1: (ic, beta * 2)})
+    with pytest.raises(FederationError, match="does not exist"):
+        fed1.evaluate_node(7, ic, beta)
+    # a model without per-node blocks cannot be viewed per node
+    with pytest.raises(FederationError, match="node_ids"):
+        NodeFederation(pooled)
+
+
+def test_ode_nodes_take_their_own_parameters_through_federated_ops():
+    from pytensor_federated_b200.models import OdeShards, synth_lv_shard
+
+    shards = [synth_lv_shard(12, 5, seed=s, device="cpu") for s in range(2)]
+    args = lambda idx: ([shards[i][0] for i in idx], [shards[i][1] for i in idx], [shards[i][2] for i in idx], [shards[i][3] for i in idx])
+    model = OdeShards(*args([0, 1]), node_ids=[0, 1], n_nodes=2)
+    assert model.n_theta_words == 8 and model.n_vals == 10
+    eng = FederatedEngine(model, backend="collective")
+    th0, th1 = np.array([1.0, 0.4, 0.8, 0.2]), np.array([0.9, 0.45, 0.75, 0.25])
+    # the ComputeFunc view: one vector for everybody -> summed gradient; one row per node -> per-node gradients
+    logp, grad_sum = eng.evaluate(th0)
+    logp2, grad_rows = eng.evaluate(np.stack([th0, th0]))
+    np.testing.assert_allclose(logp, logp2, rtol=1e-12)
+    np.testing.assert_allclose(grad_rows.sum(0), grad_sum, rtol=1e-10)
+    # node view with different parameters per node
+    fed = NodeFederation(eng)
+    res = fed.evaluate_nodes({0: (th0,), 1: (th1,)})
+    for i, th in enumerate((th0, th1)):
+        single = FederatedEngine(OdeShards(*args([i])), backend="collective")
+        want = single.logp_grad(th)
+        np.testing.assert_allclose(res[i][0], want[0], rtol=1e-10)
+        np.testing.assert_allclose(res[i][1][0], want[1][0], rtol=1e-9)
+    # federated Ops: log-potentials of both nodes in one graph, gradients w.r.t. both parameter vectors
+    ops = fed.node_ops()
+    a, b = at.vector("theta_a"), at.vector("theta_b")
+    total = ops[0](a)[0] + ops[1](b)[0]
+    fn = function([a, b], [total, *grad(total, [a, b])])
+    fed.n_launches = 0
+    val, ga, gb = fn(th0, th1)
+    assert fed.n_launches == 1
+    np.testing.assert_allclose(val, float(res[0][0]) + float(res[1][0]), rtol=1e-12)
+    np.testing.assert_allclose(ga, res[0][1][0], rtol=1e-12)
+    np.testing.assert_allclose(gb, res[1][1][0], rtol=1e-12)

@@ -373,3 +373,54 @@ def test_device_timer_trace_orders_the_phases(dev):
         t_theta, t_partial, t_result = eng.trace(5)
         assert 0 < t_theta <= t_partial <= t_result
         assert (t_result - t_theta) < 5_000_000  # the whole fused evaluation is far below 5 ms
+
+
+@pytest.mark.parametrize("K", [1, 4])
+def test_glm_tc_keeps_per_node_output_blocks(dev, K):
+    """GlmShards(node_ids=...): one [K][1+G+P] block per node from ONE launch; the blocks equal the nodes'
+    own models and add up to the pooled evaluation bit for bit across repeats."""
+    from pytensor_federated_b200.federation import NodeFederation
+
+    torch.manual_seed(21)
+    rows = [20_000, 128 * 33, 7777, 15_000]
+    node_ids = [0, 1, 1, 2]           # node 1 owns two segments
+    Xs = [torch.randn(n, 256, device=dev).to(torch.bfloat16) for n in rows]
+    ys = [(torch.rand(n, device=dev) < 0.5).float() for n in rows]
+    groups = [0, 1, 1, 0]
+    model = GlmShards(Xs, ys, groups=groups, n_groups=2, n_chains=K, kernel="tc", node_ids=node_ids, n_nodes=3)
+    rng = np.random.default_rng(3)
+    ic = rng.normal(size=(K, 2) if K > 1 else 2) * 0.1
+    beta = (rng.normal(size=(K, 256) if K > 1 else 256) * 0.03).astype(np.float32)
+    with FederatedEngine(model) as eng:
+        raw = eng.evaluate_raw([ic, beta])
+        again = eng.evaluate_raw([ic, beta])
+        assert np.array_equal(raw, again)
+        blocks = model.per_node(raw)
+        want = model.per_node(model.reference_partial([ic, beta], dtype=torch.float64))
+        for n in range(3):
+            np.testing.assert_allclose(blocks[n, :, 0], want[n, :, 0], rtol=2e-5)
+            np.testing.assert_allclose(blocks[n, :, 1:3], want[n, :, 1:3], rtol=1e-4, atol=2e-3)
+            np.testing.assert_allclose(blocks[n, :, 3:], want[n, :, 3:], rtol=1e-4, atol=0.5)
+        assert np.all(blocks[0, :, 2] == 0) and np.all(blocks[1, :, 1] == 0)   # a node only touches its own intercept
+        summed = eng.evaluate(ic, beta)
+        np.testing.assert_allclose(summed[0], want[:, :, 0].sum(0).reshape(np.shape(summed[0])), rtol=2e-5)
+        if K == 1:
+            fed = NodeFederation(eng)
+            res = fed.evaluate_nodes({1: (ic, beta), 2: (ic, beta)})
+            np.testing.assert_allclose(res[1][0], blocks[1, 0, 0], rtol=1e-12)
+            np.testing.assert_allclose(res[2][1][1], blocks[2, 0, 3:], rtol=1e-12)
+
+
+def test_ode_nodes_with_their_own_parameters_on_the_gpu(dev):
+    shards = [synth_lv_shard(200, 10, seed=s, device=dev) for s in range(3)]
+    model = OdeShards([s[0] for s in shards], [s[1] for s in shards], [s[2] for s in shards], [s[3] for s in shards],
+                      node_ids=[0, 1, 2], n_nodes=3)
+    th = np.array([[0.95, 0.42, 0.78, 0.21], [1.0, 0.4, 0.8, 0.2], [1.05, 0.38, 0.82, 0.19]])
+    with FederatedEngine(model) as eng:
+        logp, grads = eng.evaluate(th)
+        assert grads.shape == (3, 4)
+        blocks = model.per_node(eng.evaluate_raw([th]))
+    want = model.per_node(model.reference_partial([th.astype(np.float32).astype(np.float64)]))
+    np.testing.assert_allclose(blocks[:, 0], want[:, 0], rtol=2e-4)
+    np.testing.assert_allclose(blocks[:, 1:], want[:, 1:], rtol=5e-3, atol=1.0)
+    np.testing.assert_allclose(logp, want[:, 0].sum(), rtol=2e-4)
