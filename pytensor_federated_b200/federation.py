@@ -168,6 +168,25 @@ class NodeFederation:
         self.engine.shutdown()
 
 
+def register_replicas(engines: Sequence[FederatedEngine], host: str = "gpu", first_port: int = 0) -> List[Tuple[str, int]]:
+    """Replicated-shard mode: every engine holds a REPLICA of the same data (typically one per GPU); they are
+    registered as in-process nodes ``(host, first_port + i)`` and the returned address list goes to
+    ``ArraysToArraysServiceClient(hosts_and_ports=...)`` / ``LogpGradServiceClient(hosts_and_ports=...)``.
+
+    The client then behaves as it does towards replicated gRPC servers in the reference
+    (``/root/reference/pytensor_federated/service.py:239-275``, ``:407-416``): it connects to the replica with
+    the fewest clients (chains of a sampler spread over the GPUs), and when a replica is lost — its engine shut
+    down or timed out — the call is retried on a surviving one.  A *sharded* federation cannot do that (a lost
+    shard is lost data); replicas trade HBM for availability and for chain-level parallelism."""
+    from . import service
+
+    addresses = []
+    for i, eng in enumerate(engines):
+        service.register_local_node(host, first_port + i, eng.evaluate, name=f"{host}:{first_port + i}")
+        addresses.append((host, first_port + i))
+    return addresses
+
+
 def free_port() -> int:
     """An unused TCP port on 127.0.0.1 (rendezvous of a freshly launched federation)."""
     with socket.socket() as s:
@@ -249,4 +268,4 @@ def launch_federation(build_model: Callable, n_nodes: int, *, device_type: Optio
                 p.terminate()
 
 
-__all__ = ["NodeFederation", "launch_federation", "free_port"]
+__all__ = ["NodeFederation", "launch_federation", "register_replicas", "free_port"]

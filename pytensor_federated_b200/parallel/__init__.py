@@ -1,4 +1,4 @@
 """Multi-GPU execution: the fused NVLink engine and the collective (NCCL/gloo) baseline."""
-from .engine import FederatedEngine, FederationError, FederationTimeout
+from .engine import EngineClosedError, FederatedEngine, FederationError, FederationTimeout
 
-__all__ = ["FederatedEngine", "FederationError", "FederationTimeout"]
+__all__ = ["FederatedEngine", "FederationError", "FederationTimeout", "EngineClosedError"]

@@ -38,8 +38,17 @@ class FederationError(RuntimeError):
     """The engine was misused or the native runtime reported a failure (message carries the native error)."""
 
 
+class EngineClosedError(FederationError):
+    """The engine was shut down.  A client that reaches it through the local node registry treats this like a
+    lost connection and fails over to another replica."""
+
+    marks_node_lost = True
+
+
 class FederationTimeout(TimeoutError):
     """A node did not answer within the engine timeout (dead peer / lost shard)."""
+
+    marks_node_lost = True
 
 
 def _dist():
@@ -224,7 +233,7 @@ class FederatedEngine:
         is the engine's shared ``float64[n_vals]`` buffer (valid until the lock is released) and
         ``ctx`` the model's per-call context for ``unpack_result``."""
         if self._closed:
-            raise FederationError("engine is shut down")
+            raise EngineClosedError("engine is shut down")
         if not self.is_root:
             raise FederationError("only rank 0 evaluates; other ranks call serve()")
         self.n_evals += 1

@@ -662,7 +662,10 @@ class ArraysToArraysServiceClient:
         # Fast path: a cached in-process node needs no event loop at all.
         priv = _privates.get(thread_pid_id(self))
         if priv is not None and priv.local is not None and priv.local.alive:
-            return _evaluate_local(priv.local, inputs)
+            try:
+                return _evaluate_local(priv.local, inputs)
+            except StreamTerminatedError:
+                pass  # the node died under this call: the general path below reconnects (to another replica)
         loop = get_useful_event_loop()
         return loop.run_until_complete(self.evaluate_async(*inputs, **kwargs))
 
@@ -757,9 +760,18 @@ async def _bounded(coro, timeout: float):
 
 
 def _evaluate_local(node: LocalNode, inputs) -> List[np.ndarray]:
-    outputs = node.compute_func(*[np.asarray(i) for i in inputs])
-    if asyncio.iscoroutine(outputs):  # coroutine compute functions (e.g. a DynamicBatcher) work in-process too
-        outputs = get_useful_event_loop().run_until_complete(outputs)
+    try:
+        outputs = node.compute_func(*[np.asarray(i) for i in inputs])
+        if asyncio.iscoroutine(outputs):  # coroutine compute functions (e.g. a DynamicBatcher) work in-process too
+            outputs = get_useful_event_loop().run_until_complete(outputs)
+    except Exception as ex:
+        # An in-process node whose engine is gone (GPU lost, peer timed out, engine shut down) is the local
+        # counterpart of a dropped connection: the node is marked dead and the client's retry loop fails over to
+        # another replica (reference semantics: service.py:407-416).  Exceptions opt in with `marks_node_lost`.
+        if getattr(ex, "marks_node_lost", False):
+            node.alive = False
+            raise StreamTerminatedError(f"In-process node {node.name} is gone: {ex}") from ex
+        raise
     return [np.asarray(o) for o in outputs]
 
 

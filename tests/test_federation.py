@@ -191,3 +191,38 @@ def test_ode_nodes_take_their_own_parameters_through_federated_ops():
     np.testing.assert_allclose(val, float(res[0][0]) + float(res[1][0]), rtol=1e-12)
     np.testing.assert_allclose(ga, res[0][1][0], rtol=1e-12)
     np.testing.assert_allclose(gb, res[1][1][0], rtol=1e-12)
+
+
+def test_replicated_gpu_nodes_balance_and_fail_over():
+    """Replicated-shard mode: two engines hold the same data; clients spread over them by load and a lost
+    replica is replaced transparently (reference semantics: service.py:239-275, :407-416)."""
+    from pytensor_federated_b200 import service
+    from pytensor_federated_b200.federation import register_replicas
+
+    x, y, sigma = make_demo_data()
+    engines = [FederatedEngine(LinregShards([x], [y], [sigma]), backend="collective") for _ in range(2)]
+    addresses = register_replicas(engines, host="replica", first_port=10)
+    try:
+        c1 = LogpGradServiceClient(hosts_and_ports=addresses)
+        c2 = LogpGradServiceClient(hosts_and_ports=addresses)
+        want = engines[0].logp_grad(np.array(0.4), np.array(1.2))
+        for c in (c1, c2):
+            logp, grads = c.evaluate(np.array(0.4), np.array(1.2))
+            np.testing.assert_allclose(logp, want[0], rtol=1e-12)
+        ports = sorted(int(service._privates[service.thread_pid_id(c._client)].channel._port) for c in (c1, c2))
+        assert ports == [10, 11]                          # the second client went to the idle replica
+        # lose the replica c1 is connected to: its next call lands on the survivor, same answer
+        lost = int(service._privates[service.thread_pid_id(c1._client)].channel._port) - 10
+        engines[lost].shutdown()
+        logp, grads = c1.evaluate(np.array(0.4), np.array(1.2))
+        np.testing.assert_allclose(logp, want[0], rtol=1e-12)
+        np.testing.assert_allclose(grads, want[1], rtol=1e-12)
+        assert int(service._privates[service.thread_pid_id(c1._client)].channel._port) - 10 == 1 - lost
+        # both gone: a connection-level error, like a fleet of dead servers
+        engines[1 - lost].shutdown()
+        with pytest.raises((service.StreamTerminatedError, TimeoutError)):
+            c1.evaluate(np.array(0.4), np.array(1.2), retries=1)
+        del c1, c2
+    finally:
+        for host, port in addresses:
+            service.unregister_local_node(host, port)
