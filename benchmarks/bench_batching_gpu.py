@@ -55,25 +55,29 @@ def serve_in_thread(compute):
     ready = threading.Event()
     state = {}
 
+    async def node():
+        server = Server([ArraysToArraysService(compute)], tls=False)
+        state["port"] = await server.start("127.0.0.1", 0)
+        state["stop"] = asyncio.Event()
+        ready.set()
+        await state["stop"].wait()
+        if hasattr(compute, "close"):   # the batcher's worker task lives on this loop
+            await compute.close()
+        await server.close(1.0)
+
     def run():
         loop = asyncio.new_event_loop()
         asyncio.set_event_loop(loop)
-        server = Server([ArraysToArraysService(compute)], tls=False)
-        state["port"] = loop.run_until_complete(server.start("127.0.0.1", 0))
-        state["loop"], state["server"] = loop, server
-        ready.set()
-        loop.run_until_complete(server.wait_closed())
+        state["loop"] = loop
+        loop.run_until_complete(node())
 
     thread = threading.Thread(target=run, daemon=True)
     thread.start()
     ready.wait(60)
 
     def stop():
-        if hasattr(compute, "close"):   # the batcher's worker task lives on the server's loop
-            asyncio.run_coroutine_threadsafe(compute.close(), state["loop"]).result(30)
-        fut = asyncio.run_coroutine_threadsafe(state["server"].close(None), state["loop"])
-        fut.result(30)
-        thread.join(10)
+        state["loop"].call_soon_threadsafe(state["stop"].set)
+        thread.join(30)
 
     return state["port"], stop
 

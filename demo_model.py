@@ -8,8 +8,9 @@ Three ways to reach the nodes:
 
 * ``--host/--ports`` (default): gRPC to ``demo_node.py`` workers — the reference's topology; with
   ``--parallel true`` the async Ops are fused into one concurrent fan-out.
-* ``--fused N``: the nodes are N data shards resident on this machine's GPUs (CPU when none);
-  the fused graph node answers all N remote calls with ONE kernel launch per GPU.
+* ``--fused N``: the nodes are N data shards resident on this machine's GPUs (CPU when none), spread over
+  ``--gpus M`` of them (default: all visible, at most N; one process per GPU is started for you); the fused
+  graph node answers all N remote calls with ONE kernel launch per GPU.
 * PyMC available: pass ``--pymc`` to sample with ``pm.sample`` instead of the in-repo NUTS.
 """
 import argparse
@@ -88,17 +89,37 @@ def remote_ops_grpc(host: str, ports: Sequence[int], n: int, use_async: bool):
     return [op] * n, client
 
 
-def remote_ops_fused(n: int):
+class _DemoShards:
+    """Picklable model factory for ``launch_federation``: rank r of `world` holds the demo shards r, r + world, ..."""
+
+    def __init__(self, n: int) -> None:
+        self.n = n
+
+    def __call__(self, rank: int, world: int, device):
+        from pytensor_federated_b200.models import LinregShards, make_demo_data
+
+        x, y, sigma = make_demo_data()   # identical "remote" datasets, like the reference demo
+        mine = [s for s in range(self.n) if s % world == rank]
+        return LinregShards([x] * len(mine), [y] * len(mine), [sigma] * len(mine), local_ids=mine, n_shards_total=self.n,
+                            device=device)
+
+
+def remote_ops_fused(n: int, gpus: int = 0):
+    """N shards on min(N, visible GPUs) GPUs (``gpus`` overrides): one process per GPU, shard s on GPU s % M."""
+    import contextlib
+
     import torch
 
-    from pytensor_federated_b200.federation import NodeFederation
-    from pytensor_federated_b200.models import LinregShards, make_demo_data
-    from pytensor_federated_b200.parallel import FederatedEngine
+    from pytensor_federated_b200.federation import NodeFederation, launch_federation
 
-    x, y, sigma = make_demo_data()
-    dev = torch.device("cuda:0" if torch.cuda.is_available() else "cpu")
-    model = LinregShards([x] * n, [y] * n, [sigma] * n, device=dev)  # identical "remote" datasets, like the reference demo
-    fed = NodeFederation(FederatedEngine(model))
+    visible = torch.cuda.device_count() if torch.cuda.is_available() else 0
+    world = max(1, min(n, gpus or visible or 1))
+    stack = contextlib.ExitStack()
+    engine = stack.enter_context(launch_federation(_DemoShards(n), world, device_type="cuda" if visible else "cpu",
+                                                   backend="auto" if visible else "collective"))
+    _log.info("%d shards on %d %s", n, world, "GPU(s), fused NVLink data plane" if visible else "CPU process(es)")
+    fed = NodeFederation(engine)
+    fed.shutdown = lambda: (fed.unregister_services(), stack.close())   # the launcher joins the peer processes
     return fed.node_ops(), fed
 
 
@@ -109,6 +130,7 @@ if __name__ == "__main__":
     parser.add_argument("--ports", default=",".join(map(str, range(50000, 50003))), type=str)
     parser.add_argument("--parallel", default="true", choices=["true", "false"])
     parser.add_argument("--fused", default=0, type=int, help="use N on-box shards instead of gRPC workers")
+    parser.add_argument("--gpus", default=0, type=int, help="--fused: GPUs (processes) to spread the shards over; 0 = all visible")
     parser.add_argument("--nodes", default=3, type=int, help="remote calls per model evaluation")
     parser.add_argument("--tune", default=500, type=int)
     parser.add_argument("--draws", default=200, type=int)
@@ -117,7 +139,7 @@ if __name__ == "__main__":
     args, _ = parser.parse_known_args()
     runner = run_model_pymc if args.pymc else (lambda *a: run_model(*a, chains=args.chains))
     if args.fused:
-        ops, handle = remote_ops_fused(args.fused)
+        ops, handle = remote_ops_fused(args.fused, args.gpus)
         runner(ops, args.fused, args.tune, args.draws)
         handle.shutdown()
     else:

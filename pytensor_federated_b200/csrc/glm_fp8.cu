@@ -38,6 +38,7 @@
 #include "fed_comm.cuh"
 #include "models.h"
 #include "tc_common.cuh"
+#include "chunks.h"
 
 namespace fp8 {
 using namespace tc;
@@ -47,12 +48,14 @@ constexpr int kPanelF = 128;          // features per 128-byte swizzle span (1 b
 constexpr int kPanelB = kTile * 128;  // 16 KB
 constexpr int kEG = 3;                // epilogue groups; tile t belongs to group t % kEG (own eta / R buffers)
 constexpr int kThreadsF = 32 * (3 + 4 * kEG);  // warps: 0 TMA, 1 MMA#1, 2-5 group 0, 6 MMA#2, 7-10 group 1, 11-14 group 2
-constexpr int kFlushF = 32;
+constexpr int kMaxChunkF = 30;        // tiles per chunk at most (fp32 accumulation in TMEM), a multiple of kEG
+constexpr int kMinChunkF = 6;
+constexpr int kRingF = 32;            // published chunks the consumers may lag behind
+constexpr int kLLRowsF = 4 * kEG;     // epilogue warps: per-warp slots of the warp-level sums
 constexpr int kN = 16;                // MMA N for both GEMMs
 constexpr int kThetaTerms = 5;
 constexpr int kResidTerms = 4;
 constexpr int kSfRing = 2 * kEG;      // scale words are written kEG tiles ahead
-constexpr int kMaxSegsF = 64;
 
 __device__ __forceinline__ void umma_fp8_block_scaled(uint32_t tmem_d, uint64_t adesc, uint64_t bdesc, uint32_t idesc,
                                                       uint32_t accumulate, uint32_t tmem_sfa, uint32_t tmem_sfb) {
@@ -99,17 +102,20 @@ __device__ __forceinline__ void expand16(float v, uint8_t (&terms)[T]) {
 }
 
 struct SmemLayoutF {
-    uint32_t stages, stage_bytes, off_theta_b, theta_b_bytes, off_r, r_bytes, off_theta_f, off_segs, off_gi, off_red,
-        off_bars, off_tmem, total;
+    uint32_t stages, stage_bytes, off_theta_b, theta_b_bytes, off_r, r_bytes, off_theta_f, off_ring, off_bars, off_tmem, total;
 };
+// doubles per CTA row of the partial array: (hi, lo) pairs of the n_vals outputs, then the per-warp slots
+// [kLLRowsF][KF][1 + G] of the warp-level sums (log-likelihood, intercept gradients) — see csrc/glm_tc.cu
+__host__ __device__ constexpr size_t partial_row_doubles(int n_vals, int kf, int n_groups) {
+    return 2 * ((size_t)n_vals + (size_t)kLLRowsF * kf * (1 + n_groups));
+}
 __host__ __device__ inline SmemLayoutF smem_layout(int P, int n_theta, int n_groups) {
     SmemLayoutF L;
     const uint32_t panels = P / kPanelF;
     L.stage_bytes = panels * kPanelB;
     L.theta_b_bytes = panels * kN * 128;
     L.r_bytes = kTile * kN;  // 1 byte per element
-    const uint32_t fixed = L.theta_b_bytes + kEG * L.r_bytes + ((n_theta * 4 + 15) & ~15) + kMaxSegsF * (uint32_t)sizeof(GlmSegment) +
-                           ((3 * n_groups * 8 + 15) & ~15) + 32 * 8 + 512 + 1024;
+    const uint32_t fixed = L.theta_b_bytes + kEG * L.r_bytes + ((n_theta * 4 + 15) & ~15) + kRingF * 16 + 16 + 512 + 1024;
     uint32_t stages = (227u * 1024u - fixed) / L.stage_bytes;
     if (stages > 6) stages = 6;
     L.stages = stages;
@@ -117,9 +123,7 @@ __host__ __device__ inline SmemLayoutF smem_layout(int P, int n_theta, int n_gro
     L.off_theta_b = o; o += L.theta_b_bytes;
     L.off_r = o; o += kEG * L.r_bytes;
     L.off_theta_f = o; o += (n_theta * 4 + 15) & ~15;
-    L.off_segs = o; o += kMaxSegsF * (uint32_t)sizeof(GlmSegment);
-    L.off_gi = o; o += (3 * n_groups * 8 + 15) & ~15;
-    L.off_red = o; o += 32 * 8;
+    L.off_ring = o; o += kRingF * 16 + 16;   // published chunks + the publication counter
     L.off_bars = o; o += 320;
     L.off_tmem = o; o += 192;  // tmem slot, theta norms, residual-exponent exchange (DYN)
     L.total = o + 1024;
@@ -130,7 +134,8 @@ __host__ __device__ inline SmemLayoutF smem_layout(int P, int n_theta, int n_gro
 // DYN = per-row-group residual scales (families with unbounded residuals)
 template <int KF, bool DYN>
 __global__ void __launch_bounds__(kThreadsF, 1)
-fed_glm_fp8_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParams prm, const CUtensorMap* __restrict__ tmaps) {
+fed_glm_fp8_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParams prm, const CUtensorMap* __restrict__ tmaps,
+                   const GlmChunk* __restrict__ chunks, int n_chunks, unsigned int* __restrict__ work_counter) {
     extern __shared__ unsigned char smem_dyn[];
     // 1 KB alignment (128B-swizzled TMA tiles) by offsetting INSIDE the shared array: the pointer keeps its
     // shared address space, so the compiler emits LDS / STS instead of generic LD / ST for everything below
@@ -146,9 +151,8 @@ fed_glm_fp8_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParam
     unsigned char* theta_b = smem + L.off_theta_b;
     unsigned char* r_buf = smem + L.off_r;
     float* theta_f = reinterpret_cast<float*>(smem + L.off_theta_f);
-    GlmSegment* segs = reinterpret_cast<GlmSegment*>(smem + L.off_segs);
-    unsigned long long* gi_acc = reinterpret_cast<unsigned long long*>(smem + L.off_gi);  // fixed point (fed::fix_add)
-    double* red = reinterpret_cast<double*>(smem + L.off_red);
+    int4* ring = reinterpret_cast<int4*>(smem + L.off_ring);          // published chunks: (segment or -1, first tile, tiles, -)
+    uint32_t* n_published = reinterpret_cast<uint32_t*>(smem + L.off_ring + kRingF * 16);
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.off_bars);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L.off_tmem);
     float* theta_norm = reinterpret_cast<float*>(smem + L.off_tmem + 16);  // c: theta = c * sum_k t_k 16^-k
@@ -167,27 +171,50 @@ fed_glm_fp8_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParam
     const int warp = threadIdx.x >> 5;
     const int lane = threadIdx.x & 31;
 
-    fed::Prologue pro = fed::prologue(comm, theta_f);
-    const bool active = !pro.stop && !pro.timed_out;
-    const long long T = prm.total_tiles;
-    const long long n_it = (T > (long long)blockIdx.x) ? (T - blockIdx.x + gridDim.x - 1) / gridDim.x : 0;
+    // ---- theta-independent setup: BEFORE the dependency wait inside fed::prologue, so that it overlaps with the
+    // tail of the previous evaluation under programmatic dependent launch (see csrc/glm_tc.cu)
     constexpr uint32_t kTmemCols = 256;
+    for (int i = threadIdx.x; i < (int)(kEG * L.r_bytes / 16); i += blockDim.x)
+        reinterpret_cast<uint4*>(r_buf)[i] = make_uint4(0, 0, 0, 0);
+    if (threadIdx.x == 0) {
+        *pipeline_fault() = 0;
+        *n_published = 0u;
+        for (int i = 0; i < 6; ++i) { mbar_init(&bar_full[i], 1); mbar_init(&bar_empty[i], 1); }
+        for (int i = 0; i < kEG; ++i) {
+            mbar_init(&bar_eta_full[i], 1);
+            mbar_init(&bar_eta_empty[i], 128);
+            mbar_init(&bar_r_full[i], 128);
+            mbar_init(&bar_r_empty[i], 1);
+        }
+        for (int i = 0; i < 2; ++i) {
+            mbar_init(&bar_g_full[i], 1);
+            mbar_init(&bar_g_empty[i], 128);
+        }
+        for (int i = 0; i < kSfRing; ++i) mbar_init(&bar_sf_full[i], 128);
+        fence_barrier_init();
+    }
+    if (warp == 0 && lane == 0)
+        for (int i = 0; i < prm.n_segments; ++i) tma_prefetch_desc(&tmaps[i]);
+    if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
+    tc_fence_before();
+
+    fed::Prologue pro = fed::prologue(comm, theta_f);   // contains __syncthreads()
+    const bool active = !pro.stop && !pro.timed_out;
+    tc_fence_after();
+    const uint32_t tmem_base = *tmem_slot;
     constexpr float kResidNorm = 1.f / 256.f;  // r = kResidNorm * sum_k t_k 16^-k, |r| <= 1
 
     const int nch = prm.n_chains < KF ? prm.n_chains : KF;
     const int PG = G + P;  // parameters per chain
-    double ll_total[KF];
-    double g_acc[4][KF];
-#pragma unroll
-    for (int k = 0; k < KF; ++k) {
-        ll_total[k] = 0.0;
-#pragma unroll
-        for (int h = 0; h < 4; ++h) g_acc[h][k] = 0.0;
-    }
+    const int NV1 = 1 + PG;   // outputs per chain: [LL, gi[G], g[P]]
+    const int NS1 = 1 + G;    // warp-level values per chain: LL and the G intercept gradients
+    // this CTA's running sums as (hi, lo) pairs (see csrc/glm_tc.cu: dynamic chunks + double-double sums)
+    const size_t row_doubles = partial_row_doubles(comm.n_vals, KF, G);
+    double* out = comm.cta_partials + (size_t)blockIdx.x * row_doubles;
+    double* ll_slots = out + 2 * (size_t)comm.n_vals;   // [kLLRowsF][KF][1 + G] pairs
 
     if (active) {
-        for (int i = threadIdx.x; i < prm.n_segments; i += blockDim.x) segs[i] = segs_g[i];
-        for (int i = threadIdx.x; i < KF * G; i += blockDim.x) gi_acc[i] = 0ull;
+        for (size_t i = threadIdx.x; i < row_doubles / 2; i += blockDim.x) reinterpret_cast<double2*>(out)[i] = make_double2(0.0, 0.0);
         // ---- theta normalisation per chain: power of two c with max|beta| / c in [128, 256)
         if (warp < KF) {
             float m = 0.f;
@@ -226,30 +253,8 @@ fed_glm_fp8_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParam
             *reinterpret_cast<uint4*>(theta_b + pnl * (kN * 128) + n * 128 + ((j ^ (n & 7)) * 16)) =
                 make_uint4(packed[0], packed[1], packed[2], packed[3]);
         }
-        for (int i = threadIdx.x; i < (int)(kEG * L.r_bytes / 16); i += blockDim.x)
-            reinterpret_cast<uint4*>(r_buf)[i] = make_uint4(0, 0, 0, 0);
         fence_proxy_async();
-        if (threadIdx.x == 0) {
-            *pipeline_fault() = 0;
-            for (int i = 0; i < 6; ++i) { mbar_init(&bar_full[i], 1); mbar_init(&bar_empty[i], 1); }
-            for (int i = 0; i < kEG; ++i) {
-                mbar_init(&bar_eta_full[i], 1);
-                mbar_init(&bar_eta_empty[i], 128);
-                mbar_init(&bar_r_full[i], 128);
-                mbar_init(&bar_r_empty[i], 1);
-            }
-            for (int i = 0; i < 2; ++i) {
-                mbar_init(&bar_g_full[i], 1);
-                mbar_init(&bar_g_empty[i], 128);
-            }
-            for (int i = 0; i < kSfRing; ++i) mbar_init(&bar_sf_full[i], 128);
-            fence_barrier_init();
-        }
-        if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
-        tc_fence_before();
         __syncthreads();
-        tc_fence_after();
-        const uint32_t tmem_base = *tmem_slot;
         const uint32_t tmem_eta = tmem_base;                         // kEG x 16            (<= 64)
         const uint32_t tmem_g = tmem_base + 64;                      // 2 buffers x NH x 16 (<= 64)
         const uint32_t tmem_sfa1 = tmem_base + 128;                  // ring x 8 columns
@@ -258,33 +263,49 @@ fed_glm_fp8_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParam
         const uint32_t tmem_sfb_r = tmem_sfb + 4;                    // DYN: kEG R buffers x 4 columns (col 0 used)
         static_assert(128 + kSfRing * 16 + 4 + kEG * 4 <= (int)kTmemCols, "TMEM budget");
 
+        // Consumers: the j-th chunk of this CTA, or x < 0 when the producer found the work counter exhausted.
+        auto next_chunk = [&](int j) -> int4 {
+            while (ld_acquire_shared(n_published) <= (uint32_t)j) {
+            }
+            return ring[j & (kRingF - 1)];
+        };
+        // non-blocking variant for look-ahead: x == -2 when chunk j has not been published yet
+        auto peek_chunk = [&](int j) -> int4 {
+            if (ld_acquire_shared(n_published) <= (uint32_t)j) return make_int4(-2, 0, 0, 0);
+            return ring[j & (kRingF - 1)];
+        };
+
         if (warp == 0) {
-            {
-                if (lane == 0)
-                    for (int i = 0; i < prm.n_segments; ++i) tma_prefetch_desc(&tmaps[i]);
-                int s_idx = 0;
-                Ring stage;
-                long long tile = blockIdx.x;
-                long long seg_first = segs[0].first_tile;
-                long long seg_next = prm.n_segments > 1 ? segs[1].first_tile : (1ll << 62);
-                for (long long it = 0; it < n_it; ++it, tile += gridDim.x) {
-                    while (seg_next <= tile) {
-                        ++s_idx;
-                        seg_first = seg_next;
-                        seg_next = s_idx + 1 < prm.n_segments ? segs[s_idx + 1].first_tile : (1ll << 62);
-                    }
+            // ================= TMA producer + chunk scheduler (see csrc/glm_tc.cu) ==============
+            Ring stage;
+            unsigned int claim = 0, ahead = 0;
+            if (lane == 0) claim = atomicAdd(work_counter, 1u);
+            claim = __shfl_sync(0xffffffffu, claim, 0);
+            for (int j = 0;; ++j) {
+                const bool have = claim < (unsigned int)n_chunks;
+                GlmChunk ch{};
+                if (have) ch = chunks[claim];
+                if (lane == 0) {
+                    ring[j & (kRingF - 1)] = have ? make_int4(ch.seg, ch.first_tile, ch.n_tiles, 0) : make_int4(-1, 0, 0, 0);
+                    st_release_shared(n_published, (uint32_t)j + 1u);
+                    if (have) ahead = atomicAdd(work_counter, 1u);
+                }
+                __syncwarp();
+                if (!have) break;
+                for (int t = 0; t < ch.n_tiles; ++t) {
                     const int st = stage.idx;
                     mbar_wait(&bar_empty[st], stage.phase ^ 1);
-                    const int row0 = (int)(tile - seg_first) * kTile;
+                    const int row0 = (ch.first_tile + t) * kTile;
                     unsigned char* dst = smem + (size_t)st * L.stage_bytes;
                     if (elect_one()) {
                         mbar_expect_tx(&bar_full[st], L.stage_bytes);
                         for (int pnl = 0; pnl < NH; ++pnl)
-                            tma_load_2d(dst + pnl * kPanelB, &tmaps[s_idx], pnl * kPanelF, row0, &bar_full[st]);
+                            tma_load_2d(dst + pnl * kPanelB, &tmaps[ch.seg], pnl * kPanelF, row0, &bar_full[st]);
                     }
                     __syncwarp();
                     stage.advance(S);
                 }
+                claim = __shfl_sync(0xffffffffu, ahead, 0);
             }
         } else if (warp == 1) {
             {
@@ -295,7 +316,10 @@ fed_glm_fp8_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParam
                 const uint32_t x_base_a4 = smem_u32(smem) >> 4;
                 const uint32_t stage_a4 = L.stage_bytes >> 4;
                 Ring stage, buf, sf;   // TMA stages (S), eta buffers (kEG), scale-word slots (kSfRing)
-                for (long long it = 0; it < n_it; ++it) {
+                for (int j = 0;; ++j) {
+                  const int4 ch = next_chunk(j);
+                  if (ch.x < 0) break;
+                  for (int t = 0; t < ch.z; ++t) {
                     mbar_wait(&bar_sf_full[sf.idx], sf.phase);
                     mbar_wait(&bar_eta_empty[buf.idx], buf.phase ^ 1);
                     mbar_wait(&bar_full[stage.idx], stage.phase);
@@ -319,6 +343,7 @@ fed_glm_fp8_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParam
                     stage.advance(S);
                     buf.advance(kEG);
                     sf.advance(kSfRing);
+                  }
                 }
             }
         } else if (warp == 6) {
@@ -329,13 +354,15 @@ fed_glm_fp8_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParam
                 const uint32_t r_a4 = smem_u32(r_buf) >> 4;
                 const uint32_t x_base_a4 = smem_u32(smem) >> 4;
                 const uint32_t stage_a4 = L.stage_bytes >> 4;
-                Ring stage, buf, sf, flush;   // flush: tile within the kFlushF-tile accumulation period, phase = G buffer
-                uint32_t g_phase[2] = {0, 0};  // per G buffer: how many periods it has served (parity)
-                for (long long j = 0; j < n_it; ++j) {
-                    const int gb = (int)flush.phase;
-                    const bool first = flush.idx == 0;
-                    const bool last = flush.idx == kFlushF - 1 || j == n_it - 1;
-                    if (first) mbar_wait(&bar_g_empty[gb], g_phase[gb] ^ 1);
+                Ring stage, buf, sf, gbuf;   // gbuf: TMEM gradient accumulator of the current chunk (2, alternating)
+                for (int j = 0;; ++j) {
+                  const int4 ch = next_chunk(j);
+                  if (ch.x < 0) break;
+                  const int gb = gbuf.idx;
+                  mbar_wait(&bar_g_empty[gb], gbuf.phase ^ 1);   // the epilogue has drained this accumulator
+                  for (int t = 0; t < ch.z; ++t) {
+                    const bool first = t == 0;
+                    const bool last = t == ch.z - 1;
                     mbar_wait(&bar_r_full[buf.idx], buf.phase);
                     tc_fence_after();
                     const uint32_t x_a4 = x_base_a4 + (uint32_t)stage.idx * stage_a4;
@@ -359,11 +386,11 @@ fed_glm_fp8_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParam
                     if (last) umma_commit(&bar_g_full[gb]);
                     }
                     __syncwarp();
-                    if (last) g_phase[gb] ^= 1u;
                     stage.advance(S);
                     buf.advance(kEG);
                     sf.advance(kSfRing);
-                    flush.advance(kFlushF);
+                  }
+                  gbuf.advance(2);
                 }
             }
         } else {
@@ -384,175 +411,216 @@ fed_glm_fp8_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParam
 
             // Scale words of a tile: loaded from global memory early (load_scales, results are not
             // consumed until store_scales) so that the L2/HBM latency never sits on the per-tile chain.
-            auto load_scales = [&](long long t_it, int& sidx, uint4 (&pk)[4]) {
-                const long long tile = blockIdx.x + t_it * gridDim.x;
-                while (sidx + 1 < prm.n_segments && segs[sidx + 1].first_tile <= tile) ++sidx;
-                const GlmSegment& sg = segs[sidx];
+            auto load_scales = [&](int seg, int tile_in_seg, uint4 (&pk)[4]) {
                 // 16 words per tile, packed on the host in TMEM order (models/glm.py: pack_tile_scales):
                 //   words 0-7  (MMA #1): word 4g + q  = scales of (row group q, feature blocks 4g .. 4g+3)
                 //   words 8-15 (MMA #2): word 4h + qq = scales of (row groups 0..3, feature block 4h + qq)
-                const uint4* sp = reinterpret_cast<const uint4*>(sg.scales) + (tile - sg.first_tile) * 4;
+                const long long seg_tiles = (segs_g[seg].n_rows + kTile - 1) / kTile;
+                if (tile_in_seg < seg_tiles) {
+                    const uint4* sp = reinterpret_cast<const uint4*>(segs_g[seg].scales) + (size_t)tile_in_seg * 4;
 #pragma unroll
-                for (int i = 0; i < 4; ++i) pk[i] = __ldg(sp + i);
+                    for (int i = 0; i < 4; ++i) pk[i] = __ldg(sp + i);
+                } else {   // an empty tile that pads a chunk: 2^0 everywhere (its rows are all zero)
+#pragma unroll
+                    for (int i = 0; i < 4; ++i) pk[i] = make_uint4(0x7F7F7F7Fu, 0x7F7F7F7Fu, 0x7F7F7F7Fu, 0x7F7F7F7Fu);
+                }
             };
-            // writes the scale words of tile `t_it` into ring slot t_it % kSfRing
-            auto store_scales = [&](long long t_it, const uint4 (&pk)[4]) {
+            // writes the scale words of the CTA's t_it-th tile into ring slot t_it % kSfRing
+            auto store_scales = [&](int t_it, const uint4 (&pk)[4]) {
                 const uint32_t sfa1[8] = {pk[0].x, pk[0].y, pk[0].z, pk[0].w, pk[1].x, pk[1].y, pk[1].z, pk[1].w};
                 const uint32_t sfa2[8] = {pk[2].x, pk[2].y, pk[2].z, pk[2].w, pk[3].x, pk[3].y, pk[3].z, pk[3].w};
-                const int slot = (int)(t_it % kSfRing);
+                const int slot = t_it % kSfRing;
                 tmem_st_x8(tmem_sfa1 + lane_addr + slot * 8, sfa1);
                 tmem_st_x8(tmem_sfa2 + lane_addr + slot * 8, sfa2);
                 tmem_wait_st();
                 tc_fence_before();
                 mbar_arrive(&bar_sf_full[slot]);
             };
-            auto write_scales = [&](long long t_it, int& sidx) {
-                uint4 pk[4];
-                load_scales(t_it, sidx, pk);
-                store_scales(t_it, pk);
-            };
-            int sf_sidx = 0;
-            if (eg < n_it) write_scales(eg, sf_sidx);
 
-            int s_idx = 0;
-            float ll_acc[KF], gi_cur[KF];
+            const int ew = eg * 4 + q4;          // epilogue warp ordinal: row of the per-warp slots
+            const int b = eg;                    // eta / R buffer of this group
+            int it = 0;                          // tiles this CTA has been handed before the current chunk (multiple of kEG)
+            bool stored_ahead = false;           // the scales of this group's first tile of the chunk are already in TMEM
+            Ring gbuf;
+            for (int j = 0;; ++j) {
+                const int4 ch = next_chunk(j);
+                if (ch.x < 0) break;
+                const float* __restrict__ seg_y = segs_g[ch.x].y;
+                const long long seg_rows = segs_g[ch.x].n_rows;
+                const int seg_group = segs_g[ch.x].group;
+                // this warp's (hi, lo) slots: LL at +0, intercept gradient g at +(1 + g); fetched a whole chunk early
+                double* slot0 = ll_slots + 2 * (((size_t)ew * KF) * NS1);
+                double2 pre_l[KF], pre_g[KF];
+                if (lane == 0) {
 #pragma unroll
-            for (int k = 0; k < KF; ++k) ll_acc[k] = gi_cur[k] = 0.f;
-            int cur_group = -1;
-            for (long long it = eg; it < n_it; it += kEG) {
-                const long long tile = blockIdx.x + it * gridDim.x;
-                while (s_idx + 1 < prm.n_segments && segs[s_idx + 1].first_tile <= tile) ++s_idx;
-                const GlmSegment& seg = segs[s_idx];
-                if (seg.group != cur_group) {
-                    if (cur_group >= 0) {
+                    for (int k = 0; k < KF; ++k)
+                        if (k < nch) {
+                            pre_l[k] = *reinterpret_cast<const double2*>(slot0 + 2 * (size_t)k * NS1);
+                            pre_g[k] = *reinterpret_cast<const double2*>(slot0 + 2 * (size_t)k * NS1 + 2 * (1 + seg_group));
+                        }
+                }
+                if (!stored_ahead) {
+                    uint4 first[4];
+                    load_scales(ch.x, ch.y + eg, first);
+                    store_scales(it + eg, first);
+                }
+                stored_ahead = false;
+                float ll_acc[KF], gi_cur[KF];
 #pragma unroll
-                        for (int k = 0; k < KF; ++k) {
-                            fed::fix_add(&gi_acc[k * G + cur_group], (double)gi_cur[k]);
-                            gi_cur[k] = 0.f;
+                for (int k = 0; k < KF; ++k) ll_acc[k] = gi_cur[k] = 0.f;
+                for (int t = eg; t < ch.z; t += kEG) {
+                    const int itl = it + t;
+                    const long long grow = ((long long)ch.y + t) * kTile + row;
+                    const bool valid = grow < seg_rows;
+                    const float y = valid ? __ldg(seg_y + grow) : 0.f;
+                    const uint32_t bph = (uint32_t)((itl / kEG) & 1);
+                    // scale words of this group's NEXT tile (consumed at the end of this iteration): the next tile
+                    // of the chunk, or the group's first tile of the next chunk if that chunk is already known
+                    uint4 next_scales[4];
+                    int next_it = -1;
+                    if (t + kEG < ch.z) {
+                        load_scales(ch.x, ch.y + t + kEG, next_scales);
+                        next_it = itl + kEG;
+                    } else {
+                        const int4 nx = peek_chunk(j + 1);
+                        if (nx.x >= 0) {
+                            load_scales(nx.x, nx.y + eg, next_scales);
+                            next_it = it + ch.z + eg;
+                            stored_ahead = true;
                         }
                     }
-                    cur_group = seg.group;
-                }
-                const long long grow = (tile - seg.first_tile) * kTile + row;
-                const bool valid = grow < seg.n_rows;
-                const float y = valid ? __ldg(seg.y + grow) : 0.f;
-                const int b = eg;
-                const uint32_t bph = (uint32_t)((it / kEG) & 1);
-                uint4 next_scales[4];
-                if (it + kEG < n_it) load_scales(it + kEG, sf_sidx, next_scales);  // consumed at the end of this iteration
 
-                mbar_wait(&bar_eta_full[b], bph);
-                tc_fence_after();
-                float v[16];
-                tmem_ld_x16(tmem_eta + lane_addr + b * kN, v);
-                tc_fence_before();
-                mbar_arrive(&bar_eta_empty[b]);
-                uint32_t rwords[4] = {0, 0, 0, 0};  // 16 residual bytes of this row: 4 terms per chain
-                uint8_t* expo_slot = r_expo + (eg * 2 + (int)bph) * 12;
+                    mbar_wait(&bar_eta_full[b], bph);
+                    tc_fence_after();
+                    float v[16];
+                    tmem_ld_x16(tmem_eta + lane_addr + b * kN, v);
+                    tc_fence_before();
+                    mbar_arrive(&bar_eta_empty[b]);
+                    uint32_t rwords[4] = {0, 0, 0, 0};  // 16 residual bytes of this row: 4 terms per chain
+                    uint8_t* expo_slot = r_expo + (eg * 2 + (int)bph) * 12;
+#pragma unroll
+                    for (int k = 0; k < KF; ++k) {
+                        const float* vk = v + kThetaTerms * k;
+                        const float eta = c_theta[k] * (vk[0] + vk[1] * (1.f / 16) + vk[2] * (1.f / 256) + vk[3] * (1.f / 4096) +
+                                                        vk[4] * (1.f / 65536)) + theta_f[k * PG + seg_group];
+                        float ll = 0.f, r = 0.f;
+                        if (valid && k < nch) link_loglik(DYN ? prm.family : 0, y, eta, ll, r);
+                        ll_acc[k] += ll;
+                        gi_cur[k] += r;
+                        if constexpr (DYN) {
+                            // this 32-row group's scale: 2^e with max|r| / 2^e in [0.5, 1)
+                            float m = fabsf(r);
+#pragma unroll
+                            for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
+                            int e = 0;
+                            if (m > 0.f) frexpf(m, &e);
+                            e = max(-126, min(126, e));
+                            r *= __uint_as_float((uint32_t)(127 - e) << 23);
+                            if (lane == 0) expo_slot[k * 4 + q4] = (uint8_t)(127 + e);
+                        }
+                        uint8_t rt[kResidTerms];
+                        expand16<kResidTerms>(r * 256.f, rt);
+                        rwords[k] = (uint32_t)rt[0] | ((uint32_t)rt[1] << 8) | ((uint32_t)rt[2] << 16) | ((uint32_t)rt[3] << 24);
+                    }
+                    mbar_wait(&bar_r_empty[b], bph ^ 1);
+                    *reinterpret_cast<uint4*>(r_buf + b * L.r_bytes + (row >> 3) * 128 + (row & 7) * 16) =
+                        make_uint4(rwords[0], rwords[1], rwords[2], rwords[3]);
+                    fence_proxy_async();
+                    if constexpr (DYN) {
+                        // all four row-group exponents of this tile -> one word per chain; B row n = 4 * chain + term
+                        // reads it from lane n of every subpartition
+                        if (eg == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
+                        else if (eg == 1) asm volatile("bar.sync 2, 128;" ::: "memory");
+                        else asm volatile("bar.sync 3, 128;" ::: "memory");
+                        const int chn = min(lane >> 2, KF - 1);
+                        const uint32_t w = *reinterpret_cast<const uint32_t*>(expo_slot + chn * 4);
+                        tmem_st_x1(tmem_sfb_r + lane_addr + b * 4, w);
+                        tmem_wait_st();
+                        tc_fence_before();
+                    }
+                    mbar_arrive(&bar_r_full[b]);
+
+                    // scales for this group's next tile: its ring slot was last used by the tile kSfRing before it,
+                    // whose MMAs are complete (we just passed r_empty of the previous own tile and eta_full of this one)
+                    if (next_it >= 0) store_scales(next_it, next_scales);
+                }
+                // ---- end of the chunk for this group: per-thread fp32 sums -> fixed butterfly over the warp
+                // (double) -> lane 0 adds the warp's value to its own (hi, lo) slot; all chunk-determined.  The slot
+                // values were fetched at the start of the chunk (`pre`), so no L2 round trip sits here.
+                double lsum[KF], gsum[KF];
 #pragma unroll
                 for (int k = 0; k < KF; ++k) {
-                    const float* vk = v + kThetaTerms * k;
-                    const float eta = c_theta[k] * (vk[0] + vk[1] * (1.f / 16) + vk[2] * (1.f / 256) + vk[3] * (1.f / 4096) +
-                                                    vk[4] * (1.f / 65536)) + theta_f[k * PG + seg.group];
-                    float ll = 0.f, r = 0.f;
-                    if (valid && k < nch) link_loglik(DYN ? prm.family : 0, y, eta, ll, r);
-                    ll_acc[k] += ll;
-                    gi_cur[k] += r;
-                    if constexpr (DYN) {
-                        // this 32-row group's scale: 2^e with max|r| / 2^e in [0.5, 1)
-                        float m = fabsf(r);
+                    lsum[k] = (double)ll_acc[k];
+                    gsum[k] = (double)gi_cur[k];
 #pragma unroll
-                        for (int o = 16; o > 0; o >>= 1) m = fmaxf(m, __shfl_xor_sync(0xffffffffu, m, o));
-                        int e = 0;
-                        if (m > 0.f) frexpf(m, &e);
-                        e = max(-126, min(126, e));
-                        r *= __uint_as_float((uint32_t)(127 - e) << 23);
-                        if (lane == 0) expo_slot[k * 4 + q4] = (uint8_t)(127 + e);
+                    for (int o = 16; o > 0; o >>= 1) {
+                        lsum[k] += __shfl_xor_sync(0xffffffffu, lsum[k], o);
+                        gsum[k] += __shfl_xor_sync(0xffffffffu, gsum[k], o);
                     }
-                    uint8_t rt[kResidTerms];
-                    expand16<kResidTerms>(r * 256.f, rt);
-                    rwords[k] = (uint32_t)rt[0] | ((uint32_t)rt[1] << 8) | ((uint32_t)rt[2] << 16) | ((uint32_t)rt[3] << 24);
                 }
-                mbar_wait(&bar_r_empty[b], bph ^ 1);
-                *reinterpret_cast<uint4*>(r_buf + b * L.r_bytes + (row >> 3) * 128 + (row & 7) * 16) =
-                    make_uint4(rwords[0], rwords[1], rwords[2], rwords[3]);
-                fence_proxy_async();
-                if constexpr (DYN) {
-                    // all four row-group exponents of this tile -> one word per chain; B row n = 4 * chain + term
-                    // reads it from lane n of every subpartition
-                    if (eg == 0) asm volatile("bar.sync 1, 128;" ::: "memory");
-                    else if (eg == 1) asm volatile("bar.sync 2, 128;" ::: "memory");
-                    else asm volatile("bar.sync 3, 128;" ::: "memory");
-                    const int ch = min(lane >> 2, KF - 1);
-                    const uint32_t w = *reinterpret_cast<const uint32_t*>(expo_slot + ch * 4);
-                    tmem_st_x1(tmem_sfb_r + lane_addr + b * 4, w);
-                    tmem_wait_st();
-                    tc_fence_before();
+                if (lane == 0) {
+#pragma unroll
+                    for (int k = 0; k < KF; ++k)
+                        if (k < nch) {
+                            double* slot = slot0 + 2 * (size_t)k * NS1;
+                            fed::dd_add(pre_l[k].x, pre_l[k].y, lsum[k], 0.0);
+                            fed::dd_add(pre_g[k].x, pre_g[k].y, gsum[k], 0.0);
+                            *reinterpret_cast<double2*>(slot) = pre_l[k];
+                            *reinterpret_cast<double2*>(slot + 2 * (1 + seg_group)) = pre_g[k];
+                        }
                 }
-                mbar_arrive(&bar_r_full[b]);
-
-                // scales for this group's next tile (it+kEG): its ring slot was last used by tile it-kEG,
-                // whose MMAs are complete (we just passed r_empty of tile it-kEG and eta_full of tile it)
-                if (it + kEG < n_it) store_scales(it + kEG, next_scales);
-
-                // the gradient accumulator of a period is flushed by whichever group owns its last tile
-                const bool last = (it % kFlushF) == kFlushF - 1 || it == n_it - 1;
-                if (last) {
-                    const long long period = it / kFlushF;
-                    const int gb = (int)(period & 1);
-                    mbar_wait(&bar_g_full[gb], (uint32_t)((period >> 1) & 1));
+                // gradient: chunks hold a multiple of kEG tiles, so the last group always owns a chunk's last tile
+                if (eg == kEG - 1) {
+                    const int gb = gbuf.idx;
+                    mbar_wait(&bar_g_full[gb], gbuf.phase);
                     tc_fence_after();
                     for (int h = 0; h < NH; ++h) {
                         float gv[16];
                         tmem_ld_x16(tmem_g + lane_addr + (gb * NH + h) * kN, gv);
+                        if (h == NH - 1) {
+                            tc_fence_before();
+                            mbar_arrive(&bar_g_empty[gb]);
+                        }
 #pragma unroll
                         for (int k = 0; k < KF; ++k)
-                            g_acc[h][k] += (double)kResidNorm * ((double)gv[4 * k] + (double)gv[4 * k + 1] * (1.0 / 16) +
-                                                                  (double)gv[4 * k + 2] * (1.0 / 256) + (double)gv[4 * k + 3] * (1.0 / 4096));
-                    }
-                    tc_fence_before();
-                    mbar_arrive(&bar_g_empty[gb]);
-#pragma unroll
-                    for (int k = 0; k < KF; ++k) {
-                        ll_total[k] += (double)ll_acc[k];
-                        ll_acc[k] = 0.f;
+                            if (k < nch) {
+                                double* slot = out + 2 * ((size_t)k * NV1 + 1 + G + h * 128 + row);
+                                double2 cur = *reinterpret_cast<double2*>(slot);
+                                fed::dd_add(cur.x, cur.y,
+                                            (double)kResidNorm * ((double)gv[4 * k] + (double)gv[4 * k + 1] * (1.0 / 16) +
+                                                                  (double)gv[4 * k + 2] * (1.0 / 256) + (double)gv[4 * k + 3] * (1.0 / 4096)),
+                                            0.0);
+                                *reinterpret_cast<double2*>(slot) = cur;
+                            }
                     }
                 }
-            }
-#pragma unroll
-            for (int k = 0; k < KF; ++k) {
-                ll_total[k] += (double)ll_acc[k];
-                if (cur_group >= 0) fed::fix_add(&gi_acc[k * G + cur_group], (double)gi_cur[k]);
+                gbuf.advance(2);
+                it += ch.z;
             }
         }
 
         tc_fence_before();
         __syncthreads();
         tc_fence_after();
-        if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
-        double* out = comm.cta_partials + (size_t)blockIdx.x * comm.n_vals;
-#pragma unroll
-        for (int k = 0; k < KF; ++k) {
-            const double ll_block = fed::block_sum(ll_total[k], red);
-            if (threadIdx.x == 0 && k < nch) out[k * (1 + PG)] = ll_block;
-        }
-        for (int i = threadIdx.x; i < nch * G; i += blockDim.x) out[(i / G) * (1 + PG) + 1 + (i % G)] = fed::fix_get(gi_acc[i]);
-        for (int pass = 0; pass < kEG; ++pass) {  // group 0 first, then the others add their periods
-            const int my_group = (warp >= 2 && warp <= 5) ? 0 : (warp >= 7 ? (warp - 7) / 4 + 1 : -1);
-            if (my_group == pass) {
-                const int row = (warp & 3) * 32 + lane;
-                for (int h = 0; h < NH; ++h)
-#pragma unroll
-                    for (int k = 0; k < KF; ++k)
-                        if (k < nch) {
-                            double* dst = &out[k * (1 + PG) + 1 + G + h * 128 + row];
-                            *dst = pass == 0 ? g_acc[h][k] : *dst + g_acc[h][k];
-                        }
+        fed::pdl_trigger();   // the next evaluation's CTA may take this SM as soon as we exit
+        // layout per chain: [LL, gi[G], g[P]] as (hi, lo) pairs; g[] was accumulated in place, LL and gi[] are the
+        // per-warp slots summed in warp order
+        for (int i = threadIdx.x; i < nch * NS1; i += blockDim.x) {
+            const int jv = i % NS1, k = i / NS1;
+            double hi = 0.0, lo = 0.0;
+            for (int w = 0; w < kLLRowsF; ++w) {
+                const double* slot = ll_slots + 2 * (((size_t)w * KF + k) * NS1 + jv);
+                fed::dd_add(hi, lo, slot[0], slot[1]);
             }
-            __syncthreads();
+            out[2 * ((size_t)k * NV1 + jv)] = hi;
+            out[2 * ((size_t)k * NV1 + jv) + 1] = lo;
         }
     }
-    fed::epilogue(comm, pro, (active && *pipeline_fault()) ? B200FED_ERR_PIPELINE : 0ull);
+    __syncthreads();
+    if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
+    const bool fin = fed::epilogue_t<true>(comm, pro, (active && *pipeline_fault()) ? B200FED_ERR_PIPELINE : 0ull, row_doubles,
+                                           comm.group_partials);
+    if (fin && threadIdx.x == 0) *work_counter = 0u;   // every CTA has stopped claiming: ready for the next launch
 }
 
 }  // namespace fp8
@@ -574,9 +642,11 @@ EncodeTiledFn8 get_encode8() {
 }
 }  // namespace
 
-extern "C" int b200_glm_fp8_prepare(const GlmSegment* segs_host, int n_segments, const GlmParams* prm, void** tmaps_dev) {
+extern "C" int b200_glm_fp8_prepare(const GlmSegment* segs_host, int n_segments, const GlmParams* prm, int sm_count,
+                                    void** tmaps_dev, void** chunks_dev, int* n_chunks) {
     if (prm->n_features != 128 && prm->n_features != 256) return -21;   // NFB <= 8 scale columns per tile
-    if (n_segments > fp8::kMaxSegsF) return -22;
+    for (int s = 0; s < n_segments; ++s)
+        if (segs_host[s].n_rows + fp8::kTile * fp8::kEG >= (1ll << 31)) return -22;   // row coordinates are 32-bit
     if (prm->n_chains < 1 || prm->n_chains > 3 || prm->family < 0 || prm->family > 2) return -23;
     if (prm->ld % 16 != 0) return -24;
     EncodeTiledFn8 encode = get_encode8();
@@ -597,18 +667,41 @@ extern "C" int b200_glm_fp8_prepare(const GlmSegment* segs_host, int n_segments,
     cudaError_t e = cudaMalloc(tmaps_dev, sizeof(CUtensorMap) * n_segments);
     if (e == cudaSuccess) e = cudaMemcpy(*tmaps_dev, host, sizeof(CUtensorMap) * n_segments, cudaMemcpyHostToDevice);
     delete[] host;
+    if (e != cudaSuccess) return (int)e;
+    const std::vector<GlmChunk> chunks = build_chunks(segs_host, n_segments, sm_count > 0 ? sm_count : 148, fp8::kTile, fp8::kEG,
+                                                        fp8::kMaxChunkF, fp8::kMinChunkF);
+    if (*chunks_dev) cudaFree(*chunks_dev);
+    e = cudaMalloc(chunks_dev, sizeof(GlmChunk) * (chunks.size() + 1));
+    if (e == cudaSuccess) e = cudaMemcpy(*chunks_dev, chunks.data(), sizeof(GlmChunk) * chunks.size(), cudaMemcpyHostToDevice);
+    *n_chunks = (int)chunks.size();
     return e == cudaSuccess ? 0 : (int)e;
 }
 
+extern "C" size_t b200_glm_fp8_partial_row_doubles(int n_vals, int n_chains, int n_groups) {
+    return fp8::partial_row_doubles(n_vals, n_chains == 1 ? 1 : 3, n_groups);
+}
+
 extern "C" int b200_launch_glm_fp8(const FedComm* comm, const GlmSegment* segs_dev, const GlmParams* prm, const void* tmaps,
-                                   int grid, cudaStream_t stream) {
+                                   const void* chunks_dev, int n_chunks, unsigned int* work_counter, int grid,
+                                   cudaStream_t stream) {
     const fp8::SmemLayoutF L = fp8::smem_layout(prm->n_features, comm->n_theta, prm->n_groups);
     if (L.stages < 2) return -2;
     const CUtensorMap* maps = reinterpret_cast<const CUtensorMap*>(tmaps);
 #define B200FED_FP8_LAUNCH(KF, DYN)                                                                                       \
     do {                                                                                                                 \
         cudaFuncSetAttribute(fp8::fed_glm_fp8_kernel<KF, DYN>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total); \
-        fp8::fed_glm_fp8_kernel<KF, DYN><<<grid, fp8::kThreadsF, L.total, stream>>>(*comm, segs_dev, *prm, maps);         \
+        cudaLaunchConfig_t cfg{};                                                                                        \
+        cfg.gridDim = dim3(grid);                                                                                        \
+        cfg.blockDim = dim3(fp8::kThreadsF);                                                                             \
+        cfg.dynamicSmemBytes = L.total;                                                                                  \
+        cfg.stream = stream;                                                                                             \
+        cudaLaunchAttribute attr[1];                                                                                     \
+        attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;                                                 \
+        attr[0].val.programmaticStreamSerializationAllowed = 1;                                                          \
+        cfg.attrs = attr;                                                                                                \
+        cfg.numAttrs = tc::use_pdl() ? 1 : 0;                                                                            \
+        cudaLaunchKernelEx(&cfg, fp8::fed_glm_fp8_kernel<KF, DYN>, *comm, segs_dev, *prm, maps,                          \
+                           reinterpret_cast<const GlmChunk*>(chunks_dev), n_chunks, work_counter);                       \
     } while (0)
     const bool dyn = prm->family != 0;  // unbounded residuals: per-row-group scales for the R operand
     if (prm->n_chains == 1) {

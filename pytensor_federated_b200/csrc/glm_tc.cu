@@ -28,6 +28,7 @@
 #include "fed_comm.cuh"
 #include "models.h"
 #include "tc_common.cuh"
+#include "chunks.h"
 
 namespace tc {
 
@@ -96,14 +97,6 @@ __host__ __device__ constexpr size_t partial_row_doubles(int n_vals, int kc, int
     return 2 * ((size_t)n_vals + (size_t)kLLRows * n_out * kc * (1 + n_groups));
 }
 
-__device__ __forceinline__ uint32_t ld_acquire_shared(const uint32_t* p) {
-    uint32_t v;
-    asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_release_shared(uint32_t* p, uint32_t v) {
-    asm volatile("st.release.cta.shared::cta.u32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
-}
 // (hi, lo) += x on a pair that only this thread touches during the launch
 __device__ __forceinline__ void dd_accumulate(double* slot, double x) {
     double2 cur = *reinterpret_cast<double2*>(slot);
@@ -372,6 +365,7 @@ fed_glm_tc_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParams
             // columns fetched per request (power-of-two shapes; the surplus columns are allocated TMEM, ignored)
             constexpr int kEtaCols = KH == 1 ? 4 : (KH == 2 ? 8 : (KH == 4 ? 16 : 24));
             constexpr int kGCols = KH <= 2 ? 4 : (KH == 4 ? 8 : 16);
+            constexpr bool kPrefetchSlots = KH <= 2;   // few enough registers to fetch the warp's slots a whole chunk early
             const int b = tp;                       // eta / R buffer of this group's tiles
             uint32_t bph = 0;                       // its phase: flips after every tile of this group
             Ring gbuf;
@@ -382,6 +376,19 @@ fed_glm_tc_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParams
                 const long long seg_rows = segs_g[ch.x].n_rows;
                 const int seg_group = segs_g[ch.x].group;
                 const int og = segs_g[ch.x].out_group;               // output block of this chunk's segment
+                // this warp's (hi, lo) slots of the chunk's output block: LL at +0, intercept gradient g at +(1 + g)
+                double* slot0 = ll_slots + 2 * ((((size_t)ew * NOUT + og) * KC + k0) * NS1);
+                double2 pre_l[kPrefetchSlots ? KH : 1], pre_g[kPrefetchSlots ? KH : 1];
+                if constexpr (kPrefetchSlots) {
+                    if (lane == 0) {
+#pragma unroll
+                        for (int k = 0; k < KH; ++k)
+                            if ((k0 + k) < nch) {
+                                pre_l[k] = *reinterpret_cast<const double2*>(slot0 + 2 * (size_t)k * NS1);
+                                pre_g[k] = *reinterpret_cast<const double2*>(slot0 + 2 * (size_t)k * NS1 + 2 * (1 + seg_group));
+                            }
+                    }
+                }
                 float ll_acc[KH], gi_cur[KH];
 #pragma unroll
                 for (int k = 0; k < KH; ++k) ll_acc[k] = gi_cur[k] = 0.f;
@@ -440,19 +447,45 @@ fed_glm_tc_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParams
                 }
                 // ---- end of the chunk for this group: fold its sums into the CTA's running pairs ----------
                 // per-thread fp32 sums over the chunk's tiles -> fixed butterfly over the warp (double) ->
-                // lane 0 adds the warp's value to its own slot: every step depends on the chunk only
+                // lane 0 adds the warp's value to its own slot: every step depends on the chunk only.
+                // The slots live in L2: all their loads are issued together (KH <= 2: already at the start of the
+                // chunk, see `pre`), so the chunk boundary costs one round trip at most, not 2 KH.
+                constexpr int kBatch = KH <= 4 ? KH : 4;   // chains whose slots are in flight together (register budget)
 #pragma unroll
-                for (int k = 0; k < KH; ++k) {
-                    double l = (double)ll_acc[k], gsum = (double)gi_cur[k];
+                for (int kb = 0; kb < KH; kb += kBatch) {
+                    double lsum[kBatch], gsum[kBatch];
 #pragma unroll
-                    for (int o = 16; o > 0; o >>= 1) {
-                        l += __shfl_xor_sync(0xffffffffu, l, o);
-                        gsum += __shfl_xor_sync(0xffffffffu, gsum, o);
+                    for (int k = 0; k < kBatch; ++k) {
+                        lsum[k] = (double)ll_acc[kb + k];
+                        gsum[k] = (double)gi_cur[kb + k];
+#pragma unroll
+                        for (int o = 16; o > 0; o >>= 1) {
+                            lsum[k] += __shfl_xor_sync(0xffffffffu, lsum[k], o);
+                            gsum[k] += __shfl_xor_sync(0xffffffffu, gsum[k], o);
+                        }
                     }
-                    if (lane == 0 && (k0 + k) < nch) {
-                        double* slot = ll_slots + 2 * ((((size_t)ew * NOUT + og) * KC + k0 + k) * NS1);
-                        dd_accumulate(slot, l);
-                        dd_accumulate(slot + 2 * (1 + seg_group), gsum);
+                    if (lane == 0) {
+                        double2 cl[kBatch], cg[kBatch];
+#pragma unroll
+                        for (int k = 0; k < kBatch; ++k) {
+                            if constexpr (kPrefetchSlots) {
+                                cl[k] = pre_l[kb + k];
+                                cg[k] = pre_g[kb + k];
+                            } else if ((k0 + kb + k) < nch) {
+                                const double* slot = slot0 + 2 * (size_t)(kb + k) * NS1;
+                                cl[k] = *reinterpret_cast<const double2*>(slot);
+                                cg[k] = *reinterpret_cast<const double2*>(slot + 2 * (1 + seg_group));
+                            }
+                        }
+#pragma unroll
+                        for (int k = 0; k < kBatch; ++k)
+                            if ((k0 + kb + k) < nch) {
+                                double* slot = slot0 + 2 * (size_t)(kb + k) * NS1;
+                                fed::dd_add(cl[k].x, cl[k].y, lsum[k], 0.0);
+                                fed::dd_add(cg[k].x, cg[k].y, gsum[k], 0.0);
+                                *reinterpret_cast<double2*>(slot) = cl[k];
+                                *reinterpret_cast<double2*>(slot + 2 * (1 + seg_group)) = cg[k];
+                            }
                     }
                 }
                 // gradient: the group that handled the chunk's last tile (odd index) drains the TMEM accumulator
@@ -537,32 +570,6 @@ EncodeTiledFn get_encode() {
 int chains_bucket(int k) { return k <= 1 ? 1 : (k <= 4 ? 4 : (k <= 8 ? 8 : (k <= 16 ? 16 : 0))); }
 }  // namespace
 
-// Chunk table of the dynamic scheduler: consecutive tiles of one segment, an even number of them (a segment
-// with an odd tile count ends in one empty tile), kMaxChunk tiles while plenty of work is left and shrinking
-// towards kMinChunk as the remaining work approaches two chunks per SM (guided self-scheduling), so the
-// last chunks that are handed out are the small ones.
-static std::vector<GlmChunk> build_chunks(const GlmSegment* segs, int n_segments, int sm_count) {
-    std::vector<GlmChunk> out;
-    long long remaining = 0;
-    for (int s = 0; s < n_segments; ++s) remaining += (segs[s].n_rows + tc::kTileM - 1) / tc::kTileM;
-    const int min_chunk = remaining <= 8ll * sm_count ? 2 : tc::kMinChunk;
-    for (int s = 0; s < n_segments; ++s) {
-        const long long ts = (segs[s].n_rows + tc::kTileM - 1) / tc::kTileM;
-        long long t = 0;
-        while (t < ts) {
-            long long want = (remaining / (2ll * sm_count)) & ~1ll;
-            if (want < min_chunk) want = min_chunk;
-            if (want > tc::kMaxChunk) want = tc::kMaxChunk;
-            long long real = want < ts - t ? want : ts - t;
-            long long n = real + (real & 1);
-            out.push_back(GlmChunk{s, (int)t, (int)n, 0});
-            t += real;
-            remaining -= real;
-        }
-    }
-    return out;
-}
-
 // Builds one TMA descriptor per segment ([n_rows, P] bf16, box = 64 features x 128 rows, 128B swizzle) and
 // the chunk table.
 extern "C" int b200_glm_tc_prepare(const GlmSegment* segs_host, int n_segments, const GlmParams* prm, int sm_count,
@@ -591,7 +598,8 @@ extern "C" int b200_glm_tc_prepare(const GlmSegment* segs_host, int n_segments, 
     if (e == cudaSuccess) e = cudaMemcpy(*tmaps_dev, host, sizeof(CUtensorMap) * n_segments, cudaMemcpyHostToDevice);
     delete[] host;
     if (e != cudaSuccess) return (int)e;
-    const std::vector<GlmChunk> chunks = build_chunks(segs_host, n_segments, sm_count > 0 ? sm_count : 148);
+    const std::vector<GlmChunk> chunks = build_chunks(segs_host, n_segments, sm_count > 0 ? sm_count : 148, tc::kTileM, 2,
+                                                        tc::kMaxChunk, tc::kMinChunk);
     if (*chunks_dev) cudaFree(*chunks_dev);
     e = cudaMalloc(chunks_dev, sizeof(GlmChunk) * (chunks.size() + 1));
     if (e == cudaSuccess) e = cudaMemcpy(*chunks_dev, chunks.data(), sizeof(GlmChunk) * chunks.size(), cudaMemcpyHostToDevice);
@@ -601,10 +609,11 @@ extern "C" int b200_glm_tc_prepare(const GlmSegment* segs_host, int n_segments, 
 
 // The chunk table for given segment sizes (host only; tests/test_chunk_schedule.py).  Writes up to max_chunks
 // triples (seg, first_tile, n_tiles) and returns the number of chunks.
-extern "C" int b200_glm_tc_chunk_table(const long long* n_rows, int n_segments, int sm_count, int* out, int max_chunks) {
+extern "C" int b200_glm_tc_chunk_table(const long long* n_rows, int n_segments, int sm_count, int multiple, int max_chunk,
+                                       int min_chunk, int* out, int max_chunks) {
     std::vector<GlmSegment> segs(n_segments);
     for (int s = 0; s < n_segments; ++s) segs[s].n_rows = n_rows[s];
-    const std::vector<GlmChunk> chunks = build_chunks(segs.data(), n_segments, sm_count);
+    const std::vector<GlmChunk> chunks = build_chunks(segs.data(), n_segments, sm_count, tc::kTileM, multiple, max_chunk, min_chunk);
     for (size_t i = 0; i < chunks.size() && (int)i < max_chunks; ++i) {
         out[3 * i + 0] = chunks[i].seg;
         out[3 * i + 1] = chunks[i].first_tile;

@@ -40,8 +40,11 @@ int b200_glm_tc_prepare(const GlmSegment* segs_host, int n_segments, const GlmPa
                         void** chunks_dev, int* n_chunks);
 size_t b200_glm_tc_partial_row_doubles(int n_vals, int n_chains, int n_out, int n_groups);
 int b200_launch_ode(const FedComm*, const OdeShard*, int, int, cudaStream_t);
-int b200_launch_glm_fp8(const FedComm*, const GlmSegment*, const GlmParams*, const void* tmaps, int grid, cudaStream_t);
-int b200_glm_fp8_prepare(const GlmSegment* segs_host, int n_segments, const GlmParams* prm, void** tmaps_dev);
+int b200_launch_glm_fp8(const FedComm*, const GlmSegment*, const GlmParams*, const void* tmaps, const void* chunks,
+                        int n_chunks, unsigned int* work_counter, int grid, cudaStream_t stream);
+int b200_glm_fp8_prepare(const GlmSegment* segs_host, int n_segments, const GlmParams* prm, int sm_count, void** tmaps_dev,
+                         void** chunks_dev, int* n_chunks);
+size_t b200_glm_fp8_partial_row_doubles(int n_vals, int n_chains, int n_groups);
 int b200_launch_glm_generic(const FedComm*, const GlmSegment*, const GlmParams*, int elem_bytes, int grid, cudaStream_t);
 }
 
@@ -205,9 +208,14 @@ int launch_model(Engine* e, const FedComm* c) {
         case MODEL_ODE:
             rc = (e->ode_launcher ? e->ode_launcher : b200_launch_ode)(c, e->ode_dev, (int)e->ode.size(), e->grid, e->stream);
             break;
-        case MODEL_GLM_FP8:
-            rc = b200_launch_glm_fp8(c, e->glm_segs_dev, &e->glm, e->glm_tmaps_dev, e->grid, e->stream);
+        case MODEL_GLM_FP8: {
+            FedComm ct = *c;   // same partial layout as the bf16 tensor-core kernel
+            ct.cta_partials = e->tc_partials;
+            ct.group_partials = e->tc_partials + (size_t)e->sm_count * e->tc_row_doubles;
+            rc = b200_launch_glm_fp8(&ct, e->glm_segs_dev, &e->glm, e->glm_tmaps_dev, e->glm_chunks_dev, e->glm_n_chunks,
+                                     e->work_counter, e->grid, e->stream);
             break;
+        }
         case MODEL_GLM_GENERIC:
             rc = (e->custom_launcher ? e->custom_launcher : b200_launch_glm_generic)(c, e->glm_segs_dev, &e->glm,
                                                                                       e->glm_elem_bytes, e->grid, e->stream);
@@ -434,7 +442,7 @@ void b200_engine_set_idle_timeout(void* h, double seconds) { static_cast<Engine*
 void b200_engine_set_grid(void* h, int grid) {
     // the per-CTA partial array holds sm_count * 8 rows; negative values select single-CTA modes
     Engine* e = static_cast<Engine*>(h);
-    const int max_blocks = e->kind == MODEL_GLM_TC ? e->sm_count : e->sm_count * 8;   // rows of the partial array
+    const int max_blocks = (e->kind == MODEL_GLM_TC || e->kind == MODEL_GLM_FP8) ? e->sm_count : e->sm_count * 8;   // partial rows
     e->grid = grid > max_blocks ? max_blocks : (grid == 0 ? 1 : grid);
 }
 int b200_engine_grid(void* h) { return static_cast<Engine*>(h)->grid; }
@@ -511,13 +519,20 @@ int b200_engine_set_glm(void* h, int n_segments, const void** X, const float** y
         e->kind = MODEL_GLM_GENERIC;
         e->grid = e->sm_count * 2;
     } else if (use_tensor_cores == 2) {  // block-scaled fp8
-        int rc = b200_glm_fp8_prepare(e->glm_segs.data(), n_segments, &e->glm, &e->glm_tmaps_dev);
+        int rc = b200_glm_fp8_prepare(e->glm_segs.data(), n_segments, &e->glm, e->sm_count, &e->glm_tmaps_dev,
+                                      &e->glm_chunks_dev, &e->glm_n_chunks);
         if (rc != 0) {
             g_last_error = "fp8 GLM path rejected this shape (rc=" + std::to_string(rc) + ")";
             return rc;
         }
+        e->tc_row_doubles = b200_glm_fp8_partial_row_doubles(e->n_vals, n_chains, n_groups);
+        if (e->tc_partials) cudaFree(e->tc_partials);
+        const size_t fp8_doubles = (size_t)e->sm_count * e->tc_row_doubles + ((size_t)e->sm_count / 16 + 2) * e->n_vals * 2;
+        CK(cudaMalloc((void**)&e->tc_partials, fp8_doubles * 8));
+        CK(cudaMemset(e->tc_partials, 0, fp8_doubles * 8));
         e->kind = MODEL_GLM_FP8;
         e->grid = e->sm_count;
+        if (e->glm_n_chunks > 0 && e->grid > e->glm_n_chunks) e->grid = e->glm_n_chunks;
     } else if (use_tensor_cores) {
         int rc = b200_glm_tc_prepare(e->glm_segs.data(), n_segments, &e->glm, e->sm_count, &e->glm_tmaps_dev,
                                      &e->glm_chunks_dev, &e->glm_n_chunks);

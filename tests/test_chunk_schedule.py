@@ -9,12 +9,12 @@ from pytensor_federated_b200.ops import native
 TILE = 128
 
 
-def chunk_table(n_rows, sm_count=148):
+def chunk_table(n_rows, sm_count=148, multiple=2, max_chunk=32, min_chunk=4):
     lib = native.load()
     rows = (C.c_longlong * len(n_rows))(*n_rows)
     cap = 1 << 20
     out = (C.c_int * (3 * cap))()
-    n = lib.b200_glm_tc_chunk_table(rows, len(n_rows), sm_count, out, cap)
+    n = lib.b200_glm_tc_chunk_table(rows, len(n_rows), sm_count, multiple, max_chunk, min_chunk, out, cap)
     assert 0 < n <= cap
     return np.frombuffer(out, dtype=np.int32, count=3 * n).reshape(n, 3).copy()
 
@@ -51,3 +51,16 @@ def test_small_problems_still_spread_over_the_sms():
     assert len(table) >= 148
     tiny = chunk_table([9000])                # 71 tiles
     assert (tiny[:, 2] == 2).all() and len(tiny) == 36
+
+
+@pytest.mark.parametrize("n_rows", [[10_000_000] * 8, [128 * 7 + 1, 128 * 3, 50]])
+def test_fp8_kernel_chunks_hold_whole_rotations_of_its_three_epilogue_groups(n_rows):
+    table = chunk_table(n_rows, multiple=3, max_chunk=30, min_chunk=6)
+    next_tile = [0] * len(n_rows)
+    for seg, first, n in table:
+        assert n % 3 == 0 and 3 <= n <= 30 and first == next_tile[seg]
+        tiles = -(-n_rows[seg] // TILE)
+        real = min(n, tiles - first)
+        assert real >= n - 2 and real >= 1              # at most two empty tiles, at the end of a segment
+        next_tile[seg] += real
+    assert next_tile == [-(-r // TILE) for r in n_rows]
