@@ -259,7 +259,8 @@ def run_b200(args):
             raise SystemExit("launch with torch.distributed.run --nproc-per-node N for --gpus N > 1")
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)
-    if world > 1:
+    own_pg = world > 1 and not dist.is_initialized()   # benchmarks/run_configs.py runs several configs in one group
+    if own_pg:
         os.environ.setdefault("MASTER_ADDR", "127.0.0.1")
         dist.init_process_group("nccl", device_id=dev)
 
@@ -316,6 +317,8 @@ def run_b200(args):
                 err = float(max(e_lp.max(), e_gr.max()))
             max_rel = max(max_rel, err)
         tol = {"glm": 2e-4, "fp8": 3e-3, "ode": 2e-3, "linreg": 1e-9}[args.config]
+        if backend == "collective" and args.config in ("glm", "fp8"):
+            tol = 5e-3   # the NCCL baseline's eager compute rounds theta and the residuals to bf16 for its two GEMMs
         verified = bool(max_rel <= tol)
         if not verified:
             print(json.dumps({"error": "verification failed", "max_rel_err": max_rel, "tolerance": tol, "n_gpus": world}),
@@ -404,7 +407,8 @@ def run_b200(args):
     eng.shutdown()
     if world > 1:
         dist.barrier()
-        dist.destroy_process_group()
+        if own_pg:
+            dist.destroy_process_group()
     if rank != 0:
         return
 
@@ -483,6 +487,7 @@ def run_b200(args):
             fh.write(out + "\n")
     if not result["verified"]:
         raise SystemExit(3)
+    return line
 
 
 def linreg_nuts(eng, args):

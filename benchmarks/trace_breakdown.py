@@ -47,7 +47,7 @@ def summarize(tr: np.ndarray) -> dict:
     return out
 
 
-def main() -> None:
+def main(argv=None) -> None:
     p = argparse.ArgumentParser()
     p.add_argument("--shards", type=int, default=1)
     p.add_argument("--rows", type=int, default=10_000_000)
@@ -56,7 +56,7 @@ def main() -> None:
     p.add_argument("--chains", type=int, default=1)
     p.add_argument("--launches", type=int, default=6)
     p.add_argument("--out", default=None)
-    a = p.parse_args()
+    a = p.parse_args(argv)
 
     import torch
     import torch.distributed as dist
@@ -69,7 +69,8 @@ def main() -> None:
     local = int(os.environ.get("LOCAL_RANK", "0"))
     torch.cuda.set_device(local)
     dev = torch.device("cuda", local)
-    if world > 1:
+    own_pg = world > 1 and not dist.is_initialized()
+    if own_pg:
         dist.init_process_group("nccl", device_id=dev)
     mine = [s for s in range(a.shards) if s % world == rank]
     Xs, ys, scs = [], [], []
@@ -130,7 +131,8 @@ def main() -> None:
     eng.shutdown()
     if world > 1:
         dist.barrier()
-        dist.destroy_process_group()
+        if own_pg:
+            dist.destroy_process_group()
     if rank == 0:
         res["config"] = {"world": world, "shards": a.shards, "rows": a.rows, "features": a.features, "kernel": a.kernel,
                          "chains": a.chains}
