@@ -129,11 +129,13 @@ fed_glm_tc_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParams
     // shared address space, so the compiler emits LDS / STS instead of generic LD / ST for everything below
     unsigned char* smem = smem_dyn + ((1024u - (smem_u32(smem_dyn) & 1023u)) & 1023u);
 
-    const int P = prm.n_features;
+    const int P = prm.n_features;     // real number of features (theta / result layout)
+    const int PP = (P + 127) & ~127;  // features the tile is padded to: TMA zero-fills the columns past P, their
+                                      // Theta rows are zero and their gradient rows are never stored
     const int G = prm.n_groups;
-    const int NH = P / 128;           // 128-feature halves (UMMA M of MMA #2)
-    const int panels = P / kPanel;
-    const SmemLayout L = smem_layout(P, N1, N2, comm.n_theta, G, KC, RB);
+    const int NH = PP / 128;          // 128-feature halves (UMMA M of MMA #2)
+    const int panels = PP / kPanel;
+    const SmemLayout L = smem_layout(PP, N1, N2, comm.n_theta, G, KC, RB);
     const int S = (int)L.stages;
     const int nch = prm.n_chains < KC ? prm.n_chains : KC;  // chains actually present in theta
     const int NV1 = 1 + G + P;        // outputs per chain: [LL, gi[G], g[P]]
@@ -207,7 +209,8 @@ fed_glm_tc_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParams
             if (chain < nch) {
 #pragma unroll
                 for (int e = 0; e < 8; ++e) {
-                    const float v = theta_f[chain * (G + P) + G + pnl * kPanel + j * 8 + e];
+                    const int f = pnl * kPanel + j * 8 + e;
+                    const float v = f < P ? theta_f[chain * (G + P) + G + f] : 0.f;
                     const __nv_bfloat16 hi = __float2bfloat16_rn(v);
                     const float rem1 = v - __bfloat162float(hi);
                     const __nv_bfloat16 mid = __float2bfloat16_rn(rem1);
@@ -504,16 +507,17 @@ fed_glm_tc_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParams
                                 tc_fence_before();
                                 mbar_arrive(&bar_g_empty[gb]);   // MMA #2 may start the chunk after next in this buffer
                             }
+                            const bool real = h * 128 + row < P;   // rows of the padding carry zeros: nothing to add
                             double2 cur[KH];
 #pragma unroll
                             for (int k = 0; k < KH; ++k)
-                                cur[k] = (k0 + k) < nch
+                                cur[k] = ((k0 + k) < nch && real)
                                              ? *reinterpret_cast<const double2*>(out + 2 * (((size_t)og * nch + k0 + k) * NV1 + 1 + G + h * 128 + row))
                                              : make_double2(0.0, 0.0);
 #pragma unroll
                             for (int k = 0; k < KH; ++k) {
                                 fed::dd_add(cur[k].x, cur[k].y, (double)gv[2 * k] + (double)gv[2 * k + 1], 0.0);
-                                if ((k0 + k) < nch)
+                                if ((k0 + k) < nch && real)
                                     *reinterpret_cast<double2*>(out + 2 * (((size_t)og * nch + k0 + k) * NV1 + 1 + G + h * 128 + row)) = cur[k];
                             }
                         }
@@ -574,7 +578,7 @@ int chains_bucket(int k) { return k <= 1 ? 1 : (k <= 4 ? 4 : (k <= 8 ? 8 : (k <=
 // the chunk table.
 extern "C" int b200_glm_tc_prepare(const GlmSegment* segs_host, int n_segments, const GlmParams* prm, int sm_count,
                                    void** tmaps_dev, void** chunks_dev, int* n_chunks) {
-    if (prm->n_features % 128 != 0 || prm->n_features > 384 || prm->n_features < 128) return -11;
+    if (prm->n_features % 8 != 0 || prm->n_features > 384 || prm->n_features < 8) return -11;   // padded to 128s by TMA
     if (chains_bucket(prm->n_chains) == 0) return -13;
     if ((prm->ld * 2) % 16 != 0) return -14;
     EncodeTiledFn encode = get_encode();
@@ -635,7 +639,7 @@ extern "C" int b200_launch_glm_tc(const FedComm* comm, const GlmSegment* segs_de
     const CUtensorMap* maps = reinterpret_cast<const CUtensorMap*>(tmaps);
 #define LAUNCH_TC(KC)                                                                                              \
     do {                                                                                                           \
-        const tc::SmemLayout L = tc::smem_layout(prm->n_features, tc::Cfg<KC>::N1, tc::Cfg<KC>::N2, comm->n_theta,  \
+        const tc::SmemLayout L = tc::smem_layout((prm->n_features + 127) & ~127, tc::Cfg<KC>::N1, tc::Cfg<KC>::N2, comm->n_theta,  \
                                                  prm->n_groups, KC, tc::Cfg<KC>::RB);                              \
         if (L.stages < 2) return -2;                                                                               \
         cudaFuncSetAttribute(tc::fed_glm_tc_kernel<KC>, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)L.total); \

@@ -38,7 +38,8 @@ class GlmShards(ShardModel):
     n_chains
         Parameter vectors evaluated per call (K).  ``K > 1`` needs the tensor-core kernel.
     kernel
-        ``"simt"`` (one chain, any P % 8 == 0 up to 512), ``"tc"`` (tcgen05 + TMA) or ``"auto"``.
+        ``"simt"`` (one chain, any P % 8 == 0 up to 512), ``"tc"`` (tcgen05 + TMA: bf16, any P % 8 == 0 up to
+        384 — the tile is padded to whole 128-feature blocks by TMA's zero fill —, up to 16 chains) or ``"auto"``.
     node_ids, n_nodes
         Keep the result PER NODE instead of summed: segment ``s`` is (part of) node ``node_ids[s]`` of
         an ``n_nodes`` federation and the reduced vector holds one ``[K][1 + G + P]`` block per node
@@ -159,12 +160,12 @@ class GlmShards(ShardModel):
         # auto: the tcgen05 kernel wherever its shape constraints hold (it is faster even for one chain:
         # TMA streaming + the X tile reused from smem for both GEMMs), then SIMT, then the general kernel
         bf16 = X0.dtype == torch.bfloat16
-        tc_ok = (bf16 and self.n_features % 128 == 0 and 128 <= self.n_features <= 384 and self.n_chains <= 16
+        tc_ok = (bf16 and self.n_features % 8 == 0 and 8 <= self.n_features <= 384 and self.n_chains <= 16
                  and all(X.data_ptr() % 16 == 0 for X in self.Xs) and self.ld % 8 == 0)
         if tc_ok:
             return 1
         if self.n_chains > 1:
-            raise ValueError("multi-chain evaluation needs the tensor-core kernel (bf16, P % 128 == 0, P <= 384, K <= 16)")
+            raise ValueError("multi-chain evaluation needs the tensor-core kernel (bf16, P % 8 == 0, P <= 384, K <= 16)")
         simt_ok = (bf16 and self.n_features % 8 == 0 and self.n_features <= 512 and self.ld % 8 == 0
                    and all(X.data_ptr() % 16 == 0 for X in self.Xs))
         if simt_ok:

@@ -93,7 +93,7 @@ def _glm_case(dev, rows, P, groups, n_groups, seed=0):
     return Xs, ys
 
 
-@pytest.mark.parametrize("P", [256, 128, 384])
+@pytest.mark.parametrize("P", [256, 128, 384, 72, 200, 8])
 @pytest.mark.parametrize("family", ["logistic", "gaussian"])
 def test_glm_tensor_core_matches_reference(dev, family, P):
     rows = [128 * 37, 77, 4099, 128, 1]
