@@ -185,11 +185,21 @@ class GlmShards(ShardModel):
         sp = native.void_p_array([s.data_ptr() for s in kernel_scales]) if kernel_scales else None
         rows = (C.c_longlong * n)(*[X.shape[0] for X in self.Xs])
         grp = (C.c_int * n)(*self.groups)
+        code = int(self.use_tensor_cores())
+        #: which fused kernel serves this model ("tc" / "fp8" = tcgen05 tensor cores, else CUDA cores)
+        self.selected_kernel = {0: "simt", 1: "tc", 2: "fp8", 3: "generic-bf16", 4: "generic-fp32"}[code]
+        if self.kernel == "auto" and code not in (1, 2) and not hasattr(self.family, "code_id"):
+            import logging
+
+            logging.getLogger(__name__).warning(
+                "GLM with %d features (%s, row stride %d) is outside the tensor-core kernel's shapes (bf16, P %% 8 == 0, "
+                "P <= 384, 16-byte aligned rows): using the %s CUDA-core kernel — single pass, but slower",
+                self.n_features, self.Xs[0].dtype, self.ld, self.selected_kernel)
         out_grp = (C.c_int * n)(*self.node_ids) if self.node_ids is not None else None
         native.check(
             lib.b200_engine_set_glm(
                 handle, n, Xp, yp, sp, rows, grp, self.n_features, self.ld, self.n_groups,
-                self.n_chains, _family_code(self.family), int(self.use_tensor_cores()), out_grp, self.n_nodes,
+                self.n_chains, _family_code(self.family), code, out_grp, self.n_nodes,
             ),
             "set_glm",
         )
