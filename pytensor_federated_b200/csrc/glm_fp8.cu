@@ -50,7 +50,7 @@ constexpr int kEG = 3;                // epilogue groups; tile t belongs to grou
 constexpr int kThreadsF = 32 * (3 + 4 * kEG);  // warps: 0 TMA, 1 MMA#1, 2-5 group 0, 6 MMA#2, 7-10 group 1, 11-14 group 2
 constexpr int kMaxChunkF = 30;        // tiles per chunk at most (fp32 accumulation in TMEM), a multiple of kEG
 constexpr int kMinChunkF = 6;
-constexpr int kRingF = 32;            // published chunks the consumers may lag behind
+constexpr int kRingF = 16;            // published chunks the consumers may lag behind
 constexpr int kLLRowsF = 4 * kEG;     // epilogue warps: per-warp slots of the warp-level sums
 constexpr int kN = 16;                // MMA N for both GEMMs
 constexpr int kThetaTerms = 5;
@@ -115,7 +115,7 @@ __host__ __device__ inline SmemLayoutF smem_layout(int P, int n_theta, int n_gro
     L.stage_bytes = panels * kPanelB;
     L.theta_b_bytes = panels * kN * 128;
     L.r_bytes = kTile * kN;  // 1 byte per element
-    const uint32_t fixed = L.theta_b_bytes + kEG * L.r_bytes + ((n_theta * 4 + 15) & ~15) + kRingF * 16 + 16 + 512 + 1024;
+    const uint32_t fixed = L.theta_b_bytes + kEG * L.r_bytes + ((n_theta * 4 + 15) & ~15) + kRingF * 24 + 512 + 1024;
     uint32_t stages = (227u * 1024u - fixed) / L.stage_bytes;
     if (stages > 6) stages = 6;
     L.stages = stages;
@@ -123,7 +123,7 @@ __host__ __device__ inline SmemLayoutF smem_layout(int P, int n_theta, int n_gro
     L.off_theta_b = o; o += L.theta_b_bytes;
     L.off_r = o; o += kEG * L.r_bytes;
     L.off_theta_f = o; o += (n_theta * 4 + 15) & ~15;
-    L.off_ring = o; o += kRingF * 16 + 16;   // published chunks + the publication counter
+    L.off_ring = o; o += kRingF * 24;   // published chunks + one mbarrier per ring slot
     L.off_bars = o; o += 320;
     L.off_tmem = o; o += 192;  // tmem slot, theta norms, residual-exponent exchange (DYN)
     L.total = o + 1024;
@@ -152,7 +152,7 @@ fed_glm_fp8_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParam
     unsigned char* r_buf = smem + L.off_r;
     float* theta_f = reinterpret_cast<float*>(smem + L.off_theta_f);
     int4* ring = reinterpret_cast<int4*>(smem + L.off_ring);          // published chunks: (segment or -1, first tile, tiles, -)
-    uint32_t* n_published = reinterpret_cast<uint32_t*>(smem + L.off_ring + kRingF * 16);
+    uint64_t* bar_ring = reinterpret_cast<uint64_t*>(smem + L.off_ring + kRingF * 16);   // slot j % kRingF: chunk j published
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.off_bars);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L.off_tmem);
     float* theta_norm = reinterpret_cast<float*>(smem + L.off_tmem + 16);  // c: theta = c * sum_k t_k 16^-k
@@ -178,7 +178,7 @@ fed_glm_fp8_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParam
         reinterpret_cast<uint4*>(r_buf)[i] = make_uint4(0, 0, 0, 0);
     if (threadIdx.x == 0) {
         *pipeline_fault() = 0;
-        *n_published = 0u;
+        for (int i = 0; i < kRingF; ++i) mbar_init(&bar_ring[i], 1);
         for (int i = 0; i < 6; ++i) { mbar_init(&bar_full[i], 1); mbar_init(&bar_empty[i], 1); }
         for (int i = 0; i < kEG; ++i) {
             mbar_init(&bar_eta_full[i], 1);
@@ -264,14 +264,16 @@ fed_glm_fp8_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParam
         static_assert(128 + kSfRing * 16 + 4 + kEG * 4 <= (int)kTmemCols, "TMEM budget");
 
         // Consumers: the j-th chunk of this CTA, or x < 0 when the producer found the work counter exhausted.
+        // (an mbarrier per ring slot: the producer arrives after writing the entry — release —, the consumers wait
+        // on the slot's phase — acquire; slot j % kRingF is reused every kRingF chunks, consumers lag ~3 at most)
         auto next_chunk = [&](int j) -> int4 {
-            while (ld_acquire_shared(n_published) <= (uint32_t)j) {
-            }
+            mbar_wait(&bar_ring[j & (kRingF - 1)], (uint32_t)((j / kRingF) & 1));
+            if (*pipeline_fault()) return make_int4(-1, 0, 0, 0);   // a stalled pipeline ends every role loop
             return ring[j & (kRingF - 1)];
         };
         // non-blocking variant for look-ahead: x == -2 when chunk j has not been published yet
         auto peek_chunk = [&](int j) -> int4 {
-            if (ld_acquire_shared(n_published) <= (uint32_t)j) return make_int4(-2, 0, 0, 0);
+            if (!mbar_try_wait(&bar_ring[j & (kRingF - 1)], (uint32_t)((j / kRingF) & 1))) return make_int4(-2, 0, 0, 0);
             return ring[j & (kRingF - 1)];
         };
 
@@ -287,7 +289,7 @@ fed_glm_fp8_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParam
                 if (have) ch = chunks[claim];
                 if (lane == 0) {
                     ring[j & (kRingF - 1)] = have ? make_int4(ch.seg, ch.first_tile, ch.n_tiles, 0) : make_int4(-1, 0, 0, 0);
-                    st_release_shared(n_published, (uint32_t)j + 1u);
+                    mbar_arrive(&bar_ring[j & (kRingF - 1)]);
                     if (have) ahead = atomicAdd(work_counter, 1u);
                 }
                 __syncwarp();

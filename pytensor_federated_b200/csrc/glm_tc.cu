@@ -38,7 +38,7 @@ constexpr int kPanelBytes = kTileM * 128;  // 16 KB
 // warps: 0 TMA, 1 MMA#1 issuer, 2-5 epilogue group 0, 6 MMA#2 issuer, 7.. further epilogue groups
 constexpr int kMaxChunk = 32;        // tiles per chunk at most (= tiles accumulated in TMEM in fp32 before a flush)
 constexpr int kMinChunk = 4;
-constexpr int kRing = 32;            // published chunks the consumers may lag behind (needs only ~3)
+constexpr int kRing = 16;            // published chunks the consumers may lag behind (needs only ~3)
 constexpr int kLLRows = 16;          // epilogue warps at most (per-warp log-likelihood slots)
 
 struct SmemLayout {
@@ -55,7 +55,7 @@ __host__ __device__ inline SmemLayout smem_layout(int P, int n1, int n2, int n_t
     L.r_bytes = kTileM * n2 * 2;
     // theta (fp32) is staged inside the (not yet used) TMA stage ring and is dead once the bf16 B operand
     // and the intercept table are built, so it costs no shared memory of its own.
-    const uint32_t fixed = L.theta_b_bytes + r_bufs * L.r_bytes + ((chains * n_groups * 4 + 15) & ~15) + kRing * 16 + 16 + 192 +
+    const uint32_t fixed = L.theta_b_bytes + r_bufs * L.r_bytes + ((chains * n_groups * 4 + 15) & ~15) + kRing * 24 + 192 +
                            64 + 1024 /*alignment slack*/;
     uint32_t stages = (227u * 1024u - fixed) / L.stage_bytes;
     if (stages > 4) stages = 4;
@@ -65,7 +65,7 @@ __host__ __device__ inline SmemLayout smem_layout(int P, int n1, int n2, int n_t
     L.off_r = o; o += r_bufs * L.r_bytes;
     L.off_theta_f = 0;  // aliases stage 0.. (needs n_theta * 4 <= stages * stage_bytes)
     L.off_icpt = o; o += (chains * n_groups * 4 + 15) & ~15;
-    L.off_ring = o; o += kRing * 16 + 16;   // published chunks + the publication counter
+    L.off_ring = o; o += kRing * 24;   // published chunks + one mbarrier per ring slot
     L.off_bars = o; o += 192;
     L.off_tmem = o; o += 64;
     L.total = o + 1024;
@@ -145,7 +145,7 @@ fed_glm_tc_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParams
     float* theta_f = reinterpret_cast<float*>(smem + L.off_theta_f);  // valid until the setup barrier only
     float* icpt = reinterpret_cast<float*>(smem + L.off_icpt);        // [KC][G] intercepts
     int4* ring = reinterpret_cast<int4*>(smem + L.off_ring);          // (segment or -1, first row, tiles, -)
-    uint32_t* n_published = reinterpret_cast<uint32_t*>(smem + L.off_ring + kRing * 16);
+    uint64_t* bar_ring = reinterpret_cast<uint64_t*>(smem + L.off_ring + kRing * 16);   // slot j % kRing: chunk j published
     uint64_t* bars = reinterpret_cast<uint64_t*>(smem + L.off_bars);
     uint32_t* tmem_slot = reinterpret_cast<uint32_t*>(smem + L.off_tmem);
     uint64_t* bar_full = bars;            // [4]
@@ -167,7 +167,7 @@ fed_glm_tc_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParams
         reinterpret_cast<uint4*>(r_buf)[i] = make_uint4(0, 0, 0, 0);
     if (threadIdx.x == 0) {
         *pipeline_fault() = 0;
-        *n_published = 0u;
+        for (int i = 0; i < kRing; ++i) mbar_init(&bar_ring[i], 1);
         for (int i = 0; i < 4; ++i) { mbar_init(&bar_full[i], 1); mbar_init(&bar_empty[i], 1); }
         for (int i = 0; i < 2; ++i) {
             mbar_init(&bar_eta_full[i], 1);
@@ -230,9 +230,11 @@ fed_glm_tc_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParams
         const uint32_t tmem_g = tmem_base + 2 * N1;          // 2 buffers x NH x N2 columns
 
         // Consumers: the j-th chunk of this CTA, or x < 0 when the producer found the work counter exhausted.
+        // (an mbarrier per ring slot: the producer arrives after writing the entry — release —, the consumers wait
+        // on the slot's phase — acquire; slot j % kRing is reused every kRing chunks, consumers lag ~3 at most)
         auto next_chunk = [&](int j) -> int4 {
-            while (ld_acquire_shared(n_published) <= (uint32_t)j) {
-            }
+            mbar_wait(&bar_ring[j & (kRing - 1)], (uint32_t)((j / kRing) & 1));
+            if (*pipeline_fault()) return make_int4(-1, 0, 0, 0);   // a stalled pipeline ends every role loop
             return ring[j & (kRing - 1)];
         };
 
@@ -250,7 +252,7 @@ fed_glm_tc_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParams
                 if (have) ch = chunks[claim];
                 if (lane == 0) {
                     ring[j & (kRing - 1)] = have ? make_int4(ch.seg, ch.first_tile * kTileM, ch.n_tiles, 0) : make_int4(-1, 0, 0, 0);
-                    st_release_shared(n_published, (uint32_t)j + 1u);
+                    mbar_arrive(&bar_ring[j & (kRing - 1)]);
                     if (have) ahead = atomicAdd(work_counter, 1u);   // next claim: the round trip hides behind this chunk
                 }
                 __syncwarp();

@@ -176,16 +176,6 @@ inline bool use_pdl() {
     return on;
 }
 
-// Publication of the chunk ring (producer -> the other roles of the CTA)
-__device__ __forceinline__ uint32_t ld_acquire_shared(const uint32_t* p) {
-    uint32_t v;
-    asm volatile("ld.acquire.cta.shared::cta.u32 %0, [%1];" : "=r"(v) : "r"(smem_u32(p)) : "memory");
-    return v;
-}
-__device__ __forceinline__ void st_release_shared(uint32_t* p, uint32_t v) {
-    asm volatile("st.release.cta.shared::cta.u32 [%0], %1;" ::"r"(smem_u32(p)), "r"(v) : "memory");
-}
-
 // Index + phase bit of an n-deep circular buffer, advanced without division (the single-thread
 // TMA / MMA issue loops are latency chains: a 64-bit `it % n`, `it / n` pair costs ~100 instructions).
 struct Ring {
