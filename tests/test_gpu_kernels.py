@@ -424,3 +424,25 @@ def test_ode_nodes_with_their_own_parameters_on_the_gpu(dev):
     np.testing.assert_allclose(blocks[:, 0], want[:, 0], rtol=2e-4)
     np.testing.assert_allclose(blocks[:, 1:], want[:, 1:], rtol=5e-3, atol=1.0)
     np.testing.assert_allclose(logp, want[:, 0].sum(), rtol=2e-4)
+
+
+def test_glm_tensor_core_takes_many_segments_and_tiny_shards(dev):
+    """100 segments (round 1 stopped at 64), some of a single row, some empty-tile padded, 7 groups."""
+    torch.manual_seed(31)
+    rng = np.random.default_rng(31)
+    rows = [int(r) for r in rng.integers(1, 700, size=100)]
+    rows[3], rows[50], rows[99] = 1, 128, 129
+    Xs = [torch.randn(n, 128, device=dev).to(torch.bfloat16) for n in rows]
+    ys = [(torch.rand(n, device=dev) < 0.5).float() for n in rows]
+    groups = [i % 7 for i in range(100)]
+    model = GlmShards(Xs, ys, groups=groups, n_groups=7, kernel="tc")
+    ic = rng.normal(size=7) * 0.1
+    beta = (rng.normal(size=128) * 0.05).astype(np.float32)
+    with FederatedEngine(model) as eng:
+        got = eng.evaluate(ic, beta)
+        again = eng.evaluate(ic, beta)
+    want = model.unpack_result(model.reference_partial([ic, beta], dtype=torch.float64))
+    np.testing.assert_allclose(got[0], want[0], rtol=2e-5)
+    np.testing.assert_allclose(got[1], want[1], rtol=1e-4, atol=2e-3)
+    np.testing.assert_allclose(got[2], want[2], rtol=1e-4, atol=0.05)
+    assert all(np.array_equal(a, b) for a, b in zip(got, again))
