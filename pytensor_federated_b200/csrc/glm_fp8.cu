@@ -106,8 +106,8 @@ struct SmemLayoutF {
 };
 // doubles per CTA row of the partial array: (hi, lo) pairs of the n_vals outputs, then the per-warp slots
 // [kLLRowsF][KF][1 + G] of the warp-level sums (log-likelihood, intercept gradients) — see csrc/glm_tc.cu
-__host__ __device__ constexpr size_t partial_row_doubles(int n_vals, int kf, int n_groups) {
-    return 2 * ((size_t)n_vals + (size_t)kLLRowsF * kf * (1 + n_groups));
+__host__ __device__ constexpr size_t partial_row_doubles(int n_vals, int kf, int n_out, int n_groups) {
+    return 2 * ((size_t)n_vals + (size_t)kLLRowsF * n_out * kf * (1 + n_groups));
 }
 __host__ __device__ inline SmemLayoutF smem_layout(int P, int n_theta, int n_groups) {
     SmemLayoutF L;
@@ -209,9 +209,10 @@ fed_glm_fp8_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParam
     const int NV1 = 1 + PG;   // outputs per chain: [LL, gi[G], g[P]]
     const int NS1 = 1 + G;    // warp-level values per chain: LL and the G intercept gradients
     // this CTA's running sums as (hi, lo) pairs (see csrc/glm_tc.cu: dynamic chunks + double-double sums)
-    const size_t row_doubles = partial_row_doubles(comm.n_vals, KF, G);
+    const int NOUT = prm.n_out;   // output blocks (1 = everything summed; else one per node, GlmSegment::out_group)
+    const size_t row_doubles = partial_row_doubles(comm.n_vals, KF, NOUT, G);
     double* out = comm.cta_partials + (size_t)blockIdx.x * row_doubles;
-    double* ll_slots = out + 2 * (size_t)comm.n_vals;   // [kLLRowsF][KF][1 + G] pairs
+    double* ll_slots = out + 2 * (size_t)comm.n_vals;   // [kLLRowsF][NOUT][KF][1 + G] pairs
 
     if (active) {
         for (size_t i = threadIdx.x; i < row_doubles / 2; i += blockDim.x) reinterpret_cast<double2*>(out)[i] = make_double2(0.0, 0.0);
@@ -450,8 +451,9 @@ fed_glm_fp8_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParam
                 const float* __restrict__ seg_y = segs_g[ch.x].y;
                 const long long seg_rows = segs_g[ch.x].n_rows;
                 const int seg_group = segs_g[ch.x].group;
+                const int og = segs_g[ch.x].out_group;   // output block of this chunk's segment
                 // this warp's (hi, lo) slots: LL at +0, intercept gradient g at +(1 + g); fetched a whole chunk early
-                double* slot0 = ll_slots + 2 * (((size_t)ew * KF) * NS1);
+                double* slot0 = ll_slots + 2 * ((((size_t)ew * NOUT + og) * KF) * NS1);
                 double2 pre_l[KF], pre_g[KF];
                 if (lane == 0) {
 #pragma unroll
@@ -586,7 +588,7 @@ fed_glm_fp8_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParam
 #pragma unroll
                         for (int k = 0; k < KF; ++k)
                             if (k < nch) {
-                                double* slot = out + 2 * ((size_t)k * NV1 + 1 + G + h * 128 + row);
+                                double* slot = out + 2 * (((size_t)og * nch + k) * NV1 + 1 + G + h * 128 + row);
                                 double2 cur = *reinterpret_cast<double2*>(slot);
                                 fed::dd_add(cur.x, cur.y,
                                             (double)kResidNorm * ((double)gv[4 * k] + (double)gv[4 * k + 1] * (1.0 / 16) +
@@ -607,15 +609,15 @@ fed_glm_fp8_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParam
         fed::pdl_trigger();   // the next evaluation's CTA may take this SM as soon as we exit
         // layout per chain: [LL, gi[G], g[P]] as (hi, lo) pairs; g[] was accumulated in place, LL and gi[] are the
         // per-warp slots summed in warp order
-        for (int i = threadIdx.x; i < nch * NS1; i += blockDim.x) {
-            const int jv = i % NS1, k = i / NS1;
+        for (int i = threadIdx.x; i < NOUT * nch * NS1; i += blockDim.x) {
+            const int jv = i % NS1, k = (i / NS1) % nch, o = i / (NS1 * nch);
             double hi = 0.0, lo = 0.0;
             for (int w = 0; w < kLLRowsF; ++w) {
-                const double* slot = ll_slots + 2 * (((size_t)w * KF + k) * NS1 + jv);
+                const double* slot = ll_slots + 2 * ((((size_t)w * NOUT + o) * KF + k) * NS1 + jv);
                 fed::dd_add(hi, lo, slot[0], slot[1]);
             }
-            out[2 * ((size_t)k * NV1 + jv)] = hi;
-            out[2 * ((size_t)k * NV1 + jv) + 1] = lo;
+            out[2 * (((size_t)o * nch + k) * NV1 + jv)] = hi;
+            out[2 * (((size_t)o * nch + k) * NV1 + jv) + 1] = lo;
         }
     }
     __syncthreads();
@@ -679,8 +681,8 @@ extern "C" int b200_glm_fp8_prepare(const GlmSegment* segs_host, int n_segments,
     return e == cudaSuccess ? 0 : (int)e;
 }
 
-extern "C" size_t b200_glm_fp8_partial_row_doubles(int n_vals, int n_chains, int n_groups) {
-    return fp8::partial_row_doubles(n_vals, n_chains == 1 ? 1 : 3, n_groups);
+extern "C" size_t b200_glm_fp8_partial_row_doubles(int n_vals, int n_chains, int n_out, int n_groups) {
+    return fp8::partial_row_doubles(n_vals, n_chains == 1 ? 1 : 3, n_out > 0 ? n_out : 1, n_groups);
 }
 
 extern "C" int b200_launch_glm_fp8(const FedComm* comm, const GlmSegment* segs_dev, const GlmParams* prm, const void* tmaps,

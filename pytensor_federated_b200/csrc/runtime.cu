@@ -44,7 +44,7 @@ int b200_launch_glm_fp8(const FedComm*, const GlmSegment*, const GlmParams*, con
                         int n_chunks, unsigned int* work_counter, int grid, cudaStream_t stream);
 int b200_glm_fp8_prepare(const GlmSegment* segs_host, int n_segments, const GlmParams* prm, int sm_count, void** tmaps_dev,
                          void** chunks_dev, int* n_chunks);
-size_t b200_glm_fp8_partial_row_doubles(int n_vals, int n_chains, int n_groups);
+size_t b200_glm_fp8_partial_row_doubles(int n_vals, int n_chains, int n_out, int n_groups);
 int b200_launch_glm_generic(const FedComm*, const GlmSegment*, const GlmParams*, int elem_bytes, int grid, cudaStream_t);
 }
 
@@ -503,8 +503,8 @@ int b200_engine_set_glm(void* h, int n_segments, const void** X, const float** y
         tiles += (n_rows[s] + tile_rows - 1) / tile_rows;
     }
     e->glm = GlmParams{n_segments, n_features, ld, n_groups, n_chains, family, tiles, n_out > 0 ? n_out : 1, 0};
-    if (e->glm.n_out > 1 && use_tensor_cores != 1) {
-        g_last_error = "per-node outputs need the tensor-core GLM kernel (kernel='tc')";
+    if (e->glm.n_out > 1 && use_tensor_cores != 1 && use_tensor_cores != 2) {
+        g_last_error = "per-node outputs need a tensor-core GLM kernel (kernel='tc' or 'fp8')";
         return -32;
     }
     if ((long long)e->glm.n_out * n_chains * (1 + n_groups + n_features) != e->n_vals) {
@@ -525,7 +525,7 @@ int b200_engine_set_glm(void* h, int n_segments, const void** X, const float** y
             g_last_error = "fp8 GLM path rejected this shape (rc=" + std::to_string(rc) + ")";
             return rc;
         }
-        e->tc_row_doubles = b200_glm_fp8_partial_row_doubles(e->n_vals, n_chains, n_groups);
+        e->tc_row_doubles = b200_glm_fp8_partial_row_doubles(e->n_vals, n_chains, e->glm.n_out, n_groups);
         if (e->tc_partials) cudaFree(e->tc_partials);
         const size_t fp8_doubles = (size_t)e->sm_count * e->tc_row_doubles + ((size_t)e->sm_count / 16 + 2) * e->n_vals * 2;
         CK(cudaMalloc((void**)&e->tc_partials, fp8_doubles * 8));

@@ -43,7 +43,7 @@ class GlmShards(ShardModel):
     node_ids, n_nodes
         Keep the result PER NODE instead of summed: segment ``s`` is (part of) node ``node_ids[s]`` of
         an ``n_nodes`` federation and the reduced vector holds one ``[K][1 + G + P]`` block per node
-        (tensor-core kernel only).  ``evaluate`` still returns the sum; :meth:`per_node` and
+        (tensor-core kernels only: ``"tc"`` and the fp8 kernel).  ``evaluate`` still returns the sum; :meth:`per_node` and
         :class:`~pytensor_federated_b200.federation.NodeFederation` expose the blocks — the reference's
         one-Op-per-node pattern (``/root/reference/demo_model.py:28-36``) answered by one launch.
     """
@@ -363,11 +363,11 @@ class Fp8GlmShards(GlmShards):
     """
 
     def __init__(self, Xqs, scales, ys, *, groups=None, n_groups: int = 1, n_chains: int = 1,
-                 family: str = "logistic") -> None:
+                 family: str = "logistic", node_ids=None, n_nodes=None) -> None:
         if not 1 <= n_chains <= 3:
             raise ValueError("the fp8 kernel batches at most 3 chains per launch")
         super().__init__(Xqs, ys, groups=groups, n_groups=n_groups, family=family, n_chains=n_chains, kernel="fp8",
-                         scales=scales)
+                         scales=scales, node_ids=node_ids, n_nodes=n_nodes)
         self._kernel_scales = [pack_tile_scales(s, self.n_features) for s in self.scales]
 
     @classmethod

@@ -446,3 +446,25 @@ def test_glm_tensor_core_takes_many_segments_and_tiny_shards(dev):
     np.testing.assert_allclose(got[1], want[1], rtol=1e-4, atol=2e-3)
     np.testing.assert_allclose(got[2], want[2], rtol=1e-4, atol=0.05)
     assert all(np.array_equal(a, b) for a, b in zip(got, again))
+
+
+def test_glm_fp8_keeps_per_node_output_blocks(dev):
+    """The hierarchical configuration as the reference would model it: one group AND one node per shard."""
+    torch.manual_seed(9)
+    rows = [128 * 50 + 3, 9000, 128 * 7]
+    Xs = [torch.randn(n, 256, device=dev) * torch.exp(0.3 * torch.randn(256, device=dev)) for n in rows]
+    ys = [(torch.rand(n, device=dev) < 0.4).float() for n in rows]
+    model = Fp8GlmShards.from_dense(Xs, ys, groups=[0, 1, 2], n_groups=3, node_ids=[0, 1, 2], n_nodes=3)
+    ic = np.array([0.2, -0.3, 0.05])
+    beta = (np.random.default_rng(5).normal(size=256) * 0.02).astype(np.float32)
+    with FederatedEngine(model) as eng:
+        raw = eng.evaluate_raw([ic, beta])
+        assert np.array_equal(raw, eng.evaluate_raw([ic, beta]))
+        summed = eng.evaluate(ic, beta)
+    blocks = model.per_node(raw)
+    want = model.per_node(model.reference_partial([ic, beta], dtype=torch.float64))
+    for n in range(3):
+        np.testing.assert_allclose(blocks[n, 0, 0], want[n, 0, 0], rtol=2e-5)
+        np.testing.assert_allclose(blocks[n, 0, 4:], want[n, 0, 4:], rtol=2e-4, atol=2e-4 * np.abs(want[n, 0, 4:]).max())
+        assert np.count_nonzero(blocks[n, 0, 1:4]) == 1          # only the node's own intercept gradient
+    np.testing.assert_allclose(summed[0], want[:, 0, 0].sum(), rtol=2e-5)
