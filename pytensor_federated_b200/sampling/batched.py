@@ -156,12 +156,37 @@ def hmc_sample_batched(logp_dlogp_batch: BatchFn, x0: np.ndarray, *, draws: int 
 
 def glm_batch_fn(engine, n_groups: int) -> BatchFn:
     """Adapts a multi-chain ``FederatedEngine(GlmShards(..., n_chains=K))`` to the batched signature
-    with ``theta = [intercept[G], beta[P]]`` per chain (flat prior; add priors by wrapping)."""
+    with ``theta = [intercept[G], beta[P]]`` per chain (flat prior; add priors by wrapping).
+
+    Any number of chains may be passed: the kernel's capacity per launch is ``K`` (at most 16 for the bf16
+    tensor-core kernel, 3 for the fp8 kernel); more chains are evaluated in ``ceil(chains / K)`` launches and a
+    short last tile is padded by repeating its last chain, so 64 chains on a K = 16 engine cost four passes over the
+    data instead of sixty-four."""
+    cap = int(getattr(engine.model, "n_chains", 1))
+
+    def tile(theta: np.ndarray):
+        logp, d_ic, d_beta = engine.evaluate(theta[:, :n_groups], theta[:, n_groups:])
+        return np.asarray(logp).reshape(-1), np.concatenate([np.asarray(d_ic).reshape(cap, -1), np.asarray(d_beta).reshape(cap, -1)], axis=1)
 
     def fn(theta: np.ndarray):
         theta = np.asarray(theta)
-        logp, d_ic, d_beta = engine.evaluate(theta[:, :n_groups], theta[:, n_groups:])
-        return np.asarray(logp), np.concatenate([np.asarray(d_ic).reshape(theta.shape[0], -1), np.asarray(d_beta)], axis=1)
+        n = theta.shape[0]
+        if n == cap and cap > 1:
+            return tile(theta)
+        logps, grads = [], []
+        for first in range(0, n, cap):
+            block = theta[first : first + cap]
+            k = block.shape[0]
+            if k < cap:
+                block = np.concatenate([block, np.repeat(block[-1:], cap - k, axis=0)], axis=0)
+            if cap == 1:   # single-chain engines take unbatched inputs
+                logp, d_ic, d_beta = engine.evaluate(block[0, :n_groups], block[0, n_groups:])
+                lp, gr = np.asarray(logp).reshape(1), np.concatenate([np.asarray(d_ic).reshape(-1), np.asarray(d_beta)])[None]
+            else:
+                lp, gr = tile(block)
+            logps.append(lp[:k])
+            grads.append(gr[:k])
+        return np.concatenate(logps), np.concatenate(grads, axis=0)
 
     return fn
 

@@ -320,3 +320,25 @@ def test_hmc_chain_resumes_bit_identically(tmp_path):
     first.save(str(tmp_path / "chain"))
     rest = hmc_sample(fn, None, draws=30, resume=SamplerResult.load(str(tmp_path / "chain")))
     np.testing.assert_array_equal(np.concatenate([first.samples, rest.samples]), full.samples)
+
+
+def test_glm_batch_fn_tiles_more_chains_than_the_kernel_takes_per_launch():
+    """7 chains on engines with capacity 1 / 3 / 7: 7 / 3 / 1 launches, same numbers (padding rows dropped)."""
+    import torch
+
+    from pytensor_federated_b200.models import GlmShards
+    from pytensor_federated_b200.sampling import glm_batch_fn
+
+    torch.manual_seed(0)
+    X = torch.randn(300, 8).to(torch.bfloat16)
+    y = (torch.rand(300) < 0.5).float()
+    theta = np.random.default_rng(0).normal(size=(7, 9)) * 0.2
+    results = {}
+    for cap, launches in ((1, 7), (3, 3), (7, 1)):
+        eng = FederatedEngine(GlmShards([X], [y], n_chains=cap, kernel="simt" if cap == 1 else "tc"), backend="collective")
+        results[cap] = glm_batch_fn(eng, 1)(theta)
+        assert eng.n_evals == launches
+        assert results[cap][0].shape == (7,) and results[cap][1].shape == (7, 9)
+    for cap in (3, 7):
+        np.testing.assert_allclose(results[cap][0], results[1][0], rtol=1e-5)
+        np.testing.assert_allclose(results[cap][1], results[1][1], rtol=1e-4, atol=1e-4)
