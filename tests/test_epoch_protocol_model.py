@@ -9,6 +9,11 @@ checks, for random interleavings and several epochs, that
 * every CTA of every node computes with exactly the theta of its epoch (never a mix of two epochs),
 * the host receives, per epoch, exactly the rank-ordered sum of that epoch's node partials,
 * nothing dead-locks — and that the checks have teeth: dropping the fence is detected.
+
+`group > 0` models the two-level reduction of round 2 (`epilogue_t`: tickets per group of `kReduceGroup` CTAs,
+the last CTA of a group writes the group partial, the last GROUP sums the group partials): every group partial
+must be complete when it is read, exactly one CTA per node runs the final stage, and every ticket is back at
+zero when the node's next kernel starts.
 """
 import random
 
@@ -18,8 +23,13 @@ N_THETA = 3
 
 
 class World:
-    def __init__(self, nodes, ctas, epochs, rng, ll=False, fence=True):
+    def __init__(self, nodes, ctas, epochs, rng, ll=False, fence=True, group=0, reset_group_ticket=True):
         self.n, self.g, self.epochs, self.rng, self.ll, self.fence = nodes, ctas, epochs, rng, ll, fence
+        self.group, self.reset_group_ticket = group, reset_group_ticket
+        n_groups = (ctas + group - 1) // group if group else 0
+        self.group_ticket = [[0] * n_groups for _ in range(nodes)]
+        self.group_partials = [[None] * n_groups for _ in range(nodes)]
+        self.finalizers = {}
         zero_word = (0.0, 0)
         self.mail = [{"theta": [zero_word if ll else 0.0] * N_THETA, "flag": 0} for _ in range(nodes)]
         self.slots = [zero_word if ll else 0.0 for _ in range(nodes)]
@@ -83,11 +93,33 @@ class World:
         assert got == self.theta_of(epoch), f"node {node} CTA {c} computed epoch {epoch} with theta {got}"
         self.partials[node][c] = self.partial_of(got, node, c)
         yield
-        self.ticket[node] += 1                                # atomic
-        if self.ticket[node] != self.g:
-            return
-        self.ticket[node] = 0
-        node_sum = sum(self.partials[node])                   # fixed order
+        if self.group:                                        # two-level, fixed shape
+            grp, first = c // self.group, (c // self.group) * self.group
+            size = min(self.group, self.g - first)
+            n_groups = len(self.group_ticket[node])
+            self.group_ticket[node][grp] += 1                 # atomic
+            if self.group_ticket[node][grp] != size:
+                return
+            if self.reset_group_ticket:
+                self.group_ticket[node][grp] = 0
+            yield
+            self.group_partials[node][grp] = (epoch, sum(self.partials[node][first:first + size]))
+            yield
+            self.ticket[node] += 1                            # atomic
+            if self.ticket[node] != n_groups:
+                return
+            yield
+            assert all(gp is not None and gp[0] == epoch for gp in self.group_partials[node]), \
+                "the final stage read a group partial of another epoch"
+            node_sum = sum(gp[1] for gp in self.group_partials[node])
+            self.ticket[node] = 0
+        else:
+            self.ticket[node] += 1                            # atomic
+            if self.ticket[node] != self.g:
+                return
+            self.ticket[node] = 0
+            node_sum = sum(self.partials[node])               # fixed order
+        self.finalizers[(node, epoch)] = self.finalizers.get((node, epoch), 0) + 1
         word = (node_sum, epoch) if self.ll else node_sum
         self.store(writer, lambda: self.slots.__setitem__(node, word))
         if not self.ll:
@@ -117,6 +149,7 @@ class World:
             if node == 0:
                 while self.launched < epoch:
                     yield
+            assert self.ticket[node] == 0 and not any(self.group_ticket[node]), "a ticket was left armed for the next launch"
             ctas = [self.cta(node, c, epoch) for c in range(self.g)]
             while ctas:
                 c = self.rng.choice(ctas)
@@ -182,3 +215,18 @@ def test_the_model_notices_a_missing_fence():
     with pytest.raises(AssertionError):
         for _ in range(300):
             World(3, 2, 4, random.Random(rng.random()), ll=False, fence=False).run()
+
+
+@pytest.mark.parametrize("ll", [False, True], ids=["fence+flag", "flag-in-data"])
+def test_two_level_reduce_is_exact_and_runs_one_final_stage_per_node(ll):
+    rng = random.Random(7 + ll)
+    for trial in range(60):
+        nodes, ctas, epochs, group = rng.randint(1, 3), rng.randint(1, 7), rng.randint(1, 4), rng.randint(1, 3)
+        w = World(nodes, ctas, epochs, random.Random(rng.random()), ll=ll, group=group).run()
+        assert w.results == {e: w.expected(e) for e in range(1, epochs + 1)}, (nodes, ctas, epochs, group)
+        assert w.finalizers == {(n, e): 1 for n in range(nodes) for e in range(1, epochs + 1)}
+
+
+def test_the_model_notices_a_group_ticket_that_is_not_reset():
+    with pytest.raises(AssertionError):
+        World(2, 4, 3, random.Random(1), group=2, reset_group_ticket=False).run()
