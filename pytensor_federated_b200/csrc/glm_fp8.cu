@@ -196,6 +196,29 @@ fed_glm_fp8_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParam
     if (warp == 0 && lane == 0)
         for (int i = 0; i < prm.n_segments; ++i) tma_prefetch_desc(&tmaps[i]);
     if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
+    // Early loads (see csrc/glm_tc.cu): the TMA warp claims the first chunk and fills the stage ring before
+    // theta has arrived; theta has its own shared memory here, so every stage can be used.
+    unsigned int claim0 = 0;
+    int preloaded = 0;
+    if (warp == 0) {
+        __syncwarp();   // lane 0's mbarrier inits
+        fed::pdl_wait();
+        if (lane == 0) claim0 = atomicAdd(work_counter, 1u);
+        claim0 = __shfl_sync(0xffffffffu, claim0, 0);
+        if (claim0 < (unsigned int)n_chunks) {
+            const GlmChunk ch = chunks[claim0];
+            preloaded = ch.n_tiles < S ? ch.n_tiles : S;
+            if (elect_one()) {
+                for (int t = 0; t < preloaded; ++t) {
+                    mbar_expect_tx(&bar_full[t], L.stage_bytes);
+                    for (int pnl = 0; pnl < NH; ++pnl)
+                        tma_load_2d(smem + (size_t)t * L.stage_bytes + pnl * kPanelB, &tmaps[ch.seg], pnl * kPanelF,
+                                    (ch.first_tile + t) * kTile, &bar_full[t]);
+                }
+            }
+            __syncwarp();
+        }
+    }
     tc_fence_before();
 
     fed::Prologue pro = fed::prologue(comm, theta_f);   // contains __syncthreads()
@@ -281,9 +304,7 @@ fed_glm_fp8_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParam
         if (warp == 0) {
             // ================= TMA producer + chunk scheduler (see csrc/glm_tc.cu) ==============
             Ring stage;
-            unsigned int claim = 0, ahead = 0;
-            if (lane == 0) claim = atomicAdd(work_counter, 1u);
-            claim = __shfl_sync(0xffffffffu, claim, 0);
+            unsigned int claim = claim0, ahead = 0;   // the first chunk was claimed before theta arrived
             for (int j = 0;; ++j) {
                 const bool have = claim < (unsigned int)n_chunks;
                 GlmChunk ch{};
@@ -297,6 +318,10 @@ fed_glm_fp8_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParam
                 if (!have) break;
                 for (int t = 0; t < ch.n_tiles; ++t) {
                     const int st = stage.idx;
+                    if (j == 0 && t < preloaded) {   // already in flight (early loads)
+                        stage.advance(S);
+                        continue;
+                    }
                     mbar_wait(&bar_empty[st], stage.phase ^ 1);
                     const int row0 = (ch.first_tile + t) * kTile;
                     unsigned char* dst = smem + (size_t)st * L.stage_bytes;
@@ -619,6 +644,9 @@ fed_glm_fp8_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParam
             out[2 * (((size_t)o * nch + k) * NV1 + jv)] = hi;
             out[2 * (((size_t)o * nch + k) * NV1 + jv) + 1] = lo;
         }
+    } else if (warp == 0) {
+        // nothing will be computed (stop / idle): the early loads still have to land before the CTA may exit
+        for (int t = 0; t < preloaded; ++t) mbar_wait(&bar_full[t], 0u);
     }
     __syncthreads();
     if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);

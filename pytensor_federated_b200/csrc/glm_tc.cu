@@ -43,7 +43,7 @@ constexpr int kLLRows = 16;          // epilogue warps at most (per-warp log-lik
 
 struct SmemLayout {
     uint32_t stages, stage_bytes, off_theta_b, theta_b_bytes, off_r, r_bytes, off_theta_f, off_icpt, off_ring,
-        off_bars, off_tmem, total;
+        off_bars, off_tmem, total, preload;
 };
 // r_bufs: residual (R) buffers between the epilogue and MMA #2 — 2 normally; 1 for 16 chains, where the 8 KB
 // buy the third TMA stage (the epilogue of 16 chains is long enough to hide the short MMA #2 it then waits for)
@@ -53,8 +53,8 @@ __host__ __device__ inline SmemLayout smem_layout(int P, int n1, int n2, int n_t
     L.stage_bytes = panels * kPanelBytes;
     L.theta_b_bytes = panels * n1 * 128;
     L.r_bytes = kTileM * n2 * 2;
-    // theta (fp32) is staged inside the (not yet used) TMA stage ring and is dead once the bf16 B operand
-    // and the intercept table are built, so it costs no shared memory of its own.
+    // theta (fp32) is staged inside the TMA stage ring and is dead once the bf16 B operand and the intercept
+    // table are built, so it costs no shared memory of its own.
     const uint32_t fixed = L.theta_b_bytes + r_bufs * L.r_bytes + ((chains * n_groups * 4 + 15) & ~15) + kRing * 24 + 192 +
                            64 + 1024 /*alignment slack*/;
     uint32_t stages = (227u * 1024u - fixed) / L.stage_bytes;
@@ -63,7 +63,12 @@ __host__ __device__ inline SmemLayout smem_layout(int P, int n1, int n2, int n_t
     uint32_t o = stages * L.stage_bytes;
     L.off_theta_b = o; o += L.theta_b_bytes;
     L.off_r = o; o += r_bufs * L.r_bytes;
-    L.off_theta_f = 0;  // aliases stage 0.. (needs n_theta * 4 <= stages * stage_bytes)
+    // theta (fp32) sits in the LAST stage when it fits into one: the TMA warp fills the first stages - 1 stages
+    // with this CTA's first tiles BEFORE theta has arrived (`preload`), the last stage is free once the B
+    // operand is built.  (larger theta: stage 0 onwards, needs n_theta * 4 <= stages * stage_bytes, no preload)
+    const bool theta_in_last = (uint32_t)n_theta * 4u <= L.stage_bytes && stages >= 2;
+    L.off_theta_f = theta_in_last ? (stages - 1) * L.stage_bytes : 0;
+    L.preload = theta_in_last ? stages - 1 : 0;
     L.off_icpt = o; o += (chains * n_groups * 4 + 15) & ~15;
     L.off_ring = o; o += kRing * 24;   // published chunks + one mbarrier per ring slot
     L.off_bars = o; o += 192;
@@ -182,6 +187,31 @@ fed_glm_tc_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParams
     if (warp == 0 && lane == 0)
         for (int i = 0; i < prm.n_segments; ++i) tma_prefetch_desc(&tmaps[i]);
     if (warp == 1) tmem_alloc(tmem_slot, kTmemCols);
+    // Early loads: X does not depend on theta.  The TMA warp waits for the previous evaluation to retire (its
+    // last CTA re-arms the work counter), claims this CTA's first chunk and fills all stages but the one theta
+    // is staged in, so the tensor core has `preload` tiles waiting when theta arrives (peers see theta several
+    // microseconds after they became resident: root's PCIe read + the NVLink broadcast).
+    unsigned int claim0 = 0;
+    int preloaded = 0;
+    if (warp == 0) {
+        __syncwarp();   // lane 0's mbarrier inits
+        fed::pdl_wait();
+        if (lane == 0) claim0 = atomicAdd(work_counter, 1u);
+        claim0 = __shfl_sync(0xffffffffu, claim0, 0);
+        if (claim0 < (unsigned int)n_chunks) {
+            const GlmChunk ch = chunks[claim0];
+            preloaded = ch.n_tiles < (int)L.preload ? ch.n_tiles : (int)L.preload;
+            if (elect_one()) {
+                for (int t = 0; t < preloaded; ++t) {
+                    mbar_expect_tx(&bar_full[t], L.stage_bytes);
+                    for (int pnl = 0; pnl < panels; ++pnl)
+                        tma_load_2d(smem + (size_t)t * L.stage_bytes + pnl * kPanelBytes, &tmaps[ch.seg], pnl * kPanel,
+                                    (ch.first_tile + t) * kTileM, &bar_full[t]);
+                }
+            }
+            __syncwarp();
+        }
+    }
     tc_fence_before();
 
     fed::Prologue pro = fed::prologue(comm, theta_f);   // contains __syncthreads()
@@ -243,9 +273,7 @@ fed_glm_tc_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParams
             // The role loops are warp-uniform (all 32 lanes wait and count); only the issue is predicated on
             // elect.sync, so the compiler keeps addresses / descriptors in uniform registers.
             Ring stage;
-            unsigned int claim = 0, ahead = 0;
-            if (lane == 0) claim = atomicAdd(work_counter, 1u);
-            claim = __shfl_sync(0xffffffffu, claim, 0);
+            unsigned int claim = claim0, ahead = 0;   // the first chunk was claimed before theta arrived
             for (int j = 0;; ++j) {
                 const bool have = claim < (unsigned int)n_chunks;
                 GlmChunk ch{};
@@ -259,8 +287,12 @@ fed_glm_tc_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParams
                 if (!have) break;
                 for (int t = 0; t < ch.n_tiles; ++t) {
                     const int st = stage.idx;
+                    if (j == 0 && t < preloaded) {   // already in flight (early loads)
+                        stage.advance(S);
+                        continue;
+                    }
                     mbar_wait(&bar_empty[st], stage.phase ^ 1);
-                    if (j == 0 && t == 0 && lane == 0) fed::stamp(comm, 3);
+                    if (j == 0 && t == preloaded && lane == 0) fed::stamp(comm, 3);
                     const int row0 = (ch.first_tile + t) * kTileM;
                     unsigned char* dst = smem + (size_t)st * L.stage_bytes;
                     if (elect_one()) {
@@ -547,6 +579,9 @@ fed_glm_tc_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParams
             out[2 * (((size_t)o * nch + k) * NV1 + j) + 1] = lo;
         }
         if (threadIdx.x == 0) fed::stamp(comm, 6);
+    } else if (warp == 0) {
+        // nothing will be computed (stop / idle): the early loads still have to land before the CTA may exit
+        for (int t = 0; t < preloaded; ++t) mbar_wait(&bar_full[t], 0u);
     }
     __syncthreads();
     if (warp == 1) tmem_dealloc(tmem_base, kTmemCols);
