@@ -391,7 +391,10 @@ __device__ __forceinline__ bool epilogue_t(const FedComm& c, const Prologue& pro
     constexpr int kW = DD ? 2 : 1;
 
     // ---- level 1: last CTA of the group -> group partial ------------------------------------------------
-    if (threadIdx.x == 0 && status_in) atomicOr(c.ticket + 255, (unsigned int)status_in);   // any CTA's fault reaches the host
+    // any CTA's fault reaches the final stage — and so does any CTA's expired wait for theta: the bounded waits
+    // run out per CTA, so when theta arrives right at the deadline some CTAs may have computed and others not
+    const unsigned long long status_cta = status_in | ((pro.timed_out && !pro.stop) ? B200FED_ERR_THETA_TIMEOUT : 0ull);
+    if (threadIdx.x == 0 && status_cta) atomicOr(c.ticket + 255, (unsigned int)status_cta);
     __threadfence();
     __syncthreads();
     if (threadIdx.x == 0) {
@@ -432,17 +435,22 @@ __device__ __forceinline__ bool epilogue_t(const FedComm& c, const Prologue& pro
         s_status |= (unsigned long long)atomicExch(c.ticket + 255, 0u);
     }
     __syncthreads();
+    // The evaluation counts only if EVERY CTA had theta.  A mixed launch (see above) is treated like an expired
+    // wait: nothing is published; a peer leaves the epoch where it was, the serve loop re-arms it, and the next
+    // kernel finds this epoch's theta already in its mailbox and recomputes.
+    const bool any_timed_out = (s_status & B200FED_ERR_THETA_TIMEOUT) != 0ull;
 
-    if (!computed) {
+    if (!computed || any_timed_out) {
         // nothing was computed: just report and drain.  A PEER whose wait for theta expired has merely been idle
         // (the client paused between evaluations): it leaves the epoch where it was and counts an idle tick, so
         // the serve loop re-arms it instead of taking the federation down.
         if (threadIdx.x == 0) {
-            const bool idle = pro.timed_out && !pro.stop && c.rank != 0;
+            const bool timed_out = pro.timed_out || any_timed_out;
+            const bool idle = timed_out && !pro.stop && c.rank != 0;
             const unsigned long long done_epoch = idle ? epoch - 1ull : epoch;
             *c.ticket = 0;
             if (c.epoch_counter) *c.epoch_counter = done_epoch;
-            unsigned long long st = (pro.timed_out && !idle) ? B200FED_ERR_THETA_TIMEOUT : 0ull;
+            unsigned long long st = (timed_out && !idle) ? B200FED_ERR_THETA_TIMEOUT : 0ull;
             unsigned long long word = (pro.stop ? B200FED_STOP_EPOCH : done_epoch) | (st << B200FED_STATUS_SHIFT);
             if (idle && c.idle_ticks) {
                 volatile unsigned long long* ticks = c.idle_ticks;

@@ -208,6 +208,7 @@ fed_glm_fp8_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParam
         if (claim0 < (unsigned int)n_chunks) {
             const GlmChunk ch = chunks[claim0];
             preloaded = ch.n_tiles < S ? ch.n_tiles : S;
+            if (!prm.early_loads) preloaded = 0;
             if (elect_one()) {
                 for (int t = 0; t < preloaded; ++t) {
                     mbar_expect_tx(&bar_full[t], L.stage_bytes);

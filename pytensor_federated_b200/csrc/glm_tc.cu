@@ -201,6 +201,7 @@ fed_glm_tc_kernel(FedComm comm, const GlmSegment* __restrict__ segs_g, GlmParams
         if (claim0 < (unsigned int)n_chunks) {
             const GlmChunk ch = chunks[claim0];
             preloaded = ch.n_tiles < (int)L.preload ? ch.n_tiles : (int)L.preload;
+            if (!prm.early_loads) preloaded = 0;
             if (elect_one()) {
                 for (int t = 0; t < preloaded; ++t) {
                     mbar_expect_tx(&bar_full[t], L.stage_bytes);

@@ -30,6 +30,12 @@
 #include "fed_comm.cuh"
 #include "models.h"
 
+// A/B switch for the early TMA loads of the tensor-core GLM kernels (GlmParams::early_loads)
+static bool early_loads_enabled() {
+    const char* v = getenv("B200FED_NO_EARLY_LOADS");
+    return !(v && *v && *v != '0');
+}
+
 extern "C" {
 int b200_launch_linreg(const FedComm*, const LinregShard*, int, int, int, cudaStream_t);
 int b200_launch_glm_simt(const FedComm*, const GlmSegment*, const GlmParams*, int, cudaStream_t);
@@ -502,7 +508,7 @@ int b200_engine_set_glm(void* h, int n_segments, const void** X, const float** y
         e->glm_segs[s] = g;
         tiles += (n_rows[s] + tile_rows - 1) / tile_rows;
     }
-    e->glm = GlmParams{n_segments, n_features, ld, n_groups, n_chains, family, tiles, n_out > 0 ? n_out : 1, 0};
+    e->glm = GlmParams{n_segments, n_features, ld, n_groups, n_chains, family, tiles, n_out > 0 ? n_out : 1, early_loads_enabled() ? 1 : 0};
     if (e->glm.n_out > 1 && use_tensor_cores != 1 && use_tensor_cores != 2) {
         g_last_error = "per-node outputs need a tensor-core GLM kernel (kernel='tc' or 'fp8')";
         return -32;

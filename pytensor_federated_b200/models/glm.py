@@ -102,14 +102,23 @@ class GlmShards(ShardModel):
         intercept, beta = inputs
         return (np.ndim(beta) == 2, np.shape(intercept))
 
+    _pack_views = None
+
     def pack_theta(self, inputs, out: np.ndarray):
         intercept, beta = inputs
-        th = out.view(np.float32).reshape(self.n_chains, self.n_params)
-        ic = np.asarray(intercept, dtype=np.float32)
-        bt = np.asarray(beta, dtype=np.float32)
-        ctx = self._note_shapes(inputs)
-        th[:, : self.n_groups] = ic.reshape(self.n_chains, -1) if ctx[0] else ic.reshape(1, -1)
-        th[:, self.n_groups :] = bt.reshape(self.n_chains, self.n_features)
+        views = self._pack_views
+        if views is None or views[0] is not out:
+            # float32 windows into the staging buffer, built once per buffer (this runs on every evaluation)
+            th = out.view(np.float32).reshape(self.n_chains, self.n_params)
+            views = self._pack_views = (out, th[:, : self.n_groups], th[:, self.n_groups :])
+        ic = intercept if type(intercept) is np.ndarray else np.asarray(intercept)
+        bt = beta if type(beta) is np.ndarray else np.asarray(beta)
+        batched = bt.ndim == 2
+        ctx = (batched, ic.shape)
+        self._batched, self._icpt_shape = ctx
+        # the assignments convert to float32 while they copy
+        views[1][...] = ic.reshape(self.n_chains, -1) if batched else ic.reshape(1, -1)
+        views[2][...] = bt.reshape(self.n_chains, self.n_features)
         return ctx
 
     _batched = False
