@@ -63,6 +63,16 @@ fed_glm_generic_kernel(FedComm comm, const GlmSegment* __restrict__ segs, GlmPar
     if (!pro.stop && !pro.timed_out) {
         const int lane = threadIdx.x & 31, warp = threadIdx.x >> 5;
         for (int i = threadIdx.x; i < G; i += blockDim.x) gi_acc[i] = 0ull;
+        // Per-node output blocks (prm.n_out > 1, GlmSegment::out_group): a warp's contiguous row range may cross
+        // node boundaries, so its sums are flushed at every boundary (and at the end) into this CTA's row of
+        // the partial array, used as 40.24 fixed-point accumulators — integer atomics are associative, the result
+        // does not depend on the order of the warps — and converted to doubles in place before the reduction.
+        const int NOUT = prm.n_out;
+        const int NV1 = 1 + G + P;
+        double* out = comm.cta_partials + (size_t)blockIdx.x * comm.n_vals;
+        unsigned long long* fx = reinterpret_cast<unsigned long long*>(out);
+        if (NOUT > 1)
+            for (int i = threadIdx.x; i < comm.n_vals; i += blockDim.x) fx[i] = 0ull;
         __syncthreads();
         float beta[J], g[J];
 #pragma unroll
@@ -86,10 +96,23 @@ fed_glm_generic_kernel(FedComm comm, const GlmSegment* __restrict__ segs, GlmPar
         float icpt = theta[seg.group];
         for (; b < b_end; ++b) {
             while (b >= seg.first_tile + ((seg.n_rows + 7) / 8)) {
-                if (lane == 0) fed::fix_add(&gi_acc[seg.group], (double)gi);
+                if (lane == 0) fed::fix_add(NOUT > 1 ? &fx[seg.out_group * NV1 + 1 + seg.group] : &gi_acc[seg.group], (double)gi);
                 gi = 0.f;
+                const int og = seg.out_group;
                 seg = segs[++s];
                 icpt = theta[seg.group];
+                if (NOUT > 1 && seg.out_group != og) {   // node boundary: flush this warp's sums into block og
+#pragma unroll
+                    for (int j = 0; j < J; ++j) {
+                        const int f = lane + 32 * j;
+                        if (f < P) fed::fix_add(&fx[og * NV1 + 1 + G + f], (double)g[j]);
+                        g[j] = 0.f;
+                    }
+                    if (lane == 0) fed::fix_add(&fx[og * NV1], ll_total + (double)ll_acc);
+                    ll_total = 0.0;
+                    ll_acc = 0.f;
+                    flush = 0;
+                }
             }
             const T* Xs = reinterpret_cast<const T*>(seg.X);
             const long long r0 = (b - seg.first_tile) * 8;
@@ -122,11 +145,26 @@ fed_glm_generic_kernel(FedComm comm, const GlmSegment* __restrict__ segs, GlmPar
             }
         }
         ll_total += (double)ll_acc;
+        if (NOUT > 1) {
+            if (b_end > gw * T8 / W) {
+                const int og = seg.out_group;
+#pragma unroll
+                for (int j = 0; j < J; ++j) {
+                    const int f = lane + 32 * j;
+                    if (f < P) fed::fix_add(&fx[og * NV1 + 1 + G + f], (double)g[j]);
+                }
+                if (lane == 0) {
+                    fed::fix_add(&fx[og * NV1], ll_total);
+                    fed::fix_add(&fx[og * NV1 + 1 + seg.group], (double)gi);
+                }
+            }
+            __syncthreads();
+            for (int i = threadIdx.x; i < comm.n_vals; i += blockDim.x) out[i] = fed::fix_get(__ldcg(&fx[i]));
+        } else {
         if (lane == 0 && b_end > gw * T8 / W) fed::fix_add(&gi_acc[seg.group], (double)gi);
 #pragma unroll
         for (int j = 0; j < J; ++j) g_red[warp * (J * 32) + lane + 32 * j] = g[j];
         const double ll_block = fed::block_sum(ll_total, red);
-        double* out = comm.cta_partials + (size_t)blockIdx.x * comm.n_vals;
         if (threadIdx.x == 0) out[0] = ll_block;
         for (int i = threadIdx.x; i < G; i += blockDim.x) out[1 + i] = fed::fix_get(gi_acc[i]);
         for (int f = threadIdx.x; f < P; f += blockDim.x) {
@@ -134,6 +172,7 @@ fed_glm_generic_kernel(FedComm comm, const GlmSegment* __restrict__ segs, GlmPar
 #pragma unroll
             for (int w = 0; w < kWarpsG; ++w) sum += (double)g_red[w * (J * 32) + f];
             out[1 + G + f] = sum;
+        }
         }
     }
     fed::epilogue(comm, pro, 0ull);

@@ -73,6 +73,14 @@ fed_glm_simt_kernel(FedComm comm, const GlmSegment* __restrict__ segs, GlmParams
         const int lane = threadIdx.x & 31;
         const int warp = threadIdx.x >> 5;
         for (int i = threadIdx.x; i < G; i += blockDim.x) gi_acc[i] = 0ull;
+        // Per-node output blocks (prm.n_out > 1): see csrc/glm_generic.cu — warps flush their sums at node
+        // boundaries into this CTA's row of the partial array, used as fixed-point accumulators.
+        const int NOUT = prm.n_out;
+        const int NV1 = 1 + G + P;
+        double* out = comm.cta_partials + (size_t)blockIdx.x * comm.n_vals;
+        unsigned long long* fx = reinterpret_cast<unsigned long long*>(out);
+        if (NOUT > 1)
+            for (int i = threadIdx.x; i < comm.n_vals; i += blockDim.x) fx[i] = 0ull;
         __syncthreads();
 
         // this lane's slice of beta
@@ -111,10 +119,26 @@ fed_glm_simt_kernel(FedComm comm, const GlmSegment* __restrict__ segs, GlmParams
             while (b >= seg.first_tile + ((seg.n_rows + kBatch - 1) / kBatch)) {
                 // segment switch: flush the intercept gradient of the finished group
                 gi = warp_sum(gi);  // every row's r sits in 4 lanes -> x0.25
-                if (lane == 0) fed::fix_add(&gi_acc[seg.group], (double)gi * 0.25);
+                if (lane == 0) fed::fix_add(NOUT > 1 ? &fx[seg.out_group * NV1 + 1 + seg.group] : &gi_acc[seg.group], (double)gi * 0.25);
                 gi = 0.f;
+                const int og = seg.out_group;
                 seg = segs[++s];
                 icpt = theta[seg.group];
+                if (NOUT > 1 && seg.out_group != og) {   // node boundary: flush this warp's sums into block og
+#pragma unroll
+                    for (int c = 0; c < NCH; ++c)
+#pragma unroll
+                        for (int k = 0; k < 8; ++k) {
+                            if (lane_on[c]) fed::fix_add(&fx[og * NV1 + 1 + G + c * 256 + lane * 8 + k], (double)g[c][k]);
+                            g[c][k] = 0.f;
+                        }
+                    double llw = ll_total + (double)ll_acc;
+                    for (int o = 16; o > 0; o >>= 1) llw += __shfl_xor_sync(0xffffffffu, llw, o);
+                    if (lane == 0) fed::fix_add(&fx[og * NV1], llw * 0.25);
+                    ll_total = 0.0;
+                    ll_acc = 0.f;
+                    flush_count = 0;
+                }
             }
             const long long r0 = (b - seg.first_tile) * kBatch;
             const __nv_bfloat16* Xs = reinterpret_cast<const __nv_bfloat16*>(seg.X);
@@ -189,6 +213,24 @@ fed_glm_simt_kernel(FedComm comm, const GlmSegment* __restrict__ segs, GlmParams
         }
         ll_total += (double)ll_acc;
         gi = warp_sum(gi);
+        if (NOUT > 1) {
+            double llw = ll_total;
+            for (int o = 16; o > 0; o >>= 1) llw += __shfl_xor_sync(0xffffffffu, llw, o);
+            if (b_end > gw * T / W) {
+                const int og = seg.out_group;
+#pragma unroll
+                for (int c = 0; c < NCH; ++c)
+#pragma unroll
+                    for (int k = 0; k < 8; ++k)
+                        if (lane_on[c]) fed::fix_add(&fx[og * NV1 + 1 + G + c * 256 + lane * 8 + k], (double)g[c][k]);
+                if (lane == 0) {
+                    fed::fix_add(&fx[og * NV1], llw * 0.25);
+                    fed::fix_add(&fx[og * NV1 + 1 + seg.group], (double)gi * 0.25);
+                }
+            }
+            __syncthreads();
+            for (int i = threadIdx.x; i < comm.n_vals; i += blockDim.x) out[i] = fed::fix_get(__ldcg(&fx[i]));
+        } else {
         if (lane == 0 && b_end > gw * T / W) fed::fix_add(&gi_acc[seg.group], (double)gi * 0.25);
 
         // ---- CTA reduction -> cta_partials[blockIdx.x] = [LL, gi[G], g[P]] ----
@@ -197,7 +239,6 @@ fed_glm_simt_kernel(FedComm comm, const GlmSegment* __restrict__ segs, GlmParams
 #pragma unroll
             for (int k = 0; k < 8; ++k) g_red[warp * (NCH * 256) + c * 256 + lane * 8 + k] = g[c][k];
         const double ll_block = fed::block_sum(ll_total * 0.25, red);  // also syncs
-        double* out = comm.cta_partials + (size_t)blockIdx.x * comm.n_vals;
         if (threadIdx.x == 0) out[0] = ll_block;
         for (int i = threadIdx.x; i < G; i += blockDim.x) out[1 + i] = fed::fix_get(gi_acc[i]);
         for (int f = threadIdx.x; f < P; f += blockDim.x) {
@@ -205,6 +246,7 @@ fed_glm_simt_kernel(FedComm comm, const GlmSegment* __restrict__ segs, GlmParams
 #pragma unroll
             for (int w = 0; w < kWarps; ++w) sum += (double)g_red[w * (NCH * 256) + f];
             out[1 + G + f] = sum;
+        }
         }
     }
     fed::epilogue(comm, pro, 0ull);

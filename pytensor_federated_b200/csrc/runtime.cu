@@ -509,10 +509,6 @@ int b200_engine_set_glm(void* h, int n_segments, const void** X, const float** y
         tiles += (n_rows[s] + tile_rows - 1) / tile_rows;
     }
     e->glm = GlmParams{n_segments, n_features, ld, n_groups, n_chains, family, tiles, n_out > 0 ? n_out : 1, early_loads_enabled() ? 1 : 0};
-    if (e->glm.n_out > 1 && use_tensor_cores != 1 && use_tensor_cores != 2) {
-        g_last_error = "per-node outputs need a tensor-core GLM kernel (kernel='tc' or 'fp8')";
-        return -32;
-    }
     if ((long long)e->glm.n_out * n_chains * (1 + n_groups + n_features) != e->n_vals) {
         g_last_error = "n_vals does not match n_out x n_chains x (1 + n_groups + n_features)";
         return -33;

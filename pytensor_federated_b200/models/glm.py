@@ -43,7 +43,8 @@ class GlmShards(ShardModel):
     node_ids, n_nodes
         Keep the result PER NODE instead of summed: segment ``s`` is (part of) node ``node_ids[s]`` of
         an ``n_nodes`` federation and the reduced vector holds one ``[K][1 + G + P]`` block per node
-        (tensor-core kernels only: ``"tc"`` and the fp8 kernel).  ``evaluate`` still returns the sum; :meth:`per_node` and
+        (every kernel: the tensor-core kernels route a chunk's sums to its node's block, the CUDA-core kernels flush
+        at node boundaries into fixed-point accumulators).  ``evaluate`` still returns the sum; :meth:`per_node` and
         :class:`~pytensor_federated_b200.federation.NodeFederation` expose the blocks — the reference's
         one-Op-per-node pattern (``/root/reference/demo_model.py:28-36``) answered by one launch.
     """

@@ -375,6 +375,36 @@ def test_device_timer_trace_orders_the_phases(dev):
         assert (t_result - t_theta) < 5_000_000  # the whole fused evaluation is far below 5 ms
 
 
+@pytest.mark.parametrize("kernel, P, dtype", [("simt", 256, torch.bfloat16), ("simt", 504, torch.bfloat16),
+                                              ("generic", 37, torch.bfloat16), ("generic", 100, torch.float32)])
+def test_glm_cuda_core_kernels_keep_per_node_output_blocks(dev, kernel, P, dtype):
+    """The SIMT and general-shape kernels flush a warp's sums at node boundaries into fixed-point accumulators:
+    per-node blocks for every GLM shape, bit-identical across repeats although several warps share a block."""
+    torch.manual_seed(5)
+    rows = [9_001, 128 * 7, 3, 12_345, 40]      # a 3-row and a 40-row segment: warps cross several boundaries
+    node_ids = [0, 1, 1, 2, 3]
+    groups = [0, 1, 0, 1, 1]
+    Xs = [torch.randn(n, P, device=dev).to(dtype) for n in rows]
+    ys = [(torch.rand(n, device=dev) < 0.5).float() for n in rows]
+    model = GlmShards(Xs, ys, groups=groups, n_groups=2, kernel=kernel, node_ids=node_ids, n_nodes=4)
+    rng = np.random.default_rng(8)
+    ic = rng.normal(size=2) * 0.1
+    beta = (rng.normal(size=P) * 0.03).astype(np.float32)
+    with FederatedEngine(model) as eng:
+        assert model.selected_kernel.startswith(kernel)
+        raw = eng.evaluate_raw([ic, beta])
+        assert np.array_equal(raw, eng.evaluate_raw([ic, beta]))
+        blocks = model.per_node(raw)
+        want = model.per_node(model.reference_partial([ic, beta], dtype=torch.float64))
+        for n in range(4):
+            np.testing.assert_allclose(blocks[n, :, 0], want[n, :, 0], rtol=2e-5)
+            np.testing.assert_allclose(blocks[n, :, 1:], want[n, :, 1:], rtol=1e-4, atol=2e-2)
+        assert np.all(blocks[0, :, 2] == 0) and np.all(blocks[3, :, 1] == 0)   # a node only touches its own intercept
+        summed = eng.evaluate(ic, beta)
+        np.testing.assert_allclose(summed[0], want[:, :, 0].sum(), rtol=2e-5)
+        np.testing.assert_allclose(summed[2], want[:, 0, 3:].sum(0), rtol=1e-4, atol=5e-2)
+
+
 @pytest.mark.parametrize("K", [1, 4])
 def test_glm_tc_keeps_per_node_output_blocks(dev, K):
     """GlmShards(node_ids=...): one [K][1+G+P] block per node from ONE launch; the blocks equal the nodes'
