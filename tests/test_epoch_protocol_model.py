@@ -23,13 +23,20 @@ N_THETA = 3
 
 
 class World:
-    def __init__(self, nodes, ctas, epochs, rng, ll=False, fence=True, group=0, reset_group_ticket=True):
+    def __init__(self, nodes, ctas, epochs, rng, ll=False, fence=True, group=0, reset_group_ticket=True,
+                 expiry=0.0, unanimous=True):
         self.n, self.g, self.epochs, self.rng, self.ll, self.fence = nodes, ctas, epochs, rng, ll, fence
         self.group, self.reset_group_ticket = group, reset_group_ticket
         n_groups = (ctas + group - 1) // group if group else 0
         self.group_ticket = [[0] * n_groups for _ in range(nodes)]
         self.group_partials = [[None] * n_groups for _ in range(nodes)]
         self.finalizers = {}
+        # bounded waits: a peer CTA's wait for theta may run out (probability `expiry` per poll); the launch then
+        # counts as idle and the serve loop re-arms the node with a kernel for the SAME epoch
+        self.expiry, self.unanimous = expiry, unanimous
+        self.any_expired = [False] * nodes
+        self.idle = [False] * nodes
+        self.relaunches = 0
         zero_word = (0.0, 0)
         self.mail = [{"theta": [zero_word if ll else 0.0] * N_THETA, "flag": 0} for _ in range(nodes)]
         self.slots = [zero_word if ll else 0.0 for _ in range(nodes)]
@@ -79,19 +86,26 @@ class World:
                 if not self.ll:
                     self.store(writer, lambda p=peer: self.mail[p].__setitem__("flag", epoch), release=True)
         got = []
+        expired = False
+        gives_up = lambda: (not root) and self.expiry > 0 and self.rng.random() < self.expiry
         if self.ll:                                           # acquire: poll the tagged words
             for i in range(N_THETA):
-                while self.mail[node]["theta"][i][1] != epoch:
+                while not expired and self.mail[node]["theta"][i][1] != epoch:
+                    expired = gives_up()
                     yield
                 got.append(self.mail[node]["theta"][i][0])
         else:                                                 # acquire: flag, then the data
-            while self.mail[node]["flag"] < epoch:
+            while not expired and self.mail[node]["flag"] < epoch:
+                expired = gives_up()
                 yield
             for i in range(N_THETA):
                 got.append(self.mail[node]["theta"][i])
                 yield
-        assert got == self.theta_of(epoch), f"node {node} CTA {c} computed epoch {epoch} with theta {got}"
-        self.partials[node][c] = self.partial_of(got, node, c)
+        if expired:
+            self.any_expired[node] = True                     # atomicOr next to the tickets; the partial stays stale
+        else:
+            assert got == self.theta_of(epoch), f"node {node} CTA {c} computed epoch {epoch} with theta {got}"
+            self.partials[node][c] = self.partial_of(got, node, c)
         yield
         if self.group:                                        # two-level, fixed shape
             grp, first = c // self.group, (c // self.group) * self.group
@@ -119,6 +133,13 @@ class World:
                 return
             self.ticket[node] = 0
             node_sum = sum(self.partials[node])               # fixed order
+        # the final stage publishes only if EVERY CTA had theta (fed_comm.cuh: any_timed_out); the broken variant
+        # looks at its own wait only
+        if (self.any_expired[node] if self.unanimous else expired):
+            self.any_expired[node] = False
+            self.idle[node] = True
+            return
+        self.any_expired[node] = False
         self.finalizers[(node, epoch)] = self.finalizers.get((node, epoch), 0) + 1
         word = (node_sum, epoch) if self.ll else node_sum
         self.store(writer, lambda: self.slots.__setitem__(node, word))
@@ -149,15 +170,20 @@ class World:
             if node == 0:
                 while self.launched < epoch:
                     yield
-            assert self.ticket[node] == 0 and not any(self.group_ticket[node]), "a ticket was left armed for the next launch"
-            ctas = [self.cta(node, c, epoch) for c in range(self.g)]
-            while ctas:
-                c = self.rng.choice(ctas)
-                try:
-                    next(c)
-                except StopIteration:
-                    ctas.remove(c)
-                yield
+            while True:
+                assert self.ticket[node] == 0 and not any(self.group_ticket[node]), "a ticket was left armed for the next launch"
+                self.idle[node] = False
+                ctas = [self.cta(node, c, epoch) for c in range(self.g)]
+                while ctas:
+                    c = self.rng.choice(ctas)
+                    try:
+                        next(c)
+                    except StopIteration:
+                        ctas.remove(c)
+                    yield
+                if not self.idle[node]:
+                    break
+                self.relaunches += 1                          # idle tick: same epoch again
 
     def host(self):
         for epoch in range(1, self.epochs + 1):
@@ -230,3 +256,27 @@ def test_two_level_reduce_is_exact_and_runs_one_final_stage_per_node(ll):
 def test_the_model_notices_a_group_ticket_that_is_not_reset():
     with pytest.raises(AssertionError):
         World(2, 4, 3, random.Random(1), group=2, reset_group_ticket=False).run()
+
+
+@pytest.mark.parametrize("ll", [False, True], ids=["fence+flag", "flag-in-data"])
+@pytest.mark.parametrize("group", [0, 2])
+def test_expired_waits_never_publish_a_stale_partial(ll, group):
+    """Per-CTA bounded waits: theta arriving at the deadline leaves some CTAs with theta and others without.  The
+    launch must count as idle unless EVERY CTA computed; the re-armed kernel then delivers the exact result."""
+    rng = random.Random(31 + ll + group)
+    relaunches = 0
+    for trial in range(60):
+        nodes, ctas, epochs = rng.randint(2, 4), rng.randint(2, 5), rng.randint(2, 4)
+        w = World(nodes, ctas, epochs, random.Random(rng.random()), ll=ll, group=group, expiry=0.05).run()
+        assert w.results == {e: w.expected(e) for e in range(1, epochs + 1)}, (nodes, ctas, epochs)
+        assert all(v == 1 for v in w.finalizers.values())
+        relaunches += w.relaunches
+    assert relaunches > 20          # the scenario really occurs
+
+
+def test_the_model_notices_a_final_stage_that_only_checks_its_own_wait():
+    rng = random.Random(3)
+    with pytest.raises(AssertionError):
+        for _ in range(300):
+            w = World(3, 4, 3, random.Random(rng.random()), ll=True, expiry=0.05, unanimous=False).run()
+            assert w.results == {e: w.expected(e) for e in range(1, 4)}
