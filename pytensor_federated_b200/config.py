@@ -62,6 +62,7 @@ class FederationConfig:
     timeout: float = 20.0
     idle_timeout: float = 0.0     # peers: give up after this long without an evaluation (0 = never)
     serve_ahead: int = 8
+    speculative_us: float = 0.0   # root: keep kernels enqueued ahead of the next theta, each waits this long (0 = off)
     connect_sleep: Tuple[float, float] = (0.2, 2.0)
     probe_timeout: float = 5.0
     retries: int = 2
@@ -76,6 +77,7 @@ class FederationConfig:
             timeout=_env_float("B200FED_TIMEOUT", 20.0),
             idle_timeout=_env_float("B200FED_IDLE_TIMEOUT", 0.0),
             serve_ahead=_env_int("B200FED_SERVE_AHEAD", 8),
+            speculative_us=_env_float("B200FED_SPECULATIVE_US", 0.0),
             connect_sleep=_env_pair("B200FED_CONNECT_SLEEP", (0.2, 2.0)),
             probe_timeout=_env_float("B200FED_PROBE_TIMEOUT", 5.0),
             graph_backend=os.environ.get("B200FED_GRAPH_BACKEND", "auto"),

@@ -81,6 +81,14 @@ struct FedComm {
     unsigned long long* ll_mc_theta;                     // root: multicast alias or null
     unsigned long long* ll_root_slots;                   // root's slot array      [world][n_vals][2]
     unsigned long long* ll_host_result;                  // host-mapped            [n_vals][2]
+
+    // --- speculative root launches (opt-in): the root's kernel is enqueued BEFORE the client has the next theta --
+    // The client writes theta as tagged words into host-mapped memory; CTA 0 of the (already resident, set up,
+    // first tiles loaded) kernel polls them over PCIe and broadcasts.  If they do not arrive within
+    // spec_timeout_ns the launch counts as idle (epoch unchanged, idle tick) exactly like a peer's.
+    const unsigned long long* spec_theta;                // host-mapped tagged theta words [n_theta], or null
+    unsigned long long* spec_abort;                      // device word: epoch whose speculative launch gave up
+    unsigned long long spec_timeout_ns;
 };
 
 namespace fed {
@@ -137,8 +145,10 @@ __device__ __forceinline__ void ll_store_f64(unsigned long long* dst, double v, 
     st_relaxed_sys(dst + 1, ll_pack((unsigned int)(bits >> 32), epoch));
 }
 // Polls one tagged word.  0 = ok, 1 = timeout, 2 = STOP seen on the (legacy) flag.
+// `abort_flag` (optional): a device word that holds `epoch` once CTA 0 of a speculative launch has given up.
 __device__ __forceinline__ int ll_wait_word(const unsigned long long* src, unsigned long long epoch, unsigned long long timeout_ns,
-                                            const unsigned long long* stop_flag, unsigned int* payload) {
+                                            const unsigned long long* stop_flag, unsigned int* payload,
+                                            const unsigned long long* abort_flag = nullptr) {
     const unsigned long long want = epoch & 0xFFFFFFFFull;
     unsigned long long t0 = 0;
     unsigned int spins = 0;
@@ -151,6 +161,7 @@ __device__ __forceinline__ int ll_wait_word(const unsigned long long* src, unsig
         if ((++spins & 0x3F) == 0) {
             if (t0 == 0) t0 = globaltimer();
             if (stop_flag && (ld_acquire_sys(stop_flag) & B200FED_EPOCH_MASK) == B200FED_STOP_EPOCH) return 2;
+            if (abort_flag && ld_acquire_sys(abort_flag) == epoch) return 1;
             if (timeout_ns && globaltimer() - t0 > timeout_ns) return 1;
             __nanosleep(32);
         }
@@ -211,25 +222,60 @@ __device__ __forceinline__ Prologue prologue(const FedComm& c, float* theta_smem
     if (c.world == 1 && gridDim.x == 1) {
         // Single node, single CTA (tiny models): no mailbox round trip, no flags — theta goes
         // straight from (host-mapped) memory into shared memory.  Latency path.
-        for (int i = threadIdx.x; i < c.n_theta; i += blockDim.x) theta_smem[i] = c.theta_src[i];
+        int bad = 0;
+        if (c.spec_theta) {
+            // speculative launch: theta arrives as tagged words in host memory (or not at all: idle)
+            for (int i = threadIdx.x; i < c.n_theta; i += blockDim.x) {
+                unsigned int payload = 0;
+                bad |= ll_wait_word(c.spec_theta + i, epoch, c.spec_timeout_ns, c.flag_local, &payload);
+                theta_smem[i] = __uint_as_float(payload);
+            }
+        } else {
+            for (int i = threadIdx.x; i < c.n_theta; i += blockDim.x) theta_smem[i] = c.theta_src[i];
+        }
         if (threadIdx.x == 0 && c.trace) c.trace[(epoch & 255) * 4 + 0] = globaltimer();
-        __syncthreads();
+        bad = __syncthreads_or(bad);
         Prologue r0;
         r0.epoch = epoch;
-        r0.stop = false;
-        r0.timed_out = false;
+        r0.stop = (bad & 2) != 0;
+        r0.timed_out = (bad & 1) != 0;
         return r0;
     }
     if (c.ll_theta) {
         // LL broadcast: tagged theta words, no fence, no flag.  Every thread polls the words it needs.
         if (c.rank == 0 && blockIdx.x == 0) {
-            for (int i = threadIdx.x; i < c.n_theta; i += blockDim.x) {
-                const unsigned long long w = ll_pack(__float_as_uint(c.theta_src[i]), epoch);
+            auto fan_out = [&](int i, unsigned long long w) {
                 if (c.ll_mc_theta) {
                     multimem_st_relaxed_u64(c.ll_mc_theta + i, w);
                 } else {
                     for (int p = 0; p < c.world; ++p) st_relaxed_sys(c.ll_peer_theta[p] + i, w);
                 }
+            };
+            if (c.spec_theta) {
+                // speculative launch: every thread polls its own host words (one PCIe round trip once they are
+                // written); all or nothing — if any word is missing at the deadline nothing is broadcast and the
+                // other CTAs of this GPU are released through the abort word (the peers simply keep waiting)
+                constexpr int kSpecPerThread = 8;   // host side: n_theta <= 1024, blocks have >= 128 threads
+                unsigned int pay[kSpecPerThread];
+                int bad = 0;
+#pragma unroll
+                for (int k = 0; k < kSpecPerThread; ++k) {
+                    const int i = threadIdx.x + k * blockDim.x;
+                    pay[k] = 0;
+                    if (i < c.n_theta) bad |= ll_wait_word(c.spec_theta + i, epoch, c.spec_timeout_ns, c.flag_local, &pay[k]);
+                }
+                bad = __syncthreads_or(bad);
+                if (!bad) {
+#pragma unroll
+                    for (int k = 0; k < kSpecPerThread; ++k) {
+                        const int i = threadIdx.x + k * blockDim.x;
+                        if (i < c.n_theta) fan_out(i, ll_pack(pay[k], epoch));
+                    }
+                } else if (threadIdx.x == 0 && !(bad & 2)) {
+                    st_release_sys(c.spec_abort, epoch);
+                }
+            } else {
+                for (int i = threadIdx.x; i < c.n_theta; i += blockDim.x) fan_out(i, ll_pack(__float_as_uint(c.theta_src[i]), epoch));
             }
             if (threadIdx.x == 0 && c.trace) c.trace[(epoch & 255) * 4 + 0] = globaltimer();
         }
@@ -238,7 +284,8 @@ __device__ __forceinline__ Prologue prologue(const FedComm& c, float* theta_smem
         int bad = 0;
         for (int i = threadIdx.x; i < c.n_theta; i += blockDim.x) {
             unsigned int payload = 0;
-            const int rc = ll_wait_word(c.ll_theta_local + i, epoch, c.timeout_ns, c.flag_local, &payload);
+            const int rc = ll_wait_word(c.ll_theta_local + i, epoch, c.timeout_ns, c.flag_local, &payload,
+                                        c.spec_theta ? c.spec_abort : nullptr);
             if (rc) bad |= rc;
             theta_smem[i] = __uint_as_float(payload);
         }
@@ -353,6 +400,20 @@ __device__ __forceinline__ bool epilogue_t(const FedComm& c, const Prologue& pro
     if (c.world == 1 && gridDim.x == 1) {
         // latency path: the only CTA's partial IS the result
         __syncthreads();
+        if (pro.timed_out || pro.stop) {
+            // a speculative launch whose theta never came: idle (epoch unchanged, the host counts the tick)
+            if (threadIdx.x == 0) {
+                if (pro.timed_out && !pro.stop && c.spec_theta && c.idle_ticks) {
+                    volatile unsigned long long* ticks = c.idle_ticks;
+                    *ticks = *ticks + 1ull;
+                } else if (c.host_flag) {
+                    __threadfence_system();
+                    st_release_sys(c.host_flag, (pro.stop ? B200FED_STOP_EPOCH : pro.epoch) |
+                                                    ((pro.stop ? 0ull : B200FED_ERR_THETA_TIMEOUT) << B200FED_STATUS_SHIFT));
+                }
+            }
+            return true;
+        }
         auto value = [&](int v) { return DD ? c.cta_partials[2 * v] + c.cta_partials[2 * v + 1] : c.cta_partials[v]; };
         if (c.ll_mode) {
             // tagged words straight to host-mapped memory: no fence, no flag
@@ -446,7 +507,9 @@ __device__ __forceinline__ bool epilogue_t(const FedComm& c, const Prologue& pro
         // the serve loop re-arms it instead of taking the federation down.
         if (threadIdx.x == 0) {
             const bool timed_out = pro.timed_out || any_timed_out;
-            const bool idle = timed_out && !pro.stop && c.rank != 0;
+            // (the root of a speculative launch is in the same position as a peer: the client was not ready)
+            const bool idle = timed_out && !pro.stop && (c.rank != 0 || c.spec_theta != nullptr);
+            if (idle && c.rank == 0) *c.spec_abort = 0ull;   // the next launch of this epoch starts clean
             const unsigned long long done_epoch = idle ? epoch - 1ull : epoch;
             *c.ticket = 0;
             if (c.epoch_counter) *c.epoch_counter = done_epoch;

@@ -143,6 +143,22 @@ struct Engine {
     volatile unsigned long long* h_done() { return reinterpret_cast<volatile unsigned long long*>(host_block + h_off_done); }
     volatile unsigned long long* h_idle() { return reinterpret_cast<volatile unsigned long long*>(host_block + h_off_done + 64); }
     double idle_timeout_s = 0.0;   // peers: give up after this long without an evaluation (0 = keep waiting)
+
+    // speculative root launches (b200_engine_set_speculative): kernels are kept enqueued AHEAD of the client's
+    // next theta, which they pick up as tagged words from host memory; epochs live on the device (like a peer's)
+    bool spec_enabled = false;
+    unsigned long long spec_timeout_ns = 0;
+    size_t h_off_spec = 0;                       // host-mapped tagged theta words [n_theta]
+    unsigned long long* spec_abort = nullptr;    // device word (fed_comm.cuh)
+    unsigned long long spec_launched = 0;        // root launches since speculation was switched on ...
+    unsigned long long spec_base_done = 0, spec_base_idle = 0;   // ... and the counters at that moment
+    volatile unsigned long long* h_spec() { return reinterpret_cast<volatile unsigned long long*>(host_block + h_off_spec); }
+    // launches still in the stream: launched - (completed epochs + launches that gave up waiting)
+    unsigned long long spec_in_flight() {
+        const unsigned long long done = *h_done() & B200FED_EPOCH_MASK;
+        const unsigned long long finished = (done - spec_base_done) + (*h_idle() - spec_base_idle);
+        return spec_launched > finished ? spec_launched - finished : 0;
+    }
 };
 
 void fill_comm(Engine* e, FedComm* c, bool root_uses_explicit_epoch) {
@@ -188,7 +204,10 @@ void fill_comm(Engine* e, FedComm* c, bool root_uses_explicit_epoch) {
         }
         c->host_result = reinterpret_cast<double*>(e->host_block_dev + e->h_off_result);
         c->host_flag = reinterpret_cast<unsigned long long*>(e->host_block_dev + e->h_off_flag);
-        c->epoch_counter = root_uses_explicit_epoch ? nullptr : e->epoch_counter;
+        // with speculation on, the root counts epochs on the device as the peers do: a launch that gave up
+        // waiting for theta leaves the counter alone and the next launch in the stream takes the epoch over
+        c->epoch_counter = (root_uses_explicit_epoch && !e->spec_enabled) ? nullptr : e->epoch_counter;
+        c->spec_abort = e->spec_abort;
     } else {
         c->epoch_counter = e->epoch_counter;  // peers count epochs on the device
     }
@@ -245,7 +264,7 @@ void release_engine(Engine* e) {
     if (e->stream) cudaStreamSynchronize(e->stream);
     if (e->owns_comm && e->comm_local) cudaFree(e->comm_local);
     if (e->host_block) cudaFreeHost(e->host_block);
-    void* device_ptrs[] = {e->cta_partials, e->ticket,       e->epoch_counter, e->trace,  e->theta_dev, e->cta_trace,
+    void* device_ptrs[] = {e->cta_partials, e->ticket,       e->epoch_counter, e->trace,  e->theta_dev, e->cta_trace, e->spec_abort,
                            e->glm_chunks_dev, e->work_counter, e->tc_partials,
                            e->linreg_dev,   e->glm_segs_dev, e->glm_tmaps_dev, e->ode_dev};
     for (void* p : device_ptrs)
@@ -354,7 +373,8 @@ void* b200_engine_create(int device, int rank, int world, int n_theta, int n_val
     e->h_off_flag = up(e->h_off_result + (size_t)n_vals * 8);
     e->h_off_done = e->h_off_flag + 256;
     e->h_off_ll = e->h_off_done + 256;
-    const size_t hbytes = e->h_off_ll + up((size_t)n_vals * 16);
+    e->h_off_spec = e->h_off_ll + up((size_t)n_vals * 16);
+    const size_t hbytes = e->h_off_spec + up((size_t)n_theta * 8);
     // LL mode for small messages (latency-bound models); B200FED_NO_LL=1 forces the fence+flag protocol
     // (thresholds tunable with B200FED_LL_MAX_VALS / B200FED_LL_MAX_THETA)
     auto env_int = [](const char* name, int dflt) {
@@ -376,7 +396,9 @@ void* b200_engine_create(int device, int rank, int world, int n_theta, int n_val
     ok = ok && cudaMalloc((void**)&e->trace, 256 * 4 * 8) == cudaSuccess;
     ok = ok && cudaMalloc((void**)&e->cta_trace, (size_t)max_blocks * 8 * 8) == cudaSuccess;
     ok = ok && cudaMalloc((void**)&e->theta_dev, (size_t)(n_theta > 0 ? n_theta : 1) * 4) == cudaSuccess;
+    ok = ok && cudaMalloc((void**)&e->spec_abort, 256) == cudaSuccess;
     if (ok) {
+        cudaMemset(e->spec_abort, 0, 256);
         cudaMemset(e->ticket, 0, 1024);
         cudaMemset(e->work_counter, 0, 256);
         cudaMemset(e->epoch_counter, 0, 256);
@@ -431,12 +453,53 @@ int b200_engine_reset(void* h) {
     CK(cudaMemset(e->comm_local + L.off_ll_theta, 0, L.bytes - L.off_ll_theta));
     CK(cudaDeviceSynchronize());
     memset(e->host_block + e->h_off_ll, 0, (size_t)e->n_vals * 16);
+    memset(e->host_block + e->h_off_spec, 0, (size_t)e->n_theta * 8);
+    CK(cudaMemset(e->spec_abort, 0, 256));
     e->epoch = 0;
     *e->h_flag() = 0;
     *e->h_done() = 0;
     *e->h_idle() = 0;
+    e->spec_launched = e->spec_base_done = e->spec_base_idle = 0;
     e->stop_serving = 0;
     return 0;
+}
+
+// Speculation: waits until no launch is left in the stream (kernels that are still waiting for a theta nobody
+// will write give up after spec_timeout_ns each).  Everything that needs a quiet stream or explicit control over
+// what runs next (device-timed launches, STOP, reset) calls this first.
+static int spec_settle(Engine* e) {
+    if (!e->spec_enabled) return 0;
+    const auto t0 = std::chrono::steady_clock::now();
+    unsigned spins = 0;
+    while (e->spec_in_flight() != 0) {
+        if ((++spins & 0xFFF) == 0) {
+            const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
+            if (dt > 10.0 + 4e-9 * (double)e->spec_timeout_ns) {
+                g_last_error = "speculative launches did not drain";
+                return -8;
+            }
+        }
+    }
+    return 0;
+}
+
+// Root: keep kernels enqueued ahead of the client's next theta (timeout_us > 0), or go back to one launch per
+// evaluation (0).  Needs theta as tagged words (n_theta <= 1024 here).  Returns 1 if speculation is on.
+int b200_engine_set_speculative(void* h, double timeout_us) {
+    Engine* e = static_cast<Engine*>(h);
+    if (e->rank != 0) return 0;
+    CK(cudaSetDevice(e->device));
+    if (spec_settle(e) != 0) return -8;
+    CK(cudaStreamSynchronize(e->stream));
+    const bool on = timeout_us > 0.0 && e->ll_theta && e->n_theta <= 1024;
+    e->spec_enabled = on;
+    e->spec_timeout_ns = on ? (unsigned long long)(timeout_us * 1e3) : 0ull;
+    // device-resident epochs take over from the host's count (and hand it back)
+    CK(cudaMemcpy(e->epoch_counter, &e->epoch, 8, cudaMemcpyHostToDevice));
+    e->spec_launched = 0;
+    e->spec_base_done = e->epoch;
+    e->spec_base_idle = *e->h_idle();
+    return on ? 1 : 0;
 }
 
 void b200_engine_set_timeout(void* h, double seconds) {
@@ -601,15 +664,30 @@ int b200_engine_launch(void* h) {
         g_last_error = "only the root launches explicit epochs";
         return -4;
     }
+    if (spec_settle(e) != 0) return -8;
     FedComm c;
     fill_comm(e, &c, true);
     c.epoch = ++e->epoch;
-    return launch_model(e, &c);
+    const int rc = launch_model(e, &c);
+    if (rc == 0 && e->spec_enabled) e->spec_launched++;
+    return rc;
+}
+
+// One launch that takes its theta from the tagged host words and its epoch from the device counter.
+static int spec_launch(Engine* e) {
+    FedComm c;
+    fill_comm(e, &c, false);
+    c.spec_theta = reinterpret_cast<const unsigned long long*>(e->host_block_dev + e->h_off_spec);
+    c.spec_timeout_ns = e->spec_timeout_ns;
+    const int rc = launch_model(e, &c);
+    if (rc == 0) e->spec_launched++;
+    return rc;
 }
 
 int b200_engine_set_device_theta(void* h, const float* theta_host, int n, int enable) {
     Engine* e = static_cast<Engine*>(h);
     CK(cudaSetDevice(e->device));
+    if (spec_settle(e) != 0) return -8;
     if (theta_host && n > 0) CK(cudaMemcpy(e->theta_dev, theta_host, (size_t)n * 4, cudaMemcpyHostToDevice));
     e->theta_from_device = enable != 0;
     return 0;
@@ -638,6 +716,7 @@ int b200_engine_wait(void* h, unsigned long long epoch, double* out, double time
             v = *flag;
             if ((v & B200FED_EPOCH_MASK) >= epoch && (v >> B200FED_STATUS_SHIFT) != 0) return (int)(v >> B200FED_STATUS_SHIFT);
             if ((++spins & 0xFFF) == 0) {
+                if (e->spec_enabled && !e->theta_from_device && e->spec_in_flight() == 0 && spec_launch(e) != 0) return -8;
                 const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
                 if (dt > timeout_s) {
                     cudaError_t err = cudaStreamQuery(e->stream);
@@ -660,6 +739,7 @@ int b200_engine_wait(void* h, unsigned long long epoch, double* out, double time
         v = *flag;
         if ((v & B200FED_EPOCH_MASK) >= epoch) break;
         if ((++spins & 0xFFF) == 0) {
+            if (e->spec_enabled && !e->theta_from_device && e->spec_in_flight() == 0 && spec_launch(e) != 0) return -8;
             const double dt = std::chrono::duration<double>(std::chrono::steady_clock::now() - t0).count();
             if (dt > timeout_s) {
                 cudaError_t err = cudaStreamQuery(e->stream);
@@ -682,6 +762,22 @@ int b200_engine_eval(void* h, const void* theta, int n_words, double* out, doubl
         return -6;
     }
     memcpy(e->h_theta(), theta, (size_t)n_words * 4);
+    if (e->spec_enabled && !e->theta_from_device) {
+        // speculative path: a kernel enqueued by the previous call is already resident and polling; publish theta
+        // as tagged words, top the stream up to two launches (this epoch's + the next one's, which overlaps its
+        // launch latency, set-up and first loads with this evaluation) and wait for the result
+        const unsigned long long epoch = ++e->epoch;
+        const uint32_t* w = static_cast<const uint32_t*>(theta);
+        volatile unsigned long long* words = e->h_spec();
+        const unsigned long long tag = (epoch & 0xFFFFFFFFull) << 32;
+        for (int i = 0; i < n_words; ++i) words[i] = (unsigned long long)w[i] | tag;
+        std::atomic_thread_fence(std::memory_order_seq_cst);
+        while (e->spec_in_flight() < 2) {
+            const int rc = spec_launch(e);
+            if (rc != 0) return rc;
+        }
+        return b200_engine_wait(h, epoch, out, timeout_s);
+    }
     std::atomic_thread_fence(std::memory_order_release);
     int rc = b200_engine_launch(h);
     if (rc != 0) return rc;
@@ -759,6 +855,7 @@ int b200_engine_stop_peers(void* h) {
     Engine* e = static_cast<Engine*>(h);
     if (e->rank != 0) return 0;
     CK(cudaSetDevice(e->device));
+    spec_settle(e);
     FedComm c;
     fill_comm(e, &c, true);
     fed_stop_kernel<<<1, 32, 0, e->stream>>>(c);

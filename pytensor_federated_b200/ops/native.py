@@ -52,6 +52,7 @@ def _declare(lib: C.CDLL) -> None:
     sig("b200_engine_set_timeout", None, C.c_void_p, C.c_double)
     sig("b200_engine_set_grid", None, C.c_void_p, C.c_int)
     sig("b200_engine_set_idle_timeout", None, C.c_void_p, C.c_double)
+    sig("b200_engine_set_speculative", C.c_int, C.c_void_p, C.c_double)
     sig("b200_engine_grid", C.c_int, C.c_void_p)
     sig("b200_engine_launches", C.c_ulonglong, C.c_void_p)
     sig("b200_engine_epoch", C.c_ulonglong, C.c_void_p)

@@ -76,6 +76,7 @@ class FederatedEngine:
         idle_timeout: Optional[float] = None,
         comm: Optional[str] = None,
         grid: Optional[int] = None,
+        speculative_us: Optional[float] = None,
     ) -> None:
         import torch
 
@@ -88,6 +89,9 @@ class FederatedEngine:
         # as ``idle_timeout`` allows (0 = for ever; B200FED_IDLE_TIMEOUT)
         self.idle_timeout = float(cfg.idle_timeout if idle_timeout is None else idle_timeout)
         self._serve_ahead = cfg.serve_ahead
+        self._speculative_us = float(cfg.speculative_us if speculative_us is None else speculative_us)
+        #: True while the root keeps kernels enqueued ahead of the next theta (see :meth:`set_speculative`)
+        self.speculative = False
 
         self.model = model
         dist = _dist()
@@ -149,6 +153,31 @@ class FederatedEngine:
         self._out = np.zeros(m.n_vals, dtype=np.float64)
         self._stage_p = self._stage.ctypes.data_as(C.c_void_p)
         self._out_p = self._out.ctypes.data_as(C.c_void_p)
+        if self._speculative_us > 0 and self.rank == 0:
+            self.set_speculative(self._speculative_us)
+
+    def set_speculative(self, wait_us: float = 1000.0) -> bool:
+        """Root, fused backend: keep the NEXT evaluation's kernel enqueued while the client is still thinking.
+
+        ``evaluate`` then finds a kernel that is already resident, set up, with its first tiles loaded and
+        polling host memory for theta (tagged words over PCIe), and enqueues the one after it while the GPU
+        computes — launch latency, kernel start-up and the first loads leave the sequential path of a sampler
+        (~7 us per evaluation).  A kernel whose theta does not arrive within ``wait_us`` gives up (an idle tick,
+        exactly like a peer between sampling phases) and the next ``evaluate`` launches afresh, so the GPU spins
+        for at most ``2 x wait_us`` after the last evaluation; other work queued on this GPU waits that long.
+        ``wait_us=0`` switches back to one launch per evaluation.  Needs theta as tagged words (at most 1024
+        32-bit words); returns whether speculation is on.
+        """
+        from ..ops import native
+
+        if self.backend != "fused" or not self.is_root:
+            return False
+        with self._lock:
+            rc = int(self._lib.b200_engine_set_speculative(self._handle, float(wait_us)))
+            if rc < 0:
+                raise FederationError(f"set_speculative failed (rc={rc}): {native.last_error()}")
+            self.speculative = rc == 1
+            return self.speculative
 
     def _bootstrap_comm(self, comm: str) -> None:
         """Makes every node's comm block addressable from this process.

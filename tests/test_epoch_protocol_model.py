@@ -24,7 +24,7 @@ N_THETA = 3
 
 class World:
     def __init__(self, nodes, ctas, epochs, rng, ll=False, fence=True, group=0, reset_group_ticket=True,
-                 expiry=0.0, unanimous=True):
+                 expiry=0.0, unanimous=True, spec=False, all_or_nothing=True):
         self.n, self.g, self.epochs, self.rng, self.ll, self.fence = nodes, ctas, epochs, rng, ll, fence
         self.group, self.reset_group_ticket = group, reset_group_ticket
         n_groups = (ctas + group - 1) // group if group else 0
@@ -37,6 +37,12 @@ class World:
         self.any_expired = [False] * nodes
         self.idle = [False] * nodes
         self.relaunches = 0
+        # speculative root launches: the root's kernels are in the stream BEFORE the client has written theta (as
+        # tagged words in host memory); CTA 0 polls them, gives up after a while and releases the other CTAs of
+        # its GPU through the abort word; the launch is idle and the next one takes the epoch over
+        self.spec, self.all_or_nothing = spec, all_or_nothing
+        self.host_words = [(0.0, 0)] * N_THETA
+        self.abort = 0
         zero_word = (0.0, 0)
         self.mail = [{"theta": [zero_word if ll else 0.0] * N_THETA, "flag": 0} for _ in range(nodes)]
         self.slots = [zero_word if ll else 0.0 for _ in range(nodes)]
@@ -76,8 +82,21 @@ class World:
     def cta(self, node, c, epoch):
         root = node == 0
         writer = ("cta", node, c, epoch)
-        if root and c == 0:                                   # broadcast
-            theta = list(self.host_theta)
+        aborted = False
+        if root and c == 0 and self.spec:                     # speculative: wait for the client's tagged words
+            theta = []
+            for i in range(N_THETA):
+                while not aborted and self.host_words[i][1] != epoch:
+                    aborted = self.rng.random() < self.expiry
+                    yield
+                theta.append(self.host_words[i][0])
+            if aborted and self.all_or_nothing:
+                self.abort = epoch                            # nothing is broadcast
+            elif aborted:                                     # broken variant: sends what it has
+                aborted = False
+        if root and c == 0 and not aborted:                   # broadcast
+            if not self.spec:
+                theta = list(self.host_theta)
             for peer in range(self.n):
                 for i, v in enumerate(theta):
                     word = (v, epoch) if self.ll else v
@@ -87,7 +106,8 @@ class World:
                     self.store(writer, lambda p=peer: self.mail[p].__setitem__("flag", epoch), release=True)
         got = []
         expired = False
-        gives_up = lambda: (not root) and self.expiry > 0 and self.rng.random() < self.expiry
+        gives_up = lambda: ((not root) and self.expiry > 0 and self.rng.random() < self.expiry) or \
+            (root and self.spec and self.abort == epoch)
         if self.ll:                                           # acquire: poll the tagged words
             for i in range(N_THETA):
                 while not expired and self.mail[node]["theta"][i][1] != epoch:
@@ -138,6 +158,8 @@ class World:
         if (self.any_expired[node] if self.unanimous else expired):
             self.any_expired[node] = False
             self.idle[node] = True
+            if root:
+                self.abort = 0                                # the next launch of this epoch starts clean
             return
         self.any_expired[node] = False
         self.finalizers[(node, epoch)] = self.finalizers.get((node, epoch), 0) + 1
@@ -167,7 +189,7 @@ class World:
     def node_stream(self, node):
         """Kernels of one node in stream order; the root's are launched by the host, peers' are pre-enqueued."""
         for epoch in range(1, self.epochs + 1):
-            if node == 0:
+            if node == 0 and not self.spec:
                 while self.launched < epoch:
                     yield
             while True:
@@ -187,6 +209,12 @@ class World:
 
     def host(self):
         for epoch in range(1, self.epochs + 1):
+            if self.spec:                                     # the kernels are already waiting; the client takes its time
+                for _ in range(self.rng.randint(0, 30)):
+                    yield
+                for i, v in enumerate(self.theta_of(epoch)):
+                    self.host_words[i] = (v, epoch)
+                    yield
             self.host_theta = self.theta_of(epoch)            # visible to the kernel launched afterwards
             self.launched = epoch
             if self.ll:
@@ -280,3 +308,28 @@ def test_the_model_notices_a_final_stage_that_only_checks_its_own_wait():
         for _ in range(300):
             w = World(3, 4, 3, random.Random(rng.random()), ll=True, expiry=0.05, unanimous=False).run()
             assert w.results == {e: w.expected(e) for e in range(1, 4)}
+
+
+@pytest.mark.parametrize("group", [0, 2])
+def test_speculative_root_launches_pick_theta_up_or_give_up_cleanly(group):
+    """The root's kernel is in the stream before theta exists.  Whatever the timing — theta in time, too late, or
+    half written at the deadline — every epoch is computed exactly once with its own theta, by a launch in which
+    every CTA of every node had it."""
+    rng = random.Random(77 + group)
+    relaunches = 0
+    for trial in range(80):
+        nodes, ctas, epochs = rng.randint(1, 3), rng.randint(1, 4), rng.randint(2, 4)
+        w = World(nodes, ctas, epochs, random.Random(rng.random()), ll=True, group=group, spec=True, expiry=0.04).run()
+        assert w.results == {e: w.expected(e) for e in range(1, epochs + 1)}, (nodes, ctas, epochs)
+        assert all(v == 1 for v in w.finalizers.values())
+        relaunches += w.relaunches
+    assert relaunches > 20
+
+
+def test_the_model_notices_a_root_that_broadcasts_a_half_read_theta():
+    """CTA 0 gave up with some of the client's words still missing: broadcasting what it has would let the other
+    CTAs (and GPUs) compute with a mixture of two epochs."""
+    rng = random.Random(9)
+    with pytest.raises(AssertionError):
+        for _ in range(200):
+            World(2, 3, 3, random.Random(rng.random()), ll=True, spec=True, expiry=0.1, all_or_nothing=False).run()

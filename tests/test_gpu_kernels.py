@@ -498,3 +498,51 @@ def test_glm_fp8_keeps_per_node_output_blocks(dev):
         np.testing.assert_allclose(blocks[n, 0, 4:], want[n, 0, 4:], rtol=2e-4, atol=2e-4 * np.abs(want[n, 0, 4:]).max())
         assert np.count_nonzero(blocks[n, 0, 1:4]) == 1          # only the node's own intercept gradient
     np.testing.assert_allclose(summed[0], want[:, 0, 0].sum(), rtol=2e-5)
+
+
+@pytest.mark.parametrize("which", ["glm-tc", "glm-fp8", "glm-simt", "linreg-1cta", "linreg-multi"])
+def test_speculative_root_launches_give_the_same_results(dev, which):
+    """`set_speculative`: the next evaluation's kernel is enqueued before theta exists and picks it up as tagged
+    words from host memory.  Same bits as one launch per evaluation; kernels that wait in vain give up (idle
+    tick) and the next evaluate launches afresh; explicit launches and toggling keep the epochs in step."""
+    import time
+
+    torch.manual_seed(4)
+    rng = np.random.default_rng(2)
+    if which.startswith("glm"):
+        rows = [30_000, 5_000]
+        Xs = [torch.randn(n, 256, device=dev).to(torch.bfloat16) for n in rows]
+        ys = [(torch.rand(n, device=dev) < 0.5).float() for n in rows]
+        if which == "glm-fp8":
+            model = Fp8GlmShards.from_dense(Xs, ys, groups=[0, 1], n_groups=2)
+        else:
+            model = GlmShards(Xs, ys, groups=[0, 1], n_groups=2, kernel=which.split("-")[1])
+        thetas = [[rng.normal(size=2) * 0.1, (rng.normal(size=256) * 0.03).astype(np.float32)] for _ in range(12)]
+    else:
+        sizes = [10] if which == "linreg-1cta" else [10, 70001, 333]
+        xs = [rng.normal(size=n) for n in sizes]
+        ys_ = [1.0 + 0.5 * x + rng.normal(scale=0.3, size=x.size) for x in xs]
+        model = LinregShards(xs, ys_, [0.3 + 0.1 * i for i in range(len(sizes))], device=dev)
+        thetas = [[rng.normal(size=len(sizes)), np.array(rng.normal())] for _ in range(12)]
+    with FederatedEngine(model) as eng:
+        want = [eng.evaluate_raw(th) for th in thetas]
+        assert eng.set_speculative(300.0) and eng.speculative
+        n0 = eng.kernel_launches
+        got = [eng.evaluate_raw(th) for th in thetas[:6]]
+        time.sleep(0.01)                                  # both kernels in the stream give up: idle ticks
+        got += [eng.evaluate_raw(th) for th in thetas[6:9]]
+        # explicit launch + wait while speculation is on (drains the speculative kernels first)
+        e = eng.launch()
+        np.testing.assert_array_equal(eng.wait(e), want[8])
+        got += [eng.evaluate_raw(th) for th in thetas[9:]]
+        for g, w in zip(got, want):
+            np.testing.assert_array_equal(g, w)
+        assert eng.kernel_launches - n0 >= len(thetas) + 1
+        assert eng.set_speculative(0.0) is False
+        np.testing.assert_array_equal(eng.evaluate_raw(thetas[0]), want[0])
+        assert eng.set_speculative(300.0)
+        np.testing.assert_array_equal(eng.evaluate_raw(thetas[1]), want[1])
+    # a speculative engine that is closed right after an evaluation drains its waiting kernels
+    with FederatedEngine(model, speculative_us=200.0) as eng:
+        assert eng.speculative
+        np.testing.assert_array_equal(eng.evaluate_raw(thetas[2]), want[2])

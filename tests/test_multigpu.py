@@ -58,6 +58,9 @@ def _worker(rank, world, port, comm, scenario, q):
         elif scenario.startswith("glm"):
             from pytensor_federated_b200.models import Fp8GlmShards
 
+            spec = scenario.endswith("-spec")      # root keeps kernels enqueued ahead of theta (set_speculative)
+            if spec:
+                scenario = scenario[: -len("-spec")]
             kernel = scenario.split("-")[1]
             chains = int(scenario.split("-")[2]) if scenario.count("-") >= 2 else 1
             X, y, _ = synth_logistic_shard(30_000 + 17 * rank, 256, seed=50 + rank, device=dev)
@@ -78,8 +81,17 @@ def _worker(rank, world, port, comm, scenario, q):
             dist.all_gather_object(gathered, local)
             if rank == 0:
                 got = eng.evaluate(ic, beta)
+                if spec:
+                    assert eng.set_speculative(300.0)
                 again = eng.evaluate(ic, beta)   # dynamic work distribution, same bits
                 same = all(np.array_equal(np.asarray(a), np.asarray(b)) for a, b in zip(got, again))
+                if spec:
+                    import time
+
+                    for pause in (0.0, 0.0, 0.01, 0.0):      # 10 ms: the waiting kernels give up, the next call relaunches
+                        time.sleep(pause)
+                        more = eng.evaluate(ic, beta)
+                        same = same and all(np.array_equal(np.asarray(a), np.asarray(b)) for a, b in zip(got, more))
                 want = model.unpack_result(np.sum(gathered, axis=0), model.call_context([ic, beta]))
                 q.put(("root", eng.comm_mode, [np.asarray(g).tolist() for g in got], [np.asarray(w).tolist() for w in want], same))
                 eng.shutdown()
@@ -155,13 +167,13 @@ def test_linreg_across_gpus_matches_numpy(comm, world):
 
 
 @pytest.mark.parametrize("world", WORLDS)
-@pytest.mark.parametrize("kernel", ["simt", "tc", "tc-4", "tc-16", "fp8"])
+@pytest.mark.parametrize("kernel", ["simt", "tc", "tc-4", "tc-16", "fp8", "tc-1-spec", "fp8-1-spec"])
 def test_glm_across_gpus_matches_reference(kernel, world):
     results = _run(world, "auto", f"glm-{kernel}")
     root = [r for r in results if r[0] == "root"][0]
     got, want, same = root[2], root[3], root[4]
     assert same, "two evaluations of the same theta must agree bit for bit"
-    if kernel == "fp8":
+    if kernel.startswith("fp8"):
         np.testing.assert_allclose(got[0], want[0], rtol=2e-5)
         np.testing.assert_allclose(got[2], want[2], rtol=2e-4, atol=2e-4 * np.abs(want[2]).max())
         return
