@@ -31,6 +31,8 @@ def test_linreg_reference_matches_scipy_and_finite_differences():
     fd_a = (_scipy_linreg(x, y, sigma, 0.4 + eps, 1.2) - _scipy_linreg(x, y, sigma, 0.4 - eps, 1.2)) / (2 * eps)
     fd_b = (_scipy_linreg(x, y, sigma, 0.4, 1.2 + eps) - _scipy_linreg(x, y, sigma, 0.4, 1.2 - eps)) / (2 * eps)
     np.testing.assert_allclose([da, db], [fd_a, fd_b], rtol=1e-6)
+    # speculative launches belong to the fused backend; elsewhere the switch is a no-op that says so
+    assert eng.set_speculative(500.0) is False and eng.speculative is False
     eng.shutdown()
     with pytest.raises(FederationError):
         eng.evaluate(np.array(0.0), np.array(0.0))
