@@ -218,13 +218,14 @@ def _peer_main(rank: int, world: int, port: int, build_model, backend: str, devi
 
 @contextlib.contextmanager
 def launch_federation(build_model: Callable, n_nodes: int, *, device_type: Optional[str] = None,
-                      backend: str = "auto", timeout: float = 3600.0):
+                      backend: str = "auto", timeout: float = 3600.0, speculative_us: Optional[float] = None):
     """Starts ``n_nodes - 1`` peer processes (one per GPU) and yields the root's engine.
 
     ``build_model(rank, world, device) -> ShardModel`` builds each node's private shard model and
     must be picklable (module-level function).  The calling process is rank 0, the client.  On
     exit the peers are drained and joined.  ``device_type="cpu"`` runs the same topology over
-    gloo with the collective backend (plumbing tests).
+    gloo with the collective backend (plumbing tests).  ``speculative_us`` > 0 lets the root keep the next
+    evaluation's kernel enqueued ahead of theta (:meth:`FederatedEngine.set_speculative`; fused backend only).
     """
     import torch
     import torch.distributed as dist
@@ -255,7 +256,8 @@ def launch_federation(build_model: Callable, n_nodes: int, *, device_type: Optio
                 dist.init_process_group("gloo", rank=0, world_size=n_nodes)
             owns_pg = True
         dev = torch.device("cuda", 0) if device_type == "cuda" else torch.device("cpu")
-        engine = FederatedEngine(build_model(0, n_nodes, dev), backend=backend, device=dev, timeout=timeout)
+        engine = FederatedEngine(build_model(0, n_nodes, dev), backend=backend, device=dev, timeout=timeout,
+                                 speculative_us=speculative_us)
         yield engine
     finally:
         if engine is not None:
