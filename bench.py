@@ -371,11 +371,14 @@ def run_b200(args):
         # ---- end-to-end region: public API, pinned H2D of theta + D2H of the result each step -----------------
         e2e_steps = share(blocks * S)
 
+        evaluated = [0]   # evaluations of the current phase (the peers serve exactly as many as the root announced)
+
         def e2e_region():
             t0 = time.perf_counter()
             acc = 0.0
             for i in range(e2e_steps):
                 out = eng.evaluate(*thetas[W + i % S])
+                evaluated[0] += 1
                 if i < S:
                     acc += float(np.sum(out[0]))
             return time.perf_counter() - t0, acc   # evaluate() returned: the result has been read back
@@ -384,21 +387,37 @@ def run_b200(args):
         e2e_s = e2e_plain_s
         torch.cuda.synchronize()
         barrier()
-        spec_on = bool(backend == "fused" and args.speculative_us > 0 and eng.set_speculative(args.speculative_us))
+        try:
+            spec_on = bool(backend == "fused" and args.speculative_us > 0 and eng.set_speculative(args.speculative_us))
+        except Exception as ex:
+            print(f"[bench] speculative launches unavailable ({ex})", file=sys.stderr, flush=True)
+            spec_on = False
         share(3 + e2e_steps if spec_on else 0)
         if spec_on:
             # same loop, same public call; the engine keeps the next evaluation's kernel enqueued ahead of theta
-            for i in range(3):
-                eng.evaluate(*thetas[W + i % S])
-            e2e_spec_s, spec_sum = e2e_region()
-            eng.set_speculative(0.0)
-            if spec_sum != checksum:
+            evaluated[0] = 0
+            e2e_spec_s = None
+            try:
+                for i in range(3):
+                    eng.evaluate(*thetas[W + i % S])
+                    evaluated[0] += 1
+                e2e_spec_s, spec_sum = e2e_region()
+                eng.set_speculative(0.0)
+            except Exception as ex:   # the optional mode must never cost the run its line: finish the phase plainly
+                print(f"[bench] speculative end-to-end region failed ({type(ex).__name__}: {ex}); "
+                      "keeping the one-launch-per-evaluation number", file=sys.stderr, flush=True)
+                e2e_spec_s = None
+                eng.set_speculative(0.0)
+                while evaluated[0] < 3 + e2e_steps:
+                    eng.evaluate(*thetas[W])
+                    evaluated[0] += 1
+            if e2e_spec_s is not None and spec_sum != checksum:
                 raise SystemExit(f"speculative launches changed the result: {spec_sum!r} vs {checksum!r}")
             torch.cuda.synchronize()
             barrier()
             # both settings go through the same public call; the headline is the engine's better mode, and the
             # JSON line names it and carries the other number too
-            if e2e_spec_s < e2e_plain_s:
+            if e2e_spec_s is not None and e2e_spec_s < e2e_plain_s:
                 e2e_s = e2e_spec_s
             else:
                 spec_on = False
