@@ -8,7 +8,7 @@ fallback and the oracle; :func:`available` tells whether the library can be used
 from __future__ import annotations
 
 import ctypes as C
-from typing import List, Optional, Sequence, Tuple
+from typing import List, Sequence, Tuple
 
 import numpy as np
 

@@ -6,7 +6,7 @@ potentials (e.g. the ``logp`` output of a ``LogpGradOp``), and compilation of th
 """
 from __future__ import annotations
 
-from typing import Dict, List, Optional, Sequence, Tuple
+from typing import Dict, List, Optional, Tuple
 
 import numpy as np
 
