@@ -80,8 +80,8 @@ class NodeFederation:
 
     def _evaluate_linreg(self, requests):
         for node, (a, b) in requests.items():
-            self._intercepts[node] = float(np.asarray(a))
-            self._slopes[node] = float(np.asarray(b))
+            self._intercepts[node] = a.item() if hasattr(a, "item") else float(np.asarray(a))
+            self._slopes[node] = b.item() if hasattr(b, "item") else float(np.asarray(b))
         per = LinregShards.per_shard(self.engine.evaluate_raw([self._intercepts, self._slopes]))
         return {node: (np.array(per[node, 0]), [np.array(per[node, 1]), np.array(per[node, 2])]) for node in requests}
 

@@ -15,6 +15,7 @@ Names and call signatures follow PyTensor so user code ports in either direction
 from __future__ import annotations
 
 import itertools
+import operator
 from typing import Any, Callable, Dict, Iterable, List, Optional, Sequence, Tuple, Union
 
 import numpy as np
@@ -170,6 +171,12 @@ class Op:
     def grad(self, inputs: Sequence[Variable], output_grads: Sequence[Variable]) -> List[Variable]:
         raise NotImplementedError(f"{type(self).__name__} has no grad()")
 
+    def make_thunk(self, node: Apply) -> Optional[Callable]:
+        """Optional fast path of a SINGLE-output Op for the compiled :class:`Function`: a callable
+        ``f(*input_values) -> output_value`` that does what ``perform`` does without the storage cells.
+        ``None`` (the default) makes the Function call ``perform``."""
+        return None
+
     def __call__(self, *inputs, **kwargs):
         node = self.make_node(*inputs)
         if self.default_output is not None:
@@ -239,6 +246,10 @@ def _out_type(*inputs: Variable) -> TensorType:
     return TensorType(dt, (None,) * nd)
 
 
+_SCALAR_OPERATORS = {"add": operator.add, "sub": operator.sub, "mul": operator.mul, "true_div": operator.truediv,
+                     "neg": operator.neg}
+
+
 class Elemwise(Op):
     """Broadcasting NumPy ufunc with a hand-written derivative."""
 
@@ -259,6 +270,29 @@ class Elemwise(Op):
 
     def perform(self, node, inputs, output_storage) -> None:
         output_storage[0][0] = np.asarray(self._fn(*inputs), dtype=node.outputs[0].type.dtype)
+
+    def make_thunk(self, node):
+        fn, dt, asarray = self._fn, np.dtype(node.outputs[0].type.dtype), np.asarray
+        if dt.kind == "f" and node.outputs[0].type.ndim == 0 and \
+                all(isinstance(i.type, TensorType) and i.type.ndim == 0 for i in node.inputs):
+            # statically scalar: NumPy scalars instead of 0-d arrays (scalar arithmetic is several times cheaper
+            # than a ufunc call on 0-d arrays); the Function hands 0-d arrays to every other kind of consumer
+            sc = dt.type
+            f = _SCALAR_OPERATORS.get(self.name, fn)
+
+            def scalar_thunk(*inputs):
+                out = f(*inputs)
+                return out if type(out) is sc else sc(out)
+
+            scalar_thunk.returns_scalar = True
+            return scalar_thunk
+
+        def thunk(*inputs):
+            out = fn(*inputs)
+            # the ufunc of arrays of the declared dtype already returns the right thing; anything else is converted
+            return out if type(out) is np.ndarray and out.dtype == dt else asarray(out, dtype=dt)
+
+        return thunk
 
     def grad(self, inputs, output_grads):
         (g,) = output_grads
@@ -314,6 +348,10 @@ class Sum(Op):
     def perform(self, node, inputs, output_storage) -> None:
         output_storage[0][0] = np.asarray(np.sum(inputs[0], axis=self.axis))
 
+    def make_thunk(self, node):
+        axis, np_sum, asarray = self.axis, np.sum, np.asarray
+        return lambda x: asarray(np_sum(x, axis=axis))
+
     def grad(self, inputs, output_grads):
         (x,) = inputs
         (g,) = output_grads
@@ -358,6 +396,10 @@ class Subtensor(Op):
 
     def perform(self, node, inputs, output_storage) -> None:
         output_storage[0][0] = np.asarray(inputs[0][self.idx])
+
+    def make_thunk(self, node):
+        idx, asarray = self.idx, np.asarray
+        return lambda x: asarray(x[idx])
 
     def grad(self, inputs, output_grads):
         return [IncSubtensorZeros(self.idx)(inputs[0], output_grads[0])]
@@ -793,6 +835,53 @@ class MergeOptimizer(GraphRewriter):
                 changed = True
 
 
+class IdentityEliminator(GraphRewriter):
+    """Removes the arithmetic no-ops that reverse-mode differentiation leaves behind — ``g + zeros_like(x)`` for a
+    scalar ``x``, ``1.0 * g``, ``g + 0.0`` — whenever the surviving operand already has the node's type (dtype
+    and rank), so values, dtypes and shapes are untouched.  The gradient graph of a model with a few dozen
+    scalar terms loses about half of its nodes, which a sampler pays for at every model evaluation."""
+
+    @staticmethod
+    def _is_scalar_const(v: Variable, value: float) -> bool:
+        return isinstance(v, Constant) and np.ndim(v.data) == 0 and np.asarray(v.data).dtype.kind in "fiu" \
+            and float(v.data) == value
+
+    @staticmethod
+    def _is_scalar_zeros(v: Variable) -> bool:
+        node = v.owner
+        return node is not None and isinstance(node.op, ZerosLike) and node.inputs[0].type.ndim == 0
+
+    def apply(self, fgraph: FunctionGraph) -> None:
+        changed = True
+        while changed:
+            changed = False
+            pairs = []
+            for node in fgraph.toposort():
+                op = node.op
+                if not isinstance(op, Elemwise) or len(node.inputs) != 2 or op.name not in ("add", "mul"):
+                    continue
+                out = node.outputs[0]
+                for keep, other in ((node.inputs[0], node.inputs[1]), (node.inputs[1], node.inputs[0])):
+                    if not isinstance(keep.type, TensorType) or keep.type.dtype != out.type.dtype \
+                            or keep.type.ndim != out.type.ndim:
+                        continue
+                    neutral = (self._is_scalar_const(other, 0.0) or self._is_scalar_zeros(other)) if op.name == "add" \
+                        else self._is_scalar_const(other, 1.0)
+                    if neutral:
+                        pairs.append((out, keep))
+                        break
+            if pairs:
+                # one replacement may feed another (a + 0 + 0): resolve chains before rewiring
+                target = {id(old): new for old, new in pairs}
+                resolved = []
+                for old, new in pairs:
+                    while id(new) in target:
+                        new = target[id(new)]
+                    resolved.append((old, new))
+                fgraph.replace_all(resolved, reason="identity")
+                changed = True
+
+
 class OptimizerDB:
     """Named rewriters with tags and positions (``pytensor.compile.optdb`` subset)."""
 
@@ -824,6 +913,7 @@ class OptimizerDB:
 
 optdb = OptimizerDB()
 optdb.register("merge1", MergeOptimizer(), "fast_run", "fast_compile", position=0)
+optdb.register("identities", IdentityEliminator(), "fast_run", position=10)
 optdb.register("merge2", MergeOptimizer(), "fast_run", position=49)
 
 MODES = {"FAST_RUN": "fast_run", "FAST_COMPILE": "fast_compile"}
@@ -849,30 +939,122 @@ def get_mode(mode) -> Mode:
 
 
 class Function:
+    """The compiled graph: every variable gets a slot (constants are pre-filled), every Apply node becomes one
+    step — a thunk (``Op.make_thunk``) where the Op offers one, else ``perform`` with fresh storage cells — and
+    the steps are emitted as ONE generated straight-line Python function.  Statically scalar float arithmetic
+    runs on NumPy scalars (``scalar_thunk``: several times cheaper than ufunc calls on 0-d arrays); a value is
+    converted once (``x[()]`` / ``asarray``) where a consumer of the other kind needs it.  This is the per-model-
+    evaluation overhead a sampler pays on top of the federated launch."""
+
+    _ARRAY, _SCALAR = 0, 1
+
     def __init__(self, fgraph: FunctionGraph, single_output: bool) -> None:
         self.fgraph = fgraph
         self.maker = self  # pytensor spelling: fn.maker.fgraph
         self._single = single_output
         self._order = fgraph.toposort()
+        slots: Dict[int, int] = {}
+        template: List[Any] = []
+
+        def slot_of(v: Variable) -> int:
+            k = slots.get(id(v))
+            if k is None:
+                k = slots[id(v)] = len(template)
+                template.append(v.data if isinstance(v, Constant) else None)
+            return k
+
+        self._in_slots = [slot_of(v) for v in fgraph.inputs]
+        self._filters = [v.type.filter for v in fgraph.inputs]
+        form: Dict[int, int] = {}          # slot -> form its producer leaves it in (default: array)
+        steps = []
+        for node in self._order:
+            ins = tuple(slot_of(i) for i in node.inputs)
+            outs = tuple(slot_of(o) for o in node.outputs)
+            thunk = node.op.make_thunk(node) if len(outs) == 1 else None
+            wants = self._SCALAR if getattr(thunk, "returns_scalar", False) else self._ARRAY
+            # per input: None = as it is, else the form to convert to
+            conv = tuple(None if form.get(i, self._ARRAY) == wants else wants for i in ins)
+            if thunk is not None:
+                steps.append((thunk, None, ins, outs[0], conv))
+                form[outs[0]] = wants
+            else:
+                steps.append((node.op.perform, node, ins, outs, conv))
+        self._steps = steps
+        self._out_slots = [slot_of(o) for o in fgraph.outputs]
+        self._out_conv = [self._ARRAY if form.get(k, self._ARRAY) == self._SCALAR else None for k in self._out_slots]
+        self._template = template
+        self._keep = [v for node in self._order for v in node.inputs]   # ids stay unique while the plan lives
+        self._run = self._generate()
+
+    def _generate(self) -> Optional[Callable]:
+        """``def _run(v0, v1): v7 = f3(v1, c4); ...; return [v30, v31]`` with constants, thunks and ``perform``
+        methods bound as globals (``__call__`` falls back to an interpreter loop if this is not possible)."""
+        ns: Dict[str, Any] = {"_A": np.asarray}
+        const_slots = {k for k, v in enumerate(self._template) if v is not None}
+        converted: Dict[Tuple[int, int], str] = {}   # (slot, form) -> name of the converted value
+        for k in const_slots:
+            ns[f"c{k}"] = self._template[k]
+        base = lambda k: f"c{k}" if k in const_slots else f"v{k}"
+        args = [f"v{k}" for k in self._in_slots]
+        if len(set(args)) != len(args):
+            return None
+        lines = [f"def _run({', '.join(args)}):"]
+
+        def operand(k: int, to) -> str:
+            if to is None:
+                return base(k)
+            name = converted.get((k, to))
+            if name is None:
+                name = converted[(k, to)] = f"{base(k)}{'s' if to == self._SCALAR else 'a'}"
+                expr = f"{base(k)}[()]" if to == self._SCALAR else f"_A({base(k)})"
+                if k in const_slots:
+                    ns[name] = eval(expr, ns)  # noqa: S307 - a constant of the plan, converted once
+                else:
+                    lines.append(f"    {name} = {expr}")
+            return name
+
+        for n, (fn, node, ins, outs, conv) in enumerate(self._steps):
+            ns[f"f{n}"] = fn
+            call_args = ", ".join([operand(i, c) for i, c in zip(ins, conv)])
+            if node is None:
+                lines.append(f"    v{outs} = f{n}({call_args})")
+            else:
+                ns[f"n{n}"] = node
+                lines.append(f"    s = [{', '.join('[None]' for _ in outs)}]")
+                lines.append(f"    f{n}(n{n}, [{call_args}], s)")
+                for j, k in enumerate(outs):
+                    lines.append(f"    v{k} = s[{j}][0]")
+        lines.append(f"    return [{', '.join([operand(k, c) for k, c in zip(self._out_slots, self._out_conv)])}]")
+        try:
+            exec(compile("\n".join(lines), "<pytensor_federated_b200.graph.Function>", "exec"), ns)  # noqa: S102 - own plan
+        except (SyntaxError, MemoryError, RecursionError):
+            return None
+        return ns["_run"]
+
+    def _convert(self, value, to):
+        if to is None:
+            return value
+        return np.asarray(value)[()] if to == self._SCALAR else np.asarray(value)
 
     def __call__(self, *args):
-        if len(args) != len(self.fgraph.inputs):
-            raise TypeError(f"Expected {len(self.fgraph.inputs)} inputs, got {len(args)}")
-        values: Dict[int, Any] = {}
-        for var, arg in zip(self.fgraph.inputs, args):
-            values[id(var)] = var.type.filter(arg)
-
-        def value_of(v: Variable):
-            if isinstance(v, Constant):
-                return v.data
-            return values[id(v)]
-
-        for node in self._order:
-            storage: OutputStorageType = [[None] for _ in node.outputs]
-            node.op.perform(node, [value_of(i) for i in node.inputs], storage)
-            for out, cell in zip(node.outputs, storage):
-                values[id(out)] = cell[0]
-        results = [value_of(o) for o in self.fgraph.outputs]
+        if len(args) != len(self._in_slots):
+            raise TypeError(f"Expected {len(self._in_slots)} inputs, got {len(args)}")
+        if self._run is not None:
+            results = self._run(*[flt(arg) for flt, arg in zip(self._filters, args)])
+            return results[0] if self._single else results
+        vals = list(self._template)
+        for k, flt, arg in zip(self._in_slots, self._filters, args):
+            vals[k] = flt(arg)
+        for fn, node, ins, outs, conv in self._steps:
+            given = [self._convert(vals[i], c) for i, c in zip(ins, conv)]
+            if node is None:
+                vals[outs] = fn(*given)
+            else:
+                storage: OutputStorageType = [[None] for _ in outs]
+                fn(node, given, storage)
+                for k, cell in zip(outs, storage):
+                    vals[k] = cell[0]
+        results = [self._convert(vals[k], c) for k, c in zip(self._out_slots, self._out_conv)]
         return results[0] if self._single else results
 
 

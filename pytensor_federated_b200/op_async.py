@@ -133,8 +133,44 @@ class ParallelAsyncOp(AsyncOp):
             raise ParallelAsyncError(errors) from errors[0]
 
     def perform(self, node: Apply, inputs: Sequence[Any], output_storage: OutputStorageType) -> None:
+        if self._perform_fused_sync(list(inputs), output_storage):
+            return
         loop = get_useful_event_loop()
         loop.run_until_complete(self.perform_async(node, inputs, output_storage))
+
+    def _perform_fused_sync(self, inputs, output_storage) -> bool:
+        """Fast path: every child belongs to a fusable group whose engine call is synchronous anyway
+        (``FusableAsyncOp.perform_fused_sync``) — one call per group, no event loop.  Returns False (nothing
+        done) when any child needs the loop.  Errors are reported exactly like on the asynchronous path."""
+        layout = self.__dict__.get("_sync_layout")
+        if layout is None:
+            # the grouping is a property of the children (their ops and fusion keys), computed once:
+            # [[(apply, first input, end input, first output, end output), ...] per group], or () = needs the loop
+            groups, ifrom, ofrom = {}, 0, 0
+            for apply in self.applies:
+                op = apply.op
+                key = op.fusion_key() if isinstance(op, FusableAsyncOp) and op.has_sync_fused() else None
+                if key is None:
+                    groups = None
+                    break
+                groups.setdefault(key, []).append((apply, ifrom, ifrom + apply.nin, ofrom, ofrom + apply.nout))
+                ifrom += apply.nin
+                ofrom += apply.nout
+            layout = self._sync_layout = tuple(groups.values()) if groups else ()
+        if not layout:
+            return False
+        errors = []
+        for group in layout:
+            members = [(apply, inputs[i0:i1], output_storage[o0:o1]) for apply, i0, i1, o0, o1 in group]
+            try:
+                members[0][0].op.perform_fused_sync(members)
+            except Exception as ex:  # noqa: BLE001 - aggregated below, as asyncio.gather(return_exceptions=True) does
+                errors.append(ex)
+        if len(errors) == 1:
+            raise errors[0]
+        if errors:
+            raise ParallelAsyncError(errors) from errors[0]
+        return True
 
 
 class FusableAsyncOp(AsyncOp):
@@ -150,6 +186,14 @@ class FusableAsyncOp(AsyncOp):
 
     async def perform_fused(self, members) -> None:
         await asyncio.gather(*[a.op.perform_async(a, i, o) for a, i, o in members])
+
+    def has_sync_fused(self) -> bool:
+        """True if :meth:`perform_fused_sync` is implemented: the fused call blocks anyway (an engine launch), so a
+        :class:`ParallelAsyncOp` made only of such children skips the event loop."""
+        return type(self).perform_fused_sync is not FusableAsyncOp.perform_fused_sync
+
+    def perform_fused_sync(self, members) -> None:
+        raise NotImplementedError
 
 
 def _async_depths(fg: FunctionGraph, op_cls: type) -> dict:

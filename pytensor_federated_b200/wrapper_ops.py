@@ -133,6 +133,9 @@ class FederatedLogpGradOp(FusableAsyncOp, LogpGradOp):
         self._store(self.federation.evaluate_node(self.node, *inputs), output_storage)
 
     async def perform_fused(self, members) -> None:
+        self.perform_fused_sync(members)
+
+    def perform_fused_sync(self, members) -> None:
         requests = {apply.op.node: list(ins) for apply, ins, _ in members}
         results = self.federation.evaluate_nodes(requests)
         for apply, _, outs in members:

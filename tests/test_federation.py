@@ -62,6 +62,35 @@ def test_fused_federated_ops_use_one_launch_per_model_evaluation():
     assert fed.n_launches == 3
 
 
+def test_fused_federated_ops_need_no_event_loop(monkeypatch):
+    """The fused engine call blocks anyway, so a ParallelAsyncOp made only of federated Ops calls it directly
+    (`perform_fused_sync`): no asyncio machinery per model evaluation; errors surface as on the async path."""
+    from pytensor_federated_b200 import op_async
+
+    fed = NodeFederation(_three_node_engine())
+    ops = fed.node_ops()
+    a, b = at.scalar("a"), at.scalar("b")
+    total = ops[0](a, b)[0] + ops[1](a + 1.0, b)[0] + ops[2](a - 1.0, b)[0]
+    fn = function([a, b], [total, *grad(total, [a, b])])
+
+    def no_loop():
+        raise AssertionError("the synchronous fast path must not touch the event loop")
+
+    monkeypatch.setattr(op_async, "get_useful_event_loop", no_loop)
+    fed.n_launches = 0
+    val, da, db = fn(0.2, 0.4)
+    assert fed.n_launches == 1
+    want = sum(fed.evaluate_node(i, 0.2 + off, 0.4)[0] for i, off in enumerate((0.0, 1.0, -1.0)))
+    np.testing.assert_allclose(val, want, rtol=1e-12)
+
+    def boom(requests):
+        raise RuntimeError("node 1 is on fire")
+
+    monkeypatch.setattr(fed, "evaluate_nodes", boom)
+    with pytest.raises(RuntimeError, match="on fire"):
+        fn(0.2, 0.4)
+
+
 def test_nodes_are_reachable_through_the_reference_client_api():
     fed = NodeFederation(_three_node_engine())
     addresses = fed.register_services("gpu", 10)

@@ -113,3 +113,62 @@ def test_dot_transpose_and_more_elementwise_gradients():
     assert m == 2.0 and m0.tolist() == [1.0, 3.0]
     with pytest.raises(TypeError):
         at.dot(at.scalar("s"), x)
+
+
+def test_identity_eliminator_removes_autodiff_noise_without_touching_values_shapes_or_dtypes():
+    """`g + zeros_like(scalar)`, `1.0 * g`, `g + 0.0` disappear in FAST_RUN; anything that could broadcast or
+    change the dtype stays."""
+    v, s = G.vector("v"), G.scalar("s")
+    cost = (v * s).sum() + s * s + (v[1] + 2.0) * s
+    grads = G.grad(cost, [v, s])
+    fast = G.function([v, s], [cost, *grads])
+    slow = G.function([v, s], [cost, *grads], mode=G.Mode("FAST_RUN").excluding("identities"))
+    n_fast, n_slow = len(fast.maker.fgraph.toposort()), len(slow.maker.fgraph.toposort())
+    assert n_fast < n_slow
+    for args in ((np.array([0.3, -1.2, 2.0]), 0.7), (np.array([1.0, 2.0]), -3.0)):
+        for a, b in zip(fast(*args), slow(*args)):
+            assert isinstance(a, np.ndarray) and a.dtype == b.dtype and a.shape == b.shape
+            np.testing.assert_array_equal(a, b)
+
+    # not an identity: a zero VECTOR broadcasts the scalar, a float constant promotes an integer operand
+    out = s + G.zeros_like(v)
+    f = G.function([v, s], out)
+    assert any(isinstance(n.op, G.ZerosLike) for n in f.maker.fgraph.toposort())
+    np.testing.assert_array_equal(f(np.zeros(3), 2.0), [2.0, 2.0, 2.0])
+    i = G.scalar("i", dtype="int64")
+    g = G.function([i], i * 1.0)
+    assert g(np.int64(3)).dtype == np.float64 and len(g.maker.fgraph.toposort()) == 1
+
+
+def test_compiled_function_runs_scalars_as_numpy_scalars_but_hands_out_arrays():
+    """Statically scalar arithmetic runs on NumPy scalars inside the generated code; Ops that go through
+    `perform` (user functions, federated Ops) and the caller still see ndarrays, and the generated function agrees
+    with the interpreter loop it replaces."""
+    seen = []
+
+    def spy(a, b):
+        seen.append((type(a), type(b), np.shape(a), np.shape(b)))
+        return np.asarray(a * b)
+
+    op = G.FromFunctionOp(spy, [G.TensorType("float64", ()), G.TensorType("float64", (None,))], [G.TensorType("float64", (None,))])
+    s, v = G.scalar("s"), G.vector("v")
+    t = (s * 2.0 + 1.0) / 3.0                 # scalar thunks
+    out = op(t, v * t)                        # perform path fed by a scalar
+    total = out.sum() + t
+    fn = G.function([s, v], [total, t, out])
+    assert fn._run is not None
+    res = fn(1.5, np.array([1.0, 2.0]))
+    assert all(isinstance(r, np.ndarray) for r in res) and res[0].shape == () and res[1].shape == ()
+    assert seen == [(np.ndarray, np.ndarray, (), (2,))]
+    tv = (1.5 * 2.0 + 1.0) / 3.0
+    np.testing.assert_allclose(res[2], tv * np.array([1.0, 2.0]) * tv)
+    np.testing.assert_allclose(res[0], res[2].sum() + tv)
+    # the interpreter fallback computes the same thing
+    generated, fn._run = fn._run, None
+    again = fn(1.5, np.array([1.0, 2.0]))
+    fn._run = generated
+    for a, b in zip(res, again):
+        assert isinstance(b, np.ndarray) and a.shape == b.shape and a.dtype == b.dtype
+        np.testing.assert_array_equal(a, b)
+    with pytest.raises(TypeError):
+        fn(1.5)
