@@ -562,10 +562,18 @@ def linreg_nuts(eng, args):
         logp, *_ = ops[i](icpt[i] + off, slope)
         m.Potential(f"p{i}", logp)
     m.compile()
+    spec = False
+    try:
+        spec = bool(args.speculative_us > 0 and eng.set_speculative(args.speculative_us))
+    except Exception as ex:
+        print(f"[bench] speculative launches unavailable ({ex})", file=sys.stderr, flush=True)
     t0 = time.perf_counter()
     res = nuts_sample(m.logp_dlogp, np.zeros(m.dim), draws=args.nuts_draws, tune=args.nuts_draws, seed=1)
     dt = time.perf_counter() - t0
+    if spec:
+        eng.set_speculative(0.0)
     return {"nuts": {"draws": args.nuts_draws, "tune": args.nuts_draws, "seconds": dt, "n_logp_evals": res.n_logp_evals,
+                     "speculative_us": args.speculative_us if spec else 0.0,
                      "model_evals_per_s": res.n_logp_evals / dt, "node_evals_per_s": args.shards * res.n_logp_evals / dt,
                      "fused_launches": fed.n_launches, "divergences": int(res.divergences)}}
 
