@@ -250,6 +250,9 @@ _SCALAR_OPERATORS = {"add": operator.add, "sub": operator.sub, "mul": operator.m
                      "neg": operator.neg}
 
 
+_SCALAR_INFIX = {"add": "({0} + {1})", "sub": "({0} - {1})", "mul": "({0} * {1})", "true_div": "({0} / {1})", "neg": "(-{0})"}
+
+
 class Elemwise(Op):
     """Broadcasting NumPy ufunc with a hand-written derivative."""
 
@@ -285,6 +288,9 @@ class Elemwise(Op):
                 return out if type(out) is sc else sc(out)
 
             scalar_thunk.returns_scalar = True
+            # float64 (op) float64 is float64: the generated code can write the operator out instead of calling
+            if self.name in _SCALAR_INFIX and dt == np.float64 and all(i.type.dtype == "float64" for i in node.inputs):
+                scalar_thunk.inline = _SCALAR_INFIX[self.name]
             return scalar_thunk
 
         def thunk(*inputs):
@@ -1015,8 +1021,12 @@ class Function:
 
         for n, (fn, node, ins, outs, conv) in enumerate(self._steps):
             ns[f"f{n}"] = fn
-            call_args = ", ".join([operand(i, c) for i, c in zip(ins, conv)])
-            if node is None:
+            operands = [operand(i, c) for i, c in zip(ins, conv)]
+            call_args = ", ".join(operands)
+            inline = getattr(fn, "inline", None) if node is None else None
+            if inline is not None:
+                lines.append(f"    v{outs} = {inline.format(*operands)}")
+            elif node is None:
                 lines.append(f"    v{outs} = f{n}({call_args})")
             else:
                 ns[f"n{n}"] = node
