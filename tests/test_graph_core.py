@@ -172,3 +172,17 @@ def test_compiled_function_runs_scalars_as_numpy_scalars_but_hands_out_arrays():
         np.testing.assert_array_equal(a, b)
     with pytest.raises(TypeError):
         fn(1.5)
+
+
+def test_compiled_function_edge_cases_inputs_as_outputs_constants_and_mixed_dtypes():
+    s, v = G.scalar("s"), G.vector("v")
+    f = G.function([s, v], [s, v, s * 2.0, G.as_tensor(3.0), s * 2.0])
+    out = f(1.5, np.array([1.0, 2.0]))
+    assert [np.asarray(o).tolist() for o in out] == [1.5, [1.0, 2.0], 3.0, 3.0, 3.0]
+    assert isinstance(G.function([s], s)(2.0), np.ndarray)
+    i = G.scalar("i", dtype="int64")
+    r = G.function([i, s], [i + 1, i / 2, i * s, -i])(3, 0.5)
+    assert [o.dtype.kind for o in r] == ["i", "f", "f", "i"] and [o.tolist() for o in r] == [4, 1.5, 1.5, -3]
+    x = G.scalar("x", dtype="float32")
+    r = G.function([x, s], [x * x, x + s])(np.float32(1.5), 0.25)
+    assert r[0].dtype == np.float32 and r[1].dtype == np.float64 and r[1] == 1.75
