@@ -64,6 +64,9 @@ class OdeSystem:
         self.name = name
         self._lib = None
 
+    def __repr__(self) -> str:
+        return f"OdeSystem(name={self.name!r}, n_states={self.n_states}, n_params={self.n_params})"
+
     def digest(self) -> str:
         h = hashlib.sha256(f"{self.n_states}|{self.n_params}|{self.rhs_cuda}".encode())
         for f in ("ode_generic.cu", "fed_comm.cuh", "models.h"):
