@@ -570,12 +570,31 @@ def linreg_nuts(eng, args):
     t0 = time.perf_counter()
     res = nuts_sample(m.logp_dlogp, np.zeros(m.dim), draws=args.nuts_draws, tune=args.nuts_draws, seed=1)
     dt = time.perf_counter() - t0
+    # the same posterior with the WHOLE federation behind one Op (`NodeFederation.all_nodes_op`): the graph no longer
+    # grows with the number of nodes
+    from pytensor_federated_b200.graph import core as at
+
+    m1 = Model()
+    mu1 = m1.Normal("intercept_mu", 0.0, 1.0)
+    icpt1 = m1.Normal("intercept", mu1, 0.1, size=args.shards)
+    slope1 = m1.Normal("slope", 0.0, 1.0)
+    logp1, *_ = fed.all_nodes_op()(icpt1 + at.as_tensor(np.linspace(-4, 4, args.shards)), slope1)
+    m1.Potential("all", logp1)
+    m1.compile()
+    launches0 = fed.n_launches
+    t1 = time.perf_counter()
+    res1 = nuts_sample(m1.logp_dlogp, np.zeros(m1.dim), draws=args.nuts_draws, tune=args.nuts_draws, seed=1)
+    dt1 = time.perf_counter() - t1
+    one_op = {"seconds": dt1, "n_logp_evals": res1.n_logp_evals, "model_evals_per_s": res1.n_logp_evals / dt1,
+              "node_evals_per_s": args.shards * res1.n_logp_evals / dt1, "fused_launches": fed.n_launches - launches0,
+              "divergences": int(res1.divergences),
+              "same_chain_as_per_node_ops": bool(np.allclose(res1.samples, res.samples, rtol=1e-6, atol=1e-9))}
     if spec:
         eng.set_speculative(0.0)
     return {"nuts": {"draws": args.nuts_draws, "tune": args.nuts_draws, "seconds": dt, "n_logp_evals": res.n_logp_evals,
-                     "speculative_us": args.speculative_us if spec else 0.0,
+                     "speculative_us": args.speculative_us if spec else 0.0, "one_op_for_the_federation": one_op,
                      "model_evals_per_s": res.n_logp_evals / dt, "node_evals_per_s": args.shards * res.n_logp_evals / dt,
-                     "fused_launches": fed.n_launches, "divergences": int(res.divergences)}}
+                     "fused_launches": launches0, "divergences": int(res.divergences)}}
 
 
 def run_reference(args):

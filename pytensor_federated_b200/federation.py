@@ -139,11 +139,52 @@ class NodeFederation:
 
         return compute
 
+    def all_nodes_func(self) -> Callable:
+        """The WHOLE federation as one ``LogpGradFunc`` — node parameters stacked along a leading axis, the
+        summed log-likelihood and per-node gradients back, one launch:
+
+        * linear regression: ``f(intercepts, slopes) -> (logp, [d_intercepts, d_slopes])``, each argument a vector
+          ``[n_nodes]`` or a scalar shared by all nodes (its gradient is then the sum over the nodes);
+        * ODE: ``f(theta[n_nodes, n_params]) -> (logp, [d_theta])``;
+        * GLM (parameters shared by the nodes): ``f(intercept, beta) -> (logp, [d_intercept, d_beta])``.
+
+        With :meth:`all_nodes_op` the model graph has ONE federated node instead of one per data holder, so the
+        Python cost of a model evaluation no longer grows with the size of the federation."""
+        kind, eng = self._kind, self.engine
+        if kind == "linreg":
+            def func(intercepts, slopes):
+                # a scalar argument is shared by all nodes and gets the summed gradient (LinregShards.unpack_result)
+                with self._lock:
+                    self.n_launches += 1
+                    logp, da, db = eng.evaluate(intercepts, slopes)
+                    return logp, [da, db]
+        elif kind == "ode":
+            def func(theta):
+                m = eng.model
+                with self._lock:
+                    self.n_launches += 1
+                    th = np.broadcast_to(np.asarray(theta, dtype=np.float64), (self.n_nodes, m.n_params))
+                    per = m.per_node(eng.evaluate_raw([th]))
+                    return np.asarray(per[:, 0].sum()), [per[:, 1:].copy()]
+        else:
+            def func(intercept, beta):
+                with self._lock:
+                    self.n_launches += 1
+                    logp, *grads = eng.evaluate(intercept, beta)
+                    return logp, grads
+        return func
+
     # -- graph integration ---------------------------------------------------------------------
     def node_ops(self):
         from .wrapper_ops import FederatedLogpGradOp
 
         return [FederatedLogpGradOp(self, i) for i in range(self.n_nodes)]
+
+    def all_nodes_op(self):
+        """One ``LogpGradOp`` over :meth:`all_nodes_func` (vector parameters in, summed logp and vector gradients out)."""
+        from .wrapper_ops import LogpGradOp
+
+        return LogpGradOp(self.all_nodes_func())
 
     # -- reference client API ------------------------------------------------------------------
     def register_services(self, host: str = "gpu", first_port: int = 0) -> List[Tuple[str, int]]:

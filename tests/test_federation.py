@@ -220,6 +220,10 @@ def test_ode_nodes_take_their_own_parameters_through_federated_ops():
     np.testing.assert_allclose(val, float(res[0][0]) + float(res[1][0]), rtol=1e-12)
     np.testing.assert_allclose(ga, res[0][1][0], rtol=1e-12)
     np.testing.assert_allclose(gb, res[1][1][0], rtol=1e-12)
+    # the whole federation as ONE Op: a [n_nodes, n_params] matrix in, summed logp and the matrix of gradients out
+    lp, (g_all,) = fed.all_nodes_func()(np.stack([th0, th1]))
+    np.testing.assert_allclose(lp, val, rtol=1e-12)
+    np.testing.assert_allclose(g_all, np.stack([ga, gb]), rtol=1e-12)
 
 
 def test_replicated_gpu_nodes_balance_and_fail_over():
@@ -255,3 +259,32 @@ def test_replicated_gpu_nodes_balance_and_fail_over():
     finally:
         for host, port in addresses:
             service.unregister_local_node(host, port)
+
+
+def test_whole_federation_as_one_op_matches_the_per_node_ops():
+    """`all_nodes_op`: vector of node intercepts + shared slope in, summed logp and gradients out — the same numbers
+    as one Op per node, from a graph whose size does not depend on the number of nodes."""
+    fed = NodeFederation(_three_node_engine())
+    offs = np.linspace(-1.5, 1.5, 3)
+    icpt, slope = at.vector("intercept"), at.scalar("slope")
+    # one Op per node (reference pattern)
+    total = None
+    for i, op in enumerate(fed.node_ops()):
+        logp, *_ = op(icpt[i] + offs[i], slope)
+        total = logp if total is None else total + logp
+    per_node = function([icpt, slope], [total, *grad(total, [icpt, slope])])
+    # one Op for the federation
+    logp_all, *_ = fed.all_nodes_op()(icpt + at.as_tensor(offs), slope)
+    whole = function([icpt, slope], [logp_all, *grad(logp_all, [icpt, slope])])
+    assert len(whole.maker.fgraph.toposort()) < len(per_node.maker.fgraph.toposort()) / 3
+    args = (np.array([0.1, 0.2, 0.3]), 0.5)
+    fed.n_launches = 0
+    got = whole(*args)
+    assert fed.n_launches == 1
+    for g, w in zip(got, per_node(*args)):
+        np.testing.assert_allclose(g, w, rtol=1e-12)
+    f = fed.all_nodes_func()
+    lp, (da, db) = f(np.array([0.1, 0.2, 0.3]) + offs, np.array([0.5, 0.5, 0.5]))
+    np.testing.assert_allclose(lp, got[0], rtol=1e-12)
+    assert da.shape == (3,) and db.shape == (3,)
+    np.testing.assert_allclose(db.sum(), got[2], rtol=1e-12)
