@@ -588,7 +588,10 @@ def linreg_nuts(eng, args):
     one_op = {"seconds": dt1, "n_logp_evals": res1.n_logp_evals, "model_evals_per_s": res1.n_logp_evals / dt1,
               "node_evals_per_s": args.shards * res1.n_logp_evals / dt1, "fused_launches": fed.n_launches - launches0,
               "divergences": int(res1.divergences),
-              "same_chain_as_per_node_ops": bool(np.allclose(res1.samples, res.samples, rtol=1e-6, atol=1e-9))}
+              # (the two graphs add the node terms in different orders, so the chains part ways after a few
+              # hundred steps; what has to agree is the posterior)
+              "posterior_mean_max_abs_diff_vs_per_node_ops": float(np.max(np.abs(res1.samples.mean(0) - res.samples.mean(0)))),
+              "posterior_sd_max": float(np.max(res.samples.std(0)))}
     if spec:
         eng.set_speculative(0.0)
     return {"nuts": {"draws": args.nuts_draws, "tune": args.nuts_draws, "seconds": dt, "n_logp_evals": res.n_logp_evals,
