@@ -186,3 +186,43 @@ def test_compiled_function_edge_cases_inputs_as_outputs_constants_and_mixed_dtyp
     x = G.scalar("x", dtype="float32")
     r = G.function([x, s], [x * x, x + s])(np.float32(1.5), 0.25)
     assert r[0].dtype == np.float32 and r[1].dtype == np.float64 and r[1] == 1.75
+
+
+def _random_expression(rng, leaves, depth):
+    """A random expression over scalar and vector leaves (broadcasting, reductions, constants that look like
+    identities) — food for the differential test below."""
+    if depth == 0 or rng.random() < 0.15:
+        leaf = leaves[rng.integers(len(leaves))]
+        return leaf if rng.random() < 0.8 else G.as_tensor(float(rng.choice([0.0, 1.0, 2.0, -0.5])))
+    kind = rng.integers(9)
+    a = _random_expression(rng, leaves, depth - 1)
+    if kind in (0, 1, 2, 3):
+        b = _random_expression(rng, leaves, depth - 1)
+        return [G.add, G.sub, G.mul, lambda x, y: x / (y * y + 1.5)][kind](a, b)
+    if kind == 4:
+        return -a
+    if kind == 5:
+        return G.tanh(a)
+    if kind == 6:
+        return G.exp(a * 0.1)
+    if kind == 7:
+        return a.sum() if a.type.ndim else a * 1.0
+    return a + G.zeros_like(leaves[rng.integers(len(leaves))]) if rng.random() < 0.5 else a + 0.0
+
+
+@pytest.mark.parametrize("seed", range(25))
+def test_generated_code_identities_and_scalar_paths_agree_with_the_plain_interpreter(seed):
+    """Differential test of the compiled Function: FAST_RUN (identity elimination, generated straight-line code,
+    NumPy-scalar arithmetic) against the interpreter loop on the unsimplified graph, values AND gradients."""
+    rng = np.random.default_rng(seed)
+    s, t, v = G.scalar("s"), G.scalar("t"), G.vector("v")
+    expr = _random_expression(rng, [s, t, v], depth=5)
+    cost = expr.sum() if expr.type.ndim else expr
+    outputs = [cost, expr, *G.grad(cost, [s, t, v])]
+    fast = G.function([s, t, v], outputs)
+    plain = G.function([s, t, v], outputs, mode=G.Mode("FAST_RUN").excluding("identities"))
+    plain._run = None                                    # the interpreter loop
+    args = (0.7, -1.3, np.array([0.2, -0.4, 1.1]))
+    for a, b in zip(fast(*args), plain(*args)):
+        assert isinstance(a, np.ndarray) and a.shape == b.shape and a.dtype == b.dtype
+        np.testing.assert_allclose(a, b, rtol=1e-13, atol=1e-13)
