@@ -326,6 +326,18 @@ class ReduceTo(Op):
                 g = g.sum(axis=ax, keepdims=True)
         output_storage[0][0] = np.asarray(g, dtype=node.outputs[0].type.dtype).reshape(shape)
 
+    def make_thunk(self, node):
+        dt, asarray, np_shape, perform = np.dtype(node.outputs[0].type.dtype), np.asarray, np.shape, self.perform
+
+        def thunk(g, like):
+            if np_shape(g) == np_shape(like):          # nothing was broadcast: the usual case at run time
+                return g if type(g) is np.ndarray and g.dtype == dt else asarray(g, dtype=dt)
+            cell = [[None]]
+            perform(node, [g, like], cell)
+            return cell[0][0]
+
+        return thunk
+
     def grad(self, inputs, output_grads):
         g, like = inputs
         (gz,) = output_grads
@@ -355,8 +367,9 @@ class Sum(Op):
         output_storage[0][0] = np.asarray(np.sum(inputs[0], axis=self.axis))
 
     def make_thunk(self, node):
-        axis, np_sum, asarray = self.axis, np.sum, np.asarray
-        return lambda x: asarray(np_sum(x, axis=axis))
+        axis, np_sum, asarray, ndarray = self.axis, np.sum, np.asarray, np.ndarray
+        # the method skips np.sum's dispatch wrappers (a third of the cost on the short vectors of a model graph)
+        return lambda x: asarray(x.sum(axis=axis) if type(x) is ndarray else np_sum(x, axis=axis))
 
     def grad(self, inputs, output_grads):
         (x,) = inputs
@@ -428,6 +441,16 @@ class IncSubtensorZeros(Op):
         out[self.idx] = g
         output_storage[0][0] = out
 
+    def make_thunk(self, node):
+        idx, dt, zeros, np_shape = self.idx, np.dtype(node.outputs[0].type.dtype), np.zeros, np.shape
+
+        def thunk(like, g):
+            out = zeros(np_shape(like), dtype=dt)
+            out[idx] = g
+            return out
+
+        return thunk
+
     def grad(self, inputs, output_grads):
         return [DisconnectedType()(), Subtensor(self.idx)(output_grads[0])]
 
@@ -442,6 +465,10 @@ class ZerosLike(Op):
 
     def perform(self, node, inputs, output_storage) -> None:
         output_storage[0][0] = np.zeros(np.shape(inputs[0]), dtype=node.outputs[0].type.dtype)
+
+    def make_thunk(self, node):
+        dt, zeros, np_shape = np.dtype(node.outputs[0].type.dtype), np.zeros, np.shape
+        return lambda x: zeros(np_shape(x), dtype=dt)
 
     def grad(self, inputs, output_grads):
         return [DisconnectedType()()]
