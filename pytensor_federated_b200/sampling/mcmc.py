@@ -3,6 +3,7 @@ from __future__ import annotations
 
 import dataclasses
 import math
+from math import inf, isfinite
 from typing import Callable, Dict, Optional, Tuple
 
 import numpy as np
@@ -193,6 +194,16 @@ def hmc_sample(logp_dlogp: LogpDlogp, x0: np.ndarray, *, draws: int = 500, tune:
                          rng_state=rng.bit_generator.state)
 
 
+def _logaddexp(a: float, b: float) -> float:
+    """``log(exp(a) + exp(b))`` for Python floats (``np.logaddexp`` costs ten times as much on scalars)."""
+    if a == -inf:
+        return b
+    if b == -inf:
+        return a
+    m = a if a > b else b
+    return m + math.log1p(math.exp(-abs(a - b)))
+
+
 def nuts_sample(logp_dlogp: LogpDlogp, x0: Optional[np.ndarray] = None, *, draws: int = 200, tune: int = 500,
                 max_depth: int = 8, target_accept: float = 0.8, seed: int = 0, adapt_mass: bool = True,
                 resume: Optional[SamplerResult] = None) -> SamplerResult:
@@ -235,20 +246,22 @@ def nuts_sample(logp_dlogp: LogpDlogp, x0: Optional[np.ndarray] = None, *, draws
         """Returns the subtree: edges, proposal, log-weight, stop flag, accept stats."""
         if depth == 0:
             xn, pn, lpn, gn = leapfrog(xq, pq, gq, direction * e)
-            h = lpn - 0.5 * np.sum(inv_mass * pn * pn) if np.isfinite(lpn) else -np.inf
-            diverged = not np.isfinite(h) or (h0 - h) > 1000.0
+            # (scalar bookkeeping stays in the math module: this runs once per gradient evaluation)
+            h = float(lpn - 0.5 * np.sum(inv_mass * pn * pn)) if isfinite(lpn) else -inf
+            finite = isfinite(h)
+            diverged = not finite or (h0 - h) > 1000.0
             if diverged:
                 counter["div"] += 1
-            acc = min(1.0, math.exp(min(0.0, h - h0))) if np.isfinite(h) else 0.0
-            return (xn, pn, gn, xn, pn, gn, xn, lpn, gn, h - h0 if np.isfinite(h) else -np.inf, diverged, acc, 1)
+            acc = min(1.0, math.exp(min(0.0, h - h0))) if finite else 0.0
+            return (xn, pn, gn, xn, pn, gn, xn, lpn, gn, h - h0 if finite else -inf, diverged, acc, 1)
         (xm, pm, gm, xp, pp, gp, xprop, lpprop, gprop, logw, stop, acc, n) = build_tree(xq, pq, gq, direction, depth - 1, e, h0)
         if not stop:
             if direction < 0:
                 (xm, pm, gm, _, _, _, x2, lp2, g2, logw2, stop2, acc2, n2) = build_tree(xm, pm, gm, direction, depth - 1, e, h0)
             else:
                 (_, _, _, xp, pp, gp, x2, lp2, g2, logw2, stop2, acc2, n2) = build_tree(xp, pp, gp, direction, depth - 1, e, h0)
-            tot = np.logaddexp(logw, logw2)
-            if np.isfinite(logw2) and math.log(rng.uniform() + 1e-300) < logw2 - tot:
+            tot = _logaddexp(logw, logw2)
+            if isfinite(logw2) and math.log(rng.uniform() + 1e-300) < logw2 - tot:
                 xprop, lpprop, gprop = x2, lp2, g2
             logw = tot
             acc += acc2
@@ -281,9 +294,9 @@ def nuts_sample(logp_dlogp: LogpDlogp, x0: Optional[np.ndarray] = None, *, draws
             n_sum += n2
             if stop2:
                 break
-            if np.isfinite(logw2) and math.log(rng.uniform() + 1e-300) < logw2 - logw:
+            if isfinite(logw2) and math.log(rng.uniform() + 1e-300) < logw2 - logw:
                 x_new, lp_new, g_new = x2, lp2, g2
-            logw = np.logaddexp(logw, logw2)
+            logw = _logaddexp(logw, logw2)
             depth += 1
             if uturn(xm, xp, pm, pp):
                 break
