@@ -125,8 +125,25 @@ class Model:
 
     def logp_dlogp(self, theta: np.ndarray):
         fn = self._compiled or self.compile()
-        total, *grads = fn(*self.split(theta))
-        return float(total), np.concatenate([np.asarray(g, dtype=np.float64).reshape(-1) for g in grads])
+        # (start, stop, shape) of every free variable inside the flat vector; built once per compilation — this
+        # function runs once per leapfrog step
+        plan = self.__dict__.get("_flat_plan")
+        if plan is None or plan[0] is not fn:
+            spans, pos = [], 0
+            for _, _, shape in self.free:
+                n = int(np.prod(shape)) if shape else 1
+                spans.append((pos, pos + n, tuple(shape) if shape else ()))
+                pos += n
+            plan = self._flat_plan = (fn, spans, pos)
+        _, spans, dim = plan
+        theta = np.asarray(theta, dtype=np.float64).reshape(-1)
+        if theta.size != dim:
+            raise ValueError(f"expected a parameter vector of length {dim}, got {theta.size}")
+        total, *grads = fn(*[theta[a:b].reshape(shape) for a, b, shape in spans])
+        out = np.empty(dim)
+        for (a, b, _), g in zip(spans, grads):
+            out[a:b] = np.reshape(g, -1)
+        return float(total), out
 
     def names(self) -> List[str]:
         out = []
