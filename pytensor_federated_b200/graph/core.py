@@ -455,6 +455,46 @@ class IncSubtensorZeros(Op):
         return [DisconnectedType()(), Subtensor(self.idx)(output_grads[0])]
 
 
+class ScatterAdd(Op):
+    """``zeros_like(like)`` with ``out[idx_k] += g_k`` for every ``(idx_k, g_k)`` — what a sum of
+    :class:`IncSubtensorZeros` terms computes, in one allocation (built by :class:`IncSubtensorMerger`: the
+    gradient w.r.t. a vector whose elements are used one by one, e.g. one intercept per federated node)."""
+
+    __props__ = ("idx_keys",)
+
+    def __init__(self, idxs) -> None:
+        self.idxs = tuple(idxs)
+        self.idx_keys = tuple(repr(i) for i in self.idxs)
+
+    def make_node(self, like, *gs) -> Apply:
+        if len(gs) != len(self.idxs):
+            raise ValueError(f"ScatterAdd expects {len(self.idxs)} increments, got {len(gs)}")
+        like = as_tensor(like)
+        return Apply(self, [like, *[as_tensor(g) for g in gs]], [like.type()])
+
+    def perform(self, node, inputs, output_storage) -> None:
+        like, *gs = inputs
+        out = np.zeros(np.shape(like), dtype=node.outputs[0].type.dtype)
+        for idx, g in zip(self.idxs, gs):
+            out[idx] += g
+        output_storage[0][0] = out
+
+    def make_thunk(self, node):
+        idxs, dt, zeros, np_shape = self.idxs, np.dtype(node.outputs[0].type.dtype), np.zeros, np.shape
+
+        def thunk(like, *gs):
+            out = zeros(np_shape(like), dtype=dt)
+            for idx, g in zip(idxs, gs):
+                out[idx] += g
+            return out
+
+        return thunk
+
+    def grad(self, inputs, output_grads):
+        (gz,) = output_grads
+        return [DisconnectedType()(), *[Subtensor(idx)(gz) for idx in self.idxs]]
+
+
 class ZerosLike(Op):
     __props__ = ()
 
@@ -915,6 +955,70 @@ class IdentityEliminator(GraphRewriter):
                 changed = True
 
 
+class IncSubtensorMerger(GraphRewriter):
+    """``inc(like, g0)[i0] + inc(like, g1)[i1] + ... (+ other terms)`` -> ``ScatterAdd(like, g0, g1, ...) (+ other
+    terms)``: the gradient of ``sum_k f_k(x[i_k])`` w.r.t. ``x`` costs one allocation instead of one vector of zeros
+    and one vector addition per term."""
+
+    @staticmethod
+    def _is_add(node) -> bool:
+        return node is not None and isinstance(node.op, Elemwise) and node.op.name == "add" and len(node.inputs) == 2
+
+    def apply(self, fgraph: FunctionGraph) -> None:
+        order = fgraph.toposort()
+        clients: Dict[int, List[Apply]] = {}
+        for node in order:
+            for inp in node.inputs:
+                clients.setdefault(id(inp), []).append(node)
+        outputs = {id(o) for o in fgraph.outputs}
+        pairs = []
+        for node in order:
+            if not self._is_add(node):
+                continue
+            out = node.outputs[0]
+            if any(self._is_add(c) for c in clients.get(id(out), [])) and id(out) not in outputs:
+                continue                                  # an inner node of a larger sum: handled from its top
+            leaves: List[Variable] = []
+
+            def collect(v: Variable, top: bool) -> None:
+                n = v.owner
+                # descend only through sums nobody else needs (and that are not outputs themselves)
+                if self._is_add(n) and (top or (len(clients.get(id(v), [])) == 1 and id(v) not in outputs)) \
+                        and n.inputs[0].type == v.type and n.inputs[1].type == v.type:
+                    collect(n.inputs[0], False)
+                    collect(n.inputs[1], False)
+                else:
+                    leaves.append(v)
+
+            collect(out, True)
+            groups: Dict[int, List[Variable]] = {}
+            for leaf in leaves:
+                n = leaf.owner
+                if n is not None and isinstance(n.op, IncSubtensorZeros) and leaf.type == out.type:
+                    groups.setdefault(id(n.inputs[0]), []).append(leaf)
+            groups = {k: v for k, v in groups.items() if len(v) >= 2}
+            if not groups:
+                continue
+            merged_ids = {id(leaf) for group in groups.values() for leaf in group}
+            terms: List[Variable] = [leaf for leaf in leaves if id(leaf) not in merged_ids]
+            for group in groups.values():
+                like = group[0].owner.inputs[0]
+                scatter = ScatterAdd([leaf.owner.op.idx for leaf in group])(like, *[leaf.owner.inputs[1] for leaf in group])
+                if scatter.type != out.type:
+                    terms = None
+                    break
+                terms.append(scatter)
+            if not terms:
+                continue
+            total = terms[0]
+            for t in terms[1:]:
+                total = total + t
+            if total.type == out.type:
+                pairs.append((out, total))
+        if pairs:
+            fgraph.replace_all(pairs, reason="merge-inc-subtensor")
+
+
 class OptimizerDB:
     """Named rewriters with tags and positions (``pytensor.compile.optdb`` subset)."""
 
@@ -947,6 +1051,7 @@ class OptimizerDB:
 optdb = OptimizerDB()
 optdb.register("merge1", MergeOptimizer(), "fast_run", "fast_compile", position=0)
 optdb.register("identities", IdentityEliminator(), "fast_run", position=10)
+optdb.register("merge_inc_subtensor", IncSubtensorMerger(), "fast_run", position=20)
 optdb.register("merge2", MergeOptimizer(), "fast_run", position=49)
 
 MODES = {"FAST_RUN": "fast_run", "FAST_COMPILE": "fast_compile"}

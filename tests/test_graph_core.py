@@ -216,13 +216,32 @@ def test_generated_code_identities_and_scalar_paths_agree_with_the_plain_interpr
     NumPy-scalar arithmetic) against the interpreter loop on the unsimplified graph, values AND gradients."""
     rng = np.random.default_rng(seed)
     s, t, v = G.scalar("s"), G.scalar("t"), G.vector("v")
-    expr = _random_expression(rng, [s, t, v], depth=5)
+    # elements of v used one by one: their gradients are IncSubtensor terms (merged into one ScatterAdd)
+    expr = _random_expression(rng, [s, t, v, v[0], v[2], v[0] * v[1], v[0:3]], depth=5)
     cost = expr.sum() if expr.type.ndim else expr
     outputs = [cost, expr, *G.grad(cost, [s, t, v])]
     fast = G.function([s, t, v], outputs)
-    plain = G.function([s, t, v], outputs, mode=G.Mode("FAST_RUN").excluding("identities"))
+    plain = G.function([s, t, v], outputs, mode=G.Mode("FAST_RUN").excluding("identities", "merge_inc_subtensor"))
     plain._run = None                                    # the interpreter loop
     args = (0.7, -1.3, np.array([0.2, -0.4, 1.1]))
     for a, b in zip(fast(*args), plain(*args)):
         assert isinstance(a, np.ndarray) and a.shape == b.shape and a.dtype == b.dtype
         np.testing.assert_allclose(a, b, rtol=1e-13, atol=1e-13)
+
+
+def test_inc_subtensor_terms_are_merged_into_one_scatter_add():
+    """d/dv of sum_k f_k(v[k]): one ScatterAdd instead of one zeros vector + one vector add per element."""
+    v, s = G.vector("v"), G.scalar("s")
+    cost = G.exp(v[0] * s) + v[1] * v[1] + G.tanh(v[2]) * s + v[1] * 3.0 + (v * v).sum()
+    gv, gs = G.grad(cost, [v, s])
+    fast = G.function([v, s], [cost, gv, gs])
+    slow = G.function([v, s], [cost, gv, gs], mode=G.Mode("FAST_RUN").excluding("merge_inc_subtensor"))
+    kinds = [type(n.op).__name__ for n in fast.maker.fgraph.toposort()]
+    assert kinds.count("ScatterAdd") == 1 and "IncSubtensorZeros" not in kinds
+    assert len(fast.maker.fgraph.toposort()) < len(slow.maker.fgraph.toposort())
+    args = (np.array([0.3, -1.2, 2.0, 0.5]), 0.7)
+    for a, b in zip(fast(*args), slow(*args)):
+        np.testing.assert_allclose(a, b, rtol=1e-14)
+    # ScatterAdd is differentiable itself (second use of the gradient graph)
+    g2 = G.grad(gv.sum(), v)
+    np.testing.assert_allclose(G.function([v, s], g2)(*args), G.function([v, s], g2, mode="FAST_COMPILE")(*args), rtol=1e-12)
