@@ -34,7 +34,7 @@ def collect_info() -> dict:
     except ImportError:
         info["torch"] = None
     cfg = get_config()
-    info["config"] = {k: getattr(cfg, k) for k in ("comm", "multicast", "glm_kernel", "timeout", "serve_ahead")}
+    info["config"] = {k: getattr(cfg, k) for k in ("comm", "multicast", "glm_kernel", "timeout", "idle_timeout", "serve_ahead", "speculative_us")}
     tls = tls_from_env()
     info["tls"] = None if tls is None else {"ca": bool(tls.ca), "cert": bool(tls.cert), "mutual": tls.mutual,
                                             "server_name": tls.server_name}
