@@ -25,3 +25,10 @@ def test_custom_ode_example_recovers_the_parameters():
 def test_batched_serving_example_batches_requests():
     out = _run("batched_serving.py", "--chains", "3", "--evals", "10", "--rows", "2000")
     assert "dynamic batching (K=3)" in out
+
+
+def test_hierarchical_linreg_example_samples_the_same_posterior_both_ways():
+    out = _run("hierarchical_linreg.py", "--nodes", "3", "--gpus", "1", "--draws", "40")
+    lines = [l for l in out.splitlines() if "graph nodes" in l]
+    assert len(lines) == 2 and "one Op per node" in lines[0] and "one Op for the federation" in lines[1]
+    assert all("slope = 0.4" in l or "slope = 0.5" in l for l in lines)
